@@ -1,0 +1,195 @@
+"""Problem container and seeded synthetic generators.
+
+`QuadraticModel` mirrors the fields of QuadraticModels.QuadraticModel that MadIPM reads
+(reference call sites: /root/reference/test/runtests.jl:29-60, src/structure.jl:79-178):
+
+    min  c0 + c'x + 1/2 x'Hx   s.t.  lcon <= A x <= ucon,  lvar <= x <= uvar
+
+H is given by its LOWER triangle in COO form, A in COO form, both 0-based here (the Julia
+glue converts from 1-based). Pure numpy: shared byte-for-byte by the CUDA path, the oracle
+and the benchmarks, and importable without a GPU.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class QuadraticModel:
+    c: np.ndarray
+    Hrows: np.ndarray
+    Hcols: np.ndarray
+    Hvals: np.ndarray
+    Arows: np.ndarray
+    Acols: np.ndarray
+    Avals: np.ndarray
+    lcon: np.ndarray
+    ucon: np.ndarray
+    lvar: np.ndarray
+    uvar: np.ndarray
+    c0: float = 0.0
+    x0: np.ndarray = None
+    y0: np.ndarray = None
+    name: str = "qp"
+    minimize: bool = True
+    meta: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        self.c = f64(self.c)
+        self.Hrows, self.Hcols, self.Hvals = i32(self.Hrows), i32(self.Hcols), f64(self.Hvals)
+        self.Arows, self.Acols, self.Avals = i32(self.Arows), i32(self.Acols), f64(self.Avals)
+        self.lcon, self.ucon = f64(self.lcon), f64(self.ucon)
+        self.lvar, self.uvar = f64(self.lvar), f64(self.uvar)
+        self.x0 = np.zeros(self.nvar) if self.x0 is None else f64(self.x0)
+        self.y0 = np.zeros(self.ncon) if self.y0 is None else f64(self.y0)
+        assert len(self.Hrows) == len(self.Hcols) == len(self.Hvals)
+        assert len(self.Arows) == len(self.Acols) == len(self.Avals)
+        assert np.all(self.Hrows >= self.Hcols), "H must be given by its lower triangle"
+
+    @property
+    def nvar(self):
+        return len(self.c)
+
+    @property
+    def ncon(self):
+        return len(self.lcon)
+
+    @property
+    def nnzj(self):
+        return len(self.Avals)
+
+    @property
+    def nnzh(self):
+        return len(self.Hvals)
+
+
+def simple_lp():
+    """The reference's only self-contained fixture: test/runtests.jl:29-60.
+    min x1 + x2  s.t.  x1 + x2 = 1, x >= 0;  optimal objective 1.0."""
+    return QuadraticModel(
+        c=np.ones(2), Hrows=[], Hcols=[], Hvals=[],
+        Arows=[0, 0], Acols=[0, 1], Avals=[1.0, 1.0],
+        lcon=[1.0], ucon=[1.0], lvar=[0.0, 0.0], uvar=[np.inf, np.inf],
+        c0=0.0, x0=np.ones(2), name="simpleLP",
+    )
+
+
+def _sparsity(rng, m, n, k, structure, window):
+    """k structural nonzeros per column. 'uniform': rows uniform in [0,m).
+    'window': rows drawn within +-window of the column's home row j*m/n."""
+    k = min(k, m)
+    cols = np.repeat(np.arange(n, dtype=np.int64), k)
+    if structure == "uniform":
+        # k distinct rows per column: sample with a random offset + distinct strides trick is
+        # biased; use argpartition on random keys for small m, rejection for large m.
+        rows = rng.integers(0, m, size=(n, k))
+        for _ in range(64):
+            srt = np.sort(rows, axis=1)
+            dup = np.zeros_like(rows, dtype=bool)
+            dup[:, 1:] = srt[:, 1:] == srt[:, :-1]
+            if not dup.any():
+                rows = srt
+                break
+            srt[dup] = rng.integers(0, m, size=int(dup.sum()))
+            rows = srt
+        else:
+            raise RuntimeError("could not draw distinct rows")
+    elif structure == "window":
+        w = min(window, (m - 1) // 2)
+        assert 2 * w + 1 >= k
+        home = (np.arange(n, dtype=np.int64) * m) // n
+        lo = np.clip(home - w, 0, m - (2 * w + 1))
+        # k distinct offsets in [0, 2w]: take the k smallest of 2w+1 random keys
+        keys = rng.random((n, 2 * w + 1))
+        off = np.argpartition(keys, k - 1, axis=1)[:, :k]
+        rows = np.sort(lo[:, None] + off, axis=1)
+    else:
+        raise ValueError(structure)
+    return rows.reshape(-1).astype(np.int32), cols.astype(np.int32)
+
+
+def random_sparse_lp(m, n, k, seed, structure="window", window=50, ub_fraction=0.0):
+    """Feasible-and-bounded-by-construction LP:
+    A: k nnz/col, values N(0,1); x* ~ U(.5,1.5), b = A x*; y* ~ N(0,1), z* ~ U(0,1),
+    c = A'y* + z*; bounds x >= 0 (a fraction `ub_fraction` of variables also get x <= 2);
+    all constraints are equalities. max|A_ij| and ||c||_inf stay far below 100 so MadNLP's
+    gradient-based scaling is the identity."""
+    rng = np.random.default_rng(seed)
+    rows, cols = _sparsity(rng, m, n, k, structure, window)
+    vals = rng.standard_normal(len(rows))
+    # keep |A_ij| away from 0 so no structural entry is numerically void
+    vals = np.sign(vals) * np.maximum(np.abs(vals), 1e-2)
+    xs = rng.uniform(0.5, 1.5, n)
+    b = np.zeros(m)
+    np.add.at(b, rows, vals * xs[cols])
+    ys = rng.standard_normal(m)
+    zs = rng.uniform(0.0, 1.0, n)
+    c = zs.copy()
+    np.add.at(c, cols, vals * ys[rows])
+    uvar = np.full(n, np.inf)
+    if ub_fraction > 0:
+        pick = rng.random(n) < ub_fraction
+        uvar[pick] = 2.0
+    return QuadraticModel(
+        c=c, Hrows=[], Hcols=[], Hvals=[], Arows=rows, Acols=cols, Avals=vals,
+        lcon=b, ucon=b.copy(), lvar=np.zeros(n), uvar=uvar, x0=np.zeros(n),
+        name=f"lp_{structure}_m{m}_n{n}_k{k}_s{seed}",
+        meta=dict(m=m, n=n, k=k, seed=seed, structure=structure, window=window),
+    )
+
+
+def random_sparse_qp(m, n, k, seed, structure="window", window=50, q_offdiag=2):
+    """Convex QP (config C3): A as in random_sparse_lp; Q sparse, symmetric, strictly
+    diagonally dominant (hence PSD) with `q_offdiag` off-diagonals per column placed within
+    the same locality window in variable space."""
+    rng = np.random.default_rng(seed)
+    lp = random_sparse_lp(m, n, k, seed, structure, window)
+    hr, hc, hv = [np.arange(n, dtype=np.int64)], [np.arange(n, dtype=np.int64)], []
+    diag = np.full(n, 1e-3)
+    if q_offdiag > 0:
+        j = np.repeat(np.arange(n, dtype=np.int64), q_offdiag)
+        wv = max(1, min(window, n - 1))
+        i = j + rng.integers(1, wv + 1, size=len(j))
+        keep = i < n
+        i, j = i[keep], j[keep]
+        # merge duplicates (i,j)
+        key = i * n + j
+        _, first = np.unique(key, return_index=True)
+        i, j = i[first], j[first]
+        v = 0.1 * rng.standard_normal(len(i))
+        np.add.at(diag, i, np.abs(v))
+        np.add.at(diag, j, np.abs(v))
+        hr.append(i), hc.append(j), hv.append(v)
+    hv.insert(0, diag + rng.uniform(0.0, 1.0, n))
+    Hrows, Hcols, Hvals = np.concatenate(hr), np.concatenate(hc), np.concatenate(hv)
+    # shift c so the LP-feasible x* stays dual feasible: c_qp = c_lp - Q x*  is not needed for
+    # boundedness (Q PSD, x >= 0 region, feasible set non-empty) -> keep c.
+    return QuadraticModel(
+        c=lp.c, Hrows=Hrows, Hcols=Hcols, Hvals=Hvals, Arows=lp.Arows, Acols=lp.Acols,
+        Avals=lp.Avals, lcon=lp.lcon, ucon=lp.ucon, lvar=lp.lvar, uvar=lp.uvar, x0=lp.x0,
+        name=f"qp_{structure}_m{m}_n{n}_k{k}_s{seed}",
+        meta=dict(m=m, n=n, k=k, seed=seed, structure=structure, window=window),
+    )
+
+
+# The five BASELINE.json configs. C2's structure is stated explicitly: uniformly random rows
+# make chol(A A') ~90% dense (1.8e10 nonzeros at m=2e5), so the named shape is
+# generated with windowed rows (+-50 around the column's home row), as SURVEY 7.4 measured.
+def config_c1(seed=1):
+    return random_sparse_lp(2_000, 10_000, 5, seed, structure="uniform")
+
+
+def config_c2(seed=2, scale=1.0):
+    m, n = int(200_000 * scale), int(1_000_000 * scale)
+    return random_sparse_lp(m, n, 8, seed, structure="window", window=50)
+
+
+def config_c3(seed=3, scale=1.0):
+    m, n = int(150_000 * scale), int(500_000 * scale)
+    return random_sparse_qp(m, n, 5, seed, structure="window", window=50)
+
+
+def config_c5(index, seed=5):
+    return random_sparse_lp(500, 2_000, 5, seed * 100_003 + index, structure="uniform")
