@@ -1,0 +1,314 @@
+"""ctypes binding of the C ABI declared in include/madipm_b200.h.
+
+This is the same boundary the Julia glue (ext/MadIPMB200Ext) binds with `ccall`; nothing here
+computes. If libmadipm_b200.so is missing the import fails loudly -- there is no fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmadipm_b200.so")
+
+MIPM_OK, MIPM_ERR_ARG, MIPM_ERR_CUDA, MIPM_ERR_ALLOC, MIPM_ERR_STATE, MIPM_ERR_DUPLICATE, MIPM_ERR_NOT_FACTORIZED = range(7)
+MIPM_CHOLESKY, MIPM_LDL = 0, 1
+MIPM_ORDER_ND, MIPM_ORDER_NATURAL, MIPM_ORDER_USER = 0, 1, 2
+
+_ERRNAMES = {1: "MIPM_ERR_ARG", 2: "MIPM_ERR_CUDA", 3: "MIPM_ERR_ALLOC", 4: "MIPM_ERR_STATE",
+             5: "MIPM_ERR_DUPLICATE", 6: "MIPM_ERR_NOT_FACTORIZED"}
+
+
+class MipmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{_ERRNAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class LsStats(C.Structure):
+    _fields_ = [("n", C.c_int64), ("nnz_a", C.c_int64), ("nnz_l", C.c_int64), ("nnz_l_exact", C.c_int64),
+                ("flops", C.c_double), ("n_supernodes", C.c_int64), ("n_levels", C.c_int64),
+                ("max_front_cols", C.c_int64), ("max_front_rows", C.c_int64), ("update_doubles", C.c_int64),
+                ("n_launches", C.c_int64)]
+
+
+class MpcVectors(C.Structure):
+    _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("nlb", C.c_int64), ("nub", C.c_int64),
+                ("index_base", C.c_int),
+                ("d_ind_lb", C.c_void_p), ("d_ind_ub", C.c_void_p),
+                ("d_x", C.c_void_p), ("d_xl", C.c_void_p), ("d_xu", C.c_void_p), ("d_zl", C.c_void_p),
+                ("d_zu", C.c_void_p), ("d_f", C.c_void_p),
+                ("d_y", C.c_void_p), ("d_c", C.c_void_p), ("d_rhs", C.c_void_p),
+                ("d_jacl", C.c_void_p),
+                ("d_d", C.c_void_p), ("d_p", C.c_void_p), ("d_w", C.c_void_p),
+                ("d_corr_lb", C.c_void_p), ("d_corr_ub", C.c_void_p),
+                ("d_reg", C.c_void_p), ("d_pr_diag", C.c_void_p), ("d_du_diag", C.c_void_p),
+                ("d_l_diag", C.c_void_p), ("d_u_diag", C.c_void_p), ("d_l_lower", C.c_void_p),
+                ("d_u_lower", C.c_void_p)]
+
+
+# every symbol include/madipm_b200.h declares (tests check the .so exports exactly these)
+SYMBOLS = [
+    "mipm_version", "mipm_create", "mipm_destroy", "mipm_last_error", "mipm_free",
+    "mipm_coo_to_csr", "mipm_normal_symbolic", "mipm_normal_set_jacobian", "mipm_normal_assemble",
+    "mipm_k2_symbolic", "mipm_k2_transfer",
+    "mipm_ls_analyze", "mipm_ls_factorize", "mipm_ls_factorize_async", "mipm_ls_status", "mipm_ls_solve",
+    "mipm_ls_inertia", "mipm_ls_stats", "mipm_ls_symbolic",
+    "mipm_spmv_setup", "mipm_spmv",
+    "mipm_mpc_bind", "mipm_set_aug_diagonal_reg", "mipm_set_predictive_rhs", "mipm_set_correction_rhs",
+    "mipm_get_correction", "mipm_set_extra_correction", "mipm_get_complementarity_measure",
+    "mipm_get_affine_complementarity_measure", "mipm_get_alpha_max", "mipm_termination_measures",
+    "mipm_apply_step", "mipm_reduce_rhs", "mipm_finish_aug_solve", "mipm_normal_solve_stage", "mipm_kktmul",
+    "mipm_residual_norms", "mipm_init_point_stage", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_dot",
+    "mipm_launch_count", "mipm_bench_syrk",
+]
+
+_lib = None
+
+
+def load():
+    """Load libmadipm_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C madipm_jl_b200/csrc`). The CUDA library is mandatory; there is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.mipm_last_error.restype = C.c_char_p
+    lib.mipm_last_error.argtypes = [C.c_void_p]
+    lib.mipm_launch_count.restype = C.c_int64
+    lib.mipm_launch_count.argtypes = [C.c_void_p]
+    lib.mipm_free.restype = None
+    lib.mipm_free.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """Device pointer of a torch tensor, host pointer of a numpy array, or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    raise TypeError(type(a))
+
+
+def _take(ptr, count, ctype, dtype):
+    """Copy a library-owned host array into numpy and free it."""
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(max(count, 1),))[:count].astype(dtype, copy=True)
+    load().mipm_free(ptr)
+    return arr
+
+
+class Handle:
+    """RAII wrapper of mipm_handle. device=-1 gives an analysis-only (host symbolic) handle."""
+
+    def __init__(self, device=0, stream=0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        rc = self.lib.mipm_create(C.byref(self.h), C.c_int(device), C.c_void_p(stream))
+        if rc != MIPM_OK:
+            raise MipmError(rc, "mipm_create failed (no CUDA device? the library has no CPU fallback)")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.mipm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != MIPM_OK:
+            raise MipmError(rc, self.lib.mipm_last_error(self.h).decode())
+
+    # ---- host symbolic
+    def normal_symbolic(self, m, n, Ap, Aj, index_base=0):
+        Ap = np.ascontiguousarray(Ap, dtype=np.int32)
+        Aj = np.ascontiguousarray(Aj, dtype=np.int32)
+        cp, cj, nnz = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self.check(self.lib.mipm_normal_symbolic(self.h, C.c_int64(m), C.c_int64(n), _ptr(Ap), _ptr(Aj),
+                                                 C.c_int(index_base), C.byref(cp), C.byref(cj), C.byref(nnz)))
+        return _take(cp, m + 1, C.c_int32, np.int32), _take(cj, nnz.value, C.c_int32, np.int32)
+
+    def k2_symbolic(self, dim, I, J, index_base=0):
+        I = np.ascontiguousarray(I, dtype=np.int32)
+        J = np.ascontiguousarray(J, dtype=np.int32)
+        cp, rv, mp, nnz = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        self.check(self.lib.mipm_k2_symbolic(self.h, C.c_int64(dim), C.c_int64(len(I)), _ptr(I), _ptr(J),
+                                             C.c_int(index_base), C.byref(cp), C.byref(rv), C.byref(mp), C.byref(nnz)))
+        return (_take(cp, dim + 1, C.c_int32, np.int32), _take(rv, nnz.value, C.c_int32, np.int32),
+                _take(mp, len(I), C.c_int64, np.int64))
+
+    def ls_analyze(self, n, colptr, rowval, kind=MIPM_CHOLESKY, ordering=MIPM_ORDER_ND, user_perm=None, index_base=0):
+        colptr = np.ascontiguousarray(colptr, dtype=np.int32)
+        rowval = np.ascontiguousarray(rowval, dtype=np.int32)
+        up = None if user_perm is None else np.ascontiguousarray(user_perm, dtype=np.int32)
+        self.check(self.lib.mipm_ls_analyze(self.h, C.c_int64(n), _ptr(colptr), _ptr(rowval), C.c_int(index_base),
+                                            C.c_int(kind), C.c_int(ordering), _ptr(up)))
+
+    def ls_stats(self):
+        st = LsStats()
+        self.check(self.lib.mipm_ls_stats(self.h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in LsStats._fields_}
+
+    def ls_symbolic(self):
+        perm, snp, spar, rp, ri = (C.c_void_p() for _ in range(5))
+        ns = C.c_int64()
+        self.check(self.lib.mipm_ls_symbolic(self.h, C.byref(perm), C.byref(ns), C.byref(snp), C.byref(spar),
+                                             C.byref(rp), C.byref(ri)))
+        n = self.ls_stats()["n"]
+        ns = ns.value
+        row_ptr = _take(rp, ns + 1, C.c_int64, np.int64)
+        return dict(perm=_take(perm, n, C.c_int32, np.int32), sn_ptr=_take(snp, ns + 1, C.c_int32, np.int32),
+                    sn_parent=_take(spar, ns, C.c_int32, np.int32), row_ptr=row_ptr,
+                    row_idx=_take(ri, int(row_ptr[-1]), C.c_int32, np.int32))
+
+    # ---- device entry points (arguments are torch CUDA tensors)
+    def normal_set_jacobian(self, ATx):
+        self.check(self.lib.mipm_normal_set_jacobian(self.h, _ptr(ATx)))
+
+    def normal_assemble(self, pr_diag, Cx, exact_order=False):
+        self.check(self.lib.mipm_normal_assemble(self.h, _ptr(pr_diag), _ptr(Cx), C.c_int(int(exact_order))))
+
+    def k2_transfer(self, V, nz):
+        self.check(self.lib.mipm_k2_transfer(self.h, _ptr(V), _ptr(nz)))
+
+    def ls_factorize(self, nzval):
+        st = C.c_int()
+        self.check(self.lib.mipm_ls_factorize(self.h, _ptr(nzval), C.byref(st)))
+        return st.value == MIPM_OK
+
+    def ls_factorize_async(self, nzval):
+        self.check(self.lib.mipm_ls_factorize_async(self.h, _ptr(nzval)))
+
+    def ls_status(self):
+        st = C.c_int()
+        self.check(self.lib.mipm_ls_status(self.h, C.byref(st)))
+        return st.value == MIPM_OK
+
+    def ls_solve(self, x, ir_steps=0):
+        self.check(self.lib.mipm_ls_solve(self.h, _ptr(x), C.c_int(ir_steps)))
+
+    def ls_inertia(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.check(self.lib.mipm_ls_inertia(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def spmv_setup(self, m, n, Ap, Aj, index_base=0):
+        Ap = np.ascontiguousarray(Ap, dtype=np.int32)
+        Aj = np.ascontiguousarray(Aj, dtype=np.int32)
+        self.check(self.lib.mipm_spmv_setup(self.h, C.c_int64(m), C.c_int64(n), _ptr(Ap), _ptr(Aj), C.c_int(index_base)))
+
+    def spmv(self, trans, alpha, Ax, x, beta, y):
+        self.check(self.lib.mipm_spmv(self.h, C.c_int(trans), C.c_double(alpha), _ptr(Ax), _ptr(x), C.c_double(beta), _ptr(y)))
+
+    def mpc_bind(self, vec: MpcVectors):
+        self.check(self.lib.mipm_mpc_bind(self.h, C.byref(vec)))
+
+    def set_aug_diagonal_reg(self, del_w, del_c):
+        self.check(self.lib.mipm_set_aug_diagonal_reg(self.h, C.c_double(del_w), C.c_double(del_c)))
+
+    def set_predictive_rhs(self):
+        self.check(self.lib.mipm_set_predictive_rhs(self.h))
+
+    def set_correction_rhs(self, mu):
+        self.check(self.lib.mipm_set_correction_rhs(self.h, C.c_double(mu)))
+
+    def get_correction(self):
+        self.check(self.lib.mipm_get_correction(self.h))
+
+    def set_extra_correction(self, ap, ad, bmin, bmax, mu):
+        self.check(self.lib.mipm_set_extra_correction(self.h, C.c_double(ap), C.c_double(ad), C.c_double(bmin),
+                                                      C.c_double(bmax), C.c_double(mu)))
+
+    def get_complementarity_measure(self):
+        out = C.c_double()
+        self.check(self.lib.mipm_get_complementarity_measure(self.h, C.byref(out)))
+        return out.value
+
+    def get_affine_complementarity_measure(self, ap, ad):
+        out = C.c_double()
+        self.check(self.lib.mipm_get_affine_complementarity_measure(self.h, C.c_double(ap), C.c_double(ad), C.byref(out)))
+        return out.value
+
+    def get_alpha_max(self, tau):
+        a = (C.c_double * 4)()
+        i = (C.c_int64 * 4)()
+        self.check(self.lib.mipm_get_alpha_max(self.h, C.c_double(tau), a, i))
+        return list(a), list(i)
+
+    def termination_measures(self):
+        out = (C.c_double * 5)()
+        self.check(self.lib.mipm_termination_measures(self.h, out))
+        return list(out)
+
+    def apply_step(self, ap, ad, mu):
+        self.check(self.lib.mipm_apply_step(self.h, C.c_double(ap), C.c_double(ad), C.c_double(mu)))
+
+    def reduce_rhs(self, w):
+        self.check(self.lib.mipm_reduce_rhs(self.h, _ptr(w)))
+
+    def finish_aug_solve(self, w):
+        self.check(self.lib.mipm_finish_aug_solve(self.h, _ptr(w)))
+
+    def normal_solve_stage(self, stage, w, buffer_n, buffer_m):
+        self.check(self.lib.mipm_normal_solve_stage(self.h, C.c_int(stage), _ptr(w), _ptr(buffer_n), _ptr(buffer_m)))
+
+    def kktmul(self, w, v, alpha, beta):
+        self.check(self.lib.mipm_kktmul(self.h, _ptr(w), _ptr(v), C.c_double(alpha), C.c_double(beta)))
+
+    def residual_norms(self, w, p):
+        out = (C.c_double * 2)()
+        self.check(self.lib.mipm_residual_norms(self.h, _ptr(w), _ptr(p), out))
+        return out[0], out[1]
+
+    def init_point_stage(self, stage, a=0.0, b=0.0, kappa=0.0):
+        out = (C.c_double * 8)()
+        self.check(self.lib.mipm_init_point_stage(self.h, C.c_int(stage), C.c_double(a), C.c_double(b), C.c_double(kappa), out))
+        return list(out)
+
+    def axpby(self, n, alpha, x, beta, y):
+        self.check(self.lib.mipm_axpby(self.h, C.c_int64(n), C.c_double(alpha), _ptr(x), C.c_double(beta), _ptr(y)))
+
+    def fill(self, n, value, x):
+        self.check(self.lib.mipm_fill(self.h, C.c_int64(n), C.c_double(value), _ptr(x)))
+
+    def copy(self, n, src, dst):
+        self.check(self.lib.mipm_copy(self.h, C.c_int64(n), _ptr(src), _ptr(dst)))
+
+    def dot(self, n, x, y):
+        out = C.c_double()
+        self.check(self.lib.mipm_dot(self.h, C.c_int64(n), _ptr(x), _ptr(y), C.byref(out)))
+        return out.value
+
+    def launch_count(self):
+        return int(self.lib.mipm_launch_count(self.h))
+
+    def bench_syrk(self, n, k, Cmat, ldc, X, ldx):
+        self.check(self.lib.mipm_bench_syrk(self.h, C.c_int64(n), C.c_int64(k), _ptr(Cmat), C.c_int64(ldc), _ptr(X), C.c_int64(ldx)))
+
+
+def coo_to_csr(n_rows, n_cols, Ai, Aj, index_base=0):
+    """mipm_coo_to_csr: returns (Bp, Bj, Bmap)."""
+    Ai = np.ascontiguousarray(Ai, dtype=np.int32)
+    Aj = np.ascontiguousarray(Aj, dtype=np.int32)
+    nnz = len(Ai)
+    Bp = np.zeros(n_rows + 1, dtype=np.int32)
+    Bj = np.zeros(max(nnz, 1), dtype=np.int32)
+    Bm = np.zeros(max(nnz, 1), dtype=np.int64)
+    rc = load().mipm_coo_to_csr(C.c_int64(n_rows), C.c_int64(n_cols), C.c_int64(nnz), _ptr(Ai), _ptr(Aj),
+                                C.c_int(index_base), _ptr(Bp), _ptr(Bj), _ptr(Bm))
+    if rc != MIPM_OK:
+        raise MipmError(rc, "mipm_coo_to_csr")
+    return Bp, Bj[:nnz], Bm[:nnz]

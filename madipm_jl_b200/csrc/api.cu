@@ -1,0 +1,484 @@
+// C-ABI entry points: lifecycle, host symbolic builders, KKT assembly kernels, SpMV.
+// Each entry cites in include/madipm_b200.h the reference interface it replaces.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+
+using namespace mipm;
+
+namespace {
+
+template <typename T>
+T *host_copy(const std::vector<T> &v, int add) {
+    T *p = (T *)std::malloc(std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (!p) return nullptr;
+    for (size_t i = 0; i < v.size(); ++i) p[i] = (T)(v[i] + add);
+    return p;
+}
+
+// ---------------------------------------------------------------- normal-equations assembly
+__global__ void k_term_weights(int64_t T, const int32_t *__restrict__ pi, const int32_t *__restrict__ pj,
+                               const double *__restrict__ Ax, double *__restrict__ w)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) w[t] = Ax[pi[t]] * Ax[pj[t]];
+}
+
+__global__ void k_recip(int64_t n, const double *__restrict__ x, double *__restrict__ y)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __ddiv_rn(1.0, x[i]);   // D .= 1.0 ./ pr_diag  (normalkkt.jl:191)
+}
+
+// One thread per stored entry c of tril(A D A'): Cx[c] = sum_t w[t] * D[k[t]] over its segment.
+__global__ void __launch_bounds__(256)
+k_normal_assemble_fast(int64_t nnzC, const int32_t *__restrict__ term_ptr, const int32_t *__restrict__ term_k,
+                       const double *__restrict__ w, const double *__restrict__ D, double *__restrict__ Cx)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nnzC) return;
+    int32_t t0 = term_ptr[c], t1 = term_ptr[c + 1];
+    double acc = 0.0;
+    for (int32_t t = t0; t < t1; ++t) acc = fma(w[t], __ldg(D + term_k[t]), acc);
+    Cx[c] = acc;
+}
+
+// Same, reproducing the reference CPU loop's operation order (src/utils.jl:288-301):
+// buffer[k] = A[i,k]*D[k]; Cx[c] += buffer[k]*A[j,k] in row-j order, mul and add unfused.
+__global__ void __launch_bounds__(256)
+k_normal_assemble_exact(int64_t nnzC, const int32_t *__restrict__ term_ptr, const int32_t *__restrict__ pi,
+                        const int32_t *__restrict__ pj, const int32_t *__restrict__ term_k,
+                        const double *__restrict__ Ax, const double *__restrict__ D, double *__restrict__ Cx)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nnzC) return;
+    int32_t t0 = term_ptr[c], t1 = term_ptr[c + 1];
+    double acc = 0.0;
+    for (int32_t t = t0; t < t1; ++t) {
+        double b = __dmul_rn(Ax[pi[t]], D[term_k[t]]);
+        acc = __dadd_rn(acc, __dmul_rn(b, Ax[pj[t]]));
+    }
+    Cx[c] = acc;
+}
+
+// ---------------------------------------------------------------- K2 transfer (gather form)
+__global__ void __launch_bounds__(256)
+k_k2_transfer(int64_t nslots, const int64_t *__restrict__ slot_ptr, const int64_t *__restrict__ slot_src,
+              const double *__restrict__ V, double *__restrict__ nz)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nslots) return;
+    double acc = 0.0;
+    for (int64_t s = slot_ptr[c]; s < slot_ptr[c + 1]; ++s) acc = __dadd_rn(acc, V[slot_src[s]]);
+    nz[c] = acc;
+}
+
+// ---------------------------------------------------------------- SpMV
+// y = alpha * A x + beta * y, CSR, one warp per row.
+__global__ void __launch_bounds__(256)
+k_spmv_csr(int64_t m, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+           const double *__restrict__ val, const double *__restrict__ x, double alpha, double beta,
+           double *__restrict__ y)
+{
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= m) return;
+    double acc = 0.0;
+    for (int32_t p = rowptr[row] + lane; p < rowptr[row + 1]; p += 32) acc = fma(val[p], __ldg(x + col[p]), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[row] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[row];
+}
+
+// y = alpha * A' x + beta * y through the CSC index (colptr, row, pos into the CSR values):
+// 8 lanes per column (columns of A are short: k nnz/col).
+__global__ void __launch_bounds__(256)
+k_spmv_csc(int64_t n, const int32_t *__restrict__ colptr, const int32_t *__restrict__ row,
+           const int32_t *__restrict__ pos, const double *__restrict__ val, const double *__restrict__ x,
+           double alpha, double beta, double *__restrict__ y)
+{
+    int64_t colj = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    int sub = threadIdx.x & 7;
+    double acc = 0.0;
+    if (colj < n)
+        for (int32_t p = colptr[colj] + sub; p < colptr[colj + 1]; p += 8) acc = fma(__ldg(val + pos[p]), __ldg(x + row[p]), acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (colj < n && sub == 0) y[colj] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[colj];
+}
+
+inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)std::max<int64_t>(1, (n + per_block - 1) / per_block); }
+
+}  // namespace
+
+extern "C" {
+
+int mipm_version(void) { return 100; }
+
+int mipm_create(mipm_handle *out, int device, void *stream)
+{
+    if (!out) return MIPM_ERR_ARG;
+    *out = nullptr;
+    Handle *h = new (std::nothrow) Handle();
+    if (!h) return MIPM_ERR_ALLOC;
+    h->device = device;
+    h->stream = (cudaStream_t)stream;
+    if (device < 0) {
+        // analysis-only handle: host symbolic entry points work, every device entry fails loudly
+        h->host_only = true;
+        *out = (mipm_handle)h;
+        return MIPM_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device >= ndev) {
+        delete h;
+        return MIPM_ERR_CUDA;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return MIPM_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return MIPM_ERR_CUDA; }
+    h->red_blocks = prop.multiProcessorCount * 4;
+    if (h->d_partials.alloc((size_t)h->red_blocks * 16) != cudaSuccess ||
+        h->d_scal.alloc(64) != cudaSuccess || h->d_counter.alloc(4) != cudaSuccess ||
+        cudaMallocHost((void **)&h->h_scal, 64 * sizeof(double)) != cudaSuccess ||
+        h->d_info.alloc(4) != cudaSuccess) {
+        delete h;
+        return MIPM_ERR_ALLOC;
+    }
+    cudaMemsetAsync(h->d_counter.p, 0, 4 * sizeof(unsigned int), h->stream);
+    cudaMemsetAsync(h->d_info.p, 0, 4 * sizeof(int), h->stream);
+    *out = (mipm_handle)h;
+    return MIPM_OK;
+}
+
+int mipm_destroy(mipm_handle hh)
+{
+    Handle *h = (Handle *)hh;
+    if (!h) return MIPM_ERR_ARG;
+    if (!h->host_only) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        if (h->h_scal) cudaFreeHost(h->h_scal);
+    }
+    delete h;
+    return MIPM_OK;
+}
+
+const char *mipm_last_error(mipm_handle hh)
+{
+    Handle *h = (Handle *)hh;
+    return h ? h->err.c_str() : "null handle";
+}
+
+void mipm_free(void *p) { std::free(p); }
+
+int64_t mipm_launch_count(mipm_handle hh)
+{
+    Handle *h = (Handle *)hh;
+    return h ? h->launches : -1;
+}
+
+int mipm_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *Ai, const int32_t *Aj,
+                    int index_base, int32_t *Bp, int32_t *Bj, int64_t *Bmap)
+{
+    if (n_rows < 0 || n_cols < 0 || nnz < 0 || (nnz > 0 && (!Ai || !Aj)) || !Bp || (nnz > 0 && (!Bj || !Bmap)))
+        return MIPM_ERR_ARG;
+    std::vector<int32_t> i0((size_t)nnz), j0((size_t)nnz);
+    for (int64_t k = 0; k < nnz; ++k) {
+        i0[(size_t)k] = Ai[k] - index_base;
+        j0[(size_t)k] = Aj[k] - index_base;
+        if (i0[(size_t)k] < 0 || i0[(size_t)k] >= n_rows || j0[(size_t)k] < 0 || j0[(size_t)k] >= n_cols) return MIPM_ERR_ARG;
+    }
+    coo_to_csr_host(n_rows, nnz, i0.data(), j0.data(), Bp, Bj, Bmap);
+    for (int64_t i = 0; i <= n_rows; ++i) Bp[i] += index_base;
+    for (int64_t k = 0; k < nnz; ++k) { Bj[k] += index_base; Bmap[k] += index_base; }
+    return MIPM_OK;
+}
+
+int mipm_normal_symbolic(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap, const int32_t *Aj,
+                         int index_base, int32_t **Cp, int32_t **Cj, int64_t *nnzC)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !Ap || (!Aj && m > 0 && Ap[m] != index_base) || !Cp || !Cj || !nnzC) return fail(h, MIPM_ERR_ARG, "null argument");
+    std::string e = normal_symbolic_host(m, n, Ap, Aj, index_base, h->nsym);
+    if (!e.empty()) return fail(h, e.find("duplicate") != std::string::npos ? MIPM_ERR_DUPLICATE : MIPM_ERR_ARG, e);
+    *Cp = host_copy(h->nsym.Cp, index_base);
+    *Cj = host_copy(h->nsym.Cj, index_base);
+    *nnzC = h->nsym.nnz_c;
+    if (!*Cp || !*Cj) return fail(h, MIPM_ERR_ALLOC, "host allocation failed");
+    h->has_normal = true;
+    h->has_jac = false;
+    if (!h->host_only) {
+        MIPM_CUDA(h, cudaSetDevice(h->device));
+        MIPM_CUDA(h, h->d_term_ptr.upload(h->nsym.term_ptr, h->stream));
+        MIPM_CUDA(h, h->d_term_pi.upload(h->nsym.term_pi, h->stream));
+        MIPM_CUDA(h, h->d_term_pj.upload(h->nsym.term_pj, h->stream));
+        MIPM_CUDA(h, h->d_term_k.upload(h->nsym.term_k, h->stream));
+        MIPM_CUDA(h, h->d_term_w.alloc((size_t)h->nsym.n_terms));
+        MIPM_CUDA(h, h->d_D.alloc((size_t)n));
+        MIPM_CUDA(h, cudaStreamSynchronize(h->stream));   // host vectors may be reused
+    }
+    return MIPM_OK;
+}
+
+int mipm_normal_set_jacobian(mipm_handle hh, const double *d_ATx)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_normal) return fail(h, MIPM_ERR_STATE, "mipm_normal_symbolic has not been called");
+    if (!d_ATx && h->nsym.nnz_a > 0) return fail(h, MIPM_ERR_ARG, "null Jacobian values");
+    h->d_ATx = d_ATx;
+    int64_t T = h->nsym.n_terms;
+    if (T > 0) {
+        k_term_weights<<<grid_for(T, 256), 256, 0, h->stream>>>(T, h->d_term_pi.p, h->d_term_pj.p, d_ATx, h->d_term_w.p);
+        MIPM_CHECK_LAUNCH(h);
+    }
+    h->has_jac = true;
+    return MIPM_OK;
+}
+
+int mipm_normal_assemble(mipm_handle hh, const double *d_pr_diag, double *d_Cx, int exact_order)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_jac) return fail(h, MIPM_ERR_STATE, "mipm_normal_set_jacobian has not been called");
+    if (!d_pr_diag || !d_Cx) return fail(h, MIPM_ERR_ARG, "null argument");
+    const NormalSymbolic &S = h->nsym;
+    if (S.n > 0) {
+        k_recip<<<grid_for(S.n, 256), 256, 0, h->stream>>>(S.n, d_pr_diag, h->d_D.p);
+        MIPM_CHECK_LAUNCH(h);
+    }
+    if (S.nnz_c > 0) {
+        if (exact_order)
+            k_normal_assemble_exact<<<grid_for(S.nnz_c, 256), 256, 0, h->stream>>>(
+                S.nnz_c, h->d_term_ptr.p, h->d_term_pi.p, h->d_term_pj.p, h->d_term_k.p, h->d_ATx, h->d_D.p, d_Cx);
+        else
+            k_normal_assemble_fast<<<grid_for(S.nnz_c, 256), 256, 0, h->stream>>>(
+                S.nnz_c, h->d_term_ptr.p, h->d_term_k.p, h->d_term_w.p, h->d_D.p, d_Cx);
+        MIPM_CHECK_LAUNCH(h);
+    }
+    return MIPM_OK;
+}
+
+int mipm_k2_symbolic(mipm_handle hh, int64_t dim, int64_t nnz_coo, const int32_t *I, const int32_t *J,
+                     int index_base, int32_t **colptr, int32_t **rowval, int64_t **map, int64_t *nnz_csc)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || (nnz_coo > 0 && (!I || !J)) || !colptr || !rowval || !map || !nnz_csc) return fail(h, MIPM_ERR_ARG, "null argument");
+    std::string e = k2_symbolic_host(dim, nnz_coo, I, J, index_base, h->ksym);
+    if (!e.empty()) return fail(h, MIPM_ERR_ARG, e);
+    *colptr = host_copy(h->ksym.colptr, index_base);
+    *rowval = host_copy(h->ksym.rowval, index_base);
+    *map = host_copy(h->ksym.map, index_base);
+    *nnz_csc = h->ksym.nnz_csc;
+    if (!*colptr || !*rowval || !*map) return fail(h, MIPM_ERR_ALLOC, "host allocation failed");
+    h->has_k2 = true;
+    if (!h->host_only) {
+        MIPM_CUDA(h, cudaSetDevice(h->device));
+        MIPM_CUDA(h, h->d_slot_ptr.upload(h->ksym.slot_ptr, h->stream));
+        MIPM_CUDA(h, h->d_slot_src.upload(h->ksym.slot_src, h->stream));
+        MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return MIPM_OK;
+}
+
+int mipm_k2_transfer(mipm_handle hh, const double *d_V, double *d_nz)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_k2) return fail(h, MIPM_ERR_STATE, "mipm_k2_symbolic has not been called");
+    if (!d_V || !d_nz) return fail(h, MIPM_ERR_ARG, "null argument");
+    if (h->ksym.nnz_csc > 0) {
+        k_k2_transfer<<<grid_for(h->ksym.nnz_csc, 256), 256, 0, h->stream>>>(h->ksym.nnz_csc, h->d_slot_ptr.p,
+                                                                          h->d_slot_src.p, d_V, d_nz);
+        MIPM_CHECK_LAUNCH(h);
+    }
+    return MIPM_OK;
+}
+
+int mipm_spmv_setup(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap, const int32_t *Aj, int index_base)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (m < 0 || n < 0 || !Ap) return fail(h, MIPM_ERR_ARG, "bad argument");
+    int64_t nnz = Ap[m] - index_base;
+    std::vector<int32_t> rp((size_t)m + 1), cj((size_t)nnz), cp((size_t)n + 1, 0), ri((size_t)nnz), pos((size_t)nnz);
+    for (int64_t i = 0; i <= m; ++i) rp[(size_t)i] = Ap[i] - index_base;
+    for (int64_t p = 0; p < nnz; ++p) {
+        cj[(size_t)p] = Aj[p] - index_base;
+        if (cj[(size_t)p] < 0 || cj[(size_t)p] >= n) return fail(h, MIPM_ERR_ARG, "column index out of range");
+        cp[(size_t)cj[(size_t)p] + 1]++;
+    }
+    for (int64_t k = 0; k < n; ++k) cp[(size_t)k + 1] += cp[(size_t)k];
+    {
+        std::vector<int32_t> w(cp.begin(), cp.end() - 1);
+        for (int64_t i = 0; i < m; ++i)
+            for (int32_t p = rp[(size_t)i]; p < rp[(size_t)i + 1]; ++p) {
+                int32_t d = w[(size_t)cj[(size_t)p]]++;
+                ri[(size_t)d] = (int32_t)i;
+                pos[(size_t)d] = p;
+            }
+    }
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    MIPM_CUDA(h, h->d_sp_rowptr.upload(rp, h->stream));
+    MIPM_CUDA(h, h->d_sp_col.upload(cj, h->stream));
+    MIPM_CUDA(h, h->d_sp_colptr.upload(cp, h->stream));
+    MIPM_CUDA(h, h->d_sp_row.upload(ri, h->stream));
+    MIPM_CUDA(h, h->d_sp_pos.upload(pos, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->sp_m = m;
+    h->sp_n = n;
+    h->sp_nnz = nnz;
+    h->has_spmv = true;
+    return MIPM_OK;
+}
+
+int mipm_spmv(mipm_handle hh, int trans, double alpha, const double *d_Ax, const double *d_x, double beta, double *d_y)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_spmv) return fail(h, MIPM_ERR_STATE, "mipm_spmv_setup has not been called");
+    if ((!d_Ax && h->sp_nnz > 0) || !d_x || !d_y) return fail(h, MIPM_ERR_ARG, "null argument");
+    if (trans == 0) {
+        if (h->sp_m > 0) {
+            k_spmv_csr<<<grid_for(h->sp_m * 32, 256), 256, 0, h->stream>>>(h->sp_m, h->d_sp_rowptr.p, h->d_sp_col.p, d_Ax, d_x,
+                                                                        alpha, beta, d_y);
+            MIPM_CHECK_LAUNCH(h);
+        }
+    } else {
+        if (h->sp_n > 0) {
+            k_spmv_csc<<<grid_for(h->sp_n * 8, 256), 256, 0, h->stream>>>(h->sp_n, h->d_sp_colptr.p, h->d_sp_row.p, h->d_sp_pos.p,
+                                                                       d_Ax, d_x, alpha, beta, d_y);
+            MIPM_CHECK_LAUNCH(h);
+        }
+    }
+    return MIPM_OK;
+}
+
+// ---------------------------------------------------------------- linear solver front-end
+int mipm_ls_analyze(mipm_handle hh, int64_t n, const int32_t *colptr, const int32_t *rowval, int index_base,
+                    int kind, int ordering, const int32_t *user_perm)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || n < 0 || !colptr || (kind != MIPM_CHOLESKY && kind != MIPM_LDL)) return fail(h, MIPM_ERR_ARG, "bad argument");
+    int64_t nnz = colptr[n] - index_base;
+    if (nnz < 0 || (nnz > 0 && !rowval)) return fail(h, MIPM_ERR_ARG, "bad column pointer");
+    std::vector<int32_t> cp((size_t)n + 1), ri((size_t)nnz), up;
+    for (int64_t j = 0; j <= n; ++j) cp[(size_t)j] = colptr[j] - index_base;
+    for (int64_t p = 0; p < nnz; ++p) ri[(size_t)p] = rowval[p] - index_base;
+    if (ordering == MIPM_ORDER_USER && user_perm) {
+        up.resize((size_t)n);
+        for (int64_t k = 0; k < n; ++k) up[(size_t)k] = user_perm[k] - index_base;
+    }
+    LsOptions opt;
+    opt.kind = kind;
+    opt.ordering = ordering;
+    if (const char *s = std::getenv("MIPM_ND_LEAF")) opt.nd_leaf = std::max(1, atoi(s));
+    if (const char *s = std::getenv("MIPM_RELAX")) {
+        // "always,k1,z1,k2,z2,z3"
+        sscanf(s, "%d,%d,%lf,%d,%lf,%lf", &opt.relax_always, &opt.relax_k1, &opt.relax_z1, &opt.relax_k2, &opt.relax_z2, &opt.relax_z3);
+    }
+    h->has_ls = false;
+    h->factorized = false;
+    std::string e = ls_analyze(n, cp.data(), ri.data(), opt, up.empty() ? nullptr : up.data(), h->sym);
+    if (!e.empty()) return fail(h, MIPM_ERR_ARG, e);
+    h->has_ls = true;
+    if (!h->host_only) return ls_device_setup(h);
+    return MIPM_OK;
+}
+
+int mipm_ls_factorize_async(mipm_handle hh, const double *d_nzval)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_ls) return fail(h, MIPM_ERR_STATE, "mipm_ls_analyze has not been called");
+    if (!d_nzval && h->sym.nnz_a > 0) return fail(h, MIPM_ERR_ARG, "null values");
+    return ls_factorize_impl(h, d_nzval);
+}
+
+int mipm_ls_status(mipm_handle hh, int *status)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!status) return fail(h, MIPM_ERR_ARG, "null argument");
+    if (!h->factorized) return fail(h, MIPM_ERR_STATE, "no factorization");
+    int info[4];
+    MIPM_CUDA(h, cudaMemcpyAsync(info, h->d_info.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    *status = (info[0] == 0) ? MIPM_OK : MIPM_ERR_NOT_FACTORIZED;
+    return MIPM_OK;
+}
+
+int mipm_ls_factorize(mipm_handle hh, const double *d_nzval, int *status)
+{
+    int rc = mipm_ls_factorize_async(hh, d_nzval);
+    if (rc != MIPM_OK) return rc;
+    if (status) return mipm_ls_status(hh, status);
+    return MIPM_OK;
+}
+
+int mipm_ls_solve(mipm_handle hh, double *d_x, int ir_steps)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_ls || !h->factorized) return fail(h, MIPM_ERR_STATE, "solve before factorize");
+    if (!d_x && h->sym.n > 0) return fail(h, MIPM_ERR_ARG, "null argument");
+    return ls_solve_impl(h, d_x, ir_steps < 0 ? 0 : ir_steps);
+}
+
+int mipm_ls_inertia(mipm_handle hh, int64_t *num_pos, int64_t *num_zero, int64_t *num_neg)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->factorized) return fail(h, MIPM_ERR_STATE, "no factorization");
+    int info[4];
+    MIPM_CUDA(h, cudaMemcpyAsync(info, h->d_info.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (num_neg) *num_neg = info[1];
+    if (num_zero) *num_zero = info[2];
+    if (num_pos) *num_pos = h->sym.n - info[1] - info[2];
+    return MIPM_OK;
+}
+
+int mipm_ls_stats(mipm_handle hh, mipm_ls_stats_t *out)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !out) return MIPM_ERR_ARG;
+    if (!h->has_ls) return fail(h, MIPM_ERR_STATE, "mipm_ls_analyze has not been called");
+    const LsSymbolic &S = h->sym;
+    out->n = S.n;
+    out->nnz_a = S.nnz_a;
+    out->nnz_l = S.nnz_l;
+    out->nnz_l_exact = S.nnz_l_exact;
+    out->flops = S.flops;
+    out->n_supernodes = S.ns;
+    out->n_levels = S.n_levels;
+    out->max_front_cols = S.max_front_cols;
+    out->max_front_rows = S.max_front_rows;
+    out->update_doubles = S.update_doubles;
+    out->n_launches = h->n_launch_factor;
+    return MIPM_OK;
+}
+
+int mipm_ls_symbolic(mipm_handle hh, int32_t **perm, int64_t *n_sn, int32_t **sn_ptr, int32_t **sn_parent,
+                     int64_t **row_ptr, int32_t **row_idx)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || !perm || !n_sn || !sn_ptr || !sn_parent || !row_ptr || !row_idx) return MIPM_ERR_ARG;
+    if (!h->has_ls) return fail(h, MIPM_ERR_STATE, "mipm_ls_analyze has not been called");
+    const LsSymbolic &S = h->sym;
+    *perm = host_copy(S.perm, 0);
+    *n_sn = S.ns;
+    *sn_ptr = host_copy(S.sn_ptr, 0);
+    *sn_parent = host_copy(S.sn_parent, 0);
+    *row_ptr = host_copy(S.row_ptr, 0);
+    *row_idx = host_copy(S.row_idx, 0);
+    if (!*perm || !*sn_ptr || !*sn_parent || !*row_ptr || !*row_idx) return fail(h, MIPM_ERR_ALLOC, "host allocation failed");
+    return MIPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// Shared declarations for the madipm_b200 CUDA library (handle, error plumbing, device buffers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/madipm_b200.h"
+#include "host_symbolic.h"
+#include "ls_symbolic.h"
+
+namespace mipm {
+
+// Simple owning device buffer.
+template <typename T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DBuf() = default;
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    ~DBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+// One (level, block-step) of the numeric factorization schedule.
+struct FactorStep {
+    int32_t level, jb;
+    int32_t n_active;       // fronts of this level with more than jb columns
+    int64_t off_sn;         // offsets into the schedule array (int32 units)
+    int64_t off_trsm;       // prefix of trsm CTA counts   (n_active + 1)
+    int64_t off_upd;        // prefix of update CTA counts (n_active + 1)
+    int64_t n_trsm, n_upd;
+};
+struct LevelInfo {
+    int64_t off_parents;    // fronts of this level that have children (for extend-add)
+    int32_t n_parents;
+    int64_t off_ea_tasks;   // extend-add tasks (parent, col0, col1) triples
+    int64_t n_ea_tasks;
+    int64_t off_all;        // all fronts of this level
+    int32_t n_all;
+};
+
+struct Handle {
+    int device = -1;
+    bool host_only = false;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // reduction scratch
+    DBuf<double> d_partials;
+    DBuf<double> d_scal;
+    DBuf<unsigned int> d_counter;
+    double *h_scal = nullptr;   // pinned
+    int red_blocks = 0;
+
+    // ---- normal equations
+    NormalSymbolic nsym;
+    bool has_normal = false, has_jac = false;
+    DBuf<int32_t> d_term_ptr, d_term_pi, d_term_pj, d_term_k;
+    DBuf<double> d_term_w, d_D;
+    const double *d_ATx = nullptr;
+
+    // ---- K2
+    K2Symbolic ksym;
+    bool has_k2 = false;
+    DBuf<int64_t> d_slot_ptr, d_slot_src;
+
+    // ---- linear solver
+    LsSymbolic sym;
+    bool has_ls = false, factorized = false;
+    int NB = 64;
+    std::vector<FactorStep> steps;
+    std::vector<LevelInfo> levels;
+    DBuf<int32_t> d_sched;           // schedule arrays
+    DBuf<int32_t> d_sn_ptr, d_sn_parent, d_row_idx, d_rel_idx, d_perm, d_child_idx, d_full_col;
+    DBuf<int64_t> d_row_ptr, d_lp, d_up, d_child_ptr, d_a2l, d_full_ptr, d_full_val, d_wp;
+    DBuf<double> d_L, d_U, d_W, d_xp, d_uvec, d_b, d_r;
+    DBuf<int> d_info;                // [0]=first failed column+1 (0 = ok), [1]=#neg pivots, [2]=#zero pivots
+    const double *d_nzval = nullptr;
+    int64_t n_launch_factor = 0;
+
+    // ---- spmv
+    bool has_spmv = false;
+    int64_t sp_m = 0, sp_n = 0, sp_nnz = 0;
+    DBuf<int32_t> d_sp_rowptr, d_sp_col, d_sp_colptr, d_sp_row, d_sp_pos;
+
+    // ---- mpc vectors (+ inverse maps variable -> position in the lb / ub block, -1 if none)
+    DBuf<int32_t> d_inv_lb, d_inv_ub;
+    bool bound = false;
+    mipm_mpc_vectors v{};
+};
+
+inline int fail(Handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define MIPM_CUDA(h, call)                                                                  \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return mipm::fail((h), MIPM_ERR_CUDA,                                           \
+                              std::string(#call) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+#define MIPM_CHECK_LAUNCH(h)                                                                \
+    do {                                                                                    \
+        (h)->launches++;                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                               \
+        if (e__ != cudaSuccess)                                                             \
+            return mipm::fail((h), MIPM_ERR_CUDA, std::string("kernel launch: ") +         \
+                                                      cudaGetErrorString(e__));            \
+    } while (0)
+
+#define MIPM_NEED_DEVICE(h)                                                                 \
+    do {                                                                                    \
+        if (!(h)) return MIPM_ERR_ARG;                                                      \
+        if ((h)->host_only)                                                                 \
+            return mipm::fail((h), MIPM_ERR_CUDA,                                           \
+                              "analysis-only handle (device < 0): no device work possible; " \
+                              "there is no CPU fallback");                                  \
+    } while (0)
+
+// implemented in the .cu files
+int ls_device_setup(Handle *h);
+int ls_factorize_impl(Handle *h, const double *d_nzval);
+int ls_solve_impl(Handle *h, double *d_x, int ir_steps);
+
+}  // namespace mipm

@@ -1,0 +1,568 @@
+// Host symbolic analysis: ordering, elimination tree, supernodes, multifrontal structure.
+// See ls_symbolic.h. Written from the textbook algorithms (George & Liu nested dissection,
+// Liu's elimination tree / Davis's row-subtree column counts, CHOLMOD-style relaxed
+// amalgamation); nothing here comes from the reference, whose analysis lives inside the
+// closed cuDSS binary.
+#include "ls_symbolic.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace mipm {
+
+namespace {
+
+// BFS over the vertices whose region[v] == rid, starting at root. Fills `order` (BFS order)
+// and `lvl_ptr` (start of each level in `order`). `stamp[v] = tag` marks visited vertices.
+void bfs_levels(const std::vector<int64_t> &xadj, const std::vector<int32_t> &adj,
+                const std::vector<int32_t> &region, int32_t rid, int32_t root,
+                std::vector<int32_t> &stamp, int32_t tag, std::vector<int32_t> &order,
+                std::vector<int64_t> &lvl_ptr)
+{
+    order.clear();
+    lvl_ptr.clear();
+    order.push_back(root);
+    stamp[root] = tag;
+    lvl_ptr.push_back(0);
+    size_t head = 0;
+    while (head < order.size()) {
+        size_t end = order.size();
+        lvl_ptr.push_back((int64_t)end);
+        for (; head < end; ++head) {
+            int32_t v = order[head];
+            for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) {
+                int32_t w = adj[p];
+                if (region[w] == rid && stamp[w] != tag) {
+                    stamp[w] = tag;
+                    order.push_back(w);
+                }
+            }
+        }
+    }
+    // lvl_ptr currently has an entry per level start plus the final end
+    if (lvl_ptr.back() != (int64_t)order.size()) lvl_ptr.push_back((int64_t)order.size());
+}
+
+}  // namespace
+
+void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
+                             const std::vector<int32_t> &adj, int leaf_size,
+                             std::vector<int32_t> &perm)
+{
+    perm.assign((size_t)n, -1);
+    if (n == 0) return;
+    std::vector<int32_t> region((size_t)n, 0), stamp((size_t)n, -1);
+    struct Item { std::vector<int32_t> verts; int64_t lo; bool connected; };
+    std::vector<Item> stack;
+    {
+        Item it;
+        it.verts.resize((size_t)n);
+        std::iota(it.verts.begin(), it.verts.end(), 0);
+        it.lo = 0;
+        it.connected = false;
+        stack.push_back(std::move(it));
+    }
+    int32_t next_rid = 1, tag = 0;
+    std::vector<int32_t> order, best_order;
+    std::vector<int64_t> lvl, best_lvl;
+
+    auto order_leaf = [&](const std::vector<int32_t> &order_bfs, int64_t lo) {
+        // reverse Cuthill-McKee: BFS order reversed
+        int64_t nv = (int64_t)order_bfs.size();
+        for (int64_t t = 0; t < nv; ++t) perm[(size_t)(lo + t)] = order_bfs[(size_t)(nv - 1 - t)];
+    };
+
+    while (!stack.empty()) {
+        Item it = std::move(stack.back());
+        stack.pop_back();
+        const int64_t nv = (int64_t)it.verts.size();
+        if (nv == 0) continue;
+        const int32_t rid = next_rid++;
+        for (int32_t v : it.verts) region[v] = rid;
+
+        if (!it.connected) {
+            // split into connected components
+            ++tag;
+            int64_t lo = it.lo;
+            bool single = true;
+            std::vector<Item> comps;
+            for (int32_t v : it.verts) {
+                if (stamp[v] == tag) continue;
+                bfs_levels(xadj, adj, region, rid, v, stamp, tag, order, lvl);
+                if ((int64_t)order.size() == nv) break;  // one component: fall through
+                single = false;
+                Item c;
+                c.verts = order;
+                c.lo = lo;
+                c.connected = true;
+                lo += (int64_t)order.size();
+                comps.push_back(std::move(c));
+            }
+            if (!single) {
+                for (auto &c : comps) stack.push_back(std::move(c));
+                continue;
+            }
+        }
+
+        // pseudo-peripheral root: start at a minimum-degree vertex, iterate on the last level
+        int32_t root = it.verts[0];
+        {
+            int64_t bestdeg = INT64_MAX;
+            for (int32_t v : it.verts) {
+                int64_t d = xadj[v + 1] - xadj[v];
+                if (d < bestdeg) { bestdeg = d; root = v; }
+            }
+        }
+        int64_t best_h = -1;
+        for (int round = 0; round < 6; ++round) {
+            ++tag;
+            bfs_levels(xadj, adj, region, rid, root, stamp, tag, order, lvl);
+            int64_t h = (int64_t)lvl.size() - 1;
+            if (h <= best_h) break;
+            best_h = h;
+            best_order = order;
+            best_lvl = lvl;
+            // next root: minimum degree vertex in the last level
+            int64_t bestdeg = INT64_MAX;
+            for (int64_t t = lvl[(size_t)h - 1]; t < lvl[(size_t)h]; ++t) {
+                int32_t v = order[(size_t)t];
+                int64_t d = xadj[v + 1] - xadj[v];
+                if (d < bestdeg) { bestdeg = d; root = v; }
+            }
+        }
+        const int64_t nlev = best_h;
+        if (nv <= leaf_size || nlev < 3) {
+            order_leaf(best_order, it.lo);
+            continue;
+        }
+        // choose the separator level: balance the two sides, prefer small separators
+        int64_t bestj = 1;
+        double bestcost = 1e300;
+        for (int64_t j = 1; j <= nlev - 2; ++j) {
+            int64_t before = best_lvl[(size_t)j];
+            int64_t sep = best_lvl[(size_t)j + 1] - best_lvl[(size_t)j];
+            int64_t after = nv - before - sep;
+            double imb = (double)std::max(before, after) / (double)nv;   // 0.5 = perfect
+            double cost = imb + 1.0 * (double)sep / (double)nv;
+            if (cost < bestcost) { bestcost = cost; bestj = j; }
+        }
+        const int64_t j = bestj;
+        // thin the separator: keep only level-j vertices adjacent to level j+1
+        ++tag;  // stamp level j+1 vertices with tag
+        for (int64_t t = best_lvl[(size_t)j + 1]; t < best_lvl[(size_t)j + 2]; ++t)
+            stamp[best_order[(size_t)t]] = tag;
+        Item A, B;
+        std::vector<int32_t> S;
+        A.verts.assign(best_order.begin(), best_order.begin() + best_lvl[(size_t)j]);
+        for (int64_t t = best_lvl[(size_t)j]; t < best_lvl[(size_t)j + 1]; ++t) {
+            int32_t v = best_order[(size_t)t];
+            bool touches = false;
+            for (int64_t p = xadj[v]; p < xadj[v + 1] && !touches; ++p) {
+                int32_t w = adj[p];
+                touches = (region[w] == rid && stamp[w] == tag);
+            }
+            if (touches) S.push_back(v); else A.verts.push_back(v);
+        }
+        B.verts.assign(best_order.begin() + best_lvl[(size_t)j + 1], best_order.end());
+        A.lo = it.lo;
+        B.lo = it.lo + (int64_t)A.verts.size();
+        A.connected = false;
+        B.connected = false;
+        int64_t slo = B.lo + (int64_t)B.verts.size();
+        for (size_t t = 0; t < S.size(); ++t) perm[(size_t)slo + t] = S[t];
+        stack.push_back(std::move(A));
+        stack.push_back(std::move(B));
+    }
+}
+
+static inline int64_t trap(int64_t k, int64_t r) { return k * (k + 1) / 2 + k * r; }
+
+std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
+                       const LsOptions &opt, const int32_t *user_perm, LsSymbolic &S)
+{
+    S = LsSymbolic();
+    S.n = n;
+    S.kind = opt.kind;
+    if (n < 0) return "negative dimension";
+    const int64_t nnz = n > 0 ? colptr[n] : 0;
+    S.nnz_a = nnz;
+    for (int64_t j = 0; j < n; ++j) {
+        if (colptr[j + 1] < colptr[j]) return "colptr not monotone";
+        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+            int32_t i = rowval[p];
+            if (i < j || i >= n) return "rowval outside the lower triangle";
+        }
+    }
+    // ---- full symmetric adjacency (no diagonal) + full CSR with value positions
+    std::vector<int64_t> xadj((size_t)n + 1, 0);
+    S.full_ptr.assign((size_t)n + 1, 0);
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+            int32_t i = rowval[p];
+            S.full_ptr[(size_t)i + 1]++;
+            if (i != j) {
+                S.full_ptr[(size_t)j + 1]++;
+                xadj[(size_t)i + 1]++;
+                xadj[(size_t)j + 1]++;
+            }
+        }
+    for (int64_t i = 0; i < n; ++i) {
+        xadj[(size_t)i + 1] += xadj[(size_t)i];
+        S.full_ptr[(size_t)i + 1] += S.full_ptr[(size_t)i];
+    }
+    std::vector<int32_t> adj((size_t)xadj[(size_t)n]);
+    S.full_col.resize((size_t)S.full_ptr[(size_t)n]);
+    S.full_val.resize((size_t)S.full_ptr[(size_t)n]);
+    {
+        std::vector<int64_t> pa(xadj.begin(), xadj.end() - 1), pf(S.full_ptr.begin(), S.full_ptr.end() - 1);
+        // column-major sweep emits, for every row, its columns in ascending order:
+        // first the upper part (j > i) would come later, so do two sweeps to keep rows sorted.
+        // sweep 1: entries (i, j) with j < i come from column j at row i -> ascending j.
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t i = rowval[p];
+                S.full_col[(size_t)pf[(size_t)i]] = (int32_t)j;
+                S.full_val[(size_t)pf[(size_t)i]++] = p;
+                if (i != j) adj[(size_t)pa[(size_t)i]++] = (int32_t)j;
+            }
+        // sweep 2: mirrored entries (j, i) for i > j: row j gets column i, ascending i within column j
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t i = rowval[p];
+                if (i != j) {
+                    S.full_col[(size_t)pf[(size_t)j]] = i;
+                    S.full_val[(size_t)pf[(size_t)j]++] = p;
+                    adj[(size_t)pa[(size_t)j]++] = i;
+                }
+            }
+    }
+    // ---- ordering
+    std::vector<int32_t> perm0;
+    if (opt.ordering == 2 /*USER*/) {
+        if (!user_perm) return "user ordering requested without a permutation";
+        perm0.assign(user_perm, user_perm + n);
+        std::vector<char> seen((size_t)n, 0);
+        for (int64_t k = 0; k < n; ++k) {
+            if (perm0[(size_t)k] < 0 || perm0[(size_t)k] >= n || seen[(size_t)perm0[(size_t)k]]) return "user permutation invalid";
+            seen[(size_t)perm0[(size_t)k]] = 1;
+        }
+    } else if (opt.ordering == 1 /*NATURAL*/) {
+        perm0.resize((size_t)n);
+        std::iota(perm0.begin(), perm0.end(), 0);
+    } else {
+        order_nested_dissection(n, xadj, adj, opt.nd_leaf, perm0);
+    }
+    if (opt.kind == 1 /*LDL*/ && opt.ordering != 2) {
+        // Quasi-definite safeguard for K2 = [Q+Sigma A'; A delta_c I]: a vertex whose diagonal
+        // block is only the (tiny) dual regularization must not be eliminated before all of
+        // its neighbours. Such vertices are those without a structural coupling inside their
+        // own block; we cannot see values here, so the caller marks nothing and we use the
+        // structural rule "delay a vertex until one neighbour is eliminated" for vertices of
+        // the trailing block, detected as vertices whose neighbours all have smaller index
+        // (rows of A only touch primal columns, which come first in K2's numbering).
+        std::vector<int32_t> ip((size_t)n);
+        for (int64_t k = 0; k < n; ++k) ip[(size_t)perm0[(size_t)k]] = (int32_t)k;
+        std::vector<char> dual((size_t)n, 0);
+        for (int64_t v = 0; v < n; ++v) {
+            bool all_smaller = xadj[(size_t)v + 1] > xadj[(size_t)v];
+            for (int64_t p = xadj[(size_t)v]; p < xadj[(size_t)v + 1] && all_smaller; ++p)
+                all_smaller = adj[(size_t)p] < v;
+            dual[(size_t)v] = all_smaller;
+        }
+        // primal vertices with all neighbours larger are not delayed; only "dual" ones are
+        std::vector<char> done((size_t)n, 0);
+        std::vector<std::vector<int32_t>> waiting((size_t)n);  // waiting[u]: duals released when u is eliminated
+        std::vector<int32_t> out;
+        out.reserve((size_t)n);
+        for (int64_t k = 0; k < n; ++k) {
+            int32_t v = perm0[(size_t)k];
+            if (dual[(size_t)v]) {
+                bool ready = false;
+                int32_t first_nb = -1;
+                int32_t first_pos = INT32_MAX;
+                for (int64_t p = xadj[(size_t)v]; p < xadj[(size_t)v + 1]; ++p) {
+                    int32_t u = adj[(size_t)p];
+                    if (dual[(size_t)u]) continue;
+                    if (done[(size_t)u]) { ready = true; break; }
+                    if (ip[(size_t)u] < first_pos) { first_pos = ip[(size_t)u]; first_nb = u; }
+                }
+                if (!ready && first_nb >= 0) { waiting[(size_t)first_nb].push_back(v); continue; }
+            }
+            out.push_back(v);
+            done[(size_t)v] = 1;
+            for (int32_t w : waiting[(size_t)v]) { out.push_back(w); done[(size_t)w] = 1; }
+            waiting[(size_t)v].clear();
+        }
+        perm0.swap(out);
+    }
+    std::vector<int32_t> ip0((size_t)n);
+    for (int64_t k = 0; k < n; ++k) ip0[(size_t)perm0[(size_t)k]] = (int32_t)k;
+
+    // ---- strictly-lower adjacency in the permuted numbering: lowadj[r] = {c < r}
+    auto build_lowadj = [&](const std::vector<int32_t> &ip, std::vector<int64_t> &lptr, std::vector<int32_t> &lidx) {
+        lptr.assign((size_t)n + 1, 0);
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t i = rowval[p];
+                if (i == j) continue;
+                int32_t a = ip[(size_t)i], b = ip[(size_t)j];
+                lptr[(size_t)std::max(a, b) + 1]++;
+            }
+        for (int64_t i = 0; i < n; ++i) lptr[(size_t)i + 1] += lptr[(size_t)i];
+        lidx.resize((size_t)lptr[(size_t)n]);
+        std::vector<int64_t> pos(lptr.begin(), lptr.end() - 1);
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t i = rowval[p];
+                if (i == j) continue;
+                int32_t a = ip[(size_t)i], b = ip[(size_t)j];
+                lidx[(size_t)pos[(size_t)std::max(a, b)]++] = std::min(a, b);
+            }
+    };
+    std::vector<int64_t> lptr;
+    std::vector<int32_t> lidx;
+    build_lowadj(ip0, lptr, lidx);
+
+    // ---- elimination tree + off-diagonal column counts (row-subtree traversal)
+    std::vector<int32_t> parent((size_t)n, -1), flag((size_t)n);
+    std::vector<int64_t> cnt((size_t)n, 0);
+    for (int64_t k = 0; k < n; ++k) {
+        flag[(size_t)k] = (int32_t)k;
+        for (int64_t p = lptr[(size_t)k]; p < lptr[(size_t)k + 1]; ++p) {
+            int32_t i = lidx[(size_t)p];
+            for (; flag[(size_t)i] != k; i = parent[(size_t)i]) {
+                if (parent[(size_t)i] == -1) parent[(size_t)i] = (int32_t)k;
+                cnt[(size_t)i]++;
+                flag[(size_t)i] = (int32_t)k;
+            }
+        }
+    }
+    // ---- postorder (children by ascending count so a supernode-forming child comes last)
+    std::vector<int32_t> post((size_t)n);  // post[newpos] = node (in perm0 numbering)
+    {
+        std::vector<int64_t> cptr((size_t)n + 2, 0);
+        for (int64_t v = 0; v < n; ++v) cptr[(size_t)(parent[(size_t)v] + 1) + 1]++;   // slot 0 = roots
+        for (int64_t i = 0; i <= n; ++i) cptr[(size_t)i + 1] += cptr[(size_t)i];
+        std::vector<int32_t> cidx((size_t)n);
+        std::vector<int64_t> pos(cptr.begin(), cptr.end() - 1);
+        for (int64_t v = 0; v < n; ++v) cidx[(size_t)pos[(size_t)(parent[(size_t)v] + 1)]++] = (int32_t)v;
+        for (int64_t q = 0; q <= n; ++q)
+            std::stable_sort(cidx.begin() + cptr[(size_t)q], cidx.begin() + cptr[(size_t)q + 1],
+                             [&](int32_t a, int32_t b) { return cnt[(size_t)a] < cnt[(size_t)b]; });
+        // iterative DFS
+        std::vector<int32_t> stk;
+        std::vector<int64_t> it((size_t)n + 1);
+        for (int64_t q = 0; q <= n; ++q) it[(size_t)q] = cptr[(size_t)q];
+        int64_t k = 0;
+        for (int64_t r = cptr[0]; r < cptr[1]; ++r) {
+            stk.push_back(cidx[(size_t)r]);
+            while (!stk.empty()) {
+                int32_t v = stk.back();
+                int64_t &ci = it[(size_t)v + 1];
+                if (ci < cptr[(size_t)v + 2]) {
+                    stk.push_back(cidx[(size_t)ci++]);
+                } else {
+                    post[(size_t)k++] = v;
+                    stk.pop_back();
+                }
+            }
+        }
+        if (k != n) return "postorder failed";
+    }
+    S.perm.resize((size_t)n);
+    S.iperm.resize((size_t)n);
+    std::vector<int32_t> ipost((size_t)n);
+    for (int64_t k = 0; k < n; ++k) ipost[(size_t)post[(size_t)k]] = (int32_t)k;
+    for (int64_t k = 0; k < n; ++k) S.perm[(size_t)k] = perm0[(size_t)post[(size_t)k]];
+    for (int64_t k = 0; k < n; ++k) S.iperm[(size_t)S.perm[(size_t)k]] = (int32_t)k;
+    std::vector<int32_t> par((size_t)n);
+    std::vector<int64_t> cc((size_t)n);
+    for (int64_t v = 0; v < n; ++v) {
+        par[(size_t)ipost[(size_t)v]] = parent[(size_t)v] < 0 ? -1 : ipost[(size_t)parent[(size_t)v]];
+        cc[(size_t)ipost[(size_t)v]] = cnt[(size_t)v];
+    }
+    S.nnz_l_exact = 0;
+    S.flops = 0.0;
+    for (int64_t j = 0; j < n; ++j) {
+        S.nnz_l_exact += cc[(size_t)j] + 1;
+        S.flops += (double)(cc[(size_t)j] + 1) * (double)(cc[(size_t)j] + 1);
+    }
+
+    // ---- fundamental supernodes
+    std::vector<int32_t> sn0;  // start columns
+    for (int64_t j = 0; j < n; ++j) {
+        bool cont = j > 0 && par[(size_t)j - 1] == j && cc[(size_t)j - 1] == cc[(size_t)j] + 1 &&
+                    (j - sn0.back()) < opt.max_sn_cols;
+        if (!cont) sn0.push_back((int32_t)j);
+    }
+    int64_t ns0 = (int64_t)sn0.size();
+    sn0.push_back((int32_t)n);
+
+    // ---- relaxed amalgamation on (start, end, rows_below = cc[end-1], true nnz)
+    struct Sn { int32_t c0, c1; int64_t r; int64_t nnz_true; };
+    std::vector<Sn> cur;
+    cur.reserve((size_t)ns0);
+    for (int64_t s = 0; s < ns0; ++s) {
+        Sn x;
+        x.c0 = sn0[(size_t)s];
+        x.c1 = sn0[(size_t)s + 1];
+        x.r = cc[(size_t)x.c1 - 1];
+        x.nnz_true = 0;
+        for (int32_t j = x.c0; j < x.c1; ++j) x.nnz_true += cc[(size_t)j] + 1;
+        while (!cur.empty()) {
+            Sn &pv = cur.back();
+            // pv is a child of x iff the parent column of pv's last column lies inside x
+            int32_t pc = par[(size_t)pv.c1 - 1];
+            if (pv.c1 != x.c0 || pc < x.c0 || pc >= x.c1) break;
+            int64_t k = (int64_t)(x.c1 - pv.c0);
+            if (k > opt.max_sn_cols) break;
+            int64_t merged = trap(k, x.r);
+            int64_t tru = pv.nnz_true + x.nnz_true;
+            double z = (double)(merged - tru) / (double)merged;
+            bool ok = (k <= opt.relax_always) || (k <= opt.relax_k1 && z <= opt.relax_z1) ||
+                      (k <= opt.relax_k2 && z <= opt.relax_z2) || (z <= opt.relax_z3);
+            if (!ok) break;
+            x.c0 = pv.c0;
+            x.nnz_true = tru;
+            cur.pop_back();
+        }
+        cur.push_back(x);
+    }
+    S.ns = (int32_t)cur.size();
+    const int32_t ns = S.ns;
+    S.sn_ptr.resize((size_t)ns + 1);
+    for (int32_t s = 0; s < ns; ++s) S.sn_ptr[(size_t)s] = cur[(size_t)s].c0;
+    S.sn_ptr[(size_t)ns] = (int32_t)n;
+    S.col2sn.resize((size_t)n);
+    for (int32_t s = 0; s < ns; ++s)
+        for (int32_t j = S.sn_ptr[(size_t)s]; j < S.sn_ptr[(size_t)s + 1]; ++j) S.col2sn[(size_t)j] = s;
+
+    // ---- strictly-lower column structure of the permuted matrix: below[c] = {r > c}
+    std::vector<int64_t> bptr((size_t)n + 1, 0);
+    std::vector<int32_t> bidx;
+    {
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t i = rowval[p];
+                if (i == j) continue;
+                int32_t a = S.iperm[(size_t)i], b = S.iperm[(size_t)j];
+                bptr[(size_t)std::min(a, b) + 1]++;
+            }
+        for (int64_t i = 0; i < n; ++i) bptr[(size_t)i + 1] += bptr[(size_t)i];
+        bidx.resize((size_t)bptr[(size_t)n]);
+        std::vector<int64_t> pos(bptr.begin(), bptr.end() - 1);
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t i = rowval[p];
+                if (i == j) continue;
+                int32_t a = S.iperm[(size_t)i], b = S.iperm[(size_t)j];
+                bidx[(size_t)pos[(size_t)std::min(a, b)]++] = std::max(a, b);
+            }
+    }
+    // ---- supernode parents, children, row structures (merge original entries + children)
+    S.sn_parent.assign((size_t)ns, -1);
+    S.row_ptr.assign((size_t)ns + 1, 0);
+    std::vector<std::vector<int32_t>> rows((size_t)ns);
+    std::vector<std::vector<int32_t>> kids((size_t)ns);
+    {
+        std::vector<int32_t> mark((size_t)n, -1);
+        for (int32_t s = 0; s < ns; ++s) {
+            int32_t c0 = S.sn_ptr[(size_t)s], c1 = S.sn_ptr[(size_t)s + 1];
+            std::vector<int32_t> &R = rows[(size_t)s];
+            for (int32_t j = c0; j < c1; ++j)
+                for (int64_t p = bptr[(size_t)j]; p < bptr[(size_t)j + 1]; ++p) {
+                    int32_t r = bidx[(size_t)p];
+                    if (r >= c1 && mark[(size_t)r] != s) { mark[(size_t)r] = s; R.push_back(r); }
+                }
+            for (int32_t c : kids[(size_t)s])
+                for (int32_t r : rows[(size_t)c])
+                    if (r >= c1 && mark[(size_t)r] != s) { mark[(size_t)r] = s; R.push_back(r); }
+            std::sort(R.begin(), R.end());
+            if ((int64_t)R.size() != cur[(size_t)s].r) return "supernode row count mismatch (internal error)";
+            if (!R.empty()) {
+                int32_t ps = S.col2sn[(size_t)R[0]];
+                S.sn_parent[(size_t)s] = ps;
+                kids[(size_t)ps].push_back(s);
+            }
+            S.row_ptr[(size_t)s + 1] = S.row_ptr[(size_t)s] + (int64_t)R.size();
+        }
+    }
+    S.row_idx.resize((size_t)S.row_ptr[(size_t)ns]);
+    S.rel_idx.resize((size_t)S.row_ptr[(size_t)ns]);
+    S.child_ptr.assign((size_t)ns + 1, 0);
+    for (int32_t s = 0; s < ns; ++s) {
+        std::copy(rows[(size_t)s].begin(), rows[(size_t)s].end(), S.row_idx.begin() + S.row_ptr[(size_t)s]);
+        S.child_ptr[(size_t)s + 1] = S.child_ptr[(size_t)s] + (int64_t)kids[(size_t)s].size();
+    }
+    S.child_idx.resize((size_t)S.child_ptr[(size_t)ns]);
+    for (int32_t s = 0; s < ns; ++s)
+        std::copy(kids[(size_t)s].begin(), kids[(size_t)s].end(), S.child_idx.begin() + S.child_ptr[(size_t)s]);
+    // relative indices of each supernode's rows inside its parent's front (cols ++ rows)
+    for (int32_t s = 0; s < ns; ++s) {
+        int32_t ps = S.sn_parent[(size_t)s];
+        if (ps < 0) continue;
+        int32_t pc0 = S.sn_ptr[(size_t)ps], pc1 = S.sn_ptr[(size_t)ps + 1];
+        int32_t pk = pc1 - pc0;
+        const std::vector<int32_t> &PR = rows[(size_t)ps];
+        size_t q = 0;
+        for (int64_t t = S.row_ptr[(size_t)s]; t < S.row_ptr[(size_t)s + 1]; ++t) {
+            int32_t r = S.row_idx[(size_t)t];
+            if (r < pc1) {
+                S.rel_idx[(size_t)t] = r - pc0;
+            } else {
+                while (q < PR.size() && PR[q] < r) ++q;
+                if (q >= PR.size() || PR[q] != r) return "front structure not nested (internal error)";
+                S.rel_idx[(size_t)t] = pk + (int32_t)q;
+            }
+        }
+    }
+    // ---- storage offsets, levels, stats
+    S.lp.assign((size_t)ns + 1, 0);
+    S.up.assign((size_t)ns + 1, 0);
+    S.sn_level.assign((size_t)ns, 0);
+    for (int32_t s = 0; s < ns; ++s) {
+        int64_t k = S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s];
+        int64_t r = S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s];
+        S.lp[(size_t)s + 1] = S.lp[(size_t)s] + (k + r) * k;
+        S.up[(size_t)s + 1] = S.up[(size_t)s] + r * r;
+        S.max_front_cols = std::max<int32_t>(S.max_front_cols, (int32_t)k);
+        S.max_front_rows = std::max<int32_t>(S.max_front_rows, (int32_t)(k + r));
+        for (int32_t c : kids[(size_t)s]) S.sn_level[(size_t)s] = std::max(S.sn_level[(size_t)s], S.sn_level[(size_t)c] + 1);
+        S.n_levels = std::max(S.n_levels, S.sn_level[(size_t)s] + 1);
+    }
+    S.nnz_l = S.lp[(size_t)ns];
+    S.update_doubles = S.up[(size_t)ns];
+    S.level_ptr.assign((size_t)S.n_levels + 1, 0);
+    for (int32_t s = 0; s < ns; ++s) S.level_ptr[(size_t)S.sn_level[(size_t)s] + 1]++;
+    for (int32_t l = 0; l < S.n_levels; ++l) S.level_ptr[(size_t)l + 1] += S.level_ptr[(size_t)l];
+    S.level_sn.resize((size_t)ns);
+    {
+        std::vector<int64_t> pos(S.level_ptr.begin(), S.level_ptr.end() - 1);
+        for (int32_t s = 0; s < ns; ++s) S.level_sn[(size_t)pos[(size_t)S.sn_level[(size_t)s]]++] = s;
+    }
+    // ---- scatter map of the input nonzeros into the panels
+    S.a2l.resize((size_t)nnz);
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+            int32_t a = S.iperm[(size_t)rowval[p]], b = S.iperm[(size_t)j];
+            int32_t r = std::max(a, b), c = std::min(a, b);
+            int32_t s = S.col2sn[(size_t)c];
+            int32_t c0 = S.sn_ptr[(size_t)s], c1 = S.sn_ptr[(size_t)s + 1];
+            int64_t k = c1 - c0;
+            int64_t nr = S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s];
+            int64_t t;
+            if (r < c1) {
+                t = r - c0;
+            } else {
+                const int32_t *rb = S.row_idx.data() + S.row_ptr[(size_t)s];
+                const int32_t *f = std::lower_bound(rb, rb + nr, r);
+                if (f == rb + nr || *f != r) return "input entry outside the symbolic structure (internal error)";
+                t = k + (f - rb);
+            }
+            S.a2l[(size_t)p] = S.lp[(size_t)s] + (int64_t)(c - c0) * (k + nr) + t;
+        }
+    return "";
+}
+
+}  // namespace mipm

@@ -1,0 +1,62 @@
+// Host-side symbolic analysis for the supernodal multifrontal Cholesky / LDL^T.
+// Replaces the `analysis` phase of cuDSS that MadNLPGPU.CUDSSSolver runs at construction
+// (reference call site: src/KKT/normalkkt.jl:113-115). Pure C++ (no CUDA) so it can be
+// exercised on a CPU-only box through an analysis-only handle.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mipm {
+
+struct LsOptions {
+    int kind = 0;            // MIPM_CHOLESKY / MIPM_LDL
+    int ordering = 0;        // MIPM_ORDER_*
+    int nd_leaf = 96;        // stop dissecting below this many vertices
+    int relax_always = 8;    // amalgamation: merge if merged width <= this
+    int relax_k1 = 32;  double relax_z1 = 0.50;
+    int relax_k2 = 96;  double relax_z2 = 0.20;
+    double relax_z3 = 0.05;
+    int max_sn_cols = 1 << 30;
+};
+
+struct LsSymbolic {
+    int64_t n = 0, nnz_a = 0;
+    int kind = 0;
+    std::vector<int32_t> perm, iperm;          // perm[new] = old, iperm[old] = new
+    int32_t ns = 0;
+    std::vector<int32_t> sn_ptr;               // ns+1, first column of each supernode
+    std::vector<int32_t> sn_parent;            // ns, -1 for roots
+    std::vector<int32_t> sn_level;             // ns
+    std::vector<int32_t> col2sn;               // n
+    std::vector<int64_t> row_ptr;              // ns+1
+    std::vector<int32_t> row_idx;              // below-diagonal rows (permuted numbering)
+    std::vector<int32_t> rel_idx;              // same shape as row_idx: position in parent's front
+    std::vector<int64_t> lp;                   // ns+1, panel offsets in L storage (doubles)
+    std::vector<int64_t> up;                   // ns+1, update-matrix offsets
+    std::vector<int64_t> child_ptr;            // ns+1
+    std::vector<int32_t> child_idx;            // children in ascending order
+    std::vector<int64_t> level_ptr;            // nlev+1
+    std::vector<int32_t> level_sn;             // supernodes grouped by level
+    std::vector<int64_t> a2l;                  // nnz_a: destination of each input nonzero in L storage
+    // full symmetric CSR of the input matrix in ORIGINAL numbering (for refinement SpMV)
+    std::vector<int64_t> full_ptr;             // n+1
+    std::vector<int32_t> full_col;
+    std::vector<int64_t> full_val;             // index into the caller's nzval
+    // stats
+    int64_t nnz_l = 0, nnz_l_exact = 0, update_doubles = 0;
+    double flops = 0.0;
+    int32_t n_levels = 0, max_front_cols = 0, max_front_rows = 0;
+};
+
+// colptr/rowval: lower-triangular CSC, 0-based. Returns "" on success or an error message.
+std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
+                       const LsOptions &opt, const int32_t *user_perm, LsSymbolic &out);
+
+// Nested-dissection ordering (level-structure separators, George & Liu) of the graph of a
+// symmetric matrix given by its full adjacency (no self loops). perm[new] = old.
+void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
+                             const std::vector<int32_t> &adj, int leaf_size,
+                             std::vector<int32_t> &perm);
+
+}  // namespace mipm

@@ -1,0 +1,807 @@
+// Fused Mehrotra predictor-corrector vector kernels (replaces the ~40 broadcast and ~20
+// mapreduce launches per iteration that CUDA.jl generates for src/kernels.jl and
+// src/solver.jl). All reductions are single-launch, deterministic
+// ("last block folds the per-block partials in a fixed order") and return through one
+// pinned-host scalar block, so each entry point that returns a scalar costs one sync.
+//
+// Bound blocks: the reference indexes x, xl, zl, ... through ind_lb / ind_ub views
+// (src/structure.jl:146-153). At bind time we build the inverse maps (variable -> position in
+// the lb / ub block, or -1) so every kernel is one coalesced pass over the n variables.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+
+#include "common.h"
+
+namespace mipm {
+
+namespace {
+
+constexpr int TB = 256;
+
+enum { OP_SUM = 0, OP_MAX = 1, OP_MIN = 2 };
+
+__device__ __forceinline__ double comb(double a, double b, int op)
+{
+    if (op == OP_SUM) return a + b;
+    if (op == OP_MAX) return (a > b || a != a) ? a : b;     // NaN propagates like Julia's norm(.,Inf)
+    return (a < b || a != a) ? a : b;
+}
+
+// Deterministic grid-wide reduction of NV values per thread; result in out[0..NV).
+template <int NV>
+__device__ void grid_reduce_vals(double (&acc)[NV], const int (&op)[NV], double *partials, unsigned int *counter,
+                                 double *out)
+{
+    __shared__ double sm[NV][TB / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] = comb(acc[q], __shfl_xor_sync(0xffffffffu, acc[q], o), op[q]);
+        if (lane == 0) sm[q][warp] = acc[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        const int q = threadIdx.x;
+        double v = sm[q][0];
+        for (int w = 1; w < TB / 32; ++w) v = comb(v, sm[q][w], op[q]);
+        partials[(size_t)q * gridDim.x + blockIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const double ident[3] = {0.0, -DBL_MAX, DBL_MAX};
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double v = ident[op[q]];
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += TB) v = comb(v, partials[(size_t)q * gridDim.x + b], op[q]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = comb(v, __shfl_xor_sync(0xffffffffu, v, o), op[q]);
+        if (lane == 0) sm[q][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        const int q = threadIdx.x;
+        double v = sm[q][0];
+        for (int w = 1; w < TB / 32; ++w) v = comb(v, sm[q][w], op[q]);
+        out[q] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+// (value, index) arg-min pairs with the reference's tie rule: `a < b ? a : b` keeps the
+// right-most of equal values (src/kernels.jl:232), i.e. the larger index; init = (1.0, 0).
+struct VI { double v; long long i; };
+__device__ __forceinline__ VI comb_vi(VI a, VI b)
+{
+    if (a.v < b.v) return a;
+    if (b.v < a.v) return b;
+    return (a.i > b.i) ? a : b;
+}
+template <int NP>
+__device__ void grid_reduce_argmin(VI (&acc)[NP], double *partials, unsigned int *counter, double *out)
+{
+    __shared__ VI sm[NP][TB / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long *ipart = (long long *)(partials + (size_t)NP * gridDim.x);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            VI other;
+            other.v = __shfl_xor_sync(0xffffffffu, acc[q].v, o);
+            other.i = __shfl_xor_sync(0xffffffffu, acc[q].i, o);
+            acc[q] = comb_vi(acc[q], other);
+        }
+        if (lane == 0) sm[q][warp] = acc[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < NP) {
+        const int q = threadIdx.x;
+        VI v = sm[q][0];
+        for (int w = 1; w < TB / 32; ++w) v = comb_vi(v, sm[q][w]);
+        partials[(size_t)q * gridDim.x + blockIdx.x] = v.v;
+        ipart[(size_t)q * gridDim.x + blockIdx.x] = v.i;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        VI v;
+        v.v = 1.0;
+        v.i = 0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += TB) {
+            VI o;
+            o.v = partials[(size_t)q * gridDim.x + b];
+            o.i = ipart[(size_t)q * gridDim.x + b];
+            v = comb_vi(v, o);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            VI other;
+            other.v = __shfl_xor_sync(0xffffffffu, v.v, o);
+            other.i = __shfl_xor_sync(0xffffffffu, v.i, o);
+            v = comb_vi(v, other);
+        }
+        if (lane == 0) sm[q][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NP) {
+        const int q = threadIdx.x;
+        VI v = sm[q][0];
+        for (int w = 1; w < TB / 32; ++w) v = comb_vi(v, sm[q][w]);
+        out[q] = v.v;
+        out[NP + q] = (double)v.i;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+struct V {   // device view of mipm_mpc_vectors + inverse maps
+    int64_t n, m, nlb, nub;
+    const int32_t *inv_lb, *inv_ub;
+    double *x, *xl, *xu, *zl, *zu, *f, *y, *c, *rhs, *jacl, *d, *p, *w, *corr_lb, *corr_ub;
+    double *reg, *pr_diag, *du_diag, *l_diag, *u_diag, *l_lower, *u_lower;
+};
+
+#define GRID_STRIDE(i, len) for (int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x; i < (len); i += (int64_t)gridDim.x * TB)
+
+__global__ void k_build_inv(int64_t nidx, const int64_t *__restrict__ ind, int base, int32_t *__restrict__ inv)
+{
+    GRID_STRIDE(j, nidx) inv[ind[j] - base] = (int32_t)j;
+}
+
+// src/kernels.jl:124-136
+__global__ void __launch_bounds__(TB) k_set_aug_diag(V v, double del_w, double del_c)
+{
+    GRID_STRIDE(i, v.n) {
+        double pr = del_w;
+        v.reg[i] = del_w;
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) {
+            double ld = v.xl[i] - v.x[i], zl = v.zl[i];
+            v.l_diag[jl] = ld;
+            v.l_lower[jl] = zl;
+            pr = pr - zl / ld;
+        }
+        if (ju >= 0) {
+            double ud = v.x[i] - v.xu[i], zu = v.zu[i];
+            v.u_diag[ju] = ud;
+            v.u_lower[ju] = zu;
+            pr = pr - zu / ud;
+        }
+        v.pr_diag[i] = pr;
+    }
+    GRID_STRIDE(i, v.m) v.du_diag[i] = del_c;
+}
+
+// src/kernels.jl:21-58 (corr == 0: predictive; corr == 1: correction with mu)
+__global__ void __launch_bounds__(TB) k_set_rhs(V v, int corr, double mu)
+{
+    double *px = v.p, *py = v.p + v.n, *pzl = v.p + v.n + v.m, *pzu = v.p + v.n + v.m + v.nlb;
+    GRID_STRIDE(i, v.n) {
+        double x = v.x[i], zl = v.zl[i], zu = v.zu[i];
+        px[i] = ((-v.f[i] + zl) - zu) - v.jacl[i];
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) {
+            double t = (v.xl[i] - x) * zl;
+            pzl[jl] = corr ? (t + mu) - v.corr_lb[jl] : t;
+        }
+        if (ju >= 0) {
+            double t = (v.xu[i] - x) * zu;
+            pzu[ju] = corr ? (t - mu) - v.corr_ub[ju] : t;
+        }
+    }
+    GRID_STRIDE(i, v.m) py[i] = -v.c[i];
+}
+
+// src/kernels.jl:60-71
+__global__ void __launch_bounds__(TB) k_get_correction(V v)
+{
+    const double *dx = v.d, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
+    GRID_STRIDE(i, v.n) {
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) v.corr_lb[jl] = dx[i] * dzl[jl];
+        if (ju >= 0) v.corr_ub[ju] = dx[i] * dzu[ju];
+    }
+}
+
+// src/kernels.jl:74-122
+__global__ void __launch_bounds__(TB) k_set_extra_correction(V v, double ap, double ad, double tmin, double tmax)
+{
+    const double *dx = v.d, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
+    GRID_STRIDE(i, v.n) {
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) {
+            double x_ = (v.x[i] + ap * dx[i]) - v.xl[i];
+            double z_ = v.zl[i] + ad * dzl[jl];
+            double val = x_ * z_;
+            double dl = (val < tmin) ? tmin - val : ((val > tmax) ? tmax - val : 0.0);
+            v.corr_lb[jl] = v.corr_lb[jl] - dl;
+        }
+        if (ju >= 0) {
+            double x_ = (v.xu[i] - ap * dx[i]) - v.x[i];
+            double z_ = v.zu[i] + ad * dzu[ju];
+            double val = x_ * z_;
+            double dl = (val < tmin) ? tmin - val : ((val > tmax) ? tmax - val : 0.0);
+            v.corr_ub[ju] = v.corr_ub[ju] + dl;
+        }
+    }
+}
+
+// src/kernels.jl:155-208: out[0] = sum_l, out[1] = sum_u (affine == 0: current point)
+__global__ void __launch_bounds__(TB) k_compl_measure(V v, int affine, double ap, double ad, double *partials,
+                                                      unsigned int *counter, double *out)
+{
+    const double *dx = v.d, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
+    double acc[2] = {0.0, 0.0};
+    GRID_STRIDE(i, v.n) {
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) {
+            if (affine) acc[0] += ((v.x[i] + ap * dx[i]) - v.xl[i]) * (v.zl[i] + ad * dzl[jl]);
+            else acc[0] += (v.x[i] - v.xl[i]) * v.zl[i];
+        }
+        if (ju >= 0) {
+            if (affine) acc[1] += (v.xu[i] - (v.x[i] + ap * dx[i])) * (v.zu[i] + ad * dzu[ju]);
+            else acc[1] += (v.xu[i] - v.x[i]) * v.zu[i];
+        }
+    }
+    const int op[2] = {OP_SUM, OP_SUM};
+    grid_reduce_vals<2>(acc, op, partials, counter, out);
+}
+
+// src/kernels.jl:226-272: four ratio tests in one pass.
+__global__ void __launch_bounds__(TB) k_alpha_max(V v, double tau, double *partials, unsigned int *counter, double *out)
+{
+    const double *dx = v.d, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
+    VI acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { acc[q].v = 1.0; acc[q].i = 0; }
+    GRID_STRIDE(i, v.n) {
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        double dxi = dx[i];
+        if (jl >= 0) {
+            VI c;
+            c.i = jl + 1;
+            c.v = (dxi < 0.0) ? (-v.x[i] + v.xl[i]) * tau / dxi : INFINITY;
+            acc[0] = comb_vi(acc[0], c);
+            double dz = dzl[jl];
+            c.v = (dz < 0.0) ? (-v.zl[i]) * tau / dz : INFINITY;
+            acc[2] = comb_vi(acc[2], c);
+        }
+        if (ju >= 0) {
+            VI c;
+            c.i = ju + 1;
+            c.v = (dxi > 0.0) ? (-v.x[i] + v.xu[i]) * tau / dxi : INFINITY;
+            acc[1] = comb_vi(acc[1], c);
+            double dz = dzu[ju], zu = v.zu[i];
+            c.v = ((dz < 0.0) && (zu + dz < 0.0)) ? (-zu) * tau / dz : INFINITY;
+            acc[3] = comb_vi(acc[3], c);
+        }
+    }
+    grid_reduce_argmin<4>(acc, partials, counter, out);
+}
+
+// src/solver.jl:194-205 + src/kernels.jl:408-430 + src/structure.jl:193
+// out = (-y.rhs, zl_r.xl_r, zu_r.xu_r, ||c||inf, ||f-zl+zu+jacl||inf, max compl, ||dx||inf)
+__global__ void __launch_bounds__(TB) k_termination(V v, double *partials, unsigned int *counter, double *out)
+{
+    double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    GRID_STRIDE(i, v.n) {
+        double x = v.x[i], zl = v.zl[i], zu = v.zu[i];
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        double rd = fabs(((v.f[i] - zl) + zu) + v.jacl[i]);
+        acc[4] = comb(acc[4], rd, OP_MAX);
+        acc[6] = comb(acc[6], fabs(v.d[i]), OP_MAX);
+        if (jl >= 0) {
+            double xl = v.xl[i];
+            acc[1] += zl * xl;
+            acc[5] = comb(acc[5], fabs((x - xl) * zl), OP_MAX);
+        }
+        if (ju >= 0) {
+            double xu = v.xu[i];
+            acc[2] += zu * xu;
+            acc[5] = comb(acc[5], fabs((xu - x) * zu), OP_MAX);
+        }
+    }
+    GRID_STRIDE(i, v.m) {
+        acc[0] -= v.y[i] * v.rhs[i];
+        acc[3] = comb(acc[3], fabs(v.c[i]), OP_MAX);
+    }
+    const int op[7] = {OP_SUM, OP_SUM, OP_SUM, OP_MAX, OP_MAX, OP_MAX, OP_MAX};
+    grid_reduce_vals<7>(acc, op, partials, counter, out);
+}
+
+// src/solver.jl:308-317 + MadNLP.adjust_boundary!
+__global__ void __launch_bounds__(TB) k_apply_step(V v, double ap, double ad, double c1, double c2)
+{
+    const double *dx = v.d, *dy = v.d + v.n, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
+    GRID_STRIDE(i, v.n) {
+        double x = v.x[i] + ap * dx[i];
+        v.x[i] = x;
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) {
+            v.zl[i] = v.zl[i] + ad * dzl[jl];
+            double xl = v.xl[i];
+            if (x - xl < c1) v.xl[i] = xl - c2 * fmax(1.0, fabs(x));
+        }
+        if (ju >= 0) {
+            v.zu[i] = v.zu[i] + ad * dzu[ju];
+            double xu = v.xu[i];
+            if (xu - x < c1) v.xu[i] = xu + c2 * fmax(1.0, fabs(x));
+        }
+    }
+    GRID_STRIDE(i, v.m) v.y[i] = v.y[i] + ad * dy[i];
+}
+
+// MadNLP.reduce_rhs! (+ optionally r1 = wx / Sigma, r2 = wy: normalkkt.jl:197-207)
+__global__ void __launch_bounds__(TB) k_reduce_rhs(V v, double *w, double *buf_n, double *buf_m)
+{
+    double *wx = w, *wy = w + v.n, *wzl = w + v.n + v.m, *wzu = w + v.n + v.m + v.nlb;
+    GRID_STRIDE(i, v.n) {
+        double t = wx[i];
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) t = t - wzl[jl] / v.l_diag[jl];
+        if (ju >= 0) t = t - wzu[ju] / v.u_diag[ju];
+        wx[i] = t;
+        if (buf_n) buf_n[i] = t / v.pr_diag[i];
+    }
+    if (buf_m) { GRID_STRIDE(i, v.m) buf_m[i] = wy[i]; }
+}
+
+// normalkkt.jl:212-213: wy = dy (from buffer_m), r1 = wx
+__global__ void __launch_bounds__(TB) k_normal_mid(V v, double *w, double *buf_n, const double *buf_m)
+{
+    double *wx = w, *wy = w + v.n;
+    GRID_STRIDE(i, v.m) wy[i] = buf_m[i];
+    GRID_STRIDE(i, v.n) buf_n[i] = wx[i];
+}
+
+// MadNLP.finish_aug_solve! (+ optionally wx = r1 / Sigma first: normalkkt.jl:215-217)
+__global__ void __launch_bounds__(TB) k_finish_aug(V v, double *w, const double *buf_n)
+{
+    double *wx = w, *wzl = w + v.n + v.m, *wzu = w + v.n + v.m + v.nlb;
+    GRID_STRIDE(i, v.n) {
+        double t = buf_n ? buf_n[i] / v.pr_diag[i] : wx[i];
+        if (buf_n) wx[i] = t;
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) wzl[jl] = (-wzl[jl] + v.l_lower[jl] * t) / v.l_diag[jl];
+        if (ju >= 0) wzu[ju] = (wzu[ju] - v.u_lower[ju] * t) / v.u_diag[ju];
+    }
+}
+
+// MadNLP._kktmul! (App. B)
+__global__ void __launch_bounds__(TB) k_kktmul(V v, double *w, const double *vv, double alpha, double beta)
+{
+    double *wx = w, *wy = w + v.n, *wzl = w + v.n + v.m, *wzu = w + v.n + v.m + v.nlb;
+    const double *vx = vv, *vy = vv + v.n, *vzl = vv + v.n + v.m, *vzu = vv + v.n + v.m + v.nlb;
+    GRID_STRIDE(i, v.n) {
+        double t = wx[i] + alpha * v.reg[i] * vx[i];
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) {
+            t = t - alpha * vzl[jl];
+            wzl[jl] = beta * wzl[jl] + alpha * (vx[i] * v.l_lower[jl] - vzl[jl] * v.l_diag[jl]);
+        }
+        if (ju >= 0) {
+            t = t + alpha * vzu[ju];
+            wzu[ju] = beta * wzu[ju] + alpha * (vx[i] * v.u_lower[ju] + vzu[ju] * v.u_diag[ju]);
+        }
+        wx[i] = t;
+    }
+    GRID_STRIDE(i, v.m) wy[i] = wy[i] + alpha * v.du_diag[i] * vy[i];
+}
+
+__global__ void __launch_bounds__(TB) k_two_norms(int64_t len, const double *a, const double *b, double *partials,
+                                                  unsigned int *counter, double *out)
+{
+    double acc[2] = {0.0, 0.0};
+    GRID_STRIDE(i, len) {
+        acc[0] = comb(acc[0], fabs(a[i]), OP_MAX);
+        acc[1] = comb(acc[1], fabs(b[i]), OP_MAX);
+    }
+    const int op[2] = {OP_MAX, OP_MAX};
+    grid_reduce_vals<2>(acc, op, partials, counter, out);
+}
+
+// init_starting_point! stages (src/solver.jl:41-118)
+__global__ void __launch_bounds__(TB) k_init0(V v, double *partials, unsigned int *counter, double *out)
+{
+    // res = jacl (holds A'y + f); zl/zu init (solver.jl:41-66); mins for delta_x / delta_s (:68-78)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    GRID_STRIDE(i, v.n) {
+        double r = v.jacl[i], l = v.xl[i], u = v.xu[i], x = v.x[i];
+        bool fl = isfinite(l), fu = isfinite(u);
+        double zl = v.zl[i], zu = v.zu[i];
+        if (fl && fu) { zl = 0.5 * r; zu = -0.5 * r; }
+        else if (fl) zl = r;
+        else if (fu) zu = -r;
+        v.zl[i] = zl;
+        v.zu[i] = zu;
+        if (v.inv_lb[i] >= 0) { acc[0] = fmin(acc[0], x - l); acc[2] = fmin(acc[2], zl); }
+        if (v.inv_ub[i] >= 0) { acc[1] = fmin(acc[1], u - x); acc[3] = fmin(acc[3], zu); }
+    }
+    const int op[4] = {OP_MIN, OP_MIN, OP_MIN, OP_MIN};
+    grid_reduce_vals<4>(acc, op, partials, counter, out);
+}
+__global__ void __launch_bounds__(TB) k_init1(V v, double delta_x, double delta_s, double *partials, unsigned int *counter, double *out)
+{
+    // shifts (:80-83) then mu pieces and sums (:85-94)
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    GRID_STRIDE(i, v.n) {
+        bool lb = v.inv_lb[i] >= 0, ub = v.inv_ub[i] >= 0;
+        double x = v.x[i];
+        if (lb) x = x + delta_x;
+        if (ub) x = x - delta_x;
+        v.x[i] = x;
+        if (lb) {
+            double zl = v.zl[i] + (1.0 + delta_s);
+            v.zl[i] = zl;
+            double l = v.xl[i];
+            acc[0] += x * zl - l * zl;
+            acc[1] += zl;
+            acc[3] += x - l;
+        }
+        if (ub) {
+            double zu = v.zu[i] + (1.0 + delta_s);
+            v.zu[i] = zu;
+            double u = v.xu[i];
+            acc[0] += u * zu - x * zu;
+            acc[2] += zu;
+            acc[4] += u - x;
+        }
+    }
+    const int op[5] = {OP_SUM, OP_SUM, OP_SUM, OP_SUM, OP_SUM};
+    grid_reduce_vals<5>(acc, op, partials, counter, out);
+}
+__global__ void __launch_bounds__(TB) k_init2(V v, double delta_x2, double delta_s2, double kappa, double *partials,
+                                              unsigned int *counter, double *out)
+{
+    // second shifts (:96-99), projection (:102-118), interior checks (:120-123)
+    double acc[4] = {DBL_MAX, DBL_MAX, DBL_MAX, DBL_MAX};
+    GRID_STRIDE(i, v.n) {
+        bool lb = v.inv_lb[i] >= 0, ub = v.inv_ub[i] >= 0;
+        double x = v.x[i], l = v.xl[i], u = v.xu[i];
+        if (lb) x = x + delta_x2;
+        if (ub) x = x - delta_x2;
+        if (x < l) x = l + fmin(kappa * fmax(1.0, l), kappa * (u - l));
+        else if (u < x) x = u - fmin(kappa * fmax(1.0, u), kappa * (u - l));
+        v.x[i] = x;
+        if (lb) { double zl = v.zl[i] + delta_s2; v.zl[i] = zl; acc[0] = fmin(acc[0], zl); acc[2] = fmin(acc[2], x - l); }
+        if (ub) { double zu = v.zu[i] + delta_s2; v.zu[i] = zu; acc[1] = fmin(acc[1], zu); acc[3] = fmin(acc[3], u - x); }
+    }
+    const int op[4] = {OP_MIN, OP_MIN, OP_MIN, OP_MIN};
+    grid_reduce_vals<4>(acc, op, partials, counter, out);
+}
+
+__global__ void __launch_bounds__(TB) k_axpby(int64_t n, double alpha, const double *x, double beta, double *y)
+{
+    GRID_STRIDE(i, n) y[i] = (beta == 0.0) ? alpha * x[i] : alpha * x[i] + beta * y[i];
+}
+__global__ void __launch_bounds__(TB) k_fill(int64_t n, double val, double *x)
+{
+    GRID_STRIDE(i, n) x[i] = val;
+}
+__global__ void __launch_bounds__(TB) k_dot(int64_t n, const double *x, const double *y, double *partials, unsigned int *counter, double *out)
+{
+    double acc[1] = {0.0};
+    GRID_STRIDE(i, n) acc[0] = fma(x[i], y[i], acc[0]);
+    const int op[1] = {OP_SUM};
+    grid_reduce_vals<1>(acc, op, partials, counter, out);
+}
+
+}  // namespace
+
+static unsigned red_grid(Handle *h, int64_t len)
+{
+    int64_t g = (len + TB - 1) / TB;
+    g = std::max<int64_t>(1, std::min<int64_t>(g, h->red_blocks));
+    return (unsigned)g;
+}
+
+static V make_view(Handle *h, const int32_t *inv_lb, const int32_t *inv_ub)
+{
+    const mipm_mpc_vectors &m = h->v;
+    V v;
+    v.n = m.n; v.m = m.m; v.nlb = m.nlb; v.nub = m.nub;
+    v.inv_lb = inv_lb; v.inv_ub = inv_ub;
+    v.x = m.d_x; v.xl = m.d_xl; v.xu = m.d_xu; v.zl = m.d_zl; v.zu = m.d_zu; v.f = m.d_f;
+    v.y = m.d_y; v.c = m.d_c; v.rhs = m.d_rhs; v.jacl = m.d_jacl; v.d = m.d_d; v.p = m.d_p; v.w = m.d_w;
+    v.corr_lb = m.d_corr_lb; v.corr_ub = m.d_corr_ub;
+    v.reg = m.d_reg; v.pr_diag = m.d_pr_diag; v.du_diag = m.d_du_diag;
+    v.l_diag = m.d_l_diag; v.u_diag = m.d_u_diag; v.l_lower = m.d_l_lower; v.u_lower = m.d_u_lower;
+    return v;
+}
+
+static DBuf<int32_t> &inv_lb_buf(Handle *h) { return h->d_inv_lb; }
+static DBuf<int32_t> &inv_ub_buf(Handle *h) { return h->d_inv_ub; }
+
+static int fetch_scalars(Handle *h, int count, double *out)
+{
+    MIPM_CUDA(h, cudaMemcpyAsync(h->h_scal, h->d_scal.p, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < count; ++i) out[i] = h->h_scal[i];
+    return MIPM_OK;
+}
+
+}  // namespace mipm
+
+using namespace mipm;
+
+#define VIEW_OR_FAIL(h)                                                                     \
+    MIPM_NEED_DEVICE(h);                                                                    \
+    if (!(h)->bound) return fail((h), MIPM_ERR_STATE, "mipm_mpc_bind has not been called"); \
+    MIPM_CUDA(h, cudaSetDevice((h)->device));                                               \
+    V v = make_view((h), inv_lb_buf(h).p, inv_ub_buf(h).p);                                 \
+    const int64_t nmax = std::max<int64_t>(std::max(v.n, v.m), 1);                          \
+    (void)nmax
+
+extern "C" {
+
+int mipm_mpc_bind(mipm_handle hh, const mipm_mpc_vectors *mv)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!mv || mv->n < 0 || mv->m < 0 || mv->nlb < 0 || mv->nub < 0 || mv->nlb > mv->n || mv->nub > mv->n)
+        return fail(h, MIPM_ERR_ARG, "bad sizes");
+    if ((mv->nlb > 0 && !mv->d_ind_lb) || (mv->nub > 0 && !mv->d_ind_ub)) return fail(h, MIPM_ERR_ARG, "null index vector");
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    h->v = *mv;
+    const int64_t n1 = std::max<int64_t>(mv->n, 1);
+    MIPM_CUDA(h, inv_lb_buf(h).alloc((size_t)n1));
+    MIPM_CUDA(h, inv_ub_buf(h).alloc((size_t)n1));
+    MIPM_CUDA(h, cudaMemsetAsync(inv_lb_buf(h).p, 0xff, (size_t)n1 * sizeof(int32_t), h->stream));
+    MIPM_CUDA(h, cudaMemsetAsync(inv_ub_buf(h).p, 0xff, (size_t)n1 * sizeof(int32_t), h->stream));
+    if (mv->nlb > 0) {
+        k_build_inv<<<red_grid(h, mv->nlb), TB, 0, h->stream>>>(mv->nlb, mv->d_ind_lb, mv->index_base, inv_lb_buf(h).p);
+        MIPM_CHECK_LAUNCH(h);
+    }
+    if (mv->nub > 0) {
+        k_build_inv<<<red_grid(h, mv->nub), TB, 0, h->stream>>>(mv->nub, mv->d_ind_ub, mv->index_base, inv_ub_buf(h).p);
+        MIPM_CHECK_LAUNCH(h);
+    }
+    h->bound = true;
+    return MIPM_OK;
+}
+
+int mipm_set_aug_diagonal_reg(mipm_handle hh, double del_w, double del_c)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    k_set_aug_diag<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, del_w, del_c);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_set_predictive_rhs(mipm_handle hh)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    k_set_rhs<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, 0, 0.0);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_set_correction_rhs(mipm_handle hh, double mu)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    k_set_rhs<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, 1, mu);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_get_correction(mipm_handle hh)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    k_get_correction<<<red_grid(h, nmax), TB, 0, h->stream>>>(v);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_set_extra_correction(mipm_handle hh, double alpha_p, double alpha_d, double beta_min, double beta_max, double mu)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    k_set_extra_correction<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, alpha_p, alpha_d, beta_min * mu, beta_max * mu);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+static int compl_measure(Handle *h, int affine, double ap, double ad, double *out)
+{
+    VIEW_OR_FAIL(h);
+    if (!out) return fail(h, MIPM_ERR_ARG, "null argument");
+    if (v.nlb + v.nub == 0) { *out = 0.0; return MIPM_OK; }
+    k_compl_measure<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, affine, ap, ad, h->d_partials.p, h->d_counter.p, h->d_scal.p);
+    MIPM_CHECK_LAUNCH(h);
+    double s[2];
+    int rc = fetch_scalars(h, 2, s);
+    if (rc != MIPM_OK) return rc;
+    *out = (s[0] + s[1]) / (double)(v.nlb + v.nub);
+    return MIPM_OK;
+}
+
+int mipm_get_complementarity_measure(mipm_handle hh, double *out) { return compl_measure((Handle *)hh, 0, 0.0, 0.0, out); }
+
+int mipm_get_affine_complementarity_measure(mipm_handle hh, double alpha_p, double alpha_d, double *out)
+{
+    return compl_measure((Handle *)hh, 1, alpha_p, alpha_d, out);
+}
+
+int mipm_get_alpha_max(mipm_handle hh, double tau, double *alpha, int64_t *idx)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!alpha) return fail(h, MIPM_ERR_ARG, "null argument");
+    k_alpha_max<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, tau, h->d_partials.p, h->d_counter.p, h->d_scal.p);
+    MIPM_CHECK_LAUNCH(h);
+    double s[8];
+    int rc = fetch_scalars(h, 8, s);
+    if (rc != MIPM_OK) return rc;
+    for (int q = 0; q < 4; ++q) {
+        alpha[q] = s[q];
+        if (idx) idx[q] = (int64_t)s[4 + q];
+    }
+    return MIPM_OK;
+}
+
+int mipm_termination_measures(mipm_handle hh, double *out)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!out) return fail(h, MIPM_ERR_ARG, "null argument");
+    k_termination<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, h->d_partials.p, h->d_counter.p, h->d_scal.p);
+    MIPM_CHECK_LAUNCH(h);
+    double s[7];
+    int rc = fetch_scalars(h, 7, s);
+    if (rc != MIPM_OK) return rc;
+    // dual_objective (kernels.jl:408-417): dobj = -y.rhs; += zl.xl if nlb>0; -= zu.xu if nub>0
+    double dobj = s[0];
+    if (v.nlb > 0) dobj += s[1];
+    if (v.nub > 0) dobj -= s[2];
+    out[0] = dobj;
+    out[1] = s[3];
+    out[2] = s[4];
+    out[3] = s[5];
+    out[4] = s[6];
+    return MIPM_OK;
+}
+
+int mipm_apply_step(mipm_handle hh, double alpha_p, double alpha_d, double mu)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    const double eps = DBL_EPSILON;
+    k_apply_step<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, alpha_p, alpha_d, eps * mu, pow(eps, 0.75));
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_reduce_rhs(mipm_handle hh, double *d_w)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!d_w) return fail(h, MIPM_ERR_ARG, "null argument");
+    k_reduce_rhs<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, d_w, nullptr, nullptr);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_finish_aug_solve(mipm_handle hh, double *d_w)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!d_w) return fail(h, MIPM_ERR_ARG, "null argument");
+    k_finish_aug<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, d_w, nullptr);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_normal_solve_stage(mipm_handle hh, int stage, double *d_w, double *d_buffer_n, double *d_buffer_m)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!d_w || !d_buffer_n || !d_buffer_m) return fail(h, MIPM_ERR_ARG, "null argument");
+    if (stage == 0) k_reduce_rhs<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, d_w, d_buffer_n, d_buffer_m);
+    else if (stage == 1) k_normal_mid<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, d_w, d_buffer_n, d_buffer_m);
+    else if (stage == 2) k_finish_aug<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, d_w, d_buffer_n);
+    else return fail(h, MIPM_ERR_ARG, "stage must be 0, 1 or 2");
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_kktmul(mipm_handle hh, double *d_w, const double *d_v, double alpha, double beta)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!d_w || !d_v) return fail(h, MIPM_ERR_ARG, "null argument");
+    k_kktmul<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, d_w, d_v, alpha, beta);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_residual_norms(mipm_handle hh, const double *d_w, const double *d_p, double *out)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!d_w || !d_p || !out) return fail(h, MIPM_ERR_ARG, "null argument");
+    const int64_t len = v.n + v.m + v.nlb + v.nub;
+    k_two_norms<<<red_grid(h, std::max<int64_t>(len, 1)), TB, 0, h->stream>>>(len, d_w, d_p, h->d_partials.p, h->d_counter.p, h->d_scal.p);
+    MIPM_CHECK_LAUNCH(h);
+    return fetch_scalars(h, 2, out);
+}
+
+int mipm_init_point_stage(mipm_handle hh, int stage, double a, double b, double kappa, double *out)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!out) return fail(h, MIPM_ERR_ARG, "null argument");
+    int cnt;
+    if (stage == 0) { k_init0<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, h->d_partials.p, h->d_counter.p, h->d_scal.p); cnt = 4; }
+    else if (stage == 1) { k_init1<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, a, b, h->d_partials.p, h->d_counter.p, h->d_scal.p); cnt = 5; }
+    else if (stage == 2) { k_init2<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, a, b, kappa, h->d_partials.p, h->d_counter.p, h->d_scal.p); cnt = 4; }
+    else return fail(h, MIPM_ERR_ARG, "stage must be 0, 1 or 2");
+    MIPM_CHECK_LAUNCH(h);
+    return fetch_scalars(h, cnt, out);
+}
+
+int mipm_axpby(mipm_handle hh, int64_t n, double alpha, const double *d_x, double beta, double *d_y)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (n < 0 || (n > 0 && (!d_x || !d_y))) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (n == 0) return MIPM_OK;
+    k_axpby<<<red_grid(h, n), TB, 0, h->stream>>>(n, alpha, d_x, beta, d_y);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_fill(mipm_handle hh, int64_t n, double value, double *d_x)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (n < 0 || (n > 0 && !d_x)) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (n == 0) return MIPM_OK;
+    k_fill<<<red_grid(h, n), TB, 0, h->stream>>>(n, value, d_x);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_copy(mipm_handle hh, int64_t n, const double *d_src, double *d_dst)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (n < 0 || (n > 0 && (!d_src || !d_dst))) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (n == 0) return MIPM_OK;
+    MIPM_CUDA(h, cudaMemcpyAsync(d_dst, d_src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return MIPM_OK;
+}
+
+int mipm_dot(mipm_handle hh, int64_t n, const double *d_x, const double *d_y, double *out)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (n < 0 || !out || (n > 0 && (!d_x || !d_y))) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (n == 0) { *out = 0.0; return MIPM_OK; }
+    k_dot<<<red_grid(h, n), TB, 0, h->stream>>>(n, d_x, d_y, h->d_partials.p, h->d_counter.p, h->d_scal.p);
+    MIPM_CHECK_LAUNCH(h);
+    return fetch_scalars(h, 1, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,699 @@
+"""Host-side mirror of MadIPM's solver API on top of the C-ABI CUDA library.
+
+Same names, argument meaning and error behaviour as the reference's Julia host code, which in
+a Julia deployment stays Julia and reaches the same C ABI through `ccall`:
+
+    MPCSolver(qp; kwargs...)        src/structure.jl:79-178
+    solve!(solver) / madipm(qp)     src/solver.jl:362-428
+    initialize!, init_starting_point!, mpc! and its steps   src/solver.jl:6-360
+    factorize_regularized_system!, solve_system!            src/linear_solver.jl:6-44
+    NormalKKTSystem / SparseKKTSystem (K2)                   src/KKT/normalkkt.jl, MadNLP
+
+Everything numeric runs in libmadipm_b200.so on the GPU; this file only sequences calls and does
+host scalar logic (status tests, regularization schedule, barrier update). torch is used for
+device allocations and host<->device copies only. There is no CPU fallback.
+"""
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MpcVectors
+
+# MadNLP.Status names
+INITIAL = "INITIAL"
+REGULAR = "REGULAR"
+SOLVE_SUCCEEDED = "SOLVE_SUCCEEDED"
+INFEASIBLE_PROBLEM_DETECTED = "INFEASIBLE_PROBLEM_DETECTED"
+DIVERGING_ITERATES = "DIVERGING_ITERATES"
+MAXIMUM_ITERATIONS_EXCEEDED = "MAXIMUM_ITERATIONS_EXCEEDED"
+MAXIMUM_WALLTIME_EXCEEDED = "MAXIMUM_WALLTIME_EXCEEDED"
+INTERNAL_ERROR = "INTERNAL_ERROR"
+ERROR_IN_STEP_COMPUTATION = "ERROR_IN_STEP_COMPUTATION"
+
+
+class SolveException(RuntimeError):
+    """MadNLP.SolveException (thrown by solve_system!, src/linear_solver.jl:40-42)."""
+
+
+# ---- option types (src/utils.jl:17-48)
+@dataclass
+class ConservativeStep:
+    tau: float = 0.995
+
+
+@dataclass
+class AdaptiveStep:
+    tau_min: float = 0.99
+
+
+@dataclass
+class MehrotraAdaptiveStep:
+    gamma_f: float = 0.99
+
+
+class NoRegularization:
+    pass
+
+
+@dataclass
+class FixedRegularization:
+    delta_p: float
+    delta_d: float
+
+
+@dataclass
+class AdaptiveRegularization:
+    delta_p: float
+    delta_d: float
+    delta_min: float
+
+
+@dataclass
+class IPMOptions:
+    """src/utils.jl:69-105. kkt_system: "K2" (MadNLP.SparseKKTSystem, the default) or "Normal"
+    (MadIPM.NormalKKTSystem). linear-solver options of the B200 solver: ordering, ir_steps."""
+    tol: float = 1e-8
+    kkt_system: str = "K2"
+    max_iter: int = 3000
+    max_wall_time: float = 1e6
+    divergence_tol: float = 1e4
+    scaling: bool = True
+    bound_push: float = 1e-2
+    bound_fac: float = 1e-2
+    bound_relax_factor: float = 1e-12
+    regularization: object = field(default_factory=lambda: FixedRegularization(1e-10, 1e-10))
+    step_rule: object = field(default_factory=lambda: AdaptiveStep(0.99))
+    max_ncorr: int = 0
+    mu_init: float = 1e-1
+    mu_min: float = 1e-12
+    tol_linear_solve: float = 1e-8
+    check_residual: bool = False
+    rethrow_error: bool = False
+    # B200Solver options (the analogue of cudss_algorithm / ir options of MadNLPGPU.CUDSSSolver)
+    ordering: int = _lib.MIPM_ORDER_ND
+    ir_steps: int = 1
+    exact_assembly_order: bool = False
+    device: int = 0
+
+
+@dataclass
+class ExecutionStats:
+    """MadNLP.MadNLPExecutionStats subset."""
+    status: str
+    iter: int
+    objective: float
+    dual_objective: float
+    solution: np.ndarray
+    constraints: np.ndarray
+    multipliers: np.ndarray
+    multipliers_L: np.ndarray
+    multipliers_U: np.ndarray
+    trace: list
+    total_time: float
+    linear_solver_time: float
+    counters: dict
+
+
+def _dev(a, device, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)
+
+
+class B200Solver:
+    """The MadNLP.AbstractLinearSolver mirror (constructor / factorize! / solve! / is_factorized /
+    inertia / introduce), replacing MadNLPGPU.CUDSSSolver. Works on the lower-triangular CSC
+    `aug_com` handed over by the KKT system."""
+
+    def __init__(self, handle, n, colptr, rowval, nzval, kind, ordering, ir_steps):
+        self.h, self.nzval, self.ir_steps = handle, nzval, ir_steps
+        self.kind = kind
+        handle.ls_analyze(n, colptr, rowval, kind=kind, ordering=ordering)
+        self.stats = handle.ls_stats()
+
+    def factorize(self):
+        self.h.ls_factorize_async(self.nzval)
+
+    def is_factorized(self):
+        return self.h.ls_status()
+
+    def solve(self, x):
+        self.h.ls_solve(x, self.ir_steps)
+        return x
+
+    def inertia(self):
+        return self.h.ls_inertia()
+
+    def introduce(self):
+        return "madipm_b200 supernodal %s" % ("LDL^T" if self.kind == _lib.MIPM_LDL else "Cholesky")
+
+
+class MPCSolver:
+    def __init__(self, qp, **kwargs):
+        t0 = time.time()
+        self.opt = IPMOptions(**kwargs)
+        opt = self.opt
+        if not torch.cuda.is_available():
+            raise RuntimeError("madipm_jl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", opt.device)
+        torch.cuda.set_device(self.device)
+        self.qp = qp
+        # ---- MadNLP.get_index_constraints (App. B)
+        lvar, uvar, lcon, ucon = qp.lvar, qp.uvar, qp.lcon, qp.ucon
+        if np.any(lvar == uvar):
+            raise NotImplementedError("fixed variables (MadNLP.MakeParameter) are outside the hot-path scope")
+        self.ind_ineq = np.flatnonzero(lcon != ucon)
+        nx, ns = qp.nvar, len(self.ind_ineq)
+        lfull = np.concatenate([lvar, lcon[self.ind_ineq]])
+        ufull = np.concatenate([uvar, ucon[self.ind_ineq]])
+        self.ind_lb = np.flatnonzero(np.isfinite(lfull)).astype(np.int64)
+        self.ind_ub = np.flatnonzero(np.isfinite(ufull)).astype(np.int64)
+        self.nx, self.ns = nx, ns
+        self.n, self.m = nx + ns, qp.ncon
+        self.nlb, self.nub = len(self.ind_lb), len(self.ind_ub)
+        n, m, nlb, nub = self.n, self.m, self.nlb, self.nub
+        if opt.kkt_system == "Normal" and qp.nnzh > 0:
+            raise ValueError("The KKT system NormalKKTSystem supports only linear programs.")  # normalkkt.jl:45-48
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.h = _lib.Handle(device=opt.device, stream=stream)
+        dev = self.device
+        z = lambda k: torch.zeros(max(k, 0), dtype=torch.float64, device=dev)
+        # ---- iterate and buffers (structure.jl:125-153)
+        self.x, self.xl, self.xu, self.zl, self.zu, self.f = z(n), z(n), z(n), z(n), z(n), z(n)
+        self.y, self.c, self.rhs, self.jacl = z(m), z(m), z(m), z(n)
+        N = n + m + nlb + nub
+        self.d, self.p, self._w1, self._w2 = z(N), z(N), z(N), z(N)
+        self.correction_lb, self.correction_ub = z(nlb), z(nub)
+        self.d_ind_lb = _dev(self.ind_lb, dev, torch.int64)
+        self.d_ind_ub = _dev(self.ind_ub, dev, torch.int64)
+        # ---- Jacobian with slack columns (normalkkt.jl:70-79) in CSR through coo_to_csr
+        I = np.concatenate([qp.Arows, self.ind_ineq]).astype(np.int32)
+        J = np.concatenate([qp.Acols, nx + np.arange(ns)]).astype(np.int32)
+        self.A_I, self.A_J = I, J
+        self.A_V_host = np.concatenate([qp.Avals, -np.ones(ns)])
+        Ap, Aj, Amap = _lib.coo_to_csr(m, n, I, J)
+        self.Ap, self.Aj, self.A_csr_map = Ap, Aj, Amap
+        self.h.spmv_setup(m, n, Ap, Aj)
+        self.AT_x = z(len(Aj))                      # AT.nzVal: CSR-ordered values of A
+        # ---- Hessian operator (MadIPMOperator symmetric=true, cuda_wrapper.jl:62-68)
+        self.hH = None
+        if qp.nnzh > 0:
+            hr, hc, hv = qp.Hrows.astype(np.int64), qp.Hcols.astype(np.int64), qp.Hvals
+            off = hr != hc
+            fr = np.concatenate([hr, hc[off]]).astype(np.int32)
+            fc = np.concatenate([hc, hr[off]]).astype(np.int32)
+            fv = np.concatenate([hv, hv[off]])
+            Hp, Hj, Hmap = _lib.coo_to_csr(nx, nx, fr, fc)
+            self.hH = _lib.Handle(device=opt.device, stream=stream)
+            self.hH.spmv_setup(nx, nx, Hp, Hj)
+            self.H_full_host = fv[Hmap]
+            self.Hx = z(len(Hj))
+        self.cvec = z(n)
+        # ---- KKT system
+        self.buffer_n, self.buffer_m = z(n), z(m)
+        self.l_diag, self.u_diag, self.l_lower, self.u_lower = z(nlb), z(nub), z(nlb), z(nub)
+        self.reg = z(n)
+        if opt.kkt_system == "Normal":
+            self.pr_diag, self.du_diag = z(n), z(m)
+            Cp, Cj = self.h.normal_symbolic(m, n, Ap, Aj)
+            self.aug_colptr, self.aug_rowval = Cp, Cj
+            self.aug_nz = z(len(Cj))
+            self.linear_solver = B200Solver(self.h, m, Cp, Cj, self.aug_nz, _lib.MIPM_CHOLESKY, opt.ordering, opt.ir_steps)
+        elif opt.kkt_system == "K2":
+            # MadNLP.SparseKKTSystem: COO values [pr_diag; hess; jac(+slack); du_diag], lower triangular
+            nnzh, nnzj = qp.nnzh, len(I)
+            KI = np.concatenate([np.arange(n), qp.Hrows, n + I, n + np.arange(m)]).astype(np.int32)
+            KJ = np.concatenate([np.arange(n), qp.Hcols, J, n + np.arange(m)]).astype(np.int32)
+            colptr, rowval, kmap = self.h.k2_symbolic(n + m, KI, KJ)
+            self.aug_colptr, self.aug_rowval, self.aug_csc_map = colptr, rowval, kmap
+            self.aug_raw_V = z(n + nnzh + nnzj + m)
+            self.pr_diag = self.aug_raw_V[:n]                       # views, like MadNLP's _madnlp_unsafe_wrap
+            self.hess = self.aug_raw_V[n:n + nnzh]
+            self.jac = self.aug_raw_V[n + nnzh:n + nnzh + nnzj]
+            self.du_diag = self.aug_raw_V[n + nnzh + nnzj:]
+            self.aug_nz = z(len(rowval))
+            self.linear_solver = B200Solver(self.h, n + m, colptr, rowval, self.aug_nz, _lib.MIPM_LDL, opt.ordering, opt.ir_steps)
+        else:
+            raise ValueError(opt.kkt_system)
+        # ---- bind the device vectors once
+        mv = MpcVectors()
+        mv.n, mv.m, mv.nlb, mv.nub, mv.index_base = n, m, nlb, nub, 0
+        P = lambda t: t.data_ptr() if t.numel() > 0 else None
+        mv.d_ind_lb, mv.d_ind_ub = P(self.d_ind_lb), P(self.d_ind_ub)
+        for name, t in [("d_x", self.x), ("d_xl", self.xl), ("d_xu", self.xu), ("d_zl", self.zl), ("d_zu", self.zu),
+                        ("d_f", self.f), ("d_y", self.y), ("d_c", self.c), ("d_rhs", self.rhs), ("d_jacl", self.jacl),
+                        ("d_d", self.d), ("d_p", self.p), ("d_w", self._w1), ("d_corr_lb", self.correction_lb),
+                        ("d_corr_ub", self.correction_ub), ("d_reg", self.reg), ("d_pr_diag", self.pr_diag),
+                        ("d_du_diag", self.du_diag), ("d_l_diag", self.l_diag), ("d_u_diag", self.u_diag),
+                        ("d_l_lower", self.l_lower), ("d_u_lower", self.u_lower)]:
+            setattr(mv, name, P(t))
+        self._mv = mv
+        self.h.mpc_bind(mv)
+        # ---- scalars (structure.jl:62-76)
+        self.obj_val = 0.0
+        self.inf_pr = self.inf_du = self.inf_compl = 0.0
+        self.norm_b = self.norm_c = 0.0
+        self.mu = self.mu_curr = 0.0
+        self.alpha_p = self.alpha_d = 0.0
+        self.del_w = self.del_c = 0.0
+        self.best_complementarity = float("inf")
+        self.status = INITIAL
+        self.k = 0
+        self.dnorm = 0.0
+        self.obj_scale = 1.0
+        self.con_scale = np.ones(m)
+        self.trace = []
+        self.cnt = dict(linear_solver_time=0.0, init_time=time.time() - t0, factorizations=0, solves=0)
+        self._reg = self.opt.regularization
+
+    # ------------------------------------------------------------------ model callbacks (device)
+    def _eval_f(self):
+        """obj = c0 + c'x + x'Hx/2 (MadIPMCUDAExt.jl:34-38)."""
+        v = self.h.dot(self.nx, self.cvec, self.x)
+        if self.hH is not None:
+            self.hH.spmv(0, 1.0, self.Hx, self.x, 0.0, self.buffer_n)
+            v += 0.5 * self.h.dot(self.nx, self.buffer_n, self.x)
+        return self.obj_scale * self.qp.c0 + v
+
+    def _eval_grad(self):
+        """f = Hx + c (MadIPMCUDAExt.jl:40-45)."""
+        self.h.copy(self.n, self.cvec, self.f)
+        if self.hH is not None:
+            self.hH.spmv(0, 1.0, self.Hx, self.x, 1.0, self.f)
+
+    def _eval_cons(self):
+        """c(x) = A x - s - rhs with slack columns inside A (App. A)."""
+        self.h.copy(self.m, self.rhs, self.c)
+        self.h.spmv(0, 1.0, self.AT_x, self.x, -1.0, self.c)
+
+    def jtprod(self, out, y):
+        """MadNLP.jtprod!(y, kkt, x) (normalkkt.jl:176-178)."""
+        self.h.spmv(1, 1.0, self.AT_x, y, 0.0, out)
+
+    # ------------------------------------------------------------------ KKT system
+    def compress_jacobian(self):
+        """normalkkt.jl:163-172 / cuda_wrapper.jl:32-41: AT.nzVal = A.V[A_csr_map] (+ slack = -1)."""
+        V = self.A_V_host * self.con_scale[self.A_I]
+        self.AT_x.copy_(torch.from_numpy(V[self.A_csr_map]))
+        if self.opt.kkt_system == "Normal":
+            self.h.normal_set_jacobian(self.AT_x)
+        else:
+            self.jac.copy_(torch.from_numpy(V))
+
+    def compress_hessian(self):
+        if self.qp.nnzh > 0:
+            self.Hx.copy_(torch.from_numpy(self.obj_scale * self.H_full_host))
+            if self.opt.kkt_system == "K2":
+                self.hess.copy_(torch.from_numpy(self.obj_scale * self.qp.Hvals))
+
+    def build_kkt(self):
+        """build_kkt!: normalkkt.jl:180-194 (Normal) / MadNLP.transfer! (K2)."""
+        if self.opt.kkt_system == "Normal":
+            self.h.normal_assemble(self.pr_diag, self.aug_nz, self.opt.exact_assembly_order)
+        else:
+            self.h.k2_transfer(self.aug_raw_V, self.aug_nz)
+
+    def factorize_wrapper(self):
+        """MadNLP.factorize_wrapper!: build_kkt! + factorize!."""
+        self.build_kkt()
+        self.linear_solver.factorize()
+        self.cnt["factorizations"] += 1
+
+    def kkt_solve(self, w):
+        """solve!(kkt, w): normalkkt.jl:196-219 (Normal) / MadNLP (K2)."""
+        h = self.h
+        if self.opt.kkt_system == "Normal":
+            h.normal_solve_stage(0, w, self.buffer_n, self.buffer_m)
+            h.spmv(0, 1.0, self.AT_x, self.buffer_n, -1.0, self.buffer_m)     # A Sigma^-1 r1 - r2
+            self.linear_solver.solve(self.buffer_m)
+            h.normal_solve_stage(1, w, self.buffer_n, self.buffer_m)
+            h.spmv(1, -1.0, self.AT_x, self.buffer_m, 1.0, self.buffer_n)     # r1 - A' dy
+            h.normal_solve_stage(2, w, self.buffer_n, self.buffer_m)
+        else:
+            h.reduce_rhs(w)
+            self.linear_solver.solve(w)       # primal_dual(w) = first n+m entries, in place
+            h.finish_aug_solve(w)
+        self.cnt["solves"] += 1
+        return w
+
+    def kkt_mul(self, w, v, alpha, beta):
+        """mul!(w, kkt, v, alpha, beta): normalkkt.jl:221-233 (+ Hessian block for K2)."""
+        n, m = self.n, self.m
+        h = self.h
+        h.spmv(1, alpha, self.AT_x, v[n:n + m], beta, w[:n])
+        if self.hH is not None and self.opt.kkt_system == "K2":
+            self.hH.spmv(0, alpha, self.Hx, v[:self.nx], 1.0, w[:self.nx])
+        h.spmv(0, alpha, self.AT_x, v[:n], beta, w[n:n + m])
+        h.kktmul(w, v, alpha, beta)
+        return w
+
+    # ------------------------------------------------------------------ src/linear_solver.jl
+    def solve_system(self):
+        """src/linear_solver.jl:19-44."""
+        N = self.d.numel()
+        self.h.copy(N, self.p, self.d)
+        self.kkt_solve(self.d)
+        self.h.copy(N, self.p, self._w1)
+        self.kkt_mul(self._w1, self.d, -1.0, 1.0)
+        norm_w, norm_p = self.h.residual_norms(self._w1, self.p)
+        self.residual_ratio = norm_w / max(1.0, norm_p)
+        if np.isnan(self.residual_ratio) or (self.opt.check_residual and self.residual_ratio > self.opt.tol_linear_solve):
+            raise SolveException("residual %.3e" % self.residual_ratio)
+        return self.d
+
+    def factorize_regularized_system(self):
+        """src/linear_solver.jl:6-17."""
+        t0 = time.perf_counter()
+        for _ in range(3):
+            self.h.set_aug_diagonal_reg(self.del_w, self.del_c)
+            self.factorize_wrapper()
+            if self.linear_solver.is_factorized():
+                break
+            self.del_w *= 100.0
+            self.del_c *= 100.0
+        self.cnt["linear_solver_time"] += time.perf_counter() - t0
+
+    # ------------------------------------------------------------------ regularization (kernels.jl:364-401)
+    def init_regularization(self):
+        self.del_w = 1.0
+        self.del_c = 0.0 if isinstance(self._reg, NoRegularization) else self._reg.delta_d
+
+    def update_regularization(self):
+        r = self._reg
+        if isinstance(r, NoRegularization):
+            self.del_w, self.del_c = 0.0, 0.0
+        elif isinstance(r, FixedRegularization):
+            self.del_w, self.del_c = r.delta_p, r.delta_d
+        elif isinstance(r, AdaptiveRegularization):
+            r.delta_p = max(r.delta_p / 10.0, r.delta_min)
+            r.delta_d = min(r.delta_d / 10.0, -r.delta_min)
+            self.del_w, self.del_c = r.delta_p, r.delta_d
+        else:
+            raise TypeError(r)
+
+    # ------------------------------------------------------------------ initialization
+    def _madnlp_initialize(self):
+        """MadNLP.initialize!(cb, ...) + set_scaling! (App. B): one-time host preprocessing."""
+        qp, opt, nx, n, m = self.qp, self.opt, self.nx, self.n, self.m
+        x = np.zeros(n)
+        x[:nx] = qp.x0
+        xl = np.concatenate([qp.lvar, qp.lcon[self.ind_ineq]])
+        xu = np.concatenate([qp.uvar, qp.ucon[self.ind_ineq]])
+        rhs = np.where(qp.lcon == qp.ucon, qp.lcon, 0.0)
+        tol = opt.bound_relax_factor
+        xl = xl - np.maximum(1.0, np.abs(xl)) * tol
+        xu = xu + np.maximum(1.0, np.abs(xu)) * tol
+        bp, bf = opt.bound_push, opt.bound_fac
+        fl, fu = np.isfinite(xl), np.isfinite(xu)
+        both, lo, up = fl & fu, fl & ~fu, ~fl & fu
+        with np.errstate(invalid="ignore"):
+            pl = np.minimum(bp * np.maximum(1.0, np.abs(xl)), bf * (xu - xl))
+            pu = np.minimum(bp * np.maximum(1.0, np.abs(xu)), bf * (xu - xl))
+            x[both] = np.maximum(xl + pl, np.minimum(xu - pu, x))[both]
+            x[lo] = np.maximum(xl + bp * np.maximum(1.0, np.abs(xl)), x)[lo]
+            x[up] = np.minimum(xu - bp * np.maximum(1.0, np.abs(xu)), x)[up]
+        self.con_scale = np.ones(m)
+        self.obj_scale = 1.0
+        if opt.scaling:
+            rowmax = np.zeros(m)
+            np.maximum.at(rowmax, self.A_I, np.abs(self.A_V_host))
+            self.con_scale = np.minimum(1.0, 100.0 / np.maximum(rowmax, 1e-300))
+            rhs = rhs * self.con_scale
+            g = np.zeros(n)
+            g[:nx] = qp.c
+            if qp.nnzh > 0:
+                import scipy.sparse as sp
+                Hl = sp.csr_matrix((qp.Hvals, (qp.Hrows, qp.Hcols)), shape=(nx, nx))
+                g[:nx] += (Hl + sp.tril(Hl, -1).T) @ x[:nx]
+            gn = np.linalg.norm(g, np.inf)
+            self.obj_scale = min(1.0, 100.0 / gn) if gn > 0 else 1.0
+        cv = np.zeros(n)
+        cv[:nx] = self.obj_scale * qp.c
+        up_ = lambda t, a: t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        up_(self.x, x), up_(self.xl, xl), up_(self.xu, xu), up_(self.rhs, rhs), up_(self.cvec, cv)
+        up_(self.y, qp.y0)
+        self.zl.zero_(), self.zu.zero_()
+        self.norm_b = float(np.linalg.norm(rhs, np.inf)) if m else 0.0
+
+    def initialize(self):
+        """src/solver.jl:127-189."""
+        opt, h = self.opt, self.h
+        self._madnlp_initialize()
+        h.fill(self.n, 0.0, self.jacl)
+        # MadNLP.initialize!(kkt) (normalkkt.jl:150-161)
+        h.fill(self.n, 1.0, self.reg), h.fill(self.n, 1.0, self.pr_diag), h.fill(self.m, 0.0, self.du_diag)
+        h.fill(self.nlb, 0.0, self.l_lower), h.fill(self.nub, 0.0, self.u_lower)
+        h.fill(self.nlb, 1.0, self.l_diag), h.fill(self.nub, 1.0, self.u_diag)
+        self.init_regularization()
+        self.compress_hessian()
+        self.compress_jacobian()
+        self.obj_val = self._eval_f()
+        self._eval_grad()
+        self._eval_cons()
+        # norm_c = ||grad f(x0)||_inf (quirk A.9 x)
+        self.norm_c = float(self.f.abs().max().item()) if self.n else 0.0   # one-time, init only
+        self.init_starting_point()
+        self.mu = opt.mu_init
+        self.best_complementarity = float("inf")
+        self.status = REGULAR
+        self.jtprod(self.jacl, self.y)
+
+    def init_starting_point(self):
+        """src/solver.jl:6-125."""
+        h, n, m = self.h, self.n, self.m
+        N = self.p.numel()
+        h.fill(n, self.del_w, self.reg), h.fill(n, self.del_w, self.pr_diag), h.fill(m, self.del_c, self.du_diag)
+        self.factorize_wrapper()
+        if not self.linear_solver.is_factorized():
+            raise SolveException("initial factorization failed")
+        # Step 1 (kernels.jl:1-9): p = [0; -c; 0; 0]
+        h.fill(N, 0.0, self.p)
+        h.axpby(m, -1.0, self.c, 0.0, self.p[n:n + m])
+        self.solve_system()
+        h.axpby(n, 1.0, self.d[:n], 1.0, self.x)
+        # Step 2 (kernels.jl:11-19): p = [-f; 0; 0; 0]
+        h.fill(N, 0.0, self.p)
+        h.axpby(n, -1.0, self.f, 0.0, self.p[:n])
+        self.solve_system()
+        h.copy(m, self.d[n:n + m], self.y)
+        # Step 3: res = A'y + f, held in jacl like the reference (solver.jl:13,37-39)
+        self.jtprod(self.jacl, self.y)
+        h.axpby(n, 1.0, self.f, 1.0, self.jacl)
+        mins = h.init_point_stage(0)
+        delta_x = max(0.0, -1.5 * mins[0], -1.5 * mins[1])
+        delta_s = max(0.0, -1.5 * mins[2], -1.5 * mins[3])
+        s = h.init_point_stage(1, delta_x, delta_s)
+        mu = s[0]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            delta_x2 = float(np.float64(mu) / (2 * (np.float64(s[1]) + s[2])))
+            delta_s2 = float(np.float64(mu) / (2 * (np.float64(s[3]) + s[4])))
+        chk = h.init_point_stage(2, delta_x2, delta_s2, self.opt.bound_fac)
+        if self.nlb > 0 and not (chk[0] > 0.0 and chk[2] > 0.0):
+            raise AssertionError("starting point not strictly interior (lower)")
+        if self.nub > 0 and not (chk[1] > 0.0 and chk[3] > 0.0):
+            raise AssertionError("starting point not strictly interior (upper)")
+
+    # ------------------------------------------------------------------ MPC (src/solver.jl:194-360)
+    def update_termination_criteria(self):
+        opt = self.opt
+        dobj, nc, ndu, ncompl, dnorm = self.h.termination_measures()
+        self.dobj = dobj
+        self.dnorm = dnorm
+        self.inf_pr = nc / max(1.0, self.norm_b)
+        self.inf_du = ndu / max(1.0, self.norm_c)
+        self.inf_compl = ncompl / max(1.0, self.norm_c)
+        self.best_complementarity = min(self.best_complementarity, self.inf_compl)
+        if max(self.inf_pr, self.inf_du, self.inf_compl) <= opt.tol:
+            self.status = SOLVE_SUCCEEDED
+        elif (self.inf_compl > opt.divergence_tol * self.best_complementarity) and (dobj > max(10.0 * abs(self.obj_val), 1.0)):
+            self.status = INFEASIBLE_PROBLEM_DETECTED
+        elif self.obj_val < -opt.divergence_tol * max(10.0, abs(dobj), 1.0):
+            self.status = DIVERGING_ITERATES
+        elif self.k >= opt.max_iter:
+            self.status = MAXIMUM_ITERATIONS_EXCEEDED
+        elif time.time() - self.start_time >= opt.max_wall_time:
+            self.status = MAXIMUM_WALLTIME_EXCEEDED
+
+    def get_fraction_to_boundary_step(self, tau):
+        """src/kernels.jl:274-289."""
+        a, _ = self.h.get_alpha_max(tau)
+        return min(a[0], a[1]), min(a[2], a[3])
+
+    def update_barrier(self, mu_affine):
+        """src/kernels.jl:210-220 (quirk A.9 vii: has_inequalities == nlb+nub > 0)."""
+        mu_curr = self.h.get_complementarity_measure()
+        if self.nlb + self.nub > 0:
+            sigma = min(max((mu_affine / mu_curr) ** 3, 1e-6), 10.0)
+        else:
+            sigma = 1.0
+        self.mu = max(self.opt.mu_min, sigma * mu_curr)
+        return mu_curr
+
+    def prediction_step(self):
+        """src/solver.jl:230-237."""
+        self.h.set_predictive_rhs()
+        self.solve_system()
+        ap, ad = self.get_fraction_to_boundary_step(1.0)
+        mu_affine = self.h.get_affine_complementarity_measure(ap, ad)
+        self.h.get_correction()
+        self.mu_curr = self.update_barrier(mu_affine)
+
+    def mehrotra_correction_direction(self):
+        """src/solver.jl:239-243."""
+        self.h.set_correction_rhs(self.mu)
+        self.solve_system()
+
+    def gondzio_correction_direction(self):
+        """src/solver.jl:245-298."""
+        if self.opt.max_ncorr <= 0:
+            return
+        delta, bmin, bmax, tau = 0.1, 0.1, 10.0, 0.995
+        N = self.d.numel()
+        alpha_p, alpha_d = self.get_fraction_to_boundary_step(tau)
+        for _ in range(self.opt.max_ncorr):
+            tap, tad = min(alpha_p + delta, 1.0), min(alpha_d + delta, 1.0)
+            ga = self.h.get_affine_complementarity_measure(tap, tad)
+            g = self.mu_curr
+            mu = (ga / g) ** 2 * ga
+            self.h.set_extra_correction(tap, tad, bmin, bmax, mu)
+            self.h.set_correction_rhs(mu)
+            self.h.copy(N, self.d, self._w2)
+            self.solve_system()
+            hap, had = self.get_fraction_to_boundary_step(tau)
+            if (hap < 1.005 * alpha_p) or (had < 1.005 * alpha_d):
+                self.h.copy(N, self._w2, self.d)
+                break
+            alpha_p, alpha_d = hap, had
+
+    def update_step_size(self):
+        """src/kernels.jl:291-358."""
+        rule = self.opt.step_rule
+        if isinstance(rule, ConservativeStep):
+            self.alpha_p, self.alpha_d = self.get_fraction_to_boundary_step(rule.tau)
+        elif isinstance(rule, AdaptiveStep):
+            tau = max(1 - self.mu, rule.tau_min)
+            self.alpha_p, self.alpha_d = self.get_fraction_to_boundary_step(tau)
+        elif isinstance(rule, MehrotraAdaptiveStep):
+            self._mehrotra_adaptive_step(rule)
+        else:
+            raise TypeError(rule)
+
+    def _mehrotra_adaptive_step(self, rule):
+        """src/kernels.jl:309-358; the reference's scalar indexing into device arrays becomes
+        four single-element device->host reads."""
+        n, m, nlb = self.n, self.m, self.nlb
+        gamma_a = 1.0 / (1.0 - rule.gamma_f)
+        a, idx = self.h.get_alpha_max(1.0)
+        axl, axu, azl, azu = a
+        i_xl, i_xu, i_zl, i_zu = idx
+        max_ap, max_ad = min(axl, axu), min(azl, azu)
+        mu_full = self.h.get_affine_complementarity_measure(max_ap, max_ad) / gamma_a
+        ap, ad = 1.0, 1.0
+        dx, dzl, dzu = self.d[:n], self.d[n + m:n + m + nlb], self.d[n + m + nlb:]
+        g = lambda t, i: float(t[i].item())
+        if max_ap < 1.0:
+            if axl <= axu:
+                j = i_xl - 1
+                i = int(self.ind_lb[j])
+                tmp = mu_full / (g(self.zl, i) + max_ad * g(dzl, j))
+                ap = (g(self.x, i) - g(self.xl, i) - tmp) / (-g(dx, i))
+            else:
+                j = i_xu - 1
+                i = int(self.ind_ub[j])
+                tmp = mu_full / (g(self.zu, i) + max_ad * g(dzu, j))
+                ap = (g(self.xu, i) - g(self.x, i) - tmp) / (g(dx, i))
+        if max_ad < 1.0:
+            if azl <= azu:
+                j = i_zl - 1
+                i = int(self.ind_lb[j])
+                tmp = mu_full / (g(self.x, i) + max_ap * g(dx, i) - g(self.xl, i))
+                ad = -(g(self.zl, i) - tmp) / g(dzl, j)
+            else:
+                j = i_zu - 1
+                i = int(self.ind_ub[j])
+                tmp = mu_full / (g(self.xu, i) - g(self.x, i) - max_ap * g(dx, i))
+                ad = -(g(self.zu, i) - tmp) / g(dzu, j)
+        self.alpha_p = max(ap, rule.gamma_f * max_ap)
+        self.alpha_d = max(ad, rule.gamma_f * max_ad)
+
+    def apply_step(self):
+        """src/solver.jl:308-317."""
+        self.h.apply_step(self.alpha_p, self.alpha_d, self.mu)
+        self.k += 1
+
+    def evaluate_model(self):
+        """src/solver.jl:319-326."""
+        self.obj_val = self._eval_f()
+        self._eval_cons()
+        self._eval_grad()
+        self.jtprod(self.jacl, self.y)
+
+    def _record(self):
+        self.trace.append(dict(
+            k=self.k, objective=self.obj_val / self.obj_scale, dual_objective=self.dobj / self.obj_scale,
+            inf_pr=self.inf_pr, inf_du=self.inf_du, inf_compl=self.inf_compl, mu=self.mu,
+            alpha_p=self.alpha_p, alpha_d=self.alpha_d, del_w=self.del_w,
+            dnorm=0.0 if self.k == 0 else self.dnorm))
+
+    def mpc(self):
+        """src/solver.jl:332-360."""
+        while True:
+            self.update_termination_criteria()
+            self._record()
+            if self.status != REGULAR:
+                return
+            self.update_regularization()
+            self.factorize_regularized_system()
+            self.prediction_step()
+            self.mehrotra_correction_direction()
+            self.gondzio_correction_direction()
+            self.update_step_size()
+            self.apply_step()
+            self.evaluate_model()
+
+    def solve(self):
+        """solve!(solver): src/solver.jl:362-418."""
+        self.start_time = time.time()
+        t0 = time.perf_counter()
+        try:
+            self.initialize()
+            self.mpc()
+        except SolveException:
+            # the reference throws the exception *type*, so its LinearSolverException branch is
+            # missed and the status becomes INTERNAL_ERROR (solver.jl:396-404)
+            self.status = INTERNAL_ERROR
+            if self.opt.rethrow_error:
+                raise
+        except AssertionError:
+            self.status = INTERNAL_ERROR
+            if self.opt.rethrow_error:
+                raise
+        torch.cuda.synchronize(self.device)
+        total = time.perf_counter() - t0
+        x = self.x.cpu().numpy()
+        import scipy.sparse as sp
+        A0 = sp.csr_matrix((self.qp.Avals, (self.qp.Arows, self.qp.Acols)), shape=(self.m, self.nx))
+        sign = 1.0 if self.qp.minimize else -1.0
+        return ExecutionStats(
+            status=self.status, iter=self.k, objective=sign * self.obj_val / self.obj_scale,
+            dual_objective=getattr(self, "dobj", float("nan")) / self.obj_scale,
+            solution=x[: self.nx].copy(), constraints=np.asarray(A0 @ x[: self.nx]),
+            multipliers=self.y.cpu().numpy() * self.con_scale / self.obj_scale,
+            multipliers_L=self.zl.cpu().numpy()[: self.nx] / self.obj_scale,
+            multipliers_U=self.zu.cpu().numpy()[: self.nx] / self.obj_scale,
+            trace=self.trace, total_time=total, linear_solver_time=self.cnt["linear_solver_time"],
+            counters=dict(self.cnt, launches=self.h.launch_count(), ls_stats=self.linear_solver.stats),
+        )
+
+
+def solve(solver, **kwargs):
+    """MadIPM.solve!(solver; kwargs...): runtime option overrides then solve (solver.jl:370-372)."""
+    for k, v in kwargs.items():
+        setattr(solver.opt, k, v)
+    return solver.solve()
+
+
+def madipm(qp, **kwargs):
+    """madipm(m; kwargs...): src/solver.jl:425-428."""
+    return MPCSolver(qp, **kwargs).solve()

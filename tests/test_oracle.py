@@ -1,0 +1,135 @@
+"""CPU tests of the oracle itself: pinned on the reference's own fixture (simple_lp), cross-checked
+with HiGHS and algebraic identities, and guarded by committed traces."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.optimize import linprog
+
+from madipm_jl_b200.problems import random_sparse_lp, random_sparse_qp, simple_lp
+from oracle import sparse_ref
+from oracle.mpc_oracle import MPCOracle, madipm
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "traces.json")))
+
+
+def test_simple_lp_reference_pin():
+    """test/runtests.jl:144-198: objective 1.0, SOLVE_SUCCEEDED; Normal == K2 at 1e-6."""
+    ref = madipm(simple_lp(), regularization=("none",))
+    assert ref.status == "SOLVE_SUCCEEDED"
+    assert abs(ref.objective - 1.0) < 1e-8
+    k2 = madipm(simple_lp())
+    nm = madipm(simple_lp(), kkt_system="Normal", linear_solver="ldl")
+    for s in (k2, nm):
+        assert s.status == "SOLVE_SUCCEEDED"
+        assert abs(s.objective - ref.objective) < 1e-6
+        assert np.allclose(s.solution, ref.solution, atol=1e-6)
+        assert np.allclose(s.multipliers, ref.multipliers, atol=1e-6)
+        assert np.allclose(s.constraints, ref.constraints, atol=1e-6)
+    assert np.allclose(k2.solution, [0.5, 0.5], atol=1e-6)
+
+
+@pytest.mark.parametrize("rule", [("adaptive", 0.99), ("conservative", 0.99), ("mehrotra", 0.99)])
+def test_step_rules(rule):
+    """test/runtests.jl:85-97: every step rule reaches SOLVE_SUCCEEDED."""
+    qp = random_sparse_lp(40, 160, 5, 7, structure="uniform", ub_fraction=0.5)
+    assert madipm(qp, step_rule=rule).status == "SOLVE_SUCCEEDED"
+
+
+@pytest.mark.parametrize("reg", [("fixed", 1e-8, -1e-9), ("adaptive", 1e-8, -1e-9, 1e-9)])
+def test_regularizations(reg):
+    """test/runtests.jl:122-140: regularized LDL solves agree with the unregularized one at 1e-6."""
+    qp = random_sparse_qp(30, 80, 4, 5, structure="window", window=10)
+    ref = madipm(qp, regularization=("none",))
+    s = madipm(qp, regularization=reg)
+    assert s.status == ref.status == "SOLVE_SUCCEEDED"
+    assert abs(s.objective - ref.objective) < 1e-6 * max(1, abs(ref.objective))
+    assert np.allclose(s.solution, ref.solution, atol=1e-5)
+
+
+def test_gondzio():
+    qp = random_sparse_lp(40, 160, 5, 7, structure="uniform", ub_fraction=0.5)
+    a, b = madipm(qp), madipm(qp, max_ncorr=5)
+    assert a.status == b.status == "SOLVE_SUCCEEDED"
+    assert abs(a.objective - b.objective) < 1e-6 * max(1, abs(a.objective))
+
+
+@pytest.mark.parametrize("case", [(40, 160, 5, "uniform", 0.5), (300, 1500, 5, "window", 0.0)])
+def test_against_highs(case):
+    m, n, k, structure, ubf = case
+    qp = random_sparse_lp(m, n, k, 7, structure=structure, window=20, ub_fraction=ubf)
+    A = sp.csr_matrix((qp.Avals, (qp.Arows, qp.Acols)), shape=(m, n))
+    r = linprog(qp.c, A_eq=A, b_eq=qp.lcon, method="highs",
+                bounds=list(zip(qp.lvar, [None if np.isinf(u) else u for u in qp.uvar])))
+    for kkt in ("Normal", "K2"):
+        s = madipm(qp, kkt_system=kkt)
+        assert s.status == "SOLVE_SUCCEEDED"
+        assert abs(s.objective - r.fun) <= 1e-6 * max(1.0, abs(r.fun))
+        assert abs(s.objective - s.dual_objective) <= 1e-5 * max(1.0, abs(r.fun))
+
+
+@pytest.mark.parametrize("key", sorted(GOLD))
+def test_golden_traces(key):
+    """The oracle reproduces its committed per-iterate traces (regression guard)."""
+    from tests.golden.make_golden import CASES
+    name, kkt = key.split("/")
+    st = madipm(CASES[name](), kkt_system=kkt)
+    g = GOLD[key]
+    assert st.status == g["status"] and st.iter == g["iter"]
+    for a, b in zip(st.trace, g["trace"]):
+        for f in ("objective", "dual_objective", "inf_pr", "inf_du", "inf_compl", "mu", "alpha_p", "alpha_d"):
+            assert abs(a[f] - b[f]) <= 1e-9 * max(1.0, abs(b[f])), (key, a["k"], f, a[f], b[f])
+
+
+def test_unreduced_system_identity():
+    """K*d == p for the unreduced Newton system after every solve of an iteration."""
+    qp = random_sparse_lp(40, 160, 5, 3, structure="uniform", ub_fraction=0.5)
+    for kkt in ("Normal", "K2"):
+        o = MPCOracle(qp, kkt_system=kkt, regularization=("fixed", 1e-10, 0.0))
+        o.start_time = 0.0
+        o.initialize()
+        o._update_regularization()
+        o._factorize_regularized_system()
+        o._set_predictive_rhs()
+        o._solve_system()
+        assert o.residual_ratio < 1e-9, (kkt, o.residual_ratio)
+
+
+def test_normal_pattern_matches_sparse_product():
+    """build_normal_system (utils.jl:209-274) == structural pattern of tril(A A')."""
+    rng = np.random.default_rng(0)
+    m, n = 70, 200
+    A = sp.random(m, n, 0.03, random_state=1, format="coo")
+    A.data[:] = 1.0
+    Bp, Bj, Bx = sparse_ref.coo_to_csr(m, n, A.row, A.col, np.arange(A.nnz, dtype=float))
+    Cp, Cj = sparse_ref.build_normal_system(m, n, Bp, Bj)
+    P = sp.tril((A @ A.T).tocsr()).tocsc()
+    P.sort_indices()
+    # reference emits column i with rows j >= i  == lower CSC
+    assert (P.indptr == Cp).all() and (P.indices == Cj).all()
+    D = rng.uniform(0.5, 2.0, n)
+    vals = rng.standard_normal(A.nnz)
+    Cx = sparse_ref.assemble_normal_system(m, n, Bp, Bj, vals[Bx.astype(int)], Cp, Cj, D)
+    Av = sp.csr_matrix((vals, (A.row, A.col)), shape=(m, n))
+    ref = sp.tril(Av @ sp.diags(D) @ Av.T).tocsc()
+    ref.sort_indices()
+    dense = np.zeros((m, m))
+    for i in range(m):
+        dense[Cj[Cp[i]:Cp[i + 1]], i] = Cx[Cp[i]:Cp[i + 1]]
+    assert np.allclose(dense, ref.toarray(), atol=1e-12)
+
+
+def test_ldl_with_permutation():
+    rng = np.random.default_rng(0)
+    n = 40
+    B = sp.random(n, n, 0.15, random_state=1)
+    M = (B @ B.T + 2 * sp.eye(n)).toarray()
+    low = sp.csc_matrix(np.tril(M))
+    low.sort_indices()
+    for perm in (None, rng.permutation(n).astype(np.int32)):
+        L = sparse_ref.LDL(n, low.indptr.astype(np.int32), low.indices.astype(np.int32), perm)
+        assert L.factorize(low.data) and L.inertia() == (n, 0, 0)
+        b = rng.standard_normal(n)
+        assert np.abs(M @ L.solve(b) - b).max() < 1e-12
