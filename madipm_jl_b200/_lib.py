@@ -185,11 +185,13 @@ class Handle:
         self.check(self.lib.mipm_k2_transfer(self.h, _ptr(V), _ptr(nz)))
 
     def ls_factorize(self, nzval):
+        self._nz_ref = nzval      # refinement reads these values later: keep the buffer alive
         st = C.c_int()
         self.check(self.lib.mipm_ls_factorize(self.h, _ptr(nzval), C.byref(st)))
         return st.value == MIPM_OK
 
     def ls_factorize_async(self, nzval):
+        self._nz_ref = nzval
         self.check(self.lib.mipm_ls_factorize_async(self.h, _ptr(nzval)))
 
     def ls_status(self):

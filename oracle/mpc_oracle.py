@@ -603,11 +603,13 @@ class MPCOracle:
 
     @staticmethod
     def _argmin_ratio(val):
-        """mapreduce with init (1.0, 0) and strict '<' (kernels.jl:227-269): first minimum wins."""
+        """mapreduce with init (1.0, 0) and op (a, b) -> a[1] < b[1] ? a : b (kernels.jl:227-269):
+        a left fold, so on ties the RIGHT-most element wins, and an element equal to the init
+        value 1.0 beats the init."""
         best, idx = 1.0, 0
         if len(val):
-            j = int(np.argmin(val))
-            if val[j] < best:
+            j = len(val) - 1 - int(np.argmin(val[::-1]))
+            if not (best < val[j]):
                 best, idx = float(val[j]), j + 1
         return best, idx
 

@@ -1,0 +1,332 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs. Tolerances: bit-exact for patterns / integer work and for the order-preserving
+assembly; 1e-8 relative (scale max(1,|value|)) for per-iterate floating-point quantities, as
+BASELINE.json's north_star states; iteration counts within +-2."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from madipm_jl_b200 import _lib  # noqa: E402
+from madipm_jl_b200.problems import config_c1, random_sparse_lp, random_sparse_qp, simple_lp  # noqa: E402
+from oracle import sparse_ref  # noqa: E402
+from oracle.mpc_oracle import MPCOracle, madipm as oracle_madipm  # noqa: E402
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "traces.json")))
+TOL = 1e-8
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def close(a, b, tol=TOL):
+    return abs(a - b) <= tol * max(1.0, abs(a), abs(b))
+
+
+@pytest.fixture(scope="module")
+def handle(built):
+    assert torch.cuda.is_available()
+    return lambda: _lib.Handle(device=0, stream=torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------ assembly (a3, a4, a6, a7)
+@pytest.mark.parametrize("case", [(1, 2, 1, "uniform"), (60, 240, 5, "uniform"), (2000, 10000, 5, "uniform"),
+                                  (5000, 25000, 8, "window")])
+def test_normal_assembly_matches_reference_loop(handle, case):
+    m, n, k, structure = case
+    qp = random_sparse_lp(m, n, k, 4, structure=structure, window=50)
+    Bp, Bj, Bm = _lib.coo_to_csr(m, n, qp.Arows, qp.Acols)
+    h = handle()
+    Cp, Cj = h.normal_symbolic(m, n, Bp, Bj)
+    Rp, Rj = sparse_ref.build_normal_system(m, n, Bp, Bj)
+    assert (Cp == Rp).all() and (Cj == Rj).all()
+    ATx = qp.Avals[Bm]
+    pr = np.random.default_rng(0).uniform(1e-6, 1e3, n)
+    ref = sparse_ref.assemble_normal_system(m, n, Bp, Bj, ATx, Rp, Rj, 1.0 / pr)
+    d_ATx, d_pr, d_Cx = dev(ATx), dev(pr), torch.zeros(len(Cj), dtype=torch.float64, device="cuda")
+    h.normal_set_jacobian(d_ATx)
+    h.normal_assemble(d_pr, d_Cx, exact_order=True)
+    assert np.array_equal(d_Cx.cpu().numpy(), ref), "exact-order assembly must be bit-exact"
+    h.normal_assemble(d_pr, d_Cx, exact_order=False)
+    got = d_Cx.cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_k2_transfer_bit_exact(handle):
+    qp = random_sparse_qp(300, 900, 4, 2, structure="window", window=10)
+    n, m = qp.nvar, qp.ncon
+    I = np.concatenate([np.arange(n), qp.Hrows, n + qp.Arows, n + np.arange(m)]).astype(np.int32)
+    J = np.concatenate([np.arange(n), qp.Hcols, qp.Acols, n + np.arange(m)]).astype(np.int32)
+    h = handle()
+    colptr, rowval, kmap = h.k2_symbolic(n + m, I, J)
+    V = np.random.default_rng(0).standard_normal(len(I))
+    ref = sparse_ref.transfer(len(rowval), V, kmap)
+    nz = torch.full((len(rowval),), 7.0, dtype=torch.float64, device="cuda")
+    h.k2_transfer(dev(V), nz)
+    assert np.array_equal(nz.cpu().numpy(), ref)
+
+
+def test_spmv(handle):
+    qp = random_sparse_lp(700, 3000, 6, 5, structure="uniform")
+    m, n = qp.ncon, qp.nvar
+    Bp, Bj, Bm = _lib.coo_to_csr(m, n, qp.Arows, qp.Acols)
+    A = sp.csr_matrix((qp.Avals[Bm], Bj, Bp), shape=(m, n))
+    h = handle()
+    h.spmv_setup(m, n, Bp, Bj)
+    rng = np.random.default_rng(1)
+    x, y0, v, w0 = rng.standard_normal(n), rng.standard_normal(m), rng.standard_normal(m), rng.standard_normal(n)
+    dA, y, w = dev(A.data), dev(y0), dev(w0)
+    h.spmv(0, 1.5, dA, dev(x), -0.5, y)
+    h.spmv(1, -1.0, dA, dev(v), 1.0, w)
+    assert np.abs(y.cpu().numpy() - (1.5 * (A @ x) - 0.5 * y0)).max() < 1e-12
+    assert np.abs(w.cpu().numpy() - (-(A.T @ v) + w0)).max() < 1e-12
+
+
+# ------------------------------------------------------------------ linear solver (a9, a11, a21)
+def _normal_matrix(m, n, k, structure, seed):
+    qp = random_sparse_lp(m, n, k, seed, structure=structure, window=50)
+    Bp, Bj, Bm = _lib.coo_to_csr(m, n, qp.Arows, qp.Acols)
+    Cp, Cj = sparse_ref.build_normal_system(m, n, Bp, Bj)
+    pr = np.random.default_rng(seed).uniform(1e-3, 1e3, n)
+    Cx = sparse_ref.assemble_normal_system(m, n, Bp, Bj, qp.Avals[Bm], Cp, Cj, 1.0 / pr)
+    low = sp.csc_matrix((Cx, Cj, Cp), shape=(m, m))
+    return Cp, Cj, Cx, (low + sp.tril(low, -1).T).tocsr()
+
+
+@pytest.mark.parametrize("case", [(1, 3, 1, "uniform"), (50, 200, 4, "uniform"), (130, 500, 5, "uniform"),
+                                  (600, 2400, 5, "uniform"), (2000, 10000, 5, "uniform"),
+                                  (6000, 30000, 8, "window"), (20000, 100000, 8, "window")])
+@pytest.mark.parametrize("ordering", [_lib.MIPM_ORDER_ND, _lib.MIPM_ORDER_NATURAL])
+def test_cholesky_factor_solve(handle, case, ordering):
+    m, n, k, structure = case
+    if ordering == _lib.MIPM_ORDER_NATURAL and m > 6000:
+        pytest.skip("natural ordering only at small sizes")
+    Cp, Cj, Cx, K = _normal_matrix(m, n, k, structure, 3)
+    h = handle()
+    h.ls_analyze(m, Cp, Cj, kind=_lib.MIPM_CHOLESKY, ordering=ordering)
+    nz = dev(Cx)
+    assert h.ls_factorize(nz)
+    assert h.ls_inertia() == (m, 0, 0)
+    b = np.random.default_rng(0).standard_normal(m)
+    for ir, tol in ((0, 1e-9), (2, 1e-12)):
+        x = dev(b)
+        h.ls_solve(x, ir)
+        xs = x.cpu().numpy()
+        res = np.abs(K @ xs - b).max() / (np.abs(K).sum(axis=1).max() * np.abs(xs).max() + np.abs(b).max())
+        assert res < tol, (case, ir, res)
+    # refactorization with new values on the same pattern
+    nz2 = dev(Cx * 1.0)
+    nz2 += 0.0
+    assert h.ls_factorize(nz2)
+
+
+def test_cholesky_reports_breakdown(handle):
+    """A non-positive pivot maps to is_factorized == false (src/utils.jl:54-62, linear_solver.jl:11)."""
+    Cp, Cj, Cx, K = _normal_matrix(130, 500, 5, "uniform", 3)
+    h = handle()
+    h.ls_analyze(130, Cp, Cj, kind=_lib.MIPM_CHOLESKY)
+    bad = Cx.copy()
+    diag = np.flatnonzero(Cj == np.repeat(np.arange(130), np.diff(Cp)))
+    bad[diag] *= -1.0
+    assert not h.ls_factorize(dev(bad))
+    assert h.ls_factorize(dev(Cx))
+
+
+@pytest.mark.parametrize("case", [(30, 80, 4, 0), (300, 900, 4, 2), (2000, 6000, 5, 2), (8000, 30000, 6, 0)])
+def test_ldl_factor_solve_k2(handle, case):
+    m, n, k, qoff = case
+    qp = random_sparse_qp(m, n, k, 2, structure="window", window=20, q_offdiag=qoff)
+    I = np.concatenate([np.arange(n), qp.Hrows, n + qp.Arows, n + np.arange(m)]).astype(np.int32)
+    J = np.concatenate([np.arange(n), qp.Hcols, qp.Acols, n + np.arange(m)]).astype(np.int32)
+    h = handle()
+    colptr, rowval, kmap = h.k2_symbolic(n + m, I, J)
+    rng = np.random.default_rng(1)
+    V = np.concatenate([10.0 ** rng.uniform(-6, 4, n), qp.Hvals, qp.Avals, np.full(m, 1e-10)])
+    nzh = sparse_ref.transfer(len(rowval), V, kmap)
+    low = sp.csc_matrix((nzh, rowval, colptr), shape=(n + m, n + m))
+    K = (low + sp.tril(low, -1).T).tocsr()
+    h.ls_analyze(n + m, colptr, rowval, kind=_lib.MIPM_LDL)
+    nz = dev(nzh)                      # must outlive the solves: refinement re-reads the values
+    assert h.ls_factorize(nz)
+    pos, zero, neg = h.ls_inertia()
+    assert (pos, neg) == (n, m), (pos, zero, neg)
+    b = rng.standard_normal(n + m)
+    x = dev(b)
+    h.ls_solve(x, 2)
+    xs = x.cpu().numpy()
+    res = np.abs(K @ xs - b).max() / (np.abs(K).sum(axis=1).max() * np.abs(xs).max() + np.abs(b).max())
+    assert res < 1e-10, res
+
+
+# ------------------------------------------------------------------ vector kernels (a5, a14-a19)
+def _pair(qp, kkt):
+    from madipm_jl_b200.solver import MPCSolver
+    g = MPCSolver(qp, kkt_system=kkt)
+    o = MPCOracle(qp, kkt_system=kkt)
+    g.start_time = o.start_time = 0.0
+    return g, o
+
+
+def _push_state(g, o):
+    """Copy the oracle's state into the GPU solver's device buffers."""
+    for name in ("x", "xl", "xu", "zl", "zu", "f", "y", "c", "rhs", "jacl", "d", "p", "correction_lb", "correction_ub"):
+        getattr(g, name).copy_(torch.from_numpy(getattr(o, name)))
+    g.mu, g.del_w, g.del_c = o.mu, o.del_w, o.del_c
+
+
+def _cmp(t, a, tol=1e-12):
+    got = t.cpu().numpy()
+    assert got.shape == a.shape
+    if a.size == 0:
+        return
+    fin = np.isfinite(a)
+    assert np.array_equal(got[~fin], a[~fin])          # infinite bounds must match exactly
+    if fin.any():
+        scale = max(1.0, np.abs(a[fin]).max())
+        assert np.abs(got[fin] - a[fin]).max() <= tol * scale
+
+
+@pytest.mark.parametrize("kkt", ["Normal", "K2"])
+def test_vector_kernels_one_iteration(handle, kkt):
+    qp = random_sparse_lp(120, 500, 5, 8, structure="uniform", ub_fraction=0.4)
+    g, o = _pair(qp, kkt)
+    o.initialize()
+    g.initialize()
+    # starting point (a20)
+    for name in ("x", "y", "zl", "zu", "jacl", "f", "c"):
+        _cmp(getattr(g, name), getattr(o, name), 1e-9)
+    _push_state(g, o)
+    # termination measures (a18)
+    o.update_termination_criteria()
+    g.update_termination_criteria()
+    for f in ("dobj", "inf_pr", "inf_du", "inf_compl"):
+        assert close(getattr(g, f), getattr(o, f), 1e-12), f
+    # diagonals (a5)
+    o._update_regularization(), g.update_regularization()
+    o._set_aug_diagonal_reg()
+    g.h.set_aug_diagonal_reg(g.del_w, g.del_c)
+    for name in ("reg", "pr_diag", "du_diag", "l_diag", "u_diag", "l_lower", "u_lower"):
+        _cmp(getattr(g, name), getattr(o, name), 1e-14)
+    o._factorize_wrapper()
+    g.factorize_wrapper()
+    assert g.linear_solver.is_factorized()
+    # predictor rhs (a14) and solve (a10, a11)
+    o._set_predictive_rhs()
+    g.h.set_predictive_rhs()
+    _cmp(g.p, o.p, 1e-14)
+    o._solve_system()
+    g.solve_system()
+    _cmp(g.d, o.d, 1e-8)
+    assert g.residual_ratio < 1e-8
+    g.d.copy_(torch.from_numpy(o.d))
+    # ratio test (a17)
+    for tau in (1.0, 0.99):
+        a, idx = g.h.get_alpha_max(tau)
+        ra = o._get_alpha_max_primal(tau)
+        rd = o._get_alpha_max_dual(tau)
+        assert np.allclose(a, [ra[0], ra[1], rd[0], rd[1]], rtol=1e-14, atol=0)
+        assert list(idx) == [ra[2], ra[3], rd[2], rd[3]]
+    ap, ad = o._get_fraction_to_boundary_step(1.0)
+    # complementarity measures (a16), corrections (a15)
+    assert close(g.h.get_affine_complementarity_measure(ap, ad), o._get_affine_complementarity_measure(ap, ad), 1e-12)
+    assert close(g.h.get_complementarity_measure(), o._get_complementarity_measure(), 1e-12)
+    o._get_correction(), g.h.get_correction()
+    _cmp(g.correction_lb, o.correction_lb, 1e-14), _cmp(g.correction_ub, o.correction_ub, 1e-14)
+    o._set_extra_correction(0.7, 0.8, 0.1, 10.0, 0.05), g.h.set_extra_correction(0.7, 0.8, 0.1, 10.0, 0.05)
+    _cmp(g.correction_lb, o.correction_lb, 1e-14), _cmp(g.correction_ub, o.correction_ub, 1e-14)
+    o._set_correction_rhs(0.03), g.h.set_correction_rhs(0.03)
+    _cmp(g.p, o.p, 1e-14)
+    # K*d product (a12)
+    rng = np.random.default_rng(0)
+    v, w0 = rng.standard_normal(o.d.shape), rng.standard_normal(o.d.shape)
+    w_ref = o._kkt_mul(w0.copy(), v, -1.0, 0.5)
+    w = dev(w0)
+    g.kkt_mul(w, dev(v), -1.0, 0.5)
+    _cmp(w, w_ref, 1e-12)
+    # step + boundary adjustment + model evaluation (a19)
+    o.alpha_p, o.alpha_d = 0.9, 0.8
+    g.alpha_p, g.alpha_d = 0.9, 0.8
+    o.mu = g.mu = 1e300   # forces adjust_boundary! to fire everywhere
+    o._apply_step(), g.apply_step()
+    for name in ("x", "y", "zl", "zu", "xl", "xu"):
+        _cmp(getattr(g, name), getattr(o, name), 1e-14)
+    o._evaluate_model(), g.evaluate_model()
+    assert close(g.obj_val, o.obj_val, 1e-12)
+    for name in ("c", "f", "jacl"):
+        _cmp(getattr(g, name), getattr(o, name), 1e-12)
+
+
+# ------------------------------------------------------------------ end to end (a8, a20, mpc!)
+def _check_trace(got, ref_trace, ref_iter, ref_status, tol=TOL):
+    assert got.status == ref_status
+    assert abs(got.iter - ref_iter) <= 2
+    for a, b in zip(got.trace, ref_trace):
+        for f in ("objective", "dual_objective", "inf_pr", "inf_du", "inf_compl"):
+            assert close(a[f], b[f], tol), (a["k"], f, a[f], b[f])
+
+
+@pytest.mark.parametrize("key", sorted(GOLD))
+def test_end_to_end_matches_golden_traces(built, key):
+    from madipm_jl_b200.solver import madipm
+    from tests.golden.make_golden import CASES
+    name, kkt = key.split("/")
+    got = madipm(CASES[name](), kkt_system=kkt)
+    g = GOLD[key]
+    _check_trace(got, g["trace"], g["iter"], g["status"])
+    assert close(got.objective, g["objective"])
+
+
+def test_simple_lp_reference_pin_on_gpu(built):
+    """test/test_gpu.jl:4-22 + runtests.jl:144-198: status only in the reference; we also pin objective 1.0."""
+    from madipm_jl_b200.solver import madipm
+    for kkt in ("K2", "Normal"):
+        s = madipm(simple_lp(), kkt_system=kkt)
+        assert s.status == "SOLVE_SUCCEEDED" and abs(s.objective - 1.0) < 1e-8
+        assert np.allclose(s.solution, [0.5, 0.5], atol=1e-6) and np.allclose(s.multipliers, [-1.0], atol=1e-6)
+
+
+@pytest.mark.parametrize("opts", [dict(step_rule=("mehrotra", 0.99)), dict(step_rule=("conservative", 0.99)),
+                                  dict(max_ncorr=5), dict(regularization=("fixed", 1e-8, -1e-9)),
+                                  dict(regularization=("adaptive", 1e-8, -1e-9, 1e-9)), dict(regularization=("none",))])
+def test_options_parity(built, opts):
+    """Step rules, Gondzio corrections and regularization policies (test/runtests.jl:85-140)."""
+    from madipm_jl_b200 import solver as S
+    qp = random_sparse_lp(120, 500, 5, 8, structure="uniform", ub_fraction=0.4)
+    conv = dict(opts)
+    if "step_rule" in conv:
+        kind, val = conv["step_rule"]
+        conv["step_rule"] = {"mehrotra": S.MehrotraAdaptiveStep, "conservative": S.ConservativeStep}[kind](val)
+    if "regularization" in conv:
+        r = conv["regularization"]
+        conv["regularization"] = {"fixed": S.FixedRegularization, "adaptive": S.AdaptiveRegularization,
+                                  "none": S.NoRegularization}[r[0]](*r[1:])
+    for kkt in ("Normal", "K2"):
+        ref = oracle_madipm(qp, kkt_system=kkt, **opts)
+        got = S.madipm(qp, kkt_system=kkt, **conv)
+        _check_trace(got, ref.trace, ref.iter, ref.status, tol=1e-7)
+
+
+def test_c1_full_size(built):
+    """BASELINE config C1 (m=2000, n=10000, 5 nnz/col, uniform): full-size run checked through
+    size-independent properties and against the oracle's trace."""
+    from madipm_jl_b200.solver import madipm
+    qp = config_c1()
+    got = madipm(qp, kkt_system="Normal")
+    assert got.status == "SOLVE_SUCCEEDED"
+    A = sp.csr_matrix((qp.Avals, (qp.Arows, qp.Acols)), shape=(qp.ncon, qp.nvar))
+    x = got.solution
+    assert np.abs(A @ x - qp.lcon).max() <= 1e-7 * max(1.0, np.abs(qp.lcon).max())
+    assert x.min() > -1e-8
+    assert abs(got.objective - got.dual_objective) <= 1e-6 * max(1.0, abs(got.objective))
+    ref = oracle_madipm(qp, kkt_system="Normal", linear_solver="splu")
+    _check_trace(got, ref.trace, ref.iter, ref.status)
