@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric   : IPM iterations per second (plus time-to-1e-8 and factorization FP64 TFLOP/s as extra keys)
+workload : config C2 = synthetic sparse LP, m=200,000 constraints, n=1,000,000 variables, 8 nnz/col,
+           rows drawn within +-50 of each column's home row (uniformly random rows make chol(AA')
+           ~90% dense = 147 GB at this size: SURVEY fact 8), NormalKKTSystem + supernodal Cholesky.
+step     : one pass of the mpc! loop body (src/solver.jl:333-359): termination test, KKT assembly,
+           numeric factorization, predictor + corrector solves (each with residual check and one
+           round of iterative refinement), ratio tests, step, model re-evaluation.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S]
+
+N > 1: the single-instance configs do not shard ("replicas only"), so every rank runs an
+independent replica of the workload; value = total iterations of all ranks / max-over-ranks time.
+`--impl reference` times the CPU restatement of the reference (oracle/, numpy + scalar C LDL^T on the
+host cores) on the same config: the Julia reference itself cannot run in this image (no Julia).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ipm_iterations_per_second"
+UNIT = "iter/s"
+
+
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback", "fp64_tflops": 35.46, "fp64_src": "own DGEMM measurement (profiles/fp64_peak_r01.json)"}
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks["hbm_gbs"], peaks["hbm_src"] = float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    try:
+        p = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")))
+        peaks["fp64_tflops"] = float(p["fp64_tflops"])
+    except Exception:
+        pass
+    return peaks
+
+
+def make_workload(scale):
+    from madipm_jl_b200.problems import config_c2
+    qp = config_c2(seed=2, scale=scale)
+    name = "C2: LP m=%d n=%d 8 nnz/col, rows within +-50 of home row, NormalKKT + Cholesky" % (qp.ncon, qp.nvar)
+    return qp, name
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """CPU restatement of the reference on the host cores (kind = "port")."""
+    if rank != 0:
+        return
+    from oracle.mpc_oracle import MPCOracle
+    qp, wname = make_workload(args.scale)
+    t0 = time.time()
+    o = MPCOracle(qp, kkt_system="Normal", linear_solver="ldl", fast_symbolic=True)
+    o.start_time = time.time()
+    o.initialize()
+    t_setup = time.time() - t0
+    budget = 200.0
+    for _ in range(args.warmup):
+        if not o.mpc_iteration():
+            o.initialize()
+    done = 0
+    t1 = time.perf_counter()
+    while done < args.steps and (time.perf_counter() - t1) < budget:
+        if not o.mpc_iteration():
+            tpause = time.perf_counter()
+            o.initialize()
+            t1 += time.perf_counter() - tpause
+            continue
+        done += 1
+    dt = time.perf_counter() - t1
+    val = done / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wname, "kkt_system": "Normal", "linear_solver": "oracle LDL^T (Davis up-looking, RCM), 1 thread"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "%d full-size IPM iterations of the CPU restatement (oracle/), setup %.1fs untimed" % (done, t_setup)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Julia reference cannot run in this image (no Julia); cuDSS not installed",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="scale m and n of the workload (testing only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from madipm_jl_b200.solver import MPCSolver
+    peaks = load_peaks()
+    qp, wname = make_workload(args.scale)
+    t0 = time.time()
+    solver = MPCSolver(qp, kkt_system="Normal", device=local_rank)
+    t_setup = time.time() - t0
+    st = solver.linear_solver.stats
+    h = solver.h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- e2e: the public solve call with host buffers (H2D of the model, D2H of the result)
+    barrier()
+    t1 = time.perf_counter()
+    res = solver.solve()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t1
+    iters_total = res.iter
+    n, m = solver.n, solver.m
+    h2d = 8 * (5 * n + 2 * m + len(solver.Aj))
+    d2h = 8 * (3 * n + m)
+    if world > 1:
+        tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e_max = float(tt.item())
+    else:
+        t_e2e_max = t_e2e
+    e2e_val = world * iters_total / t_e2e_max
+
+    # ---------------- device-timed steps
+    solver.k = 0
+    solver.trace = []
+    solver.start_time = time.time()
+    solver.initialize()
+    for _ in range(args.warmup):
+        if not solver.mpc_iteration():
+            solver.k = 0
+            solver.initialize()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = h.launch_count()
+    done, total_ms = 0, 0.0
+    while done < args.steps:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        alive = True
+        while done < args.steps and alive:
+            alive = solver.mpc_iteration()
+            if alive:
+                done += 1
+        e1.record()
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        if not alive:   # converged inside the timed region: restart from the starting point (untimed)
+            solver.k = 0
+            solver.initialize()
+    barrier()
+    clocks = sampler.stop()
+    launches = h.launch_count() - l0
+    if world > 1:
+        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    value = world * args.steps / (total_ms * 1e-3)
+
+    # ---------------- per-stage device timing and rooflines (rank 0 reports)
+    def time_call(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    counts = np.bincount(solver.Aj, minlength=n).astype(np.float64)
+    T = float(np.sum(counts * (counts + 1) / 2))
+    nnzC = len(solver.aug_rowval)
+    asm_bytes = 12.0 * T + 12.0 * nnzC + 8.0 * n
+    asm_ms = time_call(lambda: h.normal_assemble(solver.pr_diag, solver.aug_nz, False))
+    prof = h.ls_factorize_profile(solver.aug_nz)
+    fac_ms = time_call(lambda: h.ls_factorize_async(solver.aug_nz), reps=3)
+    xb = torch.randn(m, dtype=torch.float64, device="cuda")
+    sol_ms = time_call(lambda: h.ls_solve(xb, 0), reps=3)
+    sol_bytes = 2.0 * (8.0 * st["nnz_l"] + 4.0 * (st["nnz_l"] ** 0.5))  # L read twice (fwd + bwd)
+    spmv_ms = time_call(lambda: h.spmv(0, 1.0, solver.AT_x, solver.x, 0.0, solver.buffer_m))
+    spmv_bytes = 12.0 * len(solver.Aj) + 8.0 * (n + m)
+    stages = {
+        "assembly": {"ms": asm_ms, "bound": "hbm", "achieved_gbs": asm_bytes / asm_ms / 1e6,
+                     "frac": asm_bytes / asm_ms / 1e6 / peaks["hbm_gbs"], "algorithmic_bytes": asm_bytes},
+        "factorization": {"ms": fac_ms, "tflops": st["flops"] / fac_ms / 1e9, "flops": st["flops"],
+                          "launches": st["n_launches"]},
+        "triangular_solve_pair": {"ms": sol_ms, "bound": "hbm", "achieved_gbs": sol_bytes / sol_ms / 1e6,
+                                  "frac": sol_bytes / sol_ms / 1e6 / peaks["hbm_gbs"], "algorithmic_bytes": sol_bytes},
+        "spmv": {"ms": spmv_ms, "bound": "hbm", "achieved_gbs": spmv_bytes / spmv_ms / 1e6,
+                 "frac": spmv_bytes / spmv_ms / 1e6 / peaks["hbm_gbs"]},
+        "factor_classes": prof,
+    }
+    # dominant kernel of the step: the factorization class with the largest device time
+    dom = max(prof, key=lambda kname: prof[kname]["ms"])
+    d = prof[dom]
+    per_launch_ms = d["ms"] / max(d["launches"], 1)
+    if dom in ("update", "trsm", "diag"):
+        achieved = d["work"] / d["ms"] / 1e9      # TFLOP/s
+        roof = {"kernel": "k_" + dom, "bound": "tensor", "achieved": achieved, "peak": peaks["fp64_tflops"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["fp64_tflops"], "traffic": None,
+                "peak_source": "FP64 " + peaks["fp64_src"] + "; MEASURED_PEAKS.json has no FP64 entry",
+                "launches_per_factorization": d["launches"], "avg_launch_ms": per_launch_ms,
+                "algorithmic_flops_per_factorization": d["work"]}
+    else:
+        achieved = d["work"] / d["ms"] / 1e6      # GB/s
+        roof = {"kernel": "k_" + dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["hbm_src"],
+                "launches_per_factorization": d["launches"], "avg_launch_ms": per_launch_ms,
+                "algorithmic_bytes_per_factorization": d["work"]}
+
+    # ---------------- CPU baseline: oracle on a bounded sample of the same workload (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.mpc_oracle import MPCOracle
+        tb = time.time()
+        o = MPCOracle(qp, kkt_system="Normal", linear_solver="ldl", fast_symbolic=True)
+        o.start_time = time.time()
+        o.initialize()
+        nit = 0
+        tc = time.perf_counter()
+        while nit < 3 and o.mpc_iteration():
+            nit += 1
+        dtc = time.perf_counter() - tc
+        cpu = {"value": nit / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d full-size IPM iterations of the CPU restatement (numpy + scalar C LDL^T, RCM ordering, "
+                         "nnz(L)=%d); setup %.1fs untimed; host has %d cores" % (nit, o.ls.nnzL, time.time() - tb - dtc, os.cpu_count()),
+               "timers_s": o.timers}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wname, "kkt_system": "NormalKKTSystem", "linear_solver": "supernodal Cholesky (own)",
+                       "ordering": "nested dissection", "ir_steps": solver.opt.ir_steps, "tol": solver.opt.tol,
+                       "l2": "inputs larger than L2 (L+U = %.0f MB)" % (8e-6 * (st["nnz_l"] + st["update_doubles"])),
+                       "parallelism": "replicas x%d" % world, "scale": args.scale},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / max(iters_total, 1),
+                    "d2h_bytes_per_step": d2h / max(iters_total, 1), "iterations": iters_total,
+                    "time_to_tol_s": t_e2e_max, "status": res.status,
+                    "what": "MPCSolver.solve(): host model -> H2D, init_starting_point!, mpc! to tol, D2H of x,y,zl,zu"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "time_to_1e-8_s": t_e2e_max, "iterations_to_1e-8": iters_total,
+            "factor_fp64_tflops": st["flops"] / fac_ms / 1e9,
+            "stages": stages,
+            "symbolic": {k_: st[k_] for k_ in ("n", "nnz_a", "nnz_l", "nnz_l_exact", "flops", "n_supernodes", "n_levels",
+                                              "max_front_cols", "max_front_rows", "update_doubles", "n_launches")},
+            "setup_s": t_setup, "final_objective": res.objective,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -226,6 +226,12 @@ int mipm_dot(mipm_handle h, int64_t n, const double *d_x, const double *d_y, dou
 /* ------------------------------------------------------------------ diagnostics ---- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t mipm_launch_count(mipm_handle h);
+/* One numeric factorization with a CUDA-event pair around every launch, summed per kernel class:
+ * 0 zero-fill + scatter of the input values, 1 extend-add, 2 diagonal-block factorization,
+ * 3 panel TRSM, 4 trailing DMMA update. ms[5] = device milliseconds, work[5] = algorithmic
+ * bytes (classes 0-1) or flops (classes 2-4), launches[5] = launch counts. For bench.py's roofline. */
+int mipm_ls_factorize_profile(mipm_handle h, const double *d_nzval, double *ms, double *work,
+                              int64_t *launches);
 /* Dense FP64 update-kernel micro-benchmark hook: C(n x n, lower tiles) -= X(n x k) X(n x k)'
  * with the same DMMA tile kernel the factorization uses; for roofline measurement. */
 int mipm_bench_syrk(mipm_handle h, int64_t n, int64_t k, double *d_C, int64_t ldc,

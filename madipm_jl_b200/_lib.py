@@ -60,7 +60,7 @@ SYMBOLS = [
     "mipm_get_affine_complementarity_measure", "mipm_get_alpha_max", "mipm_termination_measures",
     "mipm_apply_step", "mipm_reduce_rhs", "mipm_finish_aug_solve", "mipm_normal_solve_stage", "mipm_kktmul",
     "mipm_residual_norms", "mipm_init_point_stage", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_dot",
-    "mipm_launch_count", "mipm_bench_syrk",
+    "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk",
 ]
 
 _lib = None
@@ -293,6 +293,14 @@ class Handle:
         out = C.c_double()
         self.check(self.lib.mipm_dot(self.h, C.c_int64(n), _ptr(x), _ptr(y), C.byref(out)))
         return out.value
+
+    def ls_factorize_profile(self, nzval):
+        """Per-class device timing of one factorization: dict class -> (ms, work, launches)."""
+        self._nz_ref = nzval
+        ms, work, cnt = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int64 * 5)()
+        self.check(self.lib.mipm_ls_factorize_profile(self.h, _ptr(nzval), ms, work, cnt))
+        names = ["zero_scatter", "extend_add", "diag", "trsm", "update"]
+        return {nm: dict(ms=ms[i], work=work[i], launches=cnt[i]) for i, nm in enumerate(names)}
 
     def launch_count(self):
         return int(self.lib.mipm_launch_count(self.h))

@@ -612,18 +612,42 @@ int ls_device_setup(Handle *h)
     return MIPM_OK;
 }
 
+// Optional per-class device timing of one factorization (events around every launch).
+struct FactorProfile {
+    struct Rec { cudaEvent_t a, b; int cls; };
+    std::vector<Rec> recs;
+};
+static FactorProfile *g_prof = nullptr;   // only set inside mipm_ls_factorize_profile (single-threaded per handle)
+#define PROF_BEGIN(cls_)                                                  \
+    FactorProfile::Rec rec__;                                             \
+    if (g_prof) {                                                         \
+        cudaEventCreate(&rec__.a);                                        \
+        cudaEventCreate(&rec__.b);                                        \
+        rec__.cls = (cls_);                                               \
+        cudaEventRecord(rec__.a, st);                                     \
+    }
+#define PROF_END()                                                        \
+    if (g_prof) {                                                         \
+        cudaEventRecord(rec__.b, st);                                     \
+        g_prof->recs.push_back(rec__);                                    \
+    }
+
 template <bool LDL>
 static int factorize_t(Handle *h, const double *d_nzval)
 {
     const LsSymbolic &S = h->sym;
     cudaStream_t st = h->stream;
     const int32_t *sched = h->d_sched.p;
-    MIPM_CUDA(h, cudaMemsetAsync(h->d_L.p, 0, (size_t)std::max<int64_t>(S.nnz_l, 1) * sizeof(double), st));
-    MIPM_CUDA(h, cudaMemsetAsync(h->d_U.p, 0, (size_t)std::max<int64_t>(S.update_doubles, 1) * sizeof(double), st));
-    MIPM_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, 4 * sizeof(int), st));
-    if (S.nnz_a > 0) {
-        k_scatter_a<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.nnz_a, h->d_a2l.p, d_nzval, h->d_L.p);
-        MIPM_CHECK_LAUNCH(h);
+    {
+        PROF_BEGIN(0);
+        MIPM_CUDA(h, cudaMemsetAsync(h->d_L.p, 0, (size_t)std::max<int64_t>(S.nnz_l, 1) * sizeof(double), st));
+        MIPM_CUDA(h, cudaMemsetAsync(h->d_U.p, 0, (size_t)std::max<int64_t>(S.update_doubles, 1) * sizeof(double), st));
+        MIPM_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, 4 * sizeof(int), st));
+        if (S.nnz_a > 0) {
+            k_scatter_a<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.nnz_a, h->d_a2l.p, d_nzval, h->d_L.p);
+            MIPM_CHECK_LAUNCH(h);
+        }
+        PROF_END();
     }
     // pivot tolerance for LDL^T: relative to nothing we can see cheaply -> absolute, tiny
     const double piv_tol = 1e-13;
@@ -631,27 +655,37 @@ static int factorize_t(Handle *h, const double *d_nzval)
     for (int l = 0; l < S.n_levels; ++l) {
         const LevelInfo &li = h->levels[(size_t)l];
         if (li.n_ea_tasks > 0) {
+            PROF_BEGIN(1);
             k_extend_add<<<(unsigned)li.n_ea_tasks, 256, 0, st>>>(sched + li.off_ea_tasks, h->d_sn_ptr.p, h->d_row_ptr.p,
                                                                 h->d_lp.p, h->d_up.p, h->d_child_ptr.p, h->d_child_idx.p,
                                                                 h->d_rel_idx.p, h->d_L.p, h->d_U.p);
             MIPM_CHECK_LAUNCH(h);
+            PROF_END();
         }
         for (; si < h->steps.size() && h->steps[si].level == l; ++si) {
             const FactorStep &fs = h->steps[si];
+            {
+            PROF_BEGIN(2);
             k_factor_diag<LDL><<<(unsigned)fs.n_active, 256, 0, st>>>(sched + fs.off_sn, fs.jb, h->d_sn_ptr.p, h->d_row_ptr.p,
                                                                      h->d_lp.p, h->d_L.p, h->d_info.p, piv_tol);
             MIPM_CHECK_LAUNCH(h);
+            PROF_END();
+            }
             if (fs.n_trsm > 0) {
+                PROF_BEGIN(3);
                 k_trsm<LDL><<<(unsigned)fs.n_trsm, TRSM_ROWS, 0, st>>>(sched + fs.off_sn, sched + fs.off_trsm, fs.n_active, fs.jb,
                                                                       h->d_sn_ptr.p, h->d_row_ptr.p, h->d_lp.p, h->d_wp.p,
                                                                       h->d_L.p, h->d_W.p);
                 MIPM_CHECK_LAUNCH(h);
+                PROF_END();
             }
             if (fs.n_upd > 0) {
+                PROF_BEGIN(4);
                 k_update<LDL><<<(unsigned)fs.n_upd, 128, 0, st>>>(sched + fs.off_sn, sched + fs.off_upd, fs.n_active, fs.jb,
                                                                  h->d_sn_ptr.p, h->d_row_ptr.p, h->d_lp.p, h->d_up.p, h->d_wp.p,
                                                                  h->d_L.p, h->d_U.p, h->d_W.p);
                 MIPM_CHECK_LAUNCH(h);
+                PROF_END();
             }
         }
     }
@@ -720,6 +754,45 @@ int ls_solve_impl(Handle *h, double *d_x, int ir_steps)
 }
 
 }  // namespace mipm
+
+extern "C" int mipm_ls_factorize_profile(mipm_handle hh, const double *d_nzval, double *ms, double *work, int64_t *launches)
+{
+    using namespace mipm;
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_ls) return fail(h, MIPM_ERR_STATE, "mipm_ls_analyze has not been called");
+    if (!ms || !work || !launches) return fail(h, MIPM_ERR_ARG, "null argument");
+    const LsSymbolic &S = h->sym;
+    FactorProfile prof;
+    g_prof = &prof;
+    int rc = ls_factorize_impl(h, d_nzval);
+    g_prof = nullptr;
+    if (rc != MIPM_OK) return rc;
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < 5; ++c) { ms[c] = 0.0; work[c] = 0.0; launches[c] = 0; }
+    for (auto &r : prof.recs) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[r.cls] += t;
+        launches[r.cls] += 1;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    // algorithmic work per class: bytes for 0 (zero-fill + scatter) and 1 (extend-add), flops for 2..4
+    work[0] = 8.0 * (double)(S.nnz_l + S.update_doubles) + 24.0 * (double)S.nnz_a;
+    for (int s = 0; s < S.ns; ++s) {
+        double k = S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s];
+        double r = (double)(S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s]);
+        if (S.sn_parent[(size_t)s] >= 0) work[1] += 24.0 * r * (r + 1) / 2 + 4.0 * r;
+        for (double jb = 0; jb < k; jb += NB) {
+            double nb = std::min<double>(NB, k - jb), T = k + r - jb - nb;
+            work[2] += nb * nb * nb / 3.0;
+            work[3] += nb * nb * T;
+            work[4] += nb * T * (T + 1);
+        }
+    }
+    return MIPM_OK;
+}
 
 extern "C" int mipm_bench_syrk(mipm_handle hh, int64_t n, int64_t k, double *d_C, int64_t ldc, const double *d_X, int64_t ldx)
 {

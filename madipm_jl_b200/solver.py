@@ -636,21 +636,26 @@ class MPCSolver:
             alpha_p=self.alpha_p, alpha_d=self.alpha_d, del_w=self.del_w,
             dnorm=0.0 if self.k == 0 else self.dnorm))
 
+    def mpc_iteration(self):
+        """One pass of the loop body of mpc! (src/solver.jl:333-359). Returns False when done."""
+        self.update_termination_criteria()
+        self._record()
+        if self.status != REGULAR:
+            return False
+        self.update_regularization()
+        self.factorize_regularized_system()
+        self.prediction_step()
+        self.mehrotra_correction_direction()
+        self.gondzio_correction_direction()
+        self.update_step_size()
+        self.apply_step()
+        self.evaluate_model()
+        return True
+
     def mpc(self):
         """src/solver.jl:332-360."""
-        while True:
-            self.update_termination_criteria()
-            self._record()
-            if self.status != REGULAR:
-                return
-            self.update_regularization()
-            self.factorize_regularized_system()
-            self.prediction_step()
-            self.mehrotra_correction_direction()
-            self.gondzio_correction_direction()
-            self.update_step_size()
-            self.apply_step()
-            self.evaluate_model()
+        while self.mpc_iteration():
+            pass
 
     def solve(self):
         """solve!(solver): src/solver.jl:362-418."""

@@ -59,6 +59,10 @@ class Options:
     tol_linear_solve: float = 1e-8
     check_residual: bool = False
     ordering: str = "rcm"               # fill-reducing ordering for "ldl": "rcm" | "natural"
+    # False: literal O(m^2) build_normal_system (src/utils.jl:209-274). True: same canonical pattern
+    # from a sparse product (needed at m >= 1e5 where the literal scan takes hours; equality of
+    # the two is tested at small sizes)
+    fast_symbolic: bool = False
 
 
 @dataclass
@@ -215,7 +219,13 @@ class MPCOracle:
             self.A_csr_map = Ax.astype(np.int64)
             self.AT_p, self.AT_j = Ap, Aj
             self.AT_x = np.zeros(len(Aj))
-            self.C_p, self.C_j = sparse_ref.build_normal_system(m, n, Ap, Aj)
+            if self.opt.fast_symbolic:
+                pat = sp.csr_matrix((np.ones(len(Aj)), Aj, Ap), shape=(m, n))
+                low = sp.tril(pat @ pat.T).tocsc()
+                low.sort_indices()
+                self.C_p, self.C_j = low.indptr.astype(np.int32), low.indices.astype(np.int32)
+            else:
+                self.C_p, self.C_j = sparse_ref.build_normal_system(m, n, Ap, Aj)
             self.C_x = np.zeros(len(self.C_j))
             self.ls = _LinearSolver(m, self.C_p, self.C_j, self.opt.linear_solver, self.opt.ordering)
         elif self.opt.kkt_system == "K2":
@@ -739,29 +749,34 @@ class MPCOracle:
             dnorm=0.0 if self.k == 0 else float(np.linalg.norm(self.d[: self.n], np.inf)),
         ))
 
+    def mpc_iteration(self):
+        """One pass of the loop body of mpc! (src/solver.jl:333-359). Returns False when done."""
+        self.update_termination_criteria()
+        self._record()
+        if self.status != REGULAR:
+            return False
+        self._update_regularization()
+        self._factorize_regularized_system()
+        # prediction_step! (solver.jl:230-237)
+        self._set_predictive_rhs()
+        self._solve_system()
+        ap_aff, ad_aff = self._get_fraction_to_boundary_step(1.0)
+        mu_affine = self._get_affine_complementarity_measure(ap_aff, ad_aff)
+        self._get_correction()
+        self.mu_curr = self._update_barrier(mu_affine)
+        # mehrotra_correction_direction! (solver.jl:239-243)
+        self._set_correction_rhs(self.mu)
+        self._solve_system()
+        self._gondzio()
+        self._update_step()
+        self._apply_step()
+        self._evaluate_model()
+        return True
+
     def mpc(self):
         """src/solver.jl:332-360."""
-        while True:
-            self.update_termination_criteria()
-            self._record()
-            if self.status != REGULAR:
-                return
-            self._update_regularization()
-            self._factorize_regularized_system()
-            # prediction_step! (solver.jl:230-237)
-            self._set_predictive_rhs()
-            self._solve_system()
-            ap_aff, ad_aff = self._get_fraction_to_boundary_step(1.0)
-            mu_affine = self._get_affine_complementarity_measure(ap_aff, ad_aff)
-            self._get_correction()
-            self.mu_curr = self._update_barrier(mu_affine)
-            # mehrotra_correction_direction! (solver.jl:239-243)
-            self._set_correction_rhs(self.mu)
-            self._solve_system()
-            self._gondzio()
-            self._update_step()
-            self._apply_step()
-            self._evaluate_model()
+        while self.mpc_iteration():
+            pass
 
     def solve(self):
         """src/solver.jl:362-418."""
