@@ -40,24 +40,6 @@ struct DBuf {
     }
 };
 
-// One (level, block-step) of the numeric factorization schedule.
-struct FactorStep {
-    int32_t level, jb;
-    int32_t n_active;       // fronts of this level with more than jb columns
-    int64_t off_sn;         // offsets into the schedule array (int32 units)
-    int64_t off_trsm;       // prefix of trsm CTA counts   (n_active + 1)
-    int64_t off_upd;        // prefix of update CTA counts (n_active + 1)
-    int64_t n_trsm, n_upd;
-};
-struct LevelInfo {
-    int64_t off_parents;    // fronts of this level that have children (for extend-add)
-    int32_t n_parents;
-    int64_t off_ea_tasks;   // extend-add tasks (parent, col0, col1) triples
-    int64_t n_ea_tasks;
-    int64_t off_all;        // all fronts of this level
-    int32_t n_all;
-};
-
 struct Handle {
     int device = -1;
     bool host_only = false;
@@ -87,10 +69,13 @@ struct Handle {
     // ---- linear solver
     LsSymbolic sym;
     bool has_ls = false, factorized = false;
-    int NB = 64;
-    std::vector<FactorStep> steps;
-    std::vector<LevelInfo> levels;
-    DBuf<int32_t> d_sched;           // schedule arrays
+    int n_phases = 0, grid_factor = 0, grid_solve = 0;
+    DBuf<int32_t> d_sched;           // schedule arrays (front lists, task prefixes, extend-add triples)
+    DBuf<int64_t> d_phases, d_lvl, d_dinv_off;
+    struct FI64 { char b[64]; };
+    DBuf<FI64> d_finfo;              // FrontInfo records (64 bytes each, see factor.cu)
+    DBuf<double> d_Dinv;             // inverted 64 x 64 diagonal blocks
+    DBuf<unsigned long long> d_phase_ns;
     DBuf<int32_t> d_sn_ptr, d_sn_parent, d_row_idx, d_rel_idx, d_perm, d_child_idx, d_full_col;
     DBuf<int64_t> d_row_ptr, d_lp, d_up, d_child_ptr, d_a2l, d_full_ptr, d_full_val, d_wp;
     DBuf<double> d_L, d_U, d_W, d_xp, d_uvec, d_b, d_r;

@@ -6,16 +6,28 @@
 // Data layout (all FP64, column-major):
 //   panel of supernode s : (k+r) x k at L + lp[s], ld = k+r   (k columns, r rows below)
 //   update matrix of s   : r x r     at U + up[s], ld = r      (lower triangle used)
+//   inverse diagonal blocks: 64 x 64 at Dinv + 4096*(dinv_off[s] + jb/64)  (inv(L11 block), lower)
 //   LDL^T only: W + wp[s], (k+r) x NB scratch holding the unscaled panel block L*D
-// Schedule: fronts are grouped by elimination-tree level; inside a level the dense partial
-// factorization is blocked right-looking with block width NB=64; every (level, block step)
-// is three batched launches (diagonal block, panel TRSM, trailing DMMA update) over all
-// fronts of the level that still have columns left.
+//
+// Execution model: ONE persistent cooperative kernel per factorization and ONE per solve.
+// The schedule is a list of phases (extend-add | diagonal block | panel TRSM | trailing update
+// for every (elimination-tree level, 64-column block step)); CTAs stride over the tasks of a
+// phase and meet at a grid-wide barrier. A level-by-level multi-launch version of the same
+// schedule spent most of its time in ~60 us launch/latency floors (profiles/launches_r01_baseline.csv).
+// The dense work runs on the FP64 tensor pipe (mma.sync m8n8k4 -> DMMA): both the trailing
+// update C -= X Y' and the panel solve X = R inv(L11)' are 64x64 tile GEMMs staged k-major in
+// shared memory.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
+
+namespace cg = cooperative_groups;
 
 namespace mipm {
 
@@ -23,27 +35,55 @@ namespace {
 
 constexpr int NB = 64;          // block width of the dense partial factorization
 constexpr int LDS = 65;         // smem leading dimension for NB x NB blocks (odd: conflict-free rows)
-constexpr int TRSM_ROWS = 128;  // rows per TRSM CTA
-constexpr int EA_COLS = 32;     // parent-front columns per extend-add CTA
-constexpr int TILE = 64;        // update tile
-constexpr int KC = 32;          // K chunk staged in shared memory
-constexpr int XS = 68;          // smem row stride of the staged operands (68 % 16 == 4: conflict-free DMMA loads)
+constexpr int EA_COLS = 32;     // parent-front columns per extend-add task
+constexpr int TILE = 64;        // GEMM tile
+constexpr int XS = 68;          // smem row stride of staged operands (68 % 16 == 4: conflict-free DMMA loads)
+constexpr int SMEM_DOUBLES = 2 * TILE * XS;
+constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;   // 69,632 B
+enum { PH_EA = 0, PH_DIAG = 1, PH_TRSM = 2, PH_UPDATE = 3 };
 
-struct Front {
-    int k, r, N;
+// Everything a task needs to know about a front, in one 64-byte record (4 x 16-byte loads)
+// instead of six dependent index lookups.
+struct __align__(16) FrontInfo {
+    int32_t k, r, c0, nchild;
     int64_t lp, up;
+    int64_t wp, dinv;
+    int64_t rowp, childp;
 };
 
-__device__ __forceinline__ Front get_front(int s, const int32_t *sn_ptr, const int64_t *row_ptr,
-                                           const int64_t *lp, const int64_t *up)
+static_assert(sizeof(FrontInfo) == 64, "FrontInfo must match Handle::FI64");
+
+struct FactorParams {
+    const FrontInfo *fi;
+    const int32_t *child_idx, *rel_idx;
+    const int32_t *sched;
+    const int64_t *phases;      // 8 x int64 per phase: type, jb, n_tasks, off_tasks, 0, 0, 0, 0
+    int n_phases;
+    double *L, *U, *W, *Dinv;
+    int *info;
+    unsigned long long *phase_ns;   // device-side time of every phase (one entry per phase)
+    double piv_tol;
+};
+
+struct SolveParams {
+    const FrontInfo *fi;
+    const int32_t *child_idx, *rel_idx, *row_idx, *perm;
+    const int32_t *sched;
+    const int64_t *lvl;         // 2 x int64 per level: off_all, n_all
+    int n_levels;
+    int64_t n, n_u;
+    const double *L, *Dinv;
+    double *xp, *uvec;
+    const double *b_in;         // gathered through perm at the start
+    double *x_out;              // scattered through perm at the end
+    int accumulate;             // x_out[perm] += xp instead of =
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
 {
-    Front f;
-    f.k = sn_ptr[s + 1] - sn_ptr[s];
-    f.r = (int)(row_ptr[s + 1] - row_ptr[s]);
-    f.N = f.k + f.r;
-    f.lp = lp[s];
-    f.up = up[s];
-    return f;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 // largest i in [0, n) with prefix[i] <= x  (prefix[0] = 0, prefix[n] = total > x)
@@ -64,7 +104,52 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
                  : "d"(a), "d"(b));
 }
 
-// ------------------------------------------------------------------ assembly of the fronts
+// Stage a (nrows x ncols) column-major block into smem k-major: dst[kk * XS + rr], zero padded to 64 x 64.
+__device__ __forceinline__ void stage_tile(double *dst, const double *__restrict__ src, int64_t ld, int nrows, int ncols)
+{
+#pragma unroll
+    for (int i = 0; i < (TILE * TILE) / 256; ++i) {
+        int idx = threadIdx.x + i * 256;
+        int rr = idx & 63, kk = idx >> 6;
+        dst[kk * XS + rr] = (rr < nrows && kk < ncols) ? src[(int64_t)kk * ld + rr] : 0.0;
+    }
+}
+
+// acc(64x64) += Xs' * Ys over K: 8 warps as 2 (rows) x 4 (cols), each 32 x 16 = 4 x 2 DMMA fragments.
+__device__ __forceinline__ void mma_64x64(double (&acc)[4][2][2], const double *Xs, const double *Ys, int K)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, l3 = lane & 3;
+    const double *xa = Xs + l3 * XS + wm * 32 + g;
+    const double *yb = Ys + l3 * XS + wn * 16 + g;
+    for (int kk = 0; kk < K; kk += 4) {
+        double a[4], b[2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[mi] = xa[kk * XS + mi * 8];
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) b[ni] = yb[kk * XS + ni * 8];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+}
+
+// Visit the 16 accumulator entries of this thread with their (row, col) inside the 64 x 64 tile.
+template <typename F>
+__device__ __forceinline__ void acc_foreach(const double (&acc)[4][2][2], F f)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, l3 = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) f(wm * 32 + mi * 8 + g, wn * 16 + ni * 8 + l3 * 2 + e, acc[mi][ni][e]);
+}
+
+// ------------------------------------------------------------------ tasks of the factorization
 __global__ void __launch_bounds__(256)
 k_scatter_a(int64_t nnz, const int64_t *__restrict__ a2l, const double *__restrict__ Ax, double *__restrict__ L)
 {
@@ -75,314 +160,317 @@ k_scatter_a(int64_t nnz, const int64_t *__restrict__ a2l, const double *__restri
 // Extend-add: task = (parent s, parent-front columns [q0, q1)). The CTA walks the children of
 // s in a fixed order and adds the part of each child's update matrix that lands in its column
 // range, so every destination entry is owned by exactly one CTA -> deterministic sums.
-__global__ void __launch_bounds__(256)
-k_extend_add(const int32_t *__restrict__ tasks, const int32_t *__restrict__ sn_ptr,
-             const int64_t *__restrict__ row_ptr, const int64_t *__restrict__ lp, const int64_t *__restrict__ up,
-             const int64_t *__restrict__ child_ptr, const int32_t *__restrict__ child_idx,
-             const int32_t *__restrict__ rel_idx, double *__restrict__ L, double *__restrict__ U)
+__device__ void task_extend_add(const FactorParams &p, const int32_t *tasks, int task)
 {
-    const int s = tasks[3 * (int64_t)blockIdx.x], q0 = tasks[3 * (int64_t)blockIdx.x + 1], q1 = tasks[3 * (int64_t)blockIdx.x + 2];
-    const Front f = get_front(s, sn_ptr, row_ptr, lp, up);
-    double *P = L + f.lp;
-    double *Us = U + f.up;
-    for (int64_t ci = child_ptr[s]; ci < child_ptr[s + 1]; ++ci) {
-        const int c = child_idx[ci];
-        const int rc = (int)(row_ptr[c + 1] - row_ptr[c]);
-        const int32_t *rel = rel_idx + row_ptr[c];
-        const double *Uc = U + up[c];
-        // first b with rel[b] >= q0 / q1 (rel is strictly increasing)
-        int b0, b1;
-        {
-            int lo = 0, hi = rc;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (rel[mid] < q0) lo = mid + 1; else hi = mid; }
-            b0 = lo;
-            hi = rc;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (rel[mid] < q1) lo = mid + 1; else hi = mid; }
-            b1 = lo;
-        }
-        for (int b = b0; b < b1; ++b) {
+    // task record: (parent s, q0, q1, offset of the per-child [b0, b1) ranges computed on the host)
+    const int4 t4 = *reinterpret_cast<const int4 *>(tasks + 4 * (int64_t)task);
+    const int s = t4.x;
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, r = f.r, N = f.k + f.r;
+    double *P = p.L + f.lp;
+    double *Us = p.U + f.up;
+    const int32_t *ranges = p.sched + t4.w;
+    for (int ci = 0; ci < f.nchild; ++ci) {
+        const int b0 = ranges[2 * ci], b1 = ranges[2 * ci + 1];
+        if (b0 >= b1) continue;                      // uniform across the CTA
+        const int c = p.child_idx[f.childp + ci];
+        const FrontInfo fc = p.fi[c];
+        const int rc = fc.r;
+        const int32_t *rel = p.rel_idx + fc.rowp;
+        const double *Uc = p.U + fc.up;
+        // one warp per child column (8 columns in flight), lanes over the rows of that column
+        for (int b = b0 + (threadIdx.x >> 5); b < b1; b += 8) {
             const int tb = rel[b];
             const double *src = Uc + (int64_t)b * rc;
-            if (tb < f.k) {
-                double *dst = P + (int64_t)tb * f.N;
-                for (int a = b + threadIdx.x; a < rc; a += blockDim.x) dst[rel[a]] += src[a];
-            } else {
-                double *dst = Us + (int64_t)(tb - f.k) * f.r - f.k;
-                for (int a = b + threadIdx.x; a < rc; a += blockDim.x) dst[rel[a]] += src[a];
-            }
+            double *dst = (tb < k) ? (P + (int64_t)tb * N) : (Us + (int64_t)(tb - k) * r - k);
+            for (int a = b + (threadIdx.x & 31); a < rc; a += 32) dst[rel[a]] += src[a];
         }
         __syncthreads();
     }
 }
 
-// ------------------------------------------------------------------ diagonal block factorization
-// One CTA per active front: factor the nb x nb diagonal block at column jb in shared memory.
-// Cholesky: L11 L11' (a non-positive pivot sets info[0] and is replaced by 1 so the run stays
-// finite; the host then retries with more regularization like src/linear_solver.jl:6-17).
+// Diagonal block: factor the nb x nb block at column jb (register-tiled right-looking, one
+// barrier per column), then invert the triangular factor; both are written out.
+// Cholesky: a non-positive pivot sets info[0] and is replaced by 1 so the run stays finite (the
+// host then retries with more regularization like src/linear_solver.jl:6-17).
 // LDL^T: unit-lower L11 with D on the diagonal; |pivot| < piv_tol is replaced by +-piv_tol.
 template <bool LDL>
-__global__ void __launch_bounds__(256)
-k_factor_diag(const int32_t *__restrict__ act, int jb, const int32_t *__restrict__ sn_ptr,
-              const int64_t *__restrict__ row_ptr, const int64_t *__restrict__ lp, double *__restrict__ L,
-              int *__restrict__ info, double piv_tol)
+__device__ void task_diag(const FactorParams &p, int s, int jb, double *smem)
 {
-    __shared__ double S[NB * LDS];
-    __shared__ double diag[NB];
-    const int s = act[blockIdx.x];
-    const int k = sn_ptr[s + 1] - sn_ptr[s];
-    const int N = k + (int)(row_ptr[s + 1] - row_ptr[s]);
+    double *S = smem;                      // L11, col-major, ld LDS
+    double *colbuf = smem + NB * LDS;      // 2 x 64 (fits below Sinv: 4160 + 128 + 64 <= 4352)
+    double *invd = colbuf + 2 * NB;        // reciprocals of the pivots of L11 (1/L_jj, or 1/D_j for LDL^T)
+    double *Sinv = smem + TILE * XS;       // inv(L11), col-major, ld LDS
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, N = f.k + f.r;
     const int nb = min(NB, k - jb);
-    double *P = L + lp[s] + (int64_t)jb * N + jb;
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < nb * nb; idx += 256) {
-        int rr = idx % nb, cc = idx / nb;
-        if (rr >= cc) S[cc * LDS + rr] = P[(int64_t)cc * N + rr];
-    }
-    __syncthreads();
+    double *P = p.L + f.lp + (int64_t)jb * N + jb;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double a[4][4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int rr = 4 * ty + i, cc = 4 * tx + jj;
+            a[i][jj] = (rr < nb && cc < nb && rr >= cc) ? P[(int64_t)cc * N + rr] : ((rr == cc) ? 1.0 : 0.0);
+        }
     int nbad = 0, ntiny = 0;
-    for (int j = 0; j < nb; ++j) {
-        double d = S[j * LDS + j];
-        double scale, dmul;
-        if (!LDL) {
-            if (!(d > 0.0) || !(d < 1.0e300)) { nbad++; d = 1.0; }
-            double ljj = sqrt(d);
-            scale = 1.0 / ljj;
-            dmul = 1.0;
-            if (tid == 0) diag[j] = ljj;
-        } else {
-            if (!(fabs(d) <= 1.0e300)) { nbad++; d = 1.0; }            // NaN / Inf
-            else if (fabs(d) < piv_tol) { ntiny++; d = (d < 0.0) ? -piv_tol : piv_tol; }
-            scale = 1.0 / d;
-            dmul = d;
-            if (tid == 0) diag[j] = d;
-        }
-        for (int rr = j + 1 + tid; rr < nb; rr += 256) S[j * LDS + rr] *= scale;
-        __syncthreads();
-        const int w = nb - j - 1;
-        for (int idx = tid; idx < w * w; idx += 256) {
-            int rr = j + 1 + idx % w, cc = j + 1 + idx / w;
-            if (rr >= cc) S[cc * LDS + rr] -= S[j * LDS + rr] * (S[j * LDS + cc] * dmul);
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < nb * nb; idx += 256) {
-        int rr = idx % nb, cc = idx / nb;
-        if (rr > cc) P[(int64_t)cc * N + rr] = S[cc * LDS + rr];
-        else if (rr == cc) P[(int64_t)cc * N + rr] = diag[cc];
-    }
-    if (tid == 0) {
-        if (nbad) atomicMax(&info[0], 1);
-        if (ntiny) atomicAdd(&info[2], ntiny);
-        if (LDL) {
-            int neg = 0;
-            for (int j = 0; j < nb; ++j) neg += (diag[j] < 0.0);
-            if (neg) atomicAdd(&info[1], neg);
-        }
-    }
-}
-
-// ------------------------------------------------------------------ panel TRSM
-// Rows below the diagonal block: X = R * L11^-T (Cholesky) or X = R * L11^-T, Y = X * D^-1 (LDL^T).
-// One thread per row, the row lives in registers, L11 is broadcast from shared memory.
-template <bool LDL>
-__global__ void __launch_bounds__(TRSM_ROWS)
-k_trsm(const int32_t *__restrict__ act, const int32_t *__restrict__ prefix, int n_active, int jb,
-       const int32_t *__restrict__ sn_ptr, const int64_t *__restrict__ row_ptr, const int64_t *__restrict__ lp,
-       const int64_t *__restrict__ wp, double *__restrict__ L, double *__restrict__ W)
-{
-    __shared__ double S[NB * LDS];
-    const int fi = find_segment(prefix, n_active, (int)blockIdx.x);
-    const int lc = (int)blockIdx.x - prefix[fi];
-    const int s = act[fi];
-    const int k = sn_ptr[s + 1] - sn_ptr[s];
-    const int N = k + (int)(row_ptr[s + 1] - row_ptr[s]);
-    const int nb = min(NB, k - jb);
-    const int j1 = jb + nb;
-    double *P = L + lp[s];
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
-        int rr = idx % NB, cc = idx / NB;
-        double v = (rr == cc) ? 1.0 : 0.0;
-        if (rr < nb && cc < nb && rr >= cc) v = P[(int64_t)(jb + cc) * N + jb + rr];
-        S[cc * LDS + rr] = v;
-    }
-    __syncthreads();
-    const int row = j1 + lc * TRSM_ROWS + tid;
-    if (row >= N) return;
-    double x[NB];
+    for (int j4 = 0; j4 < NB / 4; ++j4) {
 #pragma unroll
-    for (int c = 0; c < NB; ++c) x[c] = (c < nb) ? P[(int64_t)(jb + c) * N + row] : 0.0;
+        for (int js = 0; js < 4; ++js) {
+            const int j = 4 * j4 + js;
+            double *cb = colbuf + (j & 1) * NB;
+            if (tx == j4) {
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        if (!LDL) x[c] = x[c] / S[c * LDS + c];
-#pragma unroll
-        for (int c2 = c + 1; c2 < NB; ++c2) x[c2] = fma(-x[c], S[c * LDS + c2], x[c2]);
-    }
-    if (!LDL) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-            if (c < nb) P[(int64_t)(jb + c) * N + row] = x[c];
-    } else {
-        double *Ws = W + wp[s];
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-            if (c < nb) {
-                Ws[(int64_t)c * N + row] = x[c];
-                P[(int64_t)(jb + c) * N + row] = x[c] / S[c * LDS + c];
+                for (int i = 0; i < 4; ++i) cb[4 * ty + i] = a[i][js];
             }
-    }
-}
-
-// ------------------------------------------------------------------ trailing update on FP64 tensor cores
-// C(64x64 tile) -= X(rows, 0:nb) * Y(cols, 0:nb)'.  4 warps, each a 32x32 sub-tile made of 4x4
-// DMMA m8n8k4 fragments; operands staged k-major in shared memory ([k][row], stride 68) so
-// the staging copy is a straight coalesced column copy and the fragment loads are conflict-free.
-// Only entries with (global row) >= (global col) are written.
-__device__ __forceinline__ void tile_update(const double *__restrict__ X, int64_t ldx, const double *__restrict__ Y,
-                                            int64_t ldy, int nb, int nrow, int ncol, double *__restrict__ C,
-                                            int64_t ldc, int grow0, int gcol0, double (*Xs)[XS], double (*Ys)[XS])
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1;
-    const int g = lane >> 2, l3 = lane & 3;
-    double acc[4][4][2];
+            __syncthreads();
+            double d = cb[j];
+            double scale, dval;
+            if (!LDL) {
+                if (!(d > 0.0) || !(d < 1.0e300)) { nbad++; d = 1.0; }
+                // sqrt and its reciprocal from one rsqrt + one Newton step each (the IEEE sqrt and
+                // divide sequences are ~400 cycles on the critical path of every column)
+                double rs = rsqrt(d);
+                double sq = d * rs;
+                sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);
+                rs = fma(fma(-sq, rs, 1.0), rs, rs);
+                dval = sq;
+                scale = rs;
+            } else {
+                if (!(fabs(d) <= 1.0e300)) { nbad++; d = 1.0; }
+                else if (fabs(d) < p.piv_tol) { ntiny++; d = (d < 0.0) ? -p.piv_tol : p.piv_tol; }
+                dval = d;
+                scale = __drcp_rn(d);
+            }
+            if (tid == 0) invd[j] = scale;
+            double lr[4], lc[4];
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+            for (int i = 0; i < 4; ++i) lr[i] = cb[4 * ty + i] * scale;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    for (int k0 = 0; k0 < nb; k0 += KC) {
+            for (int jj = 0; jj < 4; ++jj) lc[jj] = LDL ? cb[4 * tx + jj] : cb[4 * tx + jj] * scale;
 #pragma unroll
-        for (int i = 0; i < (KC * TILE) / 128; ++i) {
-            int idx = tid + i * 128;
-            int rr = idx % TILE, kk = idx / TILE;
-            bool kin = (k0 + kk) < nb;
-            Xs[kk][rr] = (kin && rr < nrow) ? X[(int64_t)(k0 + kk) * ldx + rr] : 0.0;
-            Ys[kk][rr] = (kin && rr < ncol) ? Y[(int64_t)(k0 + kk) * ldy + rr] : 0.0;
-        }
-        __syncthreads();
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-            double a[4], b[4];
+                for (int jj = 0; jj < 4; ++jj)
+                    if (4 * ty + i > j && 4 * tx + jj > j) a[i][jj] = fma(-lr[i], lc[jj], a[i][jj]);
+            if (tx == j4) {
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = Xs[kk + l3][wm * 32 + mi * 8 + g];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = Ys[kk + l3][wn * 32 + ni * 8 + g];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                int rr = wm * 32 + mi * 8 + g;
-                int cc = wn * 32 + ni * 8 + l3 * 2 + e;
-                if (rr < nrow && cc < ncol && (grow0 + rr) >= (gcol0 + cc)) {
-                    double *p = C + (int64_t)cc * ldc + rr;
-                    *p -= acc[mi][ni][e];
+                for (int i = 0; i < 4; ++i) {
+                    int rr = 4 * ty + i;
+                    if (rr > j) a[i][js] = lr[i];
+                    else if (rr == j) a[i][js] = dval;
                 }
             }
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int rr = 4 * ty + i, cc = 4 * tx + jj;
+            if (rr >= cc) {
+                S[cc * LDS + rr] = a[i][jj];
+                if (rr < nb && cc < nb) P[(int64_t)cc * N + rr] = a[i][jj];
+            }
+        }
+    __syncthreads();
+    // inverse of the triangular factor: column c by the 4 threads (c, q), rows i = 4t + q
+    {
+        const int c = tid >> 2, q = tid & 3, lane = tid & 31;
+        double res[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) res[t] = (4 * t + q == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int rr = 0; rr < NB; ++rr) {
+            double xr = __shfl_sync(0xffffffffu, res[rr >> 2], (lane & ~3) | (rr & 3));
+            if (!LDL) xr = xr * invd[rr];
+            if (q == (rr & 3)) Sinv[c * LDS + rr] = xr;
+#pragma unroll
+            for (int t = rr >> 2; t < 16; ++t)
+                if (4 * t + q > rr) res[t] = fma(-S[rr * LDS + 4 * t + q], xr, res[t]);
+        }
+    }
+    __syncthreads();
+    double *Dv = p.Dinv + (f.dinv + (jb >> 6)) * (int64_t)(NB * NB);
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        int rr = idx & 63, cc = idx >> 6;
+        Dv[idx] = (rr >= cc) ? Sinv[cc * LDS + rr] : 0.0;
+    }
+    if (LDL && tid < nb && S[tid * LDS + tid] < 0.0) atomicAdd(&p.info[1], 1);
+    if (tid == 0) {
+        if (nbad) atomicMax(&p.info[0], 1);
+        if (ntiny) atomicAdd(&p.info[2], ntiny);
+    }
 }
 
+// Panel TRSM as a tile GEMM with the inverted diagonal block: X = R * inv(L11)'  (64 rows per task).
 template <bool LDL>
-__global__ void __launch_bounds__(128)
-k_update(const int32_t *__restrict__ act, const int32_t *__restrict__ prefix, int n_active, int jb,
-         const int32_t *__restrict__ sn_ptr, const int64_t *__restrict__ row_ptr, const int64_t *__restrict__ lp,
-         const int64_t *__restrict__ up, const int64_t *__restrict__ wp, double *__restrict__ L,
-         double *__restrict__ U, const double *__restrict__ W)
+__device__ void task_trsm(const FactorParams &p, int s, int lc, int jb, double *smem)
 {
-    __shared__ double Xs[KC][XS];
-    __shared__ double Ys[KC][XS];
-    const int fi = find_segment(prefix, n_active, (int)blockIdx.x);
-    const int lt = (int)blockIdx.x - prefix[fi];
-    const int s = act[fi];
-    const Front f = get_front(s, sn_ptr, row_ptr, lp, up);
-    const int nb = min(NB, f.k - jb);
+    double *Xs = smem, *Ys = smem + TILE * XS;
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, N = f.k + f.r;
+    const int nb = min(NB, k - jb);
+    const int row0 = jb + nb + lc * TILE;
+    const int nrow = min(TILE, N - row0);
+    double *P = p.L + f.lp;
+    double *R = P + (int64_t)jb * N + row0;
+    const double *Dv = p.Dinv + (f.dinv + (jb >> 6)) * (int64_t)(NB * NB);
+    stage_tile(Xs, R, N, nrow, nb);
+    stage_tile(Ys, Dv, NB, NB, nb);
+    __syncthreads();
+    double acc[4][2][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    mma_64x64(acc, Xs, Ys, (nb + 3) & ~3);
+    double *Ws = LDL ? (p.W + f.wp + row0) : nullptr;
+    acc_foreach(acc, [&](int rr, int cc, double val) {
+        if (rr < nrow && cc < nb) {
+            if (!LDL) {
+                R[(int64_t)cc * N + rr] = val;
+            } else {
+                Ws[(int64_t)cc * N + rr] = val;
+                R[(int64_t)cc * N + rr] = val / P[(int64_t)(jb + cc) * N + jb + cc];
+            }
+        }
+    });
+}
+
+// Trailing update on the FP64 tensor pipe: C(tile) -= X(rows, 0:nb) * Y(cols, 0:nb)'.
+template <bool LDL>
+__device__ void task_update(const FactorParams &p, int s, int lt, int jb, double *smem)
+{
+    double *Xs = smem, *Ys = smem + TILE * XS;
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, r = f.r;
+    const int N = k + r;
+    const int nb = min(NB, k - jb);
     const int j1 = jb + nb;
-    const int nt1 = (f.k > j1) ? (f.k - j1 + TILE - 1) / TILE : 0;
+    const int nt1 = (k > j1) ? (k - j1 + TILE - 1) / TILE : 0;
     int tr = (int)((sqrt(8.0 * (double)lt + 1.0) - 1.0) * 0.5);
     while (tr * (tr + 1) / 2 > lt) --tr;
     while ((tr + 1) * (tr + 2) / 2 <= lt) ++tr;
     const int tc = lt - tr * (tr + 1) / 2;
     int row0, rend, col0, cend;
-    if (tr < nt1) { row0 = j1 + TILE * tr; rend = min(row0 + TILE, f.k); }
-    else { row0 = f.k + TILE * (tr - nt1); rend = min(row0 + TILE, f.N); }
-    if (tc < nt1) { col0 = j1 + TILE * tc; cend = min(col0 + TILE, f.k); }
-    else { col0 = f.k + TILE * (tc - nt1); cend = min(col0 + TILE, f.N); }
-    double *P = L + f.lp;
-    const double *Y = P + (int64_t)jb * f.N + col0;
-    const double *X = LDL ? (W + wp[s] + row0) : (P + (int64_t)jb * f.N + row0);
+    if (tr < nt1) { row0 = j1 + TILE * tr; rend = min(row0 + TILE, k); }
+    else { row0 = k + TILE * (tr - nt1); rend = min(row0 + TILE, N); }
+    if (tc < nt1) { col0 = j1 + TILE * tc; cend = min(col0 + TILE, k); }
+    else { col0 = k + TILE * (tc - nt1); cend = min(col0 + TILE, N); }
+    const int nrow = rend - row0, ncol = cend - col0;
+    double *P = p.L + f.lp;
+    const double *Y = P + (int64_t)jb * N + col0;
+    const double *X = LDL ? (p.W + f.wp + row0) : (P + (int64_t)jb * N + row0);
+    stage_tile(Xs, X, N, nrow, nb);
+    if (LDL || tr != tc) stage_tile(Ys, Y, N, ncol, nb); else Ys = Xs;
+    __syncthreads();
+    double acc[4][2][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    mma_64x64(acc, Xs, Ys, (nb + 3) & ~3);
     double *C;
     int64_t ldc;
-    if (col0 < f.k) { C = P + (int64_t)col0 * f.N + row0; ldc = f.N; }
-    else { C = U + f.up + (int64_t)(col0 - f.k) * f.r + (row0 - f.k); ldc = f.r; }
-    tile_update(X, f.N, Y, f.N, nb, rend - row0, cend - col0, C, ldc, row0, col0, Xs, Ys);
+    if (col0 < k) { C = P + (int64_t)col0 * N + row0; ldc = N; }
+    else { C = p.U + f.up + (int64_t)(col0 - k) * r + (row0 - k); ldc = r; }
+    acc_foreach(acc, [&](int rr, int cc, double val) {
+        if (rr < nrow && cc < ncol && (row0 + rr) >= (col0 + cc)) {
+            double *q = C + (int64_t)cc * ldc + rr;
+            *q -= val;
+        }
+    });
 }
 
-// Micro-benchmark hook for the same tile kernel: C (n x n, lower tiles) -= X X'.
-__global__ void __launch_bounds__(128)
+template <bool LDL>
+__global__ void __launch_bounds__(256, 2) k_factor_persistent(FactorParams p)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double smem[];
+    unsigned long long t0 = 0;
+    const bool timer = (blockIdx.x == 0 && threadIdx.x == 0);
+    if (timer) t0 = globaltimer_ns();
+    for (int ph = 0; ph < p.n_phases; ++ph) {
+        const int64_t *d = p.phases + 8 * (int64_t)ph;
+        const int type = (int)d[0], jb = (int)d[1], n_tasks = (int)d[2];
+        const int32_t *A = p.sched + d[3];
+        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+            if (type == PH_EA) {
+                task_extend_add(p, A, task);
+            } else if (type == PH_DIAG) {
+                task_diag<LDL>(p, A[task], jb, smem);
+            } else {
+                const int2 t2 = *reinterpret_cast<const int2 *>(A + 2 * (int64_t)task);   // (front, local tile)
+                if (type == PH_TRSM) task_trsm<LDL>(p, t2.x, t2.y, jb, smem);
+                else task_update<LDL>(p, t2.x, t2.y, jb, smem);
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        if (timer) {
+            unsigned long long t1 = globaltimer_ns();
+            p.phase_ns[ph] = t1 - t0;
+            t0 = t1;
+        }
+    }
+}
+
+// Micro-benchmark hook for the same tile code: C (n x n, lower tiles) -= X X' with K = kdim.
+__global__ void __launch_bounds__(256, 2)
 k_bench_syrk(int n, int kdim, double *__restrict__ C, int64_t ldc, const double *__restrict__ X, int64_t ldx)
 {
-    __shared__ double Xs[KC][XS];
-    __shared__ double Ys[KC][XS];
+    extern __shared__ double smem[];
+    double *Xs = smem, *Ys = smem + TILE * XS;
     const int lt = blockIdx.x;
     int tr = (int)((sqrt(8.0 * (double)lt + 1.0) - 1.0) * 0.5);
     while (tr * (tr + 1) / 2 > lt) --tr;
     while ((tr + 1) * (tr + 2) / 2 <= lt) ++tr;
     const int tc = lt - tr * (tr + 1) / 2;
     const int row0 = tr * TILE, col0 = tc * TILE;
-    for (int k0 = 0; k0 < kdim; k0 += NB)
-        tile_update(X + (int64_t)k0 * ldx + row0, ldx, X + (int64_t)k0 * ldx + col0, ldx, min(NB, kdim - k0),
-                    min(TILE, n - row0), min(TILE, n - col0), C + (int64_t)col0 * ldc + row0, ldc, row0, col0, Xs, Ys);
+    const int nrow = min(TILE, n - row0), ncol = min(TILE, n - col0);
+    double acc[4][2][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    for (int k0 = 0; k0 < kdim; k0 += NB) {
+        const int nb = min(NB, kdim - k0);
+        stage_tile(Xs, X + (int64_t)k0 * ldx + row0, ldx, nrow, nb);
+        stage_tile(Ys, X + (int64_t)k0 * ldx + col0, ldx, ncol, nb);
+        __syncthreads();
+        mma_64x64(acc, Xs, Ys, (nb + 3) & ~3);
+        __syncthreads();
+    }
+    acc_foreach(acc, [&](int rr, int cc, double val) {
+        if (rr < nrow && cc < ncol && (row0 + rr) >= (col0 + cc)) C[(int64_t)(col0 + cc) * ldc + row0 + rr] -= val;
+    });
 }
 
 // ------------------------------------------------------------------ triangular solves
-__global__ void __launch_bounds__(256)
-k_gather_perm(int64_t n, const int32_t *__restrict__ perm, const double *__restrict__ b, double *__restrict__ xp)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) xp[i] = b[perm[i]];
-}
-__global__ void __launch_bounds__(256)
-k_scatter_perm(int64_t n, const int32_t *__restrict__ perm, const double *__restrict__ xp, double *__restrict__ x, int accumulate)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { if (accumulate) x[perm[i]] += xp[i]; else x[perm[i]] = xp[i]; }
-}
+// One persistent cooperative kernel: gather through perm, forward sweep level by level (children's
+// update vectors are summed by the parent in a fixed order), backward sweep from the root down,
+// scatter through perm. One CTA per front per level; the 64 x 64 diagonal blocks are applied
+// through their stored inverses (mat-vec), so nothing in a front is sequential.
+constexpr int XR_MAX = 1536;    // ancestor entries of x cached in shared memory by the backward sweep
 
-// Forward substitution for all fronts of one level; one CTA per front.
-//   1. add the children's update vectors (fixed child order),
-//   2. y1 = L11^-1 x1 blocked by NB with the diagonal block in shared memory,
-//   3. x1' / u -= L21 y1 for the rows below each block.
 template <bool LDL>
-__global__ void __launch_bounds__(256)
-k_solve_fwd(const int32_t *__restrict__ fronts, const int32_t *__restrict__ sn_ptr, const int64_t *__restrict__ row_ptr,
-            const int64_t *__restrict__ lp, const int64_t *__restrict__ child_ptr, const int32_t *__restrict__ child_idx,
-            const int32_t *__restrict__ rel_idx, const double *__restrict__ L, double *__restrict__ xp,
-            double *__restrict__ uvec)
+__device__ void front_forward(const SolveParams &p, int s, double *smem)
 {
-    __shared__ double S[NB * LDS];
-    __shared__ double xb[NB];
-    const int s = fronts[blockIdx.x];
-    const int c0 = sn_ptr[s];
-    const int k = sn_ptr[s + 1] - c0;
-    const int r = (int)(row_ptr[s + 1] - row_ptr[s]);
-    const int N = k + r;
-    const double *P = L + lp[s];
-    double *x1 = xp + c0;
-    double *u = uvec + row_ptr[s];
+    double *xb = smem, *yb = smem + NB;
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, r = f.r, N = f.k + f.r;
+    const double *P = p.L + f.lp;
+    double *x1 = p.xp + f.c0;
+    double *u = p.uvec + f.rowp;
     const int tid = threadIdx.x;
-    for (int64_t ci = child_ptr[s]; ci < child_ptr[s + 1]; ++ci) {
-        const int c = child_idx[ci];
-        const int rc = (int)(row_ptr[c + 1] - row_ptr[c]);
-        const int32_t *rel = rel_idx + row_ptr[c];
-        const double *uc = uvec + row_ptr[c];
-        for (int a = tid; a < rc; a += 256) {
+    for (int ci = 0; ci < f.nchild; ++ci) {
+        const int c = p.child_idx[f.childp + ci];
+        const FrontInfo fc = p.fi[c];
+        const int32_t *rel = p.rel_idx + fc.rowp;
+        const double *uc = p.uvec + fc.rowp;
+        for (int a = tid; a < fc.r; a += 256) {
             int t = rel[a];
             if (t < k) x1[t] += uc[a]; else u[t - k] += uc[a];
         }
@@ -390,92 +478,129 @@ k_solve_fwd(const int32_t *__restrict__ fronts, const int32_t *__restrict__ sn_p
     }
     for (int jb = 0; jb < k; jb += NB) {
         const int nb = min(NB, k - jb);
-        for (int idx = tid; idx < nb * nb; idx += 256) {
-            int rr = idx % nb, cc = idx / nb;
-            if (rr >= cc) S[cc * LDS + rr] = P[(int64_t)(jb + cc) * N + jb + rr];
-        }
-        if (tid < nb) xb[tid] = x1[jb + tid];
+        const double *Dv = p.Dinv + (f.dinv + (jb >> 6)) * (int64_t)(NB * NB);
+        if (tid < NB) xb[tid] = (tid < nb) ? x1[jb + tid] : 0.0;
         __syncthreads();
-        if (tid < 32) {
-            for (int j = 0; j < nb; ++j) {
-                double xj = xb[j];
-                if (!LDL) xj = xj / S[j * LDS + j];
-                __syncwarp();
-                if (tid == 0) xb[j] = xj;
-                for (int i = j + 1 + tid; i < nb; i += 32) xb[i] -= S[j * LDS + i] * xj;
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        if (tid < nb) x1[jb + tid] = xb[tid];
-        for (int i = jb + nb + tid; i < N; i += 256) {
+        {   // y = inv(L11 block) * xb : row rr by the 4 threads (rr, q), columns pp = q, q+4, ...
+            const int rr = tid >> 2, q = tid & 3;
             double acc = 0.0;
+#pragma unroll 4
+            for (int pp = q; pp <= rr; pp += 4) acc = fma(Dv[pp * NB + rr], xb[pp], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (q == 0) { yb[rr] = acc; if (rr < nb) x1[jb + rr] = acc; }
+        }
+        __syncthreads();
+        for (int i = jb + nb + tid; i < N; i += 256) {
+            double acc0 = 0.0, acc1 = 0.0;
             const double *col = P + (int64_t)jb * N + i;
-            for (int j = 0; j < nb; ++j) acc = fma(col[(int64_t)j * N], xb[j], acc);
-            if (i < k) x1[i] -= acc; else u[i - k] -= acc;
+            int j = 0;
+#pragma unroll 4
+            for (; j + 1 < nb; j += 2) {
+                acc0 = fma(col[(int64_t)j * N], yb[j], acc0);
+                acc1 = fma(col[(int64_t)(j + 1) * N], yb[j + 1], acc1);
+            }
+            if (j < nb) acc0 = fma(col[(int64_t)j * N], yb[j], acc0);
+            if (i < k) x1[i] -= acc0 + acc1; else u[i - k] -= acc0 + acc1;
         }
         __syncthreads();
     }
 }
 
-// Backward substitution for all fronts of one level (levels processed from the root down).
-//   x1 = L11^-T (y1 [/ D] - L21' x_anc), blocked from the last block to the first.
 template <bool LDL>
-__global__ void __launch_bounds__(256)
-k_solve_bwd(const int32_t *__restrict__ fronts, const int32_t *__restrict__ sn_ptr, const int64_t *__restrict__ row_ptr,
-            const int64_t *__restrict__ lp, const int32_t *__restrict__ row_idx, const double *__restrict__ L,
-            double *__restrict__ xp)
+__device__ void front_backward(const SolveParams &p, int s, double *smem)
 {
-    __shared__ double S[NB * LDS];
-    __shared__ double xb[NB];
-    const int s = fronts[blockIdx.x];
-    const int c0 = sn_ptr[s];
-    const int k = sn_ptr[s + 1] - c0;
-    const int r = (int)(row_ptr[s + 1] - row_ptr[s]);
-    const int N = k + r;
-    const double *P = L + lp[s];
-    double *x1 = xp + c0;
-    const int32_t *rows = row_idx + row_ptr[s];
+    double *S = smem;                 // inverse block, col-major ld LDS
+    double *wb = smem + NB * LDS;     // 64
+    double *xr = wb + NB;             // XR_MAX: x at the front's below-diagonal rows
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, r = f.r, N = f.k + f.r;
+    const double *P = p.L + f.lp;
+    double *x1 = p.xp + f.c0;
+    const int32_t *rows = p.row_idx + f.rowp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool cached = r <= XR_MAX;
+    if (cached) for (int i = tid; i < r; i += 256) xr[i] = p.xp[rows[i]];
     const int nblk = (k + NB - 1) / NB;
     for (int b = nblk - 1; b >= 0; --b) {
         const int jb = b * NB;
         const int nb = min(NB, k - jb);
-        for (int idx = tid; idx < nb * nb; idx += 256) {
-            int rr = idx % nb, cc = idx / nb;
-            if (rr >= cc) S[cc * LDS + rr] = P[(int64_t)(jb + cc) * N + jb + rr];
-        }
-        // w[q] = y[q] (/ D[q]) - sum_{i >= jb+nb} L[i][q] * xfull[i]; one warp per column q
-        for (int q = warp; q < nb; q += 8) {
-            const double *col = P + (int64_t)(jb + q) * N;
-            double acc = 0.0;
-            for (int i = jb + nb + lane; i < N; i += 32) {
-                double xv = (i < k) ? x1[i] : xp[rows[i - k]];
-                acc = fma(col[i], xv, acc);
-            }
+        const double *Dv = p.Dinv + (f.dinv + b) * (int64_t)(NB * NB);
+        for (int idx = tid; idx < NB * NB; idx += 256) S[(idx >> 6) * LDS + (idx & 63)] = Dv[idx];
+        if (tid < NB) wb[tid] = 0.0;
+        __syncthreads();
+        // w[q] = y[q] (/ D[q]) - sum_{i >= jb+nb} L[i][q] * xfull[i]; each warp owns 8 consecutive
+        // columns and walks the rows once for all of them (8 independent loads per lane in flight)
+        {
+            const int q0 = warp * 8;
+            if (q0 < nb) {
+                double acc[8];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) {
-                double y = x1[jb + q];
-                if (LDL) y = y / col[jb + q];
-                xb[q] = y - acc;
+                for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+                const double *col = P + (int64_t)(jb + q0) * N;
+                for (int i = jb + nb + lane; i < N; i += 32) {
+                    double xv = (i < k) ? x1[i] : (cached ? xr[i - k] : p.xp[rows[i - k]]);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (q0 + c < nb) acc[c] = fma(col[(int64_t)c * N + i], xv, acc[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                }
+                if (lane < 8 && q0 + lane < nb) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) if (lane == c) a = acc[c];
+                    double y = x1[jb + q0 + lane];
+                    if (LDL) y = y / col[(int64_t)lane * N + jb + q0 + lane];
+                    wb[q0 + lane] = y - a;
+                }
             }
         }
         __syncthreads();
-        if (tid < 32) {
-            for (int j = nb - 1; j >= 0; --j) {
-                double xj = xb[j];
-                if (!LDL) xj = xj / S[j * LDS + j];
-                __syncwarp();
-                if (tid == 0) xb[j] = xj;
-                for (int i = tid; i < j; i += 32) xb[i] -= S[i * LDS + j] * xj;
-                __syncwarp();
-            }
+        {   // x = inv(L11 block)' * w : column cc by the 4 threads (cc, q)
+            const int cc = tid >> 2, q = tid & 3;
+            double acc = 0.0;
+            for (int rr = cc + q; rr < NB; rr += 4) acc = fma(S[cc * LDS + rr], wb[rr], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (q == 0 && cc < nb) x1[jb + cc] = acc;
         }
-        __syncthreads();
-        if (tid < nb) x1[jb + tid] = xb[tid];
         __syncthreads();
     }
+}
+
+template <bool LDL>
+__global__ void __launch_bounds__(256, 4) k_solve_persistent(SolveParams p)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double smem[NB * LDS + NB + XR_MAX];
+    const int64_t gtid = (int64_t)blockIdx.x * 256 + threadIdx.x, gsz = (int64_t)gridDim.x * 256;
+    for (int64_t i = gtid; i < p.n; i += gsz) p.xp[i] = p.b_in[p.perm[i]];
+    for (int64_t i = gtid; i < p.n_u; i += gsz) p.uvec[i] = 0.0;
+    grid.sync();
+    for (int l = 0; l < p.n_levels; ++l) {
+        const int32_t *fr = p.sched + p.lvl[2 * l];
+        const int nf = (int)p.lvl[2 * l + 1];
+        for (int t = blockIdx.x; t < nf; t += gridDim.x) {
+            front_forward<LDL>(p, fr[t], smem);
+            __syncthreads();
+        }
+        grid.sync();
+    }
+    for (int l = p.n_levels - 1; l >= 0; --l) {
+        const int32_t *fr = p.sched + p.lvl[2 * l];
+        const int nf = (int)p.lvl[2 * l + 1];
+        for (int t = blockIdx.x; t < nf; t += gridDim.x) {
+            front_backward<LDL>(p, fr[t], smem);
+            __syncthreads();
+        }
+        grid.sync();
+    }
+    if (p.accumulate) { for (int64_t i = gtid; i < p.n; i += gsz) p.x_out[p.perm[i]] += p.xp[i]; }
+    else { for (int64_t i = gtid; i < p.n; i += gsz) p.x_out[p.perm[i]] = p.xp[i]; }
 }
 
 // r = b - K x with K symmetric, given by its full CSR index into the caller's lower-CSC values.
@@ -488,7 +613,7 @@ k_sym_residual(int64_t n, const int64_t *__restrict__ ptr, const int32_t *__rest
     int lane = threadIdx.x & 31;
     if (row >= n) return;
     double acc = 0.0;
-    for (int64_t p = ptr[row] + lane; p < ptr[row + 1]; p += 32) acc = fma(__ldg(val + vpos[p]), __ldg(x + col[p]), acc);
+    for (int64_t q = ptr[row] + lane; q < ptr[row + 1]; q += 32) acc = fma(__ldg(val + vpos[q]), __ldg(x + col[q]), acc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) rout[row] = b[row] - acc;
@@ -504,87 +629,129 @@ int ls_device_setup(Handle *h)
     const LsSymbolic &S = h->sym;
     const int ns = S.ns;
     MIPM_CUDA(h, cudaSetDevice(h->device));
-    // ---- build the schedule
+    // ---- build the schedule: per level [extend-add], then per block step diag / trsm / update.
+    // Every phase owns a flat array of task records in `sched` (no searching on the device):
+    //   DIAG: (front)   TRSM / UPDATE: (front, local tile)   EA: (parent, q0, q1, offset of child ranges)
     std::vector<int32_t> sched;
-    h->steps.clear();
-    h->levels.assign((size_t)S.n_levels, LevelInfo());
-    std::vector<int64_t> wp((size_t)ns + 1, 0);
+    std::vector<int64_t> phases, lvl;
+    std::vector<int64_t> wp((size_t)ns + 1, 0), dinv_off((size_t)ns + 1, 0);
+    std::vector<FrontInfo> finfo((size_t)std::max(ns, 1));
     for (int s = 0; s < ns; ++s) {
         int64_t k = S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s];
         int64_t r = S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s];
         wp[(size_t)s + 1] = wp[(size_t)s] + (S.kind == MIPM_LDL ? (k + r) * NB : 0);
+        dinv_off[(size_t)s + 1] = dinv_off[(size_t)s] + (k + NB - 1) / NB;
+        FrontInfo &f = finfo[(size_t)s];
+        f.k = (int32_t)k; f.r = (int32_t)r; f.c0 = S.sn_ptr[(size_t)s];
+        f.nchild = (int32_t)(S.child_ptr[(size_t)s + 1] - S.child_ptr[(size_t)s]);
+        f.lp = S.lp[(size_t)s]; f.up = S.up[(size_t)s]; f.wp = wp[(size_t)s]; f.dinv = dinv_off[(size_t)s];
+        f.rowp = S.row_ptr[(size_t)s]; f.childp = S.child_ptr[(size_t)s];
     }
-    int64_t n_launch = 3;  // two memsets + scatter
+    auto align4 = [&]() { while (sched.size() % 4) sched.push_back(0); };
+    auto push_phase = [&](int type, int jb, int64_t n_tasks, int64_t off_tasks) {
+        int64_t d[8] = {type, jb, n_tasks, off_tasks, 0, 0, 0, 0};
+        phases.insert(phases.end(), d, d + 8);
+    };
     for (int l = 0; l < S.n_levels; ++l) {
-        LevelInfo &li = h->levels[(size_t)l];
         const int64_t f0 = S.level_ptr[(size_t)l], f1 = S.level_ptr[(size_t)l + 1];
-        li.off_all = (int64_t)sched.size();
-        li.n_all = (int32_t)(f1 - f0);
+        lvl.push_back((int64_t)sched.size());
+        lvl.push_back(f1 - f0);
         int kmax = 0;
         for (int64_t t = f0; t < f1; ++t) {
             int s = S.level_sn[(size_t)t];
             sched.push_back(s);
             kmax = std::max(kmax, S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s]);
         }
-        li.off_parents = (int64_t)sched.size();
-        li.n_parents = 0;
+        // extend-add: per-child column ranges first, then the task records that point at them
+        std::vector<int32_t> ea;
         for (int64_t t = f0; t < f1; ++t) {
             int s = S.level_sn[(size_t)t];
-            if (S.child_ptr[(size_t)s + 1] > S.child_ptr[(size_t)s]) { sched.push_back(s); li.n_parents++; }
-        }
-        li.off_ea_tasks = (int64_t)sched.size();
-        li.n_ea_tasks = 0;
-        for (int64_t t = 0; t < li.n_parents; ++t) {
-            int s = sched[(size_t)(li.off_parents + t)];
-            int N = (S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s]) + (int)(S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s]);
+            const FrontInfo &f = finfo[(size_t)s];
+            if (f.nchild == 0) continue;
+            int N = f.k + f.r;
             for (int q0 = 0; q0 < N; q0 += EA_COLS) {
-                sched.push_back(s);
-                sched.push_back(q0);
-                sched.push_back(std::min(N, q0 + EA_COLS));
-                li.n_ea_tasks++;
+                int q1 = std::min(N, q0 + EA_COLS);
+                int64_t off_r = (int64_t)sched.size();
+                bool any = false;
+                for (int ci = 0; ci < f.nchild; ++ci) {
+                    int c = S.child_idx[(size_t)(f.childp + ci)];
+                    const int32_t *rel = S.rel_idx.data() + S.row_ptr[(size_t)c];
+                    int rc = finfo[(size_t)c].r;
+                    int b0 = (int)(std::lower_bound(rel, rel + rc, q0) - rel);
+                    int b1 = (int)(std::lower_bound(rel, rel + rc, q1) - rel);
+                    sched.push_back(b0);
+                    sched.push_back(b1);
+                    any = any || (b1 > b0);
+                }
+                if (!any) { sched.resize((size_t)off_r); continue; }
+                if (off_r > INT32_MAX) return fail(h, MIPM_ERR_ARG, "schedule too large");
+                ea.push_back(s); ea.push_back(q0); ea.push_back(q1); ea.push_back((int32_t)off_r);
             }
         }
-        if (li.n_ea_tasks) n_launch++;
+        if (!ea.empty()) {
+            align4();
+            push_phase(PH_EA, 0, (int64_t)ea.size() / 4, (int64_t)sched.size());
+            sched.insert(sched.end(), ea.begin(), ea.end());
+        }
         for (int jb = 0; jb < kmax; jb += NB) {
-            FactorStep st;
-            st.level = l;
-            st.jb = jb;
-            st.off_sn = (int64_t)sched.size();
-            st.n_active = 0;
+            std::vector<int32_t> td, tt, tu;
             for (int64_t t = f0; t < f1; ++t) {
                 int s = S.level_sn[(size_t)t];
-                if (S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s] > jb) { sched.push_back(s); st.n_active++; }
+                const FrontInfo &f = finfo[(size_t)s];
+                if (f.k <= jb) continue;
+                td.push_back(s);
+                int nb = std::min(NB, f.k - jb), j1 = jb + nb, N = f.k + f.r;
+                int ntr = (N - j1 + TILE - 1) / TILE;
+                for (int i = 0; i < ntr; ++i) { tt.push_back(s); tt.push_back(i); }
+                int64_t nt1 = (f.k > j1) ? (f.k - j1 + TILE - 1) / TILE : 0, nt2 = (f.r + TILE - 1) / TILE;
+                int64_t ntl = nt1 + nt2, nup = ntl * (ntl + 1) / 2;
+                if (nup > (1 << 28)) return fail(h, MIPM_ERR_ARG, "front too large for the tile schedule");
+                for (int i = 0; i < (int)nup; ++i) { tu.push_back(s); tu.push_back(i); }
             }
-            st.off_trsm = (int64_t)sched.size();
-            sched.resize(sched.size() + (size_t)st.n_active + 1);
-            st.off_upd = (int64_t)sched.size();
-            sched.resize(sched.size() + (size_t)st.n_active + 1);
-            int64_t nt = 0, nu = 0;
-            for (int t = 0; t < st.n_active; ++t) {
-                int s = sched[(size_t)(st.off_sn + t)];
-                int k = S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s];
-                int r = (int)(S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s]);
-                int nb = std::min(NB, k - jb), j1 = jb + nb, N = k + r;
-                sched[(size_t)(st.off_trsm + t)] = (int32_t)nt;
-                sched[(size_t)(st.off_upd + t)] = (int32_t)nu;
-                nt += (N - j1 + TRSM_ROWS - 1) / TRSM_ROWS;
-                int64_t nt1 = (k > j1) ? (k - j1 + TILE - 1) / TILE : 0, nt2 = (r + TILE - 1) / TILE;
-                int64_t ntl = nt1 + nt2;
-                nu += ntl * (ntl + 1) / 2;
-                if (nu > INT32_MAX || nt > INT32_MAX) return fail(h, MIPM_ERR_ARG, "front too large for the 32-bit tile schedule");
+            if (sched.size() + td.size() + tt.size() + tu.size() + 16 > (size_t)INT32_MAX)
+                return fail(h, MIPM_ERR_ARG, "schedule too large");
+            align4();
+            push_phase(PH_DIAG, jb, (int64_t)td.size(), (int64_t)sched.size());
+            sched.insert(sched.end(), td.begin(), td.end());
+            if (!tt.empty()) {
+                align4();
+                push_phase(PH_TRSM, jb, (int64_t)tt.size() / 2, (int64_t)sched.size());
+                sched.insert(sched.end(), tt.begin(), tt.end());
             }
-            sched[(size_t)(st.off_trsm + st.n_active)] = (int32_t)nt;
-            sched[(size_t)(st.off_upd + st.n_active)] = (int32_t)nu;
-            st.n_trsm = nt;
-            st.n_upd = nu;
-            n_launch += 1 + (nt > 0) + (nu > 0);
-            h->steps.push_back(st);
+            if (!tu.empty()) {
+                align4();
+                push_phase(PH_UPDATE, jb, (int64_t)tu.size() / 2, (int64_t)sched.size());
+                sched.insert(sched.end(), tu.begin(), tu.end());
+            }
         }
     }
-    h->n_launch_factor = n_launch;
+    h->n_phases = (int)(phases.size() / 8);
+    h->n_launch_factor = 2;   // scatter + persistent kernel (plus three memsets)
+    // ---- cooperative grid sizes
+    cudaDeviceProp prop;
+    MIPM_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+    if (!prop.cooperativeLaunch) return fail(h, MIPM_ERR_CUDA, "device does not support cooperative launch");
+    MIPM_CUDA(h, cudaFuncSetAttribute(k_factor_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MIPM_CUDA(h, cudaFuncSetAttribute(k_factor_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MIPM_CUDA(h, cudaFuncSetAttribute(k_bench_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int occ_f = 0, occ_s = 0;
+    if (S.kind == MIPM_LDL) {
+        MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_factor_persistent<true>, 256, SMEM_BYTES));
+        MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_solve_persistent<true>, 256, 0));
+    } else {
+        MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_factor_persistent<false>, 256, SMEM_BYTES));
+        MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_solve_persistent<false>, 256, 0));
+    }
+    if (occ_f < 1 || occ_s < 1) return fail(h, MIPM_ERR_CUDA, "persistent kernels do not fit on an SM");
+    h->grid_factor = prop.multiProcessorCount * occ_f;
+    h->grid_solve = prop.multiProcessorCount * std::min(occ_s, 4);
     // ---- uploads and workspaces
     cudaStream_t st = h->stream;
     MIPM_CUDA(h, h->d_sched.upload(sched, st));
+    MIPM_CUDA(h, h->d_finfo.alloc(finfo.size()));
+    MIPM_CUDA(h, cudaMemcpyAsync(h->d_finfo.p, finfo.data(), finfo.size() * sizeof(FrontInfo), cudaMemcpyHostToDevice, st));
+    MIPM_CUDA(h, h->d_phases.upload(phases, st));
+    MIPM_CUDA(h, h->d_lvl.upload(lvl, st));
     MIPM_CUDA(h, h->d_sn_ptr.upload(S.sn_ptr, st));
     MIPM_CUDA(h, h->d_sn_parent.upload(S.sn_parent, st));
     MIPM_CUDA(h, h->d_row_ptr.upload(S.row_ptr, st));
@@ -594,6 +761,7 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, h->d_lp.upload(S.lp, st));
     MIPM_CUDA(h, h->d_up.upload(S.up, st));
     MIPM_CUDA(h, h->d_wp.upload(wp, st));
+    MIPM_CUDA(h, h->d_dinv_off.upload(dinv_off, st));
     MIPM_CUDA(h, h->d_child_ptr.upload(S.child_ptr, st));
     MIPM_CUDA(h, h->d_child_idx.upload(S.child_idx, st));
     MIPM_CUDA(h, h->d_a2l.upload(S.a2l, st));
@@ -603,124 +771,59 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, h->d_L.alloc((size_t)std::max<int64_t>(S.nnz_l, 1)));
     MIPM_CUDA(h, h->d_U.alloc((size_t)std::max<int64_t>(S.update_doubles, 1)));
     MIPM_CUDA(h, h->d_W.alloc((size_t)std::max<int64_t>(wp[(size_t)ns], 1)));
+    MIPM_CUDA(h, h->d_Dinv.alloc((size_t)std::max<int64_t>(dinv_off[(size_t)ns], 1) * NB * NB));
     MIPM_CUDA(h, h->d_xp.alloc((size_t)std::max<int64_t>(S.n, 1)));
     MIPM_CUDA(h, h->d_uvec.alloc((size_t)std::max<int64_t>(S.row_ptr[(size_t)ns], 1)));
     MIPM_CUDA(h, h->d_b.alloc((size_t)std::max<int64_t>(S.n, 1)));
     MIPM_CUDA(h, h->d_r.alloc((size_t)std::max<int64_t>(S.n, 1)));
+    MIPM_CUDA(h, h->d_phase_ns.alloc((size_t)h->n_phases + 8));
     MIPM_CUDA(h, cudaStreamSynchronize(st));
     h->factorized = false;
     return MIPM_OK;
 }
 
-// Optional per-class device timing of one factorization (events around every launch).
-struct FactorProfile {
-    struct Rec { cudaEvent_t a, b; int cls; };
-    std::vector<Rec> recs;
-};
-static FactorProfile *g_prof = nullptr;   // only set inside mipm_ls_factorize_profile (single-threaded per handle)
-#define PROF_BEGIN(cls_)                                                  \
-    FactorProfile::Rec rec__;                                             \
-    if (g_prof) {                                                         \
-        cudaEventCreate(&rec__.a);                                        \
-        cudaEventCreate(&rec__.b);                                        \
-        rec__.cls = (cls_);                                               \
-        cudaEventRecord(rec__.a, st);                                     \
-    }
-#define PROF_END()                                                        \
-    if (g_prof) {                                                         \
-        cudaEventRecord(rec__.b, st);                                     \
-        g_prof->recs.push_back(rec__);                                    \
-    }
-
-template <bool LDL>
-static int factorize_t(Handle *h, const double *d_nzval)
+int ls_factorize_impl(Handle *h, const double *d_nzval)
 {
     const LsSymbolic &S = h->sym;
     cudaStream_t st = h->stream;
-    const int32_t *sched = h->d_sched.p;
-    {
-        PROF_BEGIN(0);
-        MIPM_CUDA(h, cudaMemsetAsync(h->d_L.p, 0, (size_t)std::max<int64_t>(S.nnz_l, 1) * sizeof(double), st));
-        MIPM_CUDA(h, cudaMemsetAsync(h->d_U.p, 0, (size_t)std::max<int64_t>(S.update_doubles, 1) * sizeof(double), st));
-        MIPM_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, 4 * sizeof(int), st));
-        if (S.nnz_a > 0) {
-            k_scatter_a<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.nnz_a, h->d_a2l.p, d_nzval, h->d_L.p);
-            MIPM_CHECK_LAUNCH(h);
-        }
-        PROF_END();
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    MIPM_CUDA(h, cudaMemsetAsync(h->d_L.p, 0, (size_t)std::max<int64_t>(S.nnz_l, 1) * sizeof(double), st));
+    MIPM_CUDA(h, cudaMemsetAsync(h->d_U.p, 0, (size_t)std::max<int64_t>(S.update_doubles, 1) * sizeof(double), st));
+    MIPM_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, 4 * sizeof(int), st));
+    if (S.nnz_a > 0) {
+        k_scatter_a<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.nnz_a, h->d_a2l.p, d_nzval, h->d_L.p);
+        MIPM_CHECK_LAUNCH(h);
     }
-    // pivot tolerance for LDL^T: relative to nothing we can see cheaply -> absolute, tiny
-    const double piv_tol = 1e-13;
-    size_t si = 0;
-    for (int l = 0; l < S.n_levels; ++l) {
-        const LevelInfo &li = h->levels[(size_t)l];
-        if (li.n_ea_tasks > 0) {
-            PROF_BEGIN(1);
-            k_extend_add<<<(unsigned)li.n_ea_tasks, 256, 0, st>>>(sched + li.off_ea_tasks, h->d_sn_ptr.p, h->d_row_ptr.p,
-                                                                h->d_lp.p, h->d_up.p, h->d_child_ptr.p, h->d_child_idx.p,
-                                                                h->d_rel_idx.p, h->d_L.p, h->d_U.p);
-            MIPM_CHECK_LAUNCH(h);
-            PROF_END();
-        }
-        for (; si < h->steps.size() && h->steps[si].level == l; ++si) {
-            const FactorStep &fs = h->steps[si];
-            {
-            PROF_BEGIN(2);
-            k_factor_diag<LDL><<<(unsigned)fs.n_active, 256, 0, st>>>(sched + fs.off_sn, fs.jb, h->d_sn_ptr.p, h->d_row_ptr.p,
-                                                                     h->d_lp.p, h->d_L.p, h->d_info.p, piv_tol);
-            MIPM_CHECK_LAUNCH(h);
-            PROF_END();
-            }
-            if (fs.n_trsm > 0) {
-                PROF_BEGIN(3);
-                k_trsm<LDL><<<(unsigned)fs.n_trsm, TRSM_ROWS, 0, st>>>(sched + fs.off_sn, sched + fs.off_trsm, fs.n_active, fs.jb,
-                                                                      h->d_sn_ptr.p, h->d_row_ptr.p, h->d_lp.p, h->d_wp.p,
-                                                                      h->d_L.p, h->d_W.p);
-                MIPM_CHECK_LAUNCH(h);
-                PROF_END();
-            }
-            if (fs.n_upd > 0) {
-                PROF_BEGIN(4);
-                k_update<LDL><<<(unsigned)fs.n_upd, 128, 0, st>>>(sched + fs.off_sn, sched + fs.off_upd, fs.n_active, fs.jb,
-                                                                 h->d_sn_ptr.p, h->d_row_ptr.p, h->d_lp.p, h->d_up.p, h->d_wp.p,
-                                                                 h->d_L.p, h->d_U.p, h->d_W.p);
-                MIPM_CHECK_LAUNCH(h);
-                PROF_END();
-            }
-        }
+    if (h->n_phases > 0) {
+        FactorParams p;
+        p.fi = (const FrontInfo *)h->d_finfo.p; p.child_idx = h->d_child_idx.p; p.rel_idx = h->d_rel_idx.p;
+        p.sched = h->d_sched.p; p.phases = h->d_phases.p; p.n_phases = h->n_phases;
+        p.L = h->d_L.p; p.U = h->d_U.p; p.W = h->d_W.p; p.Dinv = h->d_Dinv.p; p.info = h->d_info.p;
+        p.phase_ns = h->d_phase_ns.p;
+        p.piv_tol = 1e-13;   // LDL^T: absolute floor on |pivot|
+        void *args[] = {&p};
+        const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_factor_persistent<true> : (const void *)k_factor_persistent<false>;
+        MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)h->grid_factor), dim3(256), args, SMEM_BYTES, st));
+        h->launches++;
     }
     h->d_nzval = d_nzval;
     h->factorized = true;
     return MIPM_OK;
 }
 
-int ls_factorize_impl(Handle *h, const double *d_nzval)
+static int solve_once(Handle *h, const double *b_in, double *x_out, int accumulate)
 {
-    MIPM_CUDA(h, cudaSetDevice(h->device));
-    return h->sym.kind == MIPM_LDL ? factorize_t<true>(h, d_nzval) : factorize_t<false>(h, d_nzval);
-}
-
-template <bool LDL>
-static int solve_permuted(Handle *h)
-{
-    // solves in place on h->d_xp (permuted numbering)
     const LsSymbolic &S = h->sym;
-    cudaStream_t st = h->stream;
-    const int32_t *sched = h->d_sched.p;
-    MIPM_CUDA(h, cudaMemsetAsync(h->d_uvec.p, 0, (size_t)std::max<int64_t>(S.row_ptr[(size_t)S.ns], 1) * sizeof(double), st));
-    for (int l = 0; l < S.n_levels; ++l) {
-        const LevelInfo &li = h->levels[(size_t)l];
-        k_solve_fwd<LDL><<<(unsigned)li.n_all, 256, 0, st>>>(sched + li.off_all, h->d_sn_ptr.p, h->d_row_ptr.p, h->d_lp.p,
-                                                            h->d_child_ptr.p, h->d_child_idx.p, h->d_rel_idx.p, h->d_L.p,
-                                                            h->d_xp.p, h->d_uvec.p);
-        MIPM_CHECK_LAUNCH(h);
-    }
-    for (int l = S.n_levels - 1; l >= 0; --l) {
-        const LevelInfo &li = h->levels[(size_t)l];
-        k_solve_bwd<LDL><<<(unsigned)li.n_all, 256, 0, st>>>(sched + li.off_all, h->d_sn_ptr.p, h->d_row_ptr.p, h->d_lp.p,
-                                                            h->d_row_idx.p, h->d_L.p, h->d_xp.p);
-        MIPM_CHECK_LAUNCH(h);
-    }
+    SolveParams p;
+    p.fi = (const FrontInfo *)h->d_finfo.p; p.child_idx = h->d_child_idx.p; p.rel_idx = h->d_rel_idx.p; p.row_idx = h->d_row_idx.p;
+    p.perm = h->d_perm.p; p.sched = h->d_sched.p; p.lvl = h->d_lvl.p; p.n_levels = S.n_levels;
+    p.n = S.n; p.n_u = S.row_ptr[(size_t)S.ns];
+    p.L = h->d_L.p; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
+    p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
+    void *args[] = {&p};
+    const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_solve_persistent<true> : (const void *)k_solve_persistent<false>;
+    MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)h->grid_solve), dim3(256), args, 0, h->stream));
+    h->launches++;
     return MIPM_OK;
 }
 
@@ -731,24 +834,17 @@ int ls_solve_impl(Handle *h, double *d_x, int ir_steps)
     MIPM_CUDA(h, cudaSetDevice(h->device));
     const int64_t n = S.n;
     if (n == 0) return MIPM_OK;
-    const bool ldl = S.kind == MIPM_LDL;
-    if (ir_steps > 0) MIPM_CUDA(h, cudaMemcpyAsync(h->d_b.p, d_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    k_gather_perm<<<grid_for(n, 256), 256, 0, st>>>(n, h->d_perm.p, d_x, h->d_xp.p);
-    MIPM_CHECK_LAUNCH(h);
-    int rc = ldl ? solve_permuted<true>(h) : solve_permuted<false>(h);
+    // b is needed after x is overwritten (refinement) and the solve reads b through perm while
+    // writing x through perm: always work from a copy of the right-hand side
+    MIPM_CUDA(h, cudaMemcpyAsync(h->d_b.p, d_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    int rc = solve_once(h, h->d_b.p, d_x, 0);
     if (rc != MIPM_OK) return rc;
-    k_scatter_perm<<<grid_for(n, 256), 256, 0, st>>>(n, h->d_perm.p, h->d_xp.p, d_x, 0);
-    MIPM_CHECK_LAUNCH(h);
     for (int it = 0; it < ir_steps; ++it) {
         k_sym_residual<<<grid_for(n * 32, 256), 256, 0, st>>>(n, h->d_full_ptr.p, h->d_full_col.p, h->d_full_val.p, h->d_nzval,
                                                             d_x, h->d_b.p, h->d_r.p);
         MIPM_CHECK_LAUNCH(h);
-        k_gather_perm<<<grid_for(n, 256), 256, 0, st>>>(n, h->d_perm.p, h->d_r.p, h->d_xp.p);
-        MIPM_CHECK_LAUNCH(h);
-        rc = ldl ? solve_permuted<true>(h) : solve_permuted<false>(h);
+        rc = solve_once(h, h->d_r.p, d_x, 1);
         if (rc != MIPM_OK) return rc;
-        k_scatter_perm<<<grid_for(n, 256), 256, 0, st>>>(n, h->d_perm.p, h->d_xp.p, d_x, 1);
-        MIPM_CHECK_LAUNCH(h);
     }
     return MIPM_OK;
 }
@@ -763,22 +859,41 @@ extern "C" int mipm_ls_factorize_profile(mipm_handle hh, const double *d_nzval, 
     if (!h->has_ls) return fail(h, MIPM_ERR_STATE, "mipm_ls_analyze has not been called");
     if (!ms || !work || !launches) return fail(h, MIPM_ERR_ARG, "null argument");
     const LsSymbolic &S = h->sym;
-    FactorProfile prof;
-    g_prof = &prof;
+    cudaEvent_t e0, e1;
+    MIPM_CUDA(h, cudaEventCreate(&e0));
+    MIPM_CUDA(h, cudaEventCreate(&e1));
+    MIPM_CUDA(h, cudaEventRecord(e0, h->stream));
     int rc = ls_factorize_impl(h, d_nzval);
-    g_prof = nullptr;
     if (rc != MIPM_OK) return rc;
+    MIPM_CUDA(h, cudaEventRecord(e1, h->stream));
     MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
-    for (int c = 0; c < 5; ++c) { ms[c] = 0.0; work[c] = 0.0; launches[c] = 0; }
-    for (auto &r : prof.recs) {
-        float t = 0.f;
-        cudaEventElapsedTime(&t, r.a, r.b);
-        ms[r.cls] += t;
-        launches[r.cls] += 1;
-        cudaEventDestroy(r.a);
-        cudaEventDestroy(r.b);
+    float total = 0.f;
+    cudaEventElapsedTime(&total, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    std::vector<unsigned long long> ns((size_t)h->n_phases + 8, 0);
+    std::vector<int64_t> ph((size_t)h->n_phases * 8 + 8, 0);
+    if (h->n_phases) {
+        MIPM_CUDA(h, cudaMemcpy(ns.data(), h->d_phase_ns.p, (size_t)h->n_phases * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        MIPM_CUDA(h, cudaMemcpy(ph.data(), h->d_phases.p, (size_t)h->n_phases * 8 * sizeof(int64_t), cudaMemcpyDeviceToHost));
     }
-    // algorithmic work per class: bytes for 0 (zero-fill + scatter) and 1 (extend-add), flops for 2..4
+    // classes: 0 zero-fill + scatter (= total - in-kernel phases), 1 extend-add, 2 diag, 3 trsm, 4 update
+    for (int c = 0; c < 5; ++c) { ms[c] = 0.0; work[c] = 0.0; launches[c] = 0; }
+    double inside = 0.0;
+    FILE *logf = nullptr;
+    if (const char *pth = std::getenv("MIPM_PHASE_LOG")) logf = std::fopen(pth, "w");
+    if (logf) std::fprintf(logf, "phase,type,jb,n_tasks,us\n");
+    for (int i = 0; i < h->n_phases; ++i) {
+        int type = (int)ph[(size_t)i * 8];
+        double t = (double)ns[(size_t)i] * 1e-6;
+        ms[type + 1] += t;
+        launches[type + 1] += 1;
+        inside += t;
+        if (logf) std::fprintf(logf, "%d,%d,%d,%lld,%.2f\n", i, type, (int)ph[(size_t)i * 8 + 1], (long long)ph[(size_t)i * 8 + 2], t * 1e3);
+    }
+    if (logf) std::fclose(logf);
+    ms[0] = std::max(0.0, (double)total - inside);
+    launches[0] = 4;
     work[0] = 8.0 * (double)(S.nnz_l + S.update_doubles) + 24.0 * (double)S.nnz_a;
     for (int s = 0; s < S.ns; ++s) {
         double k = S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s];
@@ -803,7 +918,8 @@ extern "C" int mipm_bench_syrk(mipm_handle hh, int64_t n, int64_t k, double *d_C
     int64_t nt = (n + TILE - 1) / TILE;
     int64_t tiles = nt * (nt + 1) / 2;
     if (tiles > INT32_MAX) return fail(h, MIPM_ERR_ARG, "too many tiles");
-    k_bench_syrk<<<(unsigned)tiles, 128, 0, h->stream>>>((int)n, (int)k, d_C, ldc, d_X, ldx);
+    MIPM_CUDA(h, cudaFuncSetAttribute(k_bench_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    k_bench_syrk<<<(unsigned)tiles, 256, SMEM_BYTES, h->stream>>>((int)n, (int)k, d_C, ldc, d_X, ldx);
     MIPM_CHECK_LAUNCH(h);
     return MIPM_OK;
 }

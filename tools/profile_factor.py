@@ -1,0 +1,44 @@
+"""Small driver for ncu: C2 (or a scaled C2) normal matrix -> analyze, 2 factorizations, 2 solves.
+Usage: python tools/profile_factor.py [scale]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from madipm_jl_b200 import _lib  # noqa: E402
+from madipm_jl_b200.problems import config_c2  # noqa: E402
+
+
+def main():
+    scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+    qp = config_c2(seed=2, scale=scale)
+    m, n = qp.ncon, qp.nvar
+    Bp, Bj, Bm = _lib.coo_to_csr(m, n, qp.Arows, qp.Acols)
+    h = _lib.Handle(device=0, stream=torch.cuda.current_stream().cuda_stream)
+    Cp, Cj = h.normal_symbolic(m, n, Bp, Bj)
+    ATx = torch.from_numpy(qp.Avals[Bm]).cuda()
+    pr = torch.from_numpy(np.random.default_rng(0).uniform(1e-2, 1e2, n)).cuda()
+    Cx = torch.zeros(len(Cj), dtype=torch.float64, device="cuda")
+    h.normal_set_jacobian(ATx)
+    h.ls_analyze(m, Cp, Cj)
+    print(h.ls_stats())
+    for _ in range(2):
+        h.normal_assemble(pr, Cx)
+        assert h.ls_factorize(Cx)
+    b = torch.randn(m, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        x = b.clone()
+        h.ls_solve(x, 0)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    h.ls_factorize(Cx)
+    torch.cuda.synchronize()
+    print("factor ms", 1e3 * (time.perf_counter() - t))
+    print(h.ls_factorize_profile(Cx))
+
+
+if __name__ == "__main__":
+    main()
