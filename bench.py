@@ -318,7 +318,8 @@ def main():
                        "parallelism": "replicas x%d" % world, "scale": args.scale},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / max(iters_total, 1),
                     "d2h_bytes_per_step": d2h / max(iters_total, 1), "iterations": iters_total,
-                    "time_to_tol_s": t_e2e_max, "status": res.status,
+                    "time_to_tol_s": t_e2e_max, "status": res.status, "initialize_s": res.counters.get("initialize_time"),
+                    "refinements": res.counters.get("refinements", 0),
                     "what": "MPCSolver.solve(): host model -> H2D, init_starting_point!, mpc! to tol, D2H of x,y,zl,zu"},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -220,6 +220,10 @@ int mipm_init_point_stage(mipm_handle h, int stage, double a, double b, double k
 int mipm_axpby(mipm_handle h, int64_t n, double alpha, const double *d_x, double beta, double *d_y);
 int mipm_fill(mipm_handle h, int64_t n, double value, double *d_x);
 int mipm_copy(mipm_handle h, int64_t n, const double *d_src, double *d_dst);
+/* dst[i] = src[map[i] - index_base], i < n: the device gather behind
+ * `kkt.AT.nzVal .= kkt.A.V[kkt.A_csr_map]` (cuda_wrapper.jl:39). map is Int64 like Julia's Vector{Int}. */
+int mipm_gather(mipm_handle h, int64_t n, const double *d_src, const int64_t *d_map, int index_base,
+                double *d_dst);
 /* dot(x, y) with a deterministic two-level reduction (used for obj = c'x + x'Qx/2). */
 int mipm_dot(mipm_handle h, int64_t n, const double *d_x, const double *d_y, double *out);
 

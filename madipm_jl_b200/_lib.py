@@ -59,7 +59,7 @@ SYMBOLS = [
     "mipm_get_correction", "mipm_set_extra_correction", "mipm_get_complementarity_measure",
     "mipm_get_affine_complementarity_measure", "mipm_get_alpha_max", "mipm_termination_measures",
     "mipm_apply_step", "mipm_reduce_rhs", "mipm_finish_aug_solve", "mipm_normal_solve_stage", "mipm_kktmul",
-    "mipm_residual_norms", "mipm_init_point_stage", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_dot",
+    "mipm_residual_norms", "mipm_init_point_stage", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_gather", "mipm_dot",
     "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk",
 ]
 
@@ -288,6 +288,9 @@ class Handle:
 
     def copy(self, n, src, dst):
         self.check(self.lib.mipm_copy(self.h, C.c_int64(n), _ptr(src), _ptr(dst)))
+
+    def gather(self, n, src, map_, dst, index_base=0):
+        self.check(self.lib.mipm_gather(self.h, C.c_int64(n), _ptr(src), _ptr(map_), C.c_int(index_base), _ptr(dst)))
 
     def dot(self, n, x, y):
         out = C.c_double()

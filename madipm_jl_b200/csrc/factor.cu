@@ -39,6 +39,7 @@ constexpr int EA_COLS = 32;     // parent-front columns per extend-add task
 constexpr int TILE = 64;        // GEMM tile
 constexpr int XS = 68;          // smem row stride of staged operands (68 % 16 == 4: conflict-free DMMA loads)
 constexpr int SMEM_DOUBLES = 2 * TILE * XS;
+static_assert(2 * NB * LDS + 4 * NB <= SMEM_DOUBLES, "diag task: S + scratch + Sinv must fit the tile buffers");
 constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;   // 69,632 B
 enum { PH_EA = 0, PH_DIAG = 1, PH_TRSM = 2, PH_UPDATE = 3 };
 
@@ -62,6 +63,7 @@ struct FactorParams {
     double *L, *U, *W, *Dinv;
     int *info;
     unsigned long long *phase_ns;   // device-side time of every phase (one entry per phase)
+    long long *dbg;                 // optional: clock64 stamps of the last diag task (debug)
     double piv_tol;
 };
 
@@ -198,14 +200,15 @@ template <bool LDL>
 __device__ void task_diag(const FactorParams &p, int s, int jb, double *smem)
 {
     double *S = smem;                      // L11, col-major, ld LDS
-    double *colbuf = smem + NB * LDS;      // 2 x 64 (fits below Sinv: 4160 + 128 + 64 <= 4352)
+    double *colbuf = smem + NB * LDS;      // 2 x 64 column buffers, then invd and dv (4160 + 4*64 <= 4352... see static_assert)
     double *invd = colbuf + 2 * NB;        // reciprocals of the pivots of L11 (1/L_jj, or 1/D_j for LDL^T)
-    double *Sinv = smem + TILE * XS;       // inv(L11), col-major, ld LDS
+    double *Sinv = smem + NB * LDS + 4 * NB;   // inv(L11), col-major, ld LDS
     const FrontInfo f = p.fi[s];
     const int k = f.k, N = f.k + f.r;
     const int nb = min(NB, k - jb);
     double *P = p.L + f.lp + (int64_t)jb * N + jb;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    long long c0 = clock64();
     double a[4][4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
@@ -214,67 +217,81 @@ __device__ void task_diag(const FactorParams &p, int s, int jb, double *smem)
             int rr = 4 * ty + i, cc = 4 * tx + jj;
             a[i][jj] = (rr < nb && cc < nb && rr >= cc) ? P[(int64_t)cc * N + rr] : ((rr == cc) ? 1.0 : 0.0);
         }
+    long long c1 = clock64();
+    // Square-root-free right-looking elimination (L unit-lower, pivots d_j): the only
+    // serial floating-point chain per column is one reciprocal, one multiply and one FMA.
+    // For Cholesky the columns are scaled by sqrt(d_j) afterwards, off the critical path.
+    double *dv = colbuf + 3 * NB;          // pivots d_j
     int nbad = 0, ntiny = 0;
     for (int j4 = 0; j4 < NB / 4; ++j4) {
 #pragma unroll
         for (int js = 0; js < 4; ++js) {
             const int j = 4 * j4 + js;
             double *cb = colbuf + (j & 1) * NB;
+            // The 16 owners of column j publish it with the rows <= j zeroed, so every thread can
+            // use the buffer for both its row and its column multipliers without any masking;
+            // the pivot itself goes to dv[j].
             if (tx == j4) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cb[4 * ty + i] = a[i][js];
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = 4 * ty + i;
+                    cb[rr] = (rr > j) ? a[i][js] : 0.0;
+                    if (rr == j) dv[j] = a[i][js];
+                }
             }
             __syncthreads();
-            double d = cb[j];
-            double scale, dval;
+            double d = dv[j];
             if (!LDL) {
                 if (!(d > 0.0) || !(d < 1.0e300)) { nbad++; d = 1.0; }
-                // sqrt and its reciprocal from one rsqrt + one Newton step each (the IEEE sqrt and
-                // divide sequences are ~400 cycles on the critical path of every column)
-                double rs = rsqrt(d);
-                double sq = d * rs;
-                sq = fma(fma(-sq, sq, d), 0.5 * rs, sq);
-                rs = fma(fma(-sq, rs, 1.0), rs, rs);
-                dval = sq;
-                scale = rs;
             } else {
                 if (!(fabs(d) <= 1.0e300)) { nbad++; d = 1.0; }
                 else if (fabs(d) < p.piv_tol) { ntiny++; d = (d < 0.0) ? -p.piv_tol : p.piv_tol; }
-                dval = d;
-                scale = __drcp_rn(d);
             }
-            if (tid == 0) invd[j] = scale;
+            const double scale = 1.0 / d;
             double lr[4], lc[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) lr[i] = cb[4 * ty + i] * scale;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) lc[jj] = LDL ? cb[4 * tx + jj] : cb[4 * tx + jj] * scale;
+            for (int jj = 0; jj < 4; ++jj) lc[jj] = cb[4 * tx + jj];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                    if (4 * ty + i > j && 4 * tx + jj > j) a[i][jj] = fma(-lr[i], lc[jj], a[i][jj]);
+                for (int jj = 0; jj < 4; ++jj) a[i][jj] = fma(-lr[i], lc[jj], a[i][jj]);
             if (tx == j4) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    int rr = 4 * ty + i;
+                    const int rr = 4 * ty + i;
                     if (rr > j) a[i][js] = lr[i];
-                    else if (rr == j) a[i][js] = dval;
+                    else if (rr == j) a[i][js] = d;
                 }
+                if (4 * ty <= j && j < 4 * ty + 4) dv[j] = d;    // keep a perturbed pivot consistent
             }
         }
     }
+    long long c2 = clock64();
+    __syncthreads();
+    if (tid < NB) {
+        // invd = reciprocal of the diagonal of the stored factor: 1/sqrt(d) (Cholesky) or unused (LDL^T)
+        double d = dv[tid];
+        double sq = LDL ? d : sqrt(d);
+        dv[tid] = sq;
+        invd[tid] = LDL ? 1.0 : 1.0 / sq;
+    }
+    __syncthreads();
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int rr = 4 * ty + i, cc = 4 * tx + jj;
             if (rr >= cc) {
-                S[cc * LDS + rr] = a[i][jj];
-                if (rr < nb && cc < nb) P[(int64_t)cc * N + rr] = a[i][jj];
+                double v = a[i][jj];
+                if (!LDL) v = (rr == cc) ? dv[cc] : v * dv[cc];     // L = L_unit * sqrt(D)
+                S[cc * LDS + rr] = v;
+                if (rr < nb && cc < nb) P[(int64_t)cc * N + rr] = v;
             }
         }
     __syncthreads();
+    long long c3 = clock64();
     // inverse of the triangular factor: column c by the 4 threads (c, q), rows i = 4t + q
     {
         const int c = tid >> 2, q = tid & 3, lane = tid & 31;
@@ -292,10 +309,14 @@ __device__ void task_diag(const FactorParams &p, int s, int jb, double *smem)
         }
     }
     __syncthreads();
+    long long c4 = clock64();
     double *Dv = p.Dinv + (f.dinv + (jb >> 6)) * (int64_t)(NB * NB);
     for (int idx = tid; idx < NB * NB; idx += 256) {
         int rr = idx & 63, cc = idx >> 6;
         Dv[idx] = (rr >= cc) ? Sinv[cc * LDS + rr] : 0.0;
+    }
+    if (p.dbg && tid == 0 && blockIdx.x == 0) {
+        p.dbg[0] = c1 - c0; p.dbg[1] = c2 - c1; p.dbg[2] = c3 - c2; p.dbg[3] = c4 - c3; p.dbg[4] = clock64() - c4;
     }
     if (LDL && tid < nb && S[tid * LDS + tid] < 0.0) atomicAdd(&p.info[1], 1);
     if (tid == 0) {
@@ -385,7 +406,7 @@ __device__ void task_update(const FactorParams &p, int s, int lt, int jb, double
 }
 
 template <bool LDL>
-__global__ void __launch_bounds__(256, 2) k_factor_persistent(FactorParams p)
+__global__ void __launch_bounds__(256, 3) k_factor_persistent(FactorParams p)
 {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double smem[];
@@ -492,16 +513,20 @@ __device__ void front_forward(const SolveParams &p, int s, double *smem)
         }
         __syncthreads();
         for (int i = jb + nb + tid; i < N; i += 256) {
-            double acc0 = 0.0, acc1 = 0.0;
+            // 16 independent loads in flight per thread (the panel lives in HBM: latency-bound otherwise)
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
             const double *col = P + (int64_t)jb * N + i;
             int j = 0;
-#pragma unroll 4
-            for (; j + 1 < nb; j += 2) {
-                acc0 = fma(col[(int64_t)j * N], yb[j], acc0);
-                acc1 = fma(col[(int64_t)(j + 1) * N], yb[j + 1], acc1);
+            for (; j + 16 <= nb; j += 16) {
+                double v[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) v[t] = col[(int64_t)(j + t) * N];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) acc[t & 3] = fma(v[t], yb[j + t], acc[t & 3]);
             }
-            if (j < nb) acc0 = fma(col[(int64_t)j * N], yb[j], acc0);
-            if (i < k) x1[i] -= acc0 + acc1; else u[i - k] -= acc0 + acc1;
+            for (; j < nb; ++j) acc[j & 3] = fma(col[(int64_t)j * N], yb[j], acc[j & 3]);
+            const double tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            if (i < k) x1[i] -= tot; else u[i - k] -= tot;
         }
         __syncthreads();
     }
@@ -538,7 +563,22 @@ __device__ void front_backward(const SolveParams &p, int s, double *smem)
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[c] = 0.0;
                 const double *col = P + (int64_t)(jb + q0) * N;
-                for (int i = jb + nb + lane; i < N; i += 32) {
+                int i = jb + nb + lane;
+                for (; i + 32 < N; i += 64) {     // two row-chunks per trip: 16 loads in flight per lane
+                    const int i2 = i + 32;
+                    double xv = (i < k) ? x1[i] : (cached ? xr[i - k] : p.xp[rows[i - k]]);
+                    double xw = (i2 < k) ? x1[i2] : (cached ? xr[i2 - k] : p.xp[rows[i2 - k]]);
+                    double v[8], w[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const bool on = q0 + c < nb;
+                        v[c] = on ? col[(int64_t)c * N + i] : 0.0;
+                        w[c] = on ? col[(int64_t)c * N + i2] : 0.0;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] = fma(w[c], xw, fma(v[c], xv, acc[c]));
+                }
+                for (; i < N; i += 32) {
                     double xv = (i < k) ? x1[i] : (cached ? xr[i - k] : p.xp[rows[i - k]]);
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -800,6 +840,7 @@ int ls_factorize_impl(Handle *h, const double *d_nzval)
         p.sched = h->d_sched.p; p.phases = h->d_phases.p; p.n_phases = h->n_phases;
         p.L = h->d_L.p; p.U = h->d_U.p; p.W = h->d_W.p; p.Dinv = h->d_Dinv.p; p.info = h->d_info.p;
         p.phase_ns = h->d_phase_ns.p;
+        p.dbg = std::getenv("MIPM_DIAG_DBG") ? (long long *)(h->d_phase_ns.p + h->n_phases) : nullptr;
         p.piv_tol = 1e-13;   // LDL^T: absolute floor on |pivot|
         void *args[] = {&p};
         const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_factor_persistent<true> : (const void *)k_factor_persistent<false>;
@@ -892,6 +933,11 @@ extern "C" int mipm_ls_factorize_profile(mipm_handle hh, const double *d_nzval, 
         if (logf) std::fprintf(logf, "%d,%d,%d,%lld,%.2f\n", i, type, (int)ph[(size_t)i * 8 + 1], (long long)ph[(size_t)i * 8 + 2], t * 1e3);
     }
     if (logf) std::fclose(logf);
+    if (std::getenv("MIPM_DIAG_DBG")) {
+        long long dbg[5];
+        MIPM_CUDA(h, cudaMemcpy(dbg, h->d_phase_ns.p + h->n_phases, sizeof(dbg), cudaMemcpyDeviceToHost));
+        std::fprintf(stderr, "diag task cycles: load %lld potrf %lld scale %lld inverse %lld store %lld\n", dbg[0], dbg[1], dbg[2], dbg[3], dbg[4]);
+    }
     ms[0] = std::max(0.0, (double)total - inside);
     launches[0] = 4;
     work[0] = 8.0 * (double)(S.nnz_l + S.update_doubles) + 24.0 * (double)S.nnz_a;

@@ -94,7 +94,12 @@ class IPMOptions:
     rethrow_error: bool = False
     # B200Solver options (the analogue of cudss_algorithm / ir options of MadNLPGPU.CUDSSSolver)
     ordering: int = _lib.MIPM_ORDER_ND
-    ir_steps: int = 1
+    ir_steps: int = 0             # refinement rounds inside every linear solve (on the reduced system)
+    # adaptive refinement on the full unreduced KKT system, driven by the residual that
+    # solve_system! computes anyway (src/linear_solver.jl:29-35): refine while
+    # ||p - K d||_inf / max(1, ||p||_inf) > refine_tol, at most max_refine times
+    refine_tol: float = 1e-11
+    max_refine: int = 3
     exact_assembly_order: bool = False
     device: int = 0
 
@@ -196,6 +201,8 @@ class MPCSolver:
         self.Ap, self.Aj, self.A_csr_map = Ap, Aj, Amap
         self.h.spmv_setup(m, n, Ap, Aj)
         self.AT_x = z(len(Aj))                      # AT.nzVal: CSR-ordered values of A
+        self.A_V = z(len(Aj))                       # A.V: COO-ordered values (jac + slack), like kkt.A.V
+        self.d_A_csr_map = _dev(Amap, dev, torch.int64)
         # ---- Hessian operator (MadIPMOperator symmetric=true, cuda_wrapper.jl:62-68)
         self.hH = None
         if qp.nnzh > 0:
@@ -294,12 +301,13 @@ class MPCSolver:
     # ------------------------------------------------------------------ KKT system
     def compress_jacobian(self):
         """normalkkt.jl:163-172 / cuda_wrapper.jl:32-41: AT.nzVal = A.V[A_csr_map] (+ slack = -1)."""
-        V = self.A_V_host * self.con_scale[self.A_I]
-        self.AT_x.copy_(torch.from_numpy(V[self.A_csr_map]))
+        V = self.A_V_host if self._unit_con_scale else self.A_V_host * self.con_scale[self.A_I]
+        self.A_V.copy_(torch.from_numpy(V))                                   # jac_coord! result, H2D
+        self.h.gather(len(self.Aj), self.A_V, self.d_A_csr_map, self.AT_x)     # AT.nzVal .= A.V[A_csr_map]
         if self.opt.kkt_system == "Normal":
             self.h.normal_set_jacobian(self.AT_x)
         else:
-            self.jac.copy_(torch.from_numpy(V))
+            self.h.copy(len(self.Aj), self.A_V, self.jac)
 
     def compress_hessian(self):
         if self.qp.nnzh > 0:
@@ -358,6 +366,19 @@ class MPCSolver:
         self.kkt_mul(self._w1, self.d, -1.0, 1.0)
         norm_w, norm_p = self.h.residual_norms(self._w1, self.p)
         self.residual_ratio = norm_w / max(1.0, norm_p)
+        nref = 0
+        while self.residual_ratio > self.opt.refine_tol and nref < self.opt.max_refine:
+            # d += K^-1 (p - K d), then the reference's residual check again
+            self.kkt_solve(self._w1)
+            self.h.axpby(N, 1.0, self._w1, 1.0, self.d)
+            self.h.copy(N, self.p, self._w1)
+            self.kkt_mul(self._w1, self.d, -1.0, 1.0)
+            norm_w, norm_p = self.h.residual_norms(self._w1, self.p)
+            prev, self.residual_ratio = self.residual_ratio, norm_w / max(1.0, norm_p)
+            nref += 1
+            self.cnt["refinements"] = self.cnt.get("refinements", 0) + 1
+            if not (self.residual_ratio < 0.5 * prev):
+                break
         if np.isnan(self.residual_ratio) or (self.opt.check_residual and self.residual_ratio > self.opt.tol_linear_solve):
             raise SolveException("residual %.3e" % self.residual_ratio)
         return self.d
@@ -416,8 +437,12 @@ class MPCSolver:
         self.con_scale = np.ones(m)
         self.obj_scale = 1.0
         if opt.scaling:
+            # row-wise max |A_ij| over the CSR order (np.maximum.at is ~100x slower at 8e6 entries)
+            absv = np.abs(self.A_V_host)[self.A_csr_map]
             rowmax = np.zeros(m)
-            np.maximum.at(rowmax, self.A_I, np.abs(self.A_V_host))
+            nz = np.flatnonzero(np.diff(self.Ap) > 0)
+            if len(absv):
+                rowmax[nz] = np.maximum.reduceat(absv, self.Ap[:-1][nz])
             self.con_scale = np.minimum(1.0, 100.0 / np.maximum(rowmax, 1e-300))
             rhs = rhs * self.con_scale
             g = np.zeros(n)
@@ -428,6 +453,7 @@ class MPCSolver:
                 g[:nx] += (Hl + sp.tril(Hl, -1).T) @ x[:nx]
             gn = np.linalg.norm(g, np.inf)
             self.obj_scale = min(1.0, 100.0 / gn) if gn > 0 else 1.0
+        self._unit_con_scale = bool(np.all(self.con_scale == 1.0))
         cv = np.zeros(n)
         cv[:nx] = self.obj_scale * qp.c
         up_ = lambda t, a: t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
@@ -663,6 +689,8 @@ class MPCSolver:
         t0 = time.perf_counter()
         try:
             self.initialize()
+            torch.cuda.synchronize(self.device)
+            self.cnt["initialize_time"] = time.perf_counter() - t0
             self.mpc()
         except SolveException:
             # the reference throws the exception *type*, so its LinearSolverException branch is
@@ -677,13 +705,16 @@ class MPCSolver:
         torch.cuda.synchronize(self.device)
         total = time.perf_counter() - t0
         x = self.x.cpu().numpy()
-        import scipy.sparse as sp
-        A0 = sp.csr_matrix((self.qp.Avals, (self.qp.Arows, self.qp.Acols)), shape=(self.m, self.nx))
+        # stats.constraints = A0 x (unscaled, without the slack columns): device SpMV, then undo both
+        self.h.spmv(0, 1.0, self.AT_x, self.x, 0.0, self.buffer_m)
+        cons = self.buffer_m.cpu().numpy() / self.con_scale
+        if self.ns:
+            cons[self.ind_ineq] += x[self.nx:]
         sign = 1.0 if self.qp.minimize else -1.0
         return ExecutionStats(
             status=self.status, iter=self.k, objective=sign * self.obj_val / self.obj_scale,
             dual_objective=getattr(self, "dobj", float("nan")) / self.obj_scale,
-            solution=x[: self.nx].copy(), constraints=np.asarray(A0 @ x[: self.nx]),
+            solution=x[: self.nx].copy(), constraints=cons,
             multipliers=self.y.cpu().numpy() * self.con_scale / self.obj_scale,
             multipliers_L=self.zl.cpu().numpy()[: self.nx] / self.obj_scale,
             multipliers_U=self.zu.cpu().numpy()[: self.nx] / self.obj_scale,
