@@ -103,7 +103,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """CPU restatement of the reference on the host cores (kind = "port")."""
     if rank != 0:
         return
@@ -139,10 +139,20 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "Julia reference cannot run in this image (no Julia); cuDSS not installed",
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: native libraries (NCCL prints its version banner with
+    printf) get fd 1 redirected to stderr; the returned file object writes to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -156,7 +166,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch
@@ -332,7 +342,7 @@ def main():
                                               "max_front_cols", "max_front_rows", "update_doubles", "n_launches")},
             "setup_s": t_setup, "final_objective": res.objective,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
