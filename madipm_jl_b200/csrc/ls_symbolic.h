@@ -12,11 +12,13 @@ namespace mipm {
 struct LsOptions {
     int kind = 0;            // MIPM_CHOLESKY / MIPM_LDL
     int ordering = 0;        // MIPM_ORDER_*
-    int nd_leaf = 96;        // stop dissecting below this many vertices
-    int relax_always = 8;    // amalgamation: merge if merged width <= this
-    int relax_k1 = 32;  double relax_z1 = 0.50;
-    int relax_k2 = 96;  double relax_z2 = 0.20;
-    double relax_z3 = 0.05;
+    // defaults from the C2 sweep (tools/sweep_symbolic.py): larger leaves and more aggressive
+    // amalgamation trade ~3% more stored nonzeros for ~25% fewer supernodes
+    int nd_leaf = 256;       // stop dissecting below this many vertices
+    int relax_always = 16;   // amalgamation: merge if merged width <= this
+    int relax_k1 = 64;  double relax_z1 = 0.50;
+    int relax_k2 = 128; double relax_z2 = 0.30;
+    double relax_z3 = 0.10;
     int max_sn_cols = 1 << 30;
 };
 

@@ -98,7 +98,7 @@ class IPMOptions:
     # adaptive refinement on the full unreduced KKT system, driven by the residual that
     # solve_system! computes anyway (src/linear_solver.jl:29-35): refine while
     # ||p - K d||_inf / max(1, ||p||_inf) > refine_tol, at most max_refine times
-    refine_tol: float = 1e-11
+    refine_tol: float = 1e-9
     max_refine: int = 3
     exact_assembly_order: bool = False
     device: int = 0
