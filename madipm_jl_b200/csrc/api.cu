@@ -414,6 +414,7 @@ int mipm_ls_analyze(mipm_handle hh, int64_t n, const int32_t *colptr, const int3
     opt.kind = kind;
     opt.ordering = ordering;
     if (const char *s = std::getenv("MIPM_ND_LEAF")) opt.nd_leaf = std::max(1, atoi(s));
+    if (const char *s = std::getenv("MIPM_LDL_DELAY")) opt.ldl_delay_all = (std::strcmp(s, "first") != 0);
     if (const char *s = std::getenv("MIPM_RELAX")) {
         // "always,k1,z1,k2,z2,z3"
         sscanf(s, "%d,%d,%lf,%d,%lf,%lf", &opt.relax_always, &opt.relax_k1, &opt.relax_z1, &opt.relax_k2, &opt.relax_z2, &opt.relax_z3);

@@ -270,6 +270,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
                 all_smaller = adj[(size_t)p] < v;
             dual[(size_t)v] = all_smaller;
         }
+        const bool delay_all = opt.ldl_delay_all;
         // primal vertices with all neighbours larger are not delayed; only "dual" ones are
         std::vector<char> done((size_t)n, 0);
         std::vector<std::vector<int32_t>> waiting((size_t)n);  // waiting[u]: duals released when u is eliminated
@@ -278,16 +279,20 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
         for (int64_t k = 0; k < n; ++k) {
             int32_t v = perm0[(size_t)k];
             if (dual[(size_t)v]) {
-                bool ready = false;
-                int32_t first_nb = -1;
-                int32_t first_pos = INT32_MAX;
+                // wait for the LAST not-yet-eliminated primal neighbour (delay_all) or the first one
+                int32_t wait_nb = -1;
+                int32_t wait_pos = delay_all ? -1 : INT32_MAX;
+                bool ready = !delay_all ? false : true;
                 for (int64_t p = xadj[(size_t)v]; p < xadj[(size_t)v + 1]; ++p) {
                     int32_t u = adj[(size_t)p];
                     if (dual[(size_t)u]) continue;
-                    if (done[(size_t)u]) { ready = true; break; }
-                    if (ip[(size_t)u] < first_pos) { first_pos = ip[(size_t)u]; first_nb = u; }
+                    if (done[(size_t)u]) { if (!delay_all) { ready = true; break; } else continue; }
+                    if (delay_all) {
+                        ready = false;
+                        if (ip[(size_t)u] > wait_pos) { wait_pos = ip[(size_t)u]; wait_nb = u; }
+                    } else if (ip[(size_t)u] < wait_pos) { wait_pos = ip[(size_t)u]; wait_nb = u; }
                 }
-                if (!ready && first_nb >= 0) { waiting[(size_t)first_nb].push_back(v); continue; }
+                if (!ready && wait_nb >= 0) { waiting[(size_t)wait_nb].push_back(v); continue; }
             }
             out.push_back(v);
             done[(size_t)v] = 1;

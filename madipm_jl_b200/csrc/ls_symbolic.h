@@ -20,6 +20,9 @@ struct LsOptions {
     int relax_k2 = 128; double relax_z2 = 0.30;
     double relax_z3 = 0.10;
     int max_sn_cols = 1 << 30;
+    // LDL^T on K2: eliminate every dual vertex after ALL of its primal neighbours (true) or after the
+    // first one (false). 'All' is the numerically safe choice for tiny |delta_c| (quirk A.9 v).
+    bool ldl_delay_all = true;
 };
 
 struct LsSymbolic {
