@@ -185,6 +185,12 @@ int mipm_destroy(mipm_handle hh)
     if (!h->host_only) {
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
+        if (h->side) {
+            cudaStreamSynchronize(h->side);
+            cudaEventDestroy(h->ev_factor_done);
+            cudaEventDestroy(h->ev_u_zero);
+            cudaStreamDestroy(h->side);
+        }
         if (h->h_scal) cudaFreeHost(h->h_scal);
     }
     delete h;

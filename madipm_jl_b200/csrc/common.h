@@ -71,6 +71,9 @@ struct Handle {
     LsSymbolic sym;
     bool has_ls = false, factorized = false;
     int n_phases = 0, grid_factor = 0, grid_solve = 0;
+    cudaStream_t side = nullptr;     // zero-fill of the update matrices for the next factorization
+    cudaEvent_t ev_factor_done = nullptr, ev_u_zero = nullptr;
+    bool u_prezeroed = false;
     DBuf<int32_t> d_sched;           // schedule arrays (front lists, task prefixes, extend-add triples)
     DBuf<int64_t> d_phases, d_lvl, d_dinv_off;
     struct FI64 { char b[64]; };

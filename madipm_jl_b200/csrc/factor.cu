@@ -818,6 +818,14 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, h->d_r.alloc((size_t)std::max<int64_t>(S.n, 1)));
     MIPM_CUDA(h, h->d_phase_ns.alloc((size_t)h->n_phases + 8));
     MIPM_CUDA(h, cudaStreamSynchronize(st));
+    if (!h->side) {
+        MIPM_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+        MIPM_CUDA(h, cudaEventCreateWithFlags(&h->ev_factor_done, cudaEventDisableTiming));
+        MIPM_CUDA(h, cudaEventCreateWithFlags(&h->ev_u_zero, cudaEventDisableTiming));
+    } else {
+        MIPM_CUDA(h, cudaStreamSynchronize(h->side));
+    }
+    h->u_prezeroed = false;
     h->factorized = false;
     return MIPM_OK;
 }
@@ -828,7 +836,13 @@ int ls_factorize_impl(Handle *h, const double *d_nzval)
     cudaStream_t st = h->stream;
     MIPM_CUDA(h, cudaSetDevice(h->device));
     MIPM_CUDA(h, cudaMemsetAsync(h->d_L.p, 0, (size_t)std::max<int64_t>(S.nnz_l, 1) * sizeof(double), st));
-    MIPM_CUDA(h, cudaMemsetAsync(h->d_U.p, 0, (size_t)std::max<int64_t>(S.update_doubles, 1) * sizeof(double), st));
+    // The update matrices are only live inside the factorization kernel, so their zero-fill for the
+    // NEXT factorization runs on a side stream behind this one (it overlaps the latency-bound solves).
+    if (h->u_prezeroed) {
+        MIPM_CUDA(h, cudaStreamWaitEvent(st, h->ev_u_zero, 0));
+    } else {
+        MIPM_CUDA(h, cudaMemsetAsync(h->d_U.p, 0, (size_t)std::max<int64_t>(S.update_doubles, 1) * sizeof(double), st));
+    }
     MIPM_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, 4 * sizeof(int), st));
     if (S.nnz_a > 0) {
         k_scatter_a<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.nnz_a, h->d_a2l.p, d_nzval, h->d_L.p);
@@ -846,6 +860,13 @@ int ls_factorize_impl(Handle *h, const double *d_nzval)
         const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_factor_persistent<true> : (const void *)k_factor_persistent<false>;
         MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)h->grid_factor), dim3(256), args, SMEM_BYTES, st));
         h->launches++;
+    }
+    if (h->side) {
+        MIPM_CUDA(h, cudaEventRecord(h->ev_factor_done, st));
+        MIPM_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_factor_done, 0));
+        MIPM_CUDA(h, cudaMemsetAsync(h->d_U.p, 0, (size_t)std::max<int64_t>(S.update_doubles, 1) * sizeof(double), h->side));
+        MIPM_CUDA(h, cudaEventRecord(h->ev_u_zero, h->side));
+        h->u_prezeroed = true;
     }
     h->d_nzval = d_nzval;
     h->factorized = true;
