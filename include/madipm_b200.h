@@ -147,6 +147,13 @@ int mipm_spmv_setup(mipm_handle h, int64_t m, int64_t n, const int32_t *Ap, cons
 int mipm_spmv(mipm_handle h, int trans, double alpha, const double *d_Ax, const double *d_x,
               double beta, double *d_y);
 
+/* Hessian operator for obj / grad / the (1,1) block of mul!: replaces MadIPMOperator(H; symmetric=true),
+ * cuda_wrapper.jl:62-68 (H expanded to its full symmetric CSR by the caller, as `tril(A,-1) + A'` does):
+ * y = alpha * H x + beta * y with d_Hx the CSR-ordered values. */
+int mipm_hess_setup(mipm_handle h, int64_t n, const int32_t *Hp, const int32_t *Hj, int index_base);
+int mipm_hess_spmv(mipm_handle h, double alpha, const double *d_Hx, const double *d_x, double beta,
+                   double *d_y);
+
 /* ------------------------------------------------------------------ MPC vectors ---- */
 /* Device buffers of one MPCSolver (src/structure.jl:1-77, 125-153) and of its KKT system
  * (normalkkt.jl:58-67). KKT vectors d, p, w are [xp(n); y(m); zl(nlb); zu(nub)]
@@ -226,6 +233,38 @@ int mipm_gather(mipm_handle h, int64_t n, const double *d_src, const int64_t *d_
                 double *d_dst);
 /* dot(x, y) with a deterministic two-level reduction (used for obj = c'x + x'Qx/2). */
 int mipm_dot(mipm_handle h, int64_t n, const double *d_x, const double *d_y, double *out);
+
+/* ------------------------------------------------------------------ fused iteration - */
+/* One mpc! iteration (src/solver.jl:332-360) with device-resident scalars: the step lengths, the
+ * centering parameter and the barrier value never leave the GPU, so an iteration costs ONE host
+ * synchronisation (termination measures + factorization status) instead of ~20.
+ * Same kernels and operation order as the fine-grained entry points above.
+ *   mipm_mpc_set_model : which KKT system (0 = NormalKKTSystem, 1 = K2 SparseKKTSystem) and its buffers.
+ *   mipm_mpc_iter_begin: update_termination_criteria! measures + set_aug_diagonal_reg! + build_kkt! +
+ *                        factorize!, then one sync. out[16] = (dobj, ||c||inf, ||f-zl+zu+jacl||inf,
+ *                        max compl, ||dx||inf, obj c'x, x'Hx, alpha_p, alpha_d, mu, mu_curr,
+ *                        ||w||inf, ||p||inf of the predictor solve, same for the corrector solve, tau)
+ *                        where entries 5.. describe the PREVIOUS iteration's step. *status as mipm_ls_factorize.
+ *   mipm_mpc_refactor  : the retry of factorize_regularized_system! with new (del_w, del_c).
+ *   mipm_mpc_iter_rest : prediction_step! + mehrotra_correction_direction! + update_step_size!
+ *                        (step_rule 0 = AdaptiveStep(tau_param), 1 = ConservativeStep(tau_param)) +
+ *                        apply_step! + evaluate_model!; nothing is read back. */
+typedef struct {
+    int kkt_kind;                 /* 0 Normal, 1 K2 */
+    int exact_order;              /* Normal: reference operation order in the assembly */
+    int64_t nx;                   /* number of original variables (Hessian dimension) */
+    double c0;                    /* objective constant (already scaled) */
+    const double *d_ATx;          /* AT.nzVal (CSR values of A incl. slack columns) */
+    const double *d_cvec;         /* scaled linear objective, length n */
+    const double *d_Hx;           /* full symmetric CSR Hessian values or NULL */
+    double *d_aug_nz;             /* aug_com.nzVal */
+    const double *d_aug_raw_V;    /* K2: COO values [pr_diag; hess; jac; du_diag] */
+    double *d_buffer_n, *d_buffer_m;
+} mipm_mpc_model;
+int mipm_mpc_set_model(mipm_handle h, const mipm_mpc_model *model);
+int mipm_mpc_iter_begin(mipm_handle h, double del_w, double del_c, double *out, int *status);
+int mipm_mpc_refactor(mipm_handle h, double del_w, double del_c, int *status);
+int mipm_mpc_iter_rest(mipm_handle h, double mu_min, int step_rule, double tau_param, int ir_steps);
 
 /* ------------------------------------------------------------------ diagnostics ---- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */

@@ -32,6 +32,12 @@ class LsStats(C.Structure):
                 ("n_launches", C.c_int64)]
 
 
+class MpcModel(C.Structure):
+    _fields_ = [("kkt_kind", C.c_int), ("exact_order", C.c_int), ("nx", C.c_int64), ("c0", C.c_double),
+                ("d_ATx", C.c_void_p), ("d_cvec", C.c_void_p), ("d_Hx", C.c_void_p), ("d_aug_nz", C.c_void_p),
+                ("d_aug_raw_V", C.c_void_p), ("d_buffer_n", C.c_void_p), ("d_buffer_m", C.c_void_p)]
+
+
 class MpcVectors(C.Structure):
     _fields_ = [("n", C.c_int64), ("m", C.c_int64), ("nlb", C.c_int64), ("nub", C.c_int64),
                 ("index_base", C.c_int),
@@ -54,7 +60,8 @@ SYMBOLS = [
     "mipm_k2_symbolic", "mipm_k2_transfer",
     "mipm_ls_analyze", "mipm_ls_factorize", "mipm_ls_factorize_async", "mipm_ls_status", "mipm_ls_solve",
     "mipm_ls_inertia", "mipm_ls_stats", "mipm_ls_symbolic",
-    "mipm_spmv_setup", "mipm_spmv",
+    "mipm_spmv_setup", "mipm_spmv", "mipm_hess_setup", "mipm_hess_spmv",
+    "mipm_mpc_set_model", "mipm_mpc_iter_begin", "mipm_mpc_refactor", "mipm_mpc_iter_rest",
     "mipm_mpc_bind", "mipm_set_aug_diagonal_reg", "mipm_set_predictive_rhs", "mipm_set_correction_rhs",
     "mipm_get_correction", "mipm_set_extra_correction", "mipm_get_complementarity_measure",
     "mipm_get_affine_complementarity_measure", "mipm_get_alpha_max", "mipm_termination_measures",
@@ -214,6 +221,31 @@ class Handle:
 
     def spmv(self, trans, alpha, Ax, x, beta, y):
         self.check(self.lib.mipm_spmv(self.h, C.c_int(trans), C.c_double(alpha), _ptr(Ax), _ptr(x), C.c_double(beta), _ptr(y)))
+
+    def hess_setup(self, n, Hp, Hj, index_base=0):
+        Hp = np.ascontiguousarray(Hp, dtype=np.int32)
+        Hj = np.ascontiguousarray(Hj, dtype=np.int32)
+        self.check(self.lib.mipm_hess_setup(self.h, C.c_int64(n), _ptr(Hp), _ptr(Hj), C.c_int(index_base)))
+
+    def hess_spmv(self, alpha, Hx, x, beta, y):
+        self.check(self.lib.mipm_hess_spmv(self.h, C.c_double(alpha), _ptr(Hx), _ptr(x), C.c_double(beta), _ptr(y)))
+
+    def mpc_set_model(self, model: "MpcModel"):
+        self.check(self.lib.mipm_mpc_set_model(self.h, C.byref(model)))
+
+    def mpc_iter_begin(self, del_w, del_c):
+        out = (C.c_double * 16)()
+        st = C.c_int()
+        self.check(self.lib.mipm_mpc_iter_begin(self.h, C.c_double(del_w), C.c_double(del_c), out, C.byref(st)))
+        return list(out), st.value == MIPM_OK
+
+    def mpc_refactor(self, del_w, del_c):
+        st = C.c_int()
+        self.check(self.lib.mipm_mpc_refactor(self.h, C.c_double(del_w), C.c_double(del_c), C.byref(st)))
+        return st.value == MIPM_OK
+
+    def mpc_iter_rest(self, mu_min, step_rule, tau_param, ir_steps):
+        self.check(self.lib.mipm_mpc_iter_rest(self.h, C.c_double(mu_min), C.c_int(step_rule), C.c_double(tau_param), C.c_int(ir_steps)))
 
     def mpc_bind(self, vec: MpcVectors):
         self.check(self.lib.mipm_mpc_bind(self.h, C.byref(vec)))

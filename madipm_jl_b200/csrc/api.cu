@@ -401,6 +401,42 @@ int mipm_spmv(mipm_handle hh, int trans, double alpha, const double *d_Ax, const
     return MIPM_OK;
 }
 
+int mipm_hess_setup(mipm_handle hh, int64_t n, const int32_t *Hp, const int32_t *Hj, int index_base)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (n < 0 || !Hp) return fail(h, MIPM_ERR_ARG, "bad argument");
+    int64_t nnz = Hp[n] - index_base;
+    std::vector<int32_t> rp((size_t)n + 1), cj((size_t)nnz);
+    for (int64_t i = 0; i <= n; ++i) rp[(size_t)i] = Hp[i] - index_base;
+    for (int64_t p = 0; p < nnz; ++p) {
+        cj[(size_t)p] = Hj[p] - index_base;
+        if (cj[(size_t)p] < 0 || cj[(size_t)p] >= n) return fail(h, MIPM_ERR_ARG, "column index out of range");
+    }
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    MIPM_CUDA(h, h->d_hs_rowptr.upload(rp, h->stream));
+    MIPM_CUDA(h, h->d_hs_col.upload(cj, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->hs_n = n;
+    h->hs_nnz = nnz;
+    h->has_hess = true;
+    return MIPM_OK;
+}
+
+int mipm_hess_spmv(mipm_handle hh, double alpha, const double *d_Hx, const double *d_x, double beta, double *d_y)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_hess) return fail(h, MIPM_ERR_STATE, "mipm_hess_setup has not been called");
+    if ((!d_Hx && h->hs_nnz > 0) || !d_x || !d_y) return fail(h, MIPM_ERR_ARG, "null argument");
+    if (h->hs_n > 0) {
+        k_spmv_csr<<<grid_for(h->hs_n * 32, 256), 256, 0, h->stream>>>(h->hs_n, h->d_hs_rowptr.p, h->d_hs_col.p, d_Hx, d_x,
+                                                                     alpha, beta, d_y);
+        MIPM_CHECK_LAUNCH(h);
+    }
+    return MIPM_OK;
+}
+
 // ---------------------------------------------------------------- linear solver front-end
 int mipm_ls_analyze(mipm_handle hh, int64_t n, const int32_t *colptr, const int32_t *rowval, int index_base,
                     int kind, int ordering, const int32_t *user_perm)

@@ -92,6 +92,16 @@ struct Handle {
     int64_t sp_m = 0, sp_n = 0, sp_nnz = 0;
     DBuf<int32_t> d_sp_rowptr, d_sp_col, d_sp_colptr, d_sp_row, d_sp_pos;
 
+    // ---- Hessian operator (full symmetric CSR), the MadIPMOperator(H; symmetric=true) analogue
+    bool has_hess = false;
+    int64_t hs_n = 0, hs_nnz = 0;
+    DBuf<int32_t> d_hs_rowptr, d_hs_col;
+
+    // ---- fused MPC iteration: device-resident scalar block and the model / KKT buffers it drives
+    DBuf<double> d_sc;
+    bool has_model = false;
+    mipm_mpc_model model{};
+
     // ---- mpc vectors (+ inverse maps variable -> position in the lb / ub block, -1 if none)
     DBuf<int32_t> d_inv_lb, d_inv_ub;
     bool bound = false;

@@ -30,7 +30,7 @@ __device__ __forceinline__ double comb(double a, double b, int op)
 
 // Deterministic grid-wide reduction of NV values per thread; result in out[0..NV).
 template <int NV>
-__device__ void grid_reduce_vals(double (&acc)[NV], const int (&op)[NV], double *partials, unsigned int *counter,
+__device__ bool grid_reduce_vals(double (&acc)[NV], const int (&op)[NV], double *partials, unsigned int *counter,
                                  double *out)
 {
     __shared__ double sm[NV][TB / 32];
@@ -56,7 +56,7 @@ __device__ void grid_reduce_vals(double (&acc)[NV], const int (&op)[NV], double 
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) return false;
     __threadfence();
     const double ident[3] = {0.0, -DBL_MAX, DBL_MAX};
 #pragma unroll
@@ -75,6 +75,8 @@ __device__ void grid_reduce_vals(double (&acc)[NV], const int (&op)[NV], double 
         out[q] = v;
     }
     if (threadIdx.x == 0) *counter = 0;
+    __syncthreads();
+    return true;
 }
 
 // (value, index) arg-min pairs with the reference's tie rule: `a < b ? a : b` keeps the
@@ -87,7 +89,7 @@ __device__ __forceinline__ VI comb_vi(VI a, VI b)
     return (a.i > b.i) ? a : b;
 }
 template <int NP>
-__device__ void grid_reduce_argmin(VI (&acc)[NP], double *partials, unsigned int *counter, double *out)
+__device__ bool grid_reduce_argmin(VI (&acc)[NP], double *partials, unsigned int *counter, double *out)
 {
     __shared__ VI sm[NP][TB / 32];
     __shared__ bool is_last;
@@ -119,7 +121,7 @@ __device__ void grid_reduce_argmin(VI (&acc)[NP], double *partials, unsigned int
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) return false;
     __threadfence();
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
@@ -150,7 +152,18 @@ __device__ void grid_reduce_argmin(VI (&acc)[NP], double *partials, unsigned int
         out[NP + q] = (double)v.i;
     }
     if (threadIdx.x == 0) *counter = 0;
+    __syncthreads();
+    return true;
 }
+
+// Device-resident scalar block of the fused iteration (doubles).
+enum { SC_ALPHA = 0,       // alpha_xl, alpha_xu, alpha_zl, alpha_zu + 4 arg-min indices
+       SC_ALPHA_P = 8, SC_ALPHA_D = 9, SC_MU_AFF = 10, SC_MU_CURR = 11, SC_MU = 12, SC_TAU = 13,
+       SC_TERM = 16,       // 7 raw termination reductions
+       SC_RES = 24,        // ||w||, ||p|| of the predictor solve, then of the corrector solve
+       SC_OBJ = 28,        // c'x, x'Hx
+       SC_SUMS = 32,       // scratch: affine_l, affine_u, cur_l, cur_u
+       SC_COUNT = 40 };
 
 struct V {   // device view of mipm_mpc_vectors + inverse maps
     int64_t n, m, nlb, nub;
@@ -191,8 +204,9 @@ __global__ void __launch_bounds__(TB) k_set_aug_diag(V v, double del_w, double d
 }
 
 // src/kernels.jl:21-58 (corr == 0: predictive; corr == 1: correction with mu)
-__global__ void __launch_bounds__(TB) k_set_rhs(V v, int corr, double mu)
+__global__ void __launch_bounds__(TB) k_set_rhs(V v, int corr, double mu, const double *mu_dev)
 {
+    if (mu_dev) mu = *mu_dev;
     double *px = v.p, *py = v.p + v.n, *pzl = v.p + v.n + v.m, *pzu = v.p + v.n + v.m + v.nlb;
     GRID_STRIDE(i, v.n) {
         double x = v.x[i], zl = v.zl[i], zu = v.zu[i];
@@ -265,9 +279,50 @@ __global__ void __launch_bounds__(TB) k_compl_measure(V v, int affine, double ap
     grid_reduce_vals<2>(acc, op, partials, counter, out);
 }
 
-// src/kernels.jl:226-272: four ratio tests in one pass.
-__global__ void __launch_bounds__(TB) k_alpha_max(V v, double tau, double *partials, unsigned int *counter, double *out)
+// prediction_step! after the affine solve (src/solver.jl:232-235) in one pass: affine and current
+// complementarity sums (kernels.jl:155-208), get_correction! (kernels.jl:60-71) and the Mehrotra
+// barrier update (kernels.jl:210-220) by the last block. alpha_aff and the results stay on the device.
+__global__ void __launch_bounds__(TB) k_predictor_measures(V v, double mu_min, double *partials, unsigned int *counter, double *sc)
 {
+    const double *dx = v.d, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
+    const double ap = sc[SC_ALPHA_P], ad = sc[SC_ALPHA_D];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    GRID_STRIDE(i, v.n) {
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) {
+            acc[0] += ((v.x[i] + ap * dx[i]) - v.xl[i]) * (v.zl[i] + ad * dzl[jl]);
+            acc[2] += (v.x[i] - v.xl[i]) * v.zl[i];
+            v.corr_lb[jl] = dx[i] * dzl[jl];
+        }
+        if (ju >= 0) {
+            acc[1] += (v.xu[i] - (v.x[i] + ap * dx[i])) * (v.zu[i] + ad * dzu[ju]);
+            acc[3] += (v.xu[i] - v.x[i]) * v.zu[i];
+            v.corr_ub[ju] = dx[i] * dzu[ju];
+        }
+    }
+    const int op[4] = {OP_SUM, OP_SUM, OP_SUM, OP_SUM};
+    const bool last = grid_reduce_vals<4>(acc, op, partials, counter, sc + SC_SUMS);
+    if (last && threadIdx.x == 0) {
+        const double cnt = (double)(v.nlb + v.nub);
+        double mu_aff = 0.0, mu_cur = 0.0, sigma = 1.0;
+        if (cnt > 0) {
+            mu_aff = (sc[SC_SUMS + 0] + sc[SC_SUMS + 1]) / cnt;
+            mu_cur = (sc[SC_SUMS + 2] + sc[SC_SUMS + 3]) / cnt;
+            const double rr = mu_aff / mu_cur;
+            sigma = fmin(fmax(rr * rr * rr, 1e-6), 10.0);
+        }
+        sc[SC_MU_AFF] = mu_aff;
+        sc[SC_MU_CURR] = mu_cur;
+        sc[SC_MU] = fmax(mu_min, sigma * mu_cur);
+    }
+}
+
+// src/kernels.jl:226-272: four ratio tests in one pass.
+__global__ void __launch_bounds__(TB) k_alpha_max(V v, double tau, double *partials, unsigned int *counter, double *out,
+                                                  const double *sc_in, double tau_min, double *sc_out)
+{
+    // fused iteration: AdaptiveStep tau = max(1 - mu, tau_min) from the device-resident mu
+    if (sc_in) tau = fmax(1.0 - sc_in[SC_MU], tau_min);
     const double *dx = v.d, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
     VI acc[4];
 #pragma unroll
@@ -294,7 +349,12 @@ __global__ void __launch_bounds__(TB) k_alpha_max(V v, double tau, double *parti
             acc[3] = comb_vi(acc[3], c);
         }
     }
-    grid_reduce_argmin<4>(acc, partials, counter, out);
+    const bool last = grid_reduce_argmin<4>(acc, partials, counter, out);
+    if (last && sc_out && threadIdx.x == 0) {
+        sc_out[SC_ALPHA_P] = fmin(out[0], out[1]);     // get_fraction_to_boundary_step (kernels.jl:288)
+        sc_out[SC_ALPHA_D] = fmin(out[2], out[3]);
+        sc_out[SC_TAU] = tau;
+    }
 }
 
 // src/solver.jl:194-205 + src/kernels.jl:408-430 + src/structure.jl:193
@@ -328,8 +388,9 @@ __global__ void __launch_bounds__(TB) k_termination(V v, double *partials, unsig
 }
 
 // src/solver.jl:308-317 + MadNLP.adjust_boundary!
-__global__ void __launch_bounds__(TB) k_apply_step(V v, double ap, double ad, double c1, double c2)
+__global__ void __launch_bounds__(TB) k_apply_step(V v, double ap, double ad, double c1, double c2, const double *sc)
 {
+    if (sc) { ap = sc[SC_ALPHA_P]; ad = sc[SC_ALPHA_D]; c1 = DBL_EPSILON * sc[SC_MU]; }
     const double *dx = v.d, *dy = v.d + v.n, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
     GRID_STRIDE(i, v.n) {
         double x = v.x[i] + ap * dx[i];
@@ -595,7 +656,7 @@ int mipm_set_predictive_rhs(mipm_handle hh)
 {
     Handle *h = (Handle *)hh;
     VIEW_OR_FAIL(h);
-    k_set_rhs<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, 0, 0.0);
+    k_set_rhs<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, 0, 0.0, nullptr);
     MIPM_CHECK_LAUNCH(h);
     return MIPM_OK;
 }
@@ -604,7 +665,7 @@ int mipm_set_correction_rhs(mipm_handle hh, double mu)
 {
     Handle *h = (Handle *)hh;
     VIEW_OR_FAIL(h);
-    k_set_rhs<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, 1, mu);
+    k_set_rhs<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, 1, mu, nullptr);
     MIPM_CHECK_LAUNCH(h);
     return MIPM_OK;
 }
@@ -653,7 +714,7 @@ int mipm_get_alpha_max(mipm_handle hh, double tau, double *alpha, int64_t *idx)
     Handle *h = (Handle *)hh;
     VIEW_OR_FAIL(h);
     if (!alpha) return fail(h, MIPM_ERR_ARG, "null argument");
-    k_alpha_max<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, tau, h->d_partials.p, h->d_counter.p, h->d_scal.p);
+    k_alpha_max<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, tau, h->d_partials.p, h->d_counter.p, h->d_scal.p, nullptr, 0.0, nullptr);
     MIPM_CHECK_LAUNCH(h);
     double s[8];
     int rc = fetch_scalars(h, 8, s);
@@ -692,7 +753,7 @@ int mipm_apply_step(mipm_handle hh, double alpha_p, double alpha_d, double mu)
     Handle *h = (Handle *)hh;
     VIEW_OR_FAIL(h);
     const double eps = DBL_EPSILON;
-    k_apply_step<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, alpha_p, alpha_d, eps * mu, pow(eps, 0.75));
+    k_apply_step<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, alpha_p, alpha_d, eps * mu, pow(eps, 0.75), nullptr);
     MIPM_CHECK_LAUNCH(h);
     return MIPM_OK;
 }
@@ -817,6 +878,196 @@ int mipm_dot(mipm_handle hh, int64_t n, const double *d_x, const double *d_y, do
     k_dot<<<red_grid(h, n), TB, 0, h->stream>>>(n, d_x, d_y, h->d_partials.p, h->d_counter.p, h->d_scal.p);
     MIPM_CHECK_LAUNCH(h);
     return fetch_scalars(h, 1, out);
+}
+
+
+// ---------------------------------------------------------------- fused iteration
+static int fused_ready(Handle *h)
+{
+    if (!h->bound) return fail(h, MIPM_ERR_STATE, "mipm_mpc_bind has not been called");
+    if (!h->has_model) return fail(h, MIPM_ERR_STATE, "mipm_mpc_set_model has not been called");
+    if (!h->has_ls || !h->has_spmv) return fail(h, MIPM_ERR_STATE, "linear solver / SpMV not set up");
+    return MIPM_OK;
+}
+
+int mipm_mpc_set_model(mipm_handle hh, const mipm_mpc_model *md)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!md || (md->kkt_kind != 0 && md->kkt_kind != 1) || !md->d_ATx || !md->d_cvec || !md->d_aug_nz || !md->d_buffer_n ||
+        !md->d_buffer_m || (md->kkt_kind == 1 && !md->d_aug_raw_V))
+        return fail(h, MIPM_ERR_ARG, "bad model");
+    if (md->d_Hx && !h->has_hess) return fail(h, MIPM_ERR_STATE, "Hessian values given but mipm_hess_setup not called");
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    h->model = *md;
+    MIPM_CUDA(h, h->d_sc.alloc(SC_COUNT));
+    MIPM_CUDA(h, cudaMemsetAsync(h->d_sc.p, 0, SC_COUNT * sizeof(double), h->stream));
+    h->has_model = true;
+    return MIPM_OK;
+}
+
+// build_kkt! + factorize! (MadNLP.factorize_wrapper!)
+static int fused_factorize(Handle *h, double del_w, double del_c)
+{
+    int rc = mipm_set_aug_diagonal_reg((mipm_handle)h, del_w, del_c);
+    if (rc != MIPM_OK) return rc;
+    const mipm_mpc_model &md = h->model;
+    if (md.kkt_kind == 0) rc = mipm_normal_assemble((mipm_handle)h, h->v.d_pr_diag, md.d_aug_nz, md.exact_order);
+    else rc = mipm_k2_transfer((mipm_handle)h, md.d_aug_raw_V, md.d_aug_nz);
+    if (rc != MIPM_OK) return rc;
+    return mipm_ls_factorize_async((mipm_handle)h, md.d_aug_nz);
+}
+
+// solve!(kkt, w): normalkkt.jl:196-219 / MadNLP K2
+static int fused_kkt_solve(Handle *h, double *w, int ir_steps)
+{
+    mipm_handle hh = (mipm_handle)h;
+    const mipm_mpc_model &md = h->model;
+    int rc;
+    if (md.kkt_kind == 0) {
+        if ((rc = mipm_normal_solve_stage(hh, 0, w, md.d_buffer_n, md.d_buffer_m)) != MIPM_OK) return rc;
+        if ((rc = mipm_spmv(hh, 0, 1.0, md.d_ATx, md.d_buffer_n, -1.0, md.d_buffer_m)) != MIPM_OK) return rc;
+        if ((rc = mipm_ls_solve(hh, md.d_buffer_m, ir_steps)) != MIPM_OK) return rc;
+        if ((rc = mipm_normal_solve_stage(hh, 1, w, md.d_buffer_n, md.d_buffer_m)) != MIPM_OK) return rc;
+        if ((rc = mipm_spmv(hh, 1, -1.0, md.d_ATx, md.d_buffer_m, 1.0, md.d_buffer_n)) != MIPM_OK) return rc;
+        return mipm_normal_solve_stage(hh, 2, w, md.d_buffer_n, md.d_buffer_m);
+    }
+    if ((rc = mipm_reduce_rhs(hh, w)) != MIPM_OK) return rc;
+    if ((rc = mipm_ls_solve(hh, w, ir_steps)) != MIPM_OK) return rc;
+    return mipm_finish_aug_solve(hh, w);
+}
+
+// solve_system! (src/linear_solver.jl:19-44): d = K^-1 p, then w = p - K d and its norms into sc[slot..]
+static int fused_solve_system(Handle *h, int ir_steps, int slot)
+{
+    mipm_handle hh = (mipm_handle)h;
+    const mipm_mpc_vectors &m = h->v;
+    const mipm_mpc_model &md = h->model;
+    const int64_t N = m.n + m.m + m.nlb + m.nub;
+    int rc;
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_d, m.d_p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = fused_kkt_solve(h, m.d_d, ir_steps)) != MIPM_OK) return rc;
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_w, m.d_p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    // mul!(w, kkt, d, -1, 1)
+    if ((rc = mipm_spmv(hh, 1, -1.0, md.d_ATx, m.d_d + m.n, 1.0, m.d_w)) != MIPM_OK) return rc;
+    if (md.d_Hx && md.kkt_kind == 1)
+        if ((rc = mipm_hess_spmv(hh, -1.0, md.d_Hx, m.d_d, 1.0, m.d_w)) != MIPM_OK) return rc;
+    if ((rc = mipm_spmv(hh, 0, -1.0, md.d_ATx, m.d_d, 1.0, m.d_w + m.n)) != MIPM_OK) return rc;
+    if ((rc = mipm_kktmul(hh, m.d_w, m.d_d, -1.0, 1.0)) != MIPM_OK) return rc;
+    k_two_norms<<<red_grid(h, std::max<int64_t>(N, 1)), TB, 0, h->stream>>>(N, m.d_w, m.d_p, h->d_partials.p, h->d_counter.p,
+                                                                         h->d_sc.p + SC_RES + 2 * slot);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+static int fused_fetch(Handle *h, double *out, int *status)
+{
+    double sc[SC_COUNT];
+    int info[4];
+    MIPM_CUDA(h, cudaMemcpyAsync(h->h_scal, h->d_sc.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaMemcpyAsync(info, h->d_info.p, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < SC_COUNT; ++i) sc[i] = h->h_scal[i];
+    if (status) *status = (info[0] == 0) ? MIPM_OK : MIPM_ERR_NOT_FACTORIZED;
+    if (out) {
+        const mipm_mpc_vectors &m = h->v;
+        double dobj = sc[SC_TERM + 0];
+        if (m.nlb > 0) dobj += sc[SC_TERM + 1];
+        if (m.nub > 0) dobj -= sc[SC_TERM + 2];
+        out[0] = dobj;
+        out[1] = sc[SC_TERM + 3];
+        out[2] = sc[SC_TERM + 4];
+        out[3] = sc[SC_TERM + 5];
+        out[4] = sc[SC_TERM + 6];
+        out[5] = sc[SC_OBJ];
+        out[6] = sc[SC_OBJ + 1];
+        out[7] = sc[SC_ALPHA_P];
+        out[8] = sc[SC_ALPHA_D];
+        out[9] = sc[SC_MU];
+        out[10] = sc[SC_MU_CURR];
+        out[11] = sc[SC_RES + 0];
+        out[12] = sc[SC_RES + 1];
+        out[13] = sc[SC_RES + 2];
+        out[14] = sc[SC_RES + 3];
+        out[15] = sc[SC_TAU];
+    }
+    return MIPM_OK;
+}
+
+int mipm_mpc_iter_begin(mipm_handle hh, double del_w, double del_c, double *out, int *status)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    int rc = fused_ready(h);
+    if (rc != MIPM_OK) return rc;
+    if (!out || !status) return fail(h, MIPM_ERR_ARG, "null argument");
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    V v = make_view(h, inv_lb_buf(h).p, inv_ub_buf(h).p);
+    const int64_t nmax = std::max<int64_t>(std::max(v.n, v.m), 1);
+    k_termination<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, h->d_partials.p, h->d_counter.p, h->d_sc.p + SC_TERM);
+    MIPM_CHECK_LAUNCH(h);
+    if ((rc = fused_factorize(h, del_w, del_c)) != MIPM_OK) return rc;
+    return fused_fetch(h, out, status);
+}
+
+int mipm_mpc_refactor(mipm_handle hh, double del_w, double del_c, int *status)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    int rc = fused_ready(h);
+    if (rc != MIPM_OK) return rc;
+    if (!status) return fail(h, MIPM_ERR_ARG, "null argument");
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    if ((rc = fused_factorize(h, del_w, del_c)) != MIPM_OK) return rc;
+    return mipm_ls_status(hh, status);
+}
+
+int mipm_mpc_iter_rest(mipm_handle hh, double mu_min, int step_rule, double tau_param, int ir_steps)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    int rc = fused_ready(h);
+    if (rc != MIPM_OK) return rc;
+    if (step_rule != 0 && step_rule != 1) return fail(h, MIPM_ERR_ARG, "step_rule must be 0 (adaptive) or 1 (conservative)");
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    V v = make_view(h, inv_lb_buf(h).p, inv_ub_buf(h).p);
+    const mipm_mpc_model &md = h->model;
+    const int64_t nmax = std::max<int64_t>(std::max(v.n, v.m), 1);
+    const unsigned g = red_grid(h, nmax);
+    double *sc = h->d_sc.p;
+    // prediction_step! (solver.jl:230-237)
+    k_set_rhs<<<g, TB, 0, h->stream>>>(v, 0, 0.0, nullptr);
+    MIPM_CHECK_LAUNCH(h);
+    if ((rc = fused_solve_system(h, ir_steps, 0)) != MIPM_OK) return rc;
+    k_alpha_max<<<g, TB, 0, h->stream>>>(v, 1.0, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, nullptr, 0.0, sc);
+    MIPM_CHECK_LAUNCH(h);
+    k_predictor_measures<<<g, TB, 0, h->stream>>>(v, mu_min, h->d_partials.p, h->d_counter.p, sc);
+    MIPM_CHECK_LAUNCH(h);
+    // mehrotra_correction_direction! (solver.jl:239-243)
+    k_set_rhs<<<g, TB, 0, h->stream>>>(v, 1, 0.0, sc + SC_MU);
+    MIPM_CHECK_LAUNCH(h);
+    if ((rc = fused_solve_system(h, ir_steps, 1)) != MIPM_OK) return rc;
+    // update_step_size! (kernels.jl:291-305)
+    if (step_rule == 0) k_alpha_max<<<g, TB, 0, h->stream>>>(v, 0.0, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, sc, tau_param, sc);
+    else k_alpha_max<<<g, TB, 0, h->stream>>>(v, tau_param, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, nullptr, 0.0, sc);
+    MIPM_CHECK_LAUNCH(h);
+    // apply_step! (solver.jl:308-317)
+    k_apply_step<<<g, TB, 0, h->stream>>>(v, 0.0, 0.0, 0.0, pow(DBL_EPSILON, 0.75), sc);
+    MIPM_CHECK_LAUNCH(h);
+    // evaluate_model! (solver.jl:319-326): obj pieces, c(x) = A x - rhs, f = H x + c, jacl = A' y
+    const mipm_mpc_vectors &m = h->v;
+    k_dot<<<red_grid(h, std::max<int64_t>(md.nx, 1)), TB, 0, h->stream>>>(md.nx, md.d_cvec, m.d_x, h->d_partials.p, h->d_counter.p, sc + SC_OBJ);
+    MIPM_CHECK_LAUNCH(h);
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_f, md.d_cvec, (size_t)m.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (md.d_Hx) {
+        if ((rc = mipm_hess_spmv(hh, 1.0, md.d_Hx, m.d_x, 0.0, md.d_buffer_n)) != MIPM_OK) return rc;
+        k_dot<<<red_grid(h, std::max<int64_t>(md.nx, 1)), TB, 0, h->stream>>>(md.nx, md.d_buffer_n, m.d_x, h->d_partials.p, h->d_counter.p, sc + SC_OBJ + 1);
+        MIPM_CHECK_LAUNCH(h);
+        if ((rc = mipm_axpby(hh, md.nx, 1.0, md.d_buffer_n, 1.0, m.d_f)) != MIPM_OK) return rc;
+    }
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_c, m.d_rhs, (size_t)m.m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = mipm_spmv(hh, 0, 1.0, md.d_ATx, m.d_x, -1.0, m.d_c)) != MIPM_OK) return rc;
+    return mipm_spmv(hh, 1, 1.0, md.d_ATx, m.d_y, 0.0, m.d_jacl);
 }
 
 }  // extern "C"

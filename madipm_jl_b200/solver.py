@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MpcVectors
+from ._lib import MpcModel, MpcVectors
 
 # MadNLP.Status names
 INITIAL = "INITIAL"
@@ -100,6 +100,10 @@ class IPMOptions:
     # ||p - K d||_inf / max(1, ||p||_inf) > refine_tol, at most max_refine times
     refine_tol: float = 1e-9
     max_refine: int = 3
+    # one host synchronisation per iteration: step lengths, centering parameter and barrier value stay on the
+    # device (mipm_mpc_iter_begin / mipm_mpc_iter_rest). Used for the default options (no Gondzio corrections,
+    # Adaptive / Conservative step rule); otherwise the fine-grained host-driven sequence runs.
+    fused: bool = True
     exact_assembly_order: bool = False
     device: int = 0
 
@@ -212,8 +216,8 @@ class MPCSolver:
             fc = np.concatenate([hc, hr[off]]).astype(np.int32)
             fv = np.concatenate([hv, hv[off]])
             Hp, Hj, Hmap = _lib.coo_to_csr(nx, nx, fr, fc)
-            self.hH = _lib.Handle(device=opt.device, stream=stream)
-            self.hH.spmv_setup(nx, nx, Hp, Hj)
+            self.hH = self.h
+            self.h.hess_setup(nx, Hp, Hj)
             self.H_full_host = fv[Hmap]
             self.Hx = z(len(Hj))
         self.cvec = z(n)
@@ -257,6 +261,18 @@ class MPCSolver:
             setattr(mv, name, P(t))
         self._mv = mv
         self.h.mpc_bind(mv)
+        md = MpcModel()
+        md.kkt_kind = 0 if opt.kkt_system == "Normal" else 1
+        md.exact_order = int(opt.exact_assembly_order)
+        md.nx, md.c0 = nx, 0.0
+        md.d_ATx, md.d_cvec, md.d_aug_nz = P(self.AT_x), P(self.cvec), P(self.aug_nz)
+        md.d_Hx = P(self.Hx) if qp.nnzh > 0 else None
+        md.d_aug_raw_V = P(self.aug_raw_V) if opt.kkt_system == "K2" else None
+        md.d_buffer_n, md.d_buffer_m = P(self.buffer_n), P(self.buffer_m)
+        self._md = md
+        self.h.mpc_set_model(md)
+        self._fused_started = False
+        self._fused_ir = opt.ir_steps
         # ---- scalars (structure.jl:62-76)
         self.obj_val = 0.0
         self.inf_pr = self.inf_du = self.inf_compl = 0.0
@@ -279,7 +295,7 @@ class MPCSolver:
         """obj = c0 + c'x + x'Hx/2 (MadIPMCUDAExt.jl:34-38)."""
         v = self.h.dot(self.nx, self.cvec, self.x)
         if self.hH is not None:
-            self.hH.spmv(0, 1.0, self.Hx, self.x, 0.0, self.buffer_n)
+            self.hH.hess_spmv(1.0, self.Hx, self.x, 0.0, self.buffer_n)
             v += 0.5 * self.h.dot(self.nx, self.buffer_n, self.x)
         return self.obj_scale * self.qp.c0 + v
 
@@ -287,7 +303,7 @@ class MPCSolver:
         """f = Hx + c (MadIPMCUDAExt.jl:40-45)."""
         self.h.copy(self.n, self.cvec, self.f)
         if self.hH is not None:
-            self.hH.spmv(0, 1.0, self.Hx, self.x, 1.0, self.f)
+            self.hH.hess_spmv(1.0, self.Hx, self.x, 1.0, self.f)
 
     def _eval_cons(self):
         """c(x) = A x - s - rhs with slack columns inside A (App. A)."""
@@ -351,7 +367,7 @@ class MPCSolver:
         h = self.h
         h.spmv(1, alpha, self.AT_x, v[n:n + m], beta, w[:n])
         if self.hH is not None and self.opt.kkt_system == "K2":
-            self.hH.spmv(0, alpha, self.Hx, v[:self.nx], 1.0, w[:self.nx])
+            self.hH.hess_spmv(alpha, self.Hx, v[:self.nx], 1.0, w[:self.nx])
         h.spmv(0, alpha, self.AT_x, v[:n], beta, w[n:n + m])
         h.kktmul(w, v, alpha, beta)
         return w
@@ -486,6 +502,8 @@ class MPCSolver:
         self.best_complementarity = float("inf")
         self.status = REGULAR
         self.jtprod(self.jacl, self.y)
+        self._fused_started = False
+        self._fused_ir = self.opt.ir_steps
 
     def init_starting_point(self):
         """src/solver.jl:6-125."""
@@ -664,8 +682,69 @@ class MPCSolver:
             alpha_p=self.alpha_p, alpha_d=self.alpha_d, del_w=self.del_w,
             dnorm=0.0 if self.k == 0 else self.dnorm))
 
+    def _use_fused(self):
+        return (self.opt.fused and self.opt.max_ncorr <= 0 and not self.opt.check_residual
+                and isinstance(self.opt.step_rule, (AdaptiveStep, ConservativeStep)))
+
+    def _mpc_iteration_fused(self):
+        """The same loop body through mipm_mpc_iter_begin / mipm_mpc_iter_rest: one host sync."""
+        opt = self.opt
+        trace_del_w = self.del_w
+        self.update_regularization()                      # host-side schedule (kernels.jl:370-401)
+        out, ok = self.h.mpc_iter_begin(self.del_w, self.del_c)
+        if self._fused_started:                            # scalars of the step taken in the previous call
+            self.obj_val = self.obj_scale * self.qp.c0 + out[5] + 0.5 * out[6]
+            self.alpha_p, self.alpha_d, self.mu, self.mu_curr = out[7], out[8], out[9], out[10]
+            for nw, npp in ((out[11], out[12]), (out[13], out[14])):
+                ratio = nw / max(1.0, npp)
+                if np.isnan(ratio):
+                    raise SolveException("NaN residual after linear solve")
+                if ratio > opt.refine_tol:
+                    self._fused_ir = max(self._fused_ir, 1)   # later solves refine on the reduced system
+            self.residual_ratio = ratio
+        dobj, nc, ndu, ncompl, dnorm = out[:5]
+        self.dobj, self.dnorm = dobj, dnorm
+        self.inf_pr = nc / max(1.0, self.norm_b)
+        self.inf_du = ndu / max(1.0, self.norm_c)
+        self.inf_compl = ncompl / max(1.0, self.norm_c)
+        self.best_complementarity = min(self.best_complementarity, self.inf_compl)
+        if max(self.inf_pr, self.inf_du, self.inf_compl) <= opt.tol:
+            self.status = SOLVE_SUCCEEDED
+        elif (self.inf_compl > opt.divergence_tol * self.best_complementarity) and (dobj > max(10.0 * abs(self.obj_val), 1.0)):
+            self.status = INFEASIBLE_PROBLEM_DETECTED
+        elif self.obj_val < -opt.divergence_tol * max(10.0, abs(dobj), 1.0):
+            self.status = DIVERGING_ITERATES
+        elif self.k >= opt.max_iter:
+            self.status = MAXIMUM_ITERATIONS_EXCEEDED
+        elif time.time() - self.start_time >= opt.max_wall_time:
+            self.status = MAXIMUM_WALLTIME_EXCEEDED
+        new_del_w, self.del_w = self.del_w, trace_del_w
+        self._record()
+        self.del_w = new_del_w
+        if self.status != REGULAR:
+            return False
+        self.cnt["factorizations"] += 1
+        for _ in range(2):                                 # factorize_regularized_system! retries (linear_solver.jl:6-17)
+            if ok:
+                break
+            self.del_w *= 100.0
+            self.del_c *= 100.0
+            ok = self.h.mpc_refactor(self.del_w, self.del_c)
+            self.cnt["factorizations"] += 1
+        rule = opt.step_rule
+        if isinstance(rule, AdaptiveStep):
+            self.h.mpc_iter_rest(opt.mu_min, 0, rule.tau_min, self._fused_ir)
+        else:
+            self.h.mpc_iter_rest(opt.mu_min, 1, rule.tau, self._fused_ir)
+        self.cnt["solves"] += 2
+        self._fused_started = True
+        self.k += 1
+        return True
+
     def mpc_iteration(self):
         """One pass of the loop body of mpc! (src/solver.jl:333-359). Returns False when done."""
+        if self._use_fused():
+            return self._mpc_iteration_fused()
         self.update_termination_criteria()
         self._record()
         if self.status != REGULAR:

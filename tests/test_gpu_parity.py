@@ -275,12 +275,15 @@ def _check_trace(got, ref_trace, ref_iter, ref_status, tol=TOL):
             assert close(a[f], b[f], tol), (a["k"], f, a[f], b[f])
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("key", sorted(GOLD))
-def test_end_to_end_matches_golden_traces(built, key):
+def test_end_to_end_matches_golden_traces(built, key, fused):
+    """Both host sequencings -- the fused one-sync-per-iteration path (device-resident scalars) and the
+    fine-grained call-per-function path -- must reproduce the oracle's iterates."""
     from madipm_jl_b200.solver import madipm
     from tests.golden.make_golden import CASES
     name, kkt = key.split("/")
-    got = madipm(CASES[name](), kkt_system=kkt)
+    got = madipm(CASES[name](), kkt_system=kkt, fused=fused)
     g = GOLD[key]
     _check_trace(got, g["trace"], g["iter"], g["status"])
     assert close(got.objective, g["objective"])
