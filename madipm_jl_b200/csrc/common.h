@@ -71,6 +71,8 @@ struct Handle {
     LsSymbolic sym;
     bool has_ls = false, factorized = false;
     int n_phases = 0, grid_factor = 0, grid_solve = 0;
+    int64_t leaf_off = 0;            // small leaf fronts (one warp each) in d_sched
+    int n_leaf = 0;
     cudaStream_t side = nullptr;     // zero-fill of the update matrices for the next factorization
     cudaEvent_t ev_factor_done = nullptr, ev_u_zero = nullptr;
     bool u_prezeroed = false;

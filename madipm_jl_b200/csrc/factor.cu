@@ -41,7 +41,9 @@ constexpr int XS = 68;          // smem row stride of staged operands (68 % 16 =
 constexpr int SMEM_DOUBLES = 2 * TILE * XS;
 static_assert(2 * NB * LDS + 4 * NB <= SMEM_DOUBLES, "diag task: S + scratch + Sinv must fit the tile buffers");
 constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;   // 69,632 B
-enum { PH_EA = 0, PH_DIAG = 1, PH_TRSM = 2, PH_UPDATE = 3 };
+enum { PH_EA = 0, PH_DIAG = 1, PH_TRSM = 2, PH_UPDATE = 3, PH_LEAF = 4 };
+constexpr int SL_K = 8;         // small leaf front: no children, at most SL_K columns ...
+constexpr int SL_N = 32;        // ... and at most SL_N rows: one warp does the whole front in registers
 
 // Everything a task needs to know about a front, in one 64-byte record (4 x 16-byte loads)
 // instead of six dependent index lookups.
@@ -71,7 +73,9 @@ struct SolveParams {
     const FrontInfo *fi;
     const int32_t *child_idx, *rel_idx, *row_idx, *perm;
     const int32_t *sched;
-    const int64_t *lvl;         // 2 x int64 per level: off_all, n_all
+    const int64_t *lvl;         // 2 x int64 per level: off_all, n_all (level 0: regular fronts only)
+    int64_t leaf_off;           // small leaf fronts (level 0), one warp each
+    int n_leaf;
     int n_levels;
     int64_t n, n_u;
     const double *L, *Dinv;
@@ -188,6 +192,78 @@ __device__ void task_extend_add(const FactorParams &p, const int32_t *tasks, int
             for (int a = b + (threadIdx.x & 31); a < rc; a += 32) dst[rel[a]] += src[a];
         }
         __syncthreads();
+    }
+}
+
+// Small leaf front (no children, k <= SL_K, k + r <= SL_N): one warp, lane i owns row i of the
+// panel in registers; pivots and multipliers travel by shuffles; the update matrix is written
+// directly (a leaf receives nothing, so U = -L21 D L21'). K2 systems have ~10^5 of these
+// (one per primal variable), which the 64 x 64 tile machinery would handle at < 1% efficiency.
+template <bool LDL>
+__device__ void leaf_factor(const FactorParams &p, int s)
+{
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, r = f.r, N = f.k + f.r;
+    const int lane = threadIdx.x & 31;
+    double *P = p.L + f.lp;
+    double *U = p.U + f.up;
+    double pr[SL_K], dd[SL_K];
+#pragma unroll
+    for (int c = 0; c < SL_K; ++c) pr[c] = (lane < N && c < k && lane >= c) ? P[(int64_t)c * N + lane] : 0.0;
+    int nbad = 0, ntiny = 0, nneg = 0;
+#pragma unroll
+    for (int j = 0; j < SL_K; ++j) {
+        dd[j] = 1.0;
+        if (j < k) {
+            double d = __shfl_sync(0xffffffffu, pr[j], j);
+            if (!LDL) {
+                if (!(d > 0.0) || !(d < 1.0e300)) { nbad++; d = 1.0; }
+            } else {
+                if (!(fabs(d) <= 1.0e300)) { nbad++; d = 1.0; }
+                else if (fabs(d) < p.piv_tol) { ntiny++; d = (d < 0.0) ? -p.piv_tol : p.piv_tol; }
+                nneg += (d < 0.0);
+            }
+            dd[j] = d;
+            const double colj = pr[j];                       // unscaled entry (lane, j)
+            const double l = (lane > j) ? colj / d : 0.0;
+#pragma unroll
+            for (int c = j + 1; c < SL_K; ++c) {
+                if (c < k) {
+                    const double t = __shfl_sync(0xffffffffu, colj, c);   // unscaled entry (c, j)
+                    if (lane >= c) pr[c] = fma(-l, t, pr[c]);
+                }
+            }
+            pr[j] = (lane > j) ? l : ((lane == j) ? d : 0.0);
+        }
+    }
+    if (!LDL) {                                              // L = L_unit * sqrt(D)
+#pragma unroll
+        for (int j = 0; j < SL_K; ++j) {
+            const double sq = sqrt(dd[j]);
+            pr[j] = (lane == j) ? sq : pr[j] * sq;
+            dd[j] = 1.0;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < SL_K; ++c)
+        if (c < k && lane < N && lane >= c) P[(int64_t)c * N + lane] = pr[c];
+    // update matrix of the leaf: U(i, c) = -sum_j L(i, j) d_j L(c, j), k <= c <= i < N
+    double ld[SL_K];
+#pragma unroll
+    for (int j = 0; j < SL_K; ++j) ld[j] = (j < k) ? pr[j] * dd[j] : 0.0;
+    for (int c = k; c < N; ++c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < SL_K; ++j) {
+            const double lc = __shfl_sync(0xffffffffu, pr[j], c);
+            acc = fma(ld[j], lc, acc);
+        }
+        if (lane >= c && lane < N) U[(int64_t)(c - k) * r + (lane - k)] = -acc;
+    }
+    if (lane == 0) {
+        if (nbad) atomicMax(&p.info[0], 1);
+        if (ntiny) atomicAdd(&p.info[2], ntiny);
+        if (LDL && nneg) atomicAdd(&p.info[1], nneg);
     }
 }
 
@@ -418,7 +494,10 @@ __global__ void __launch_bounds__(256, 3) k_factor_persistent(FactorParams p)
         const int type = (int)d[0], jb = (int)d[1], n_tasks = (int)d[2];
         const int32_t *A = p.sched + d[3];
         for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-            if (type == PH_EA) {
+            if (type == PH_LEAF) {
+                const int li = task * 8 + (threadIdx.x >> 5);       // one warp per leaf front
+                if (li < jb) leaf_factor<LDL>(p, A[li]);             // jb carries the number of leaves
+            } else if (type == PH_EA) {
                 task_extend_add(p, A, task);
             } else if (type == PH_DIAG) {
                 task_diag<LDL>(p, A[task], jb, smem);
@@ -612,8 +691,76 @@ __device__ void front_backward(const SolveParams &p, int s, double *smem)
     }
 }
 
+// Small leaf fronts in the solves: one warp per front, L11 (k <= SL_K) applied by direct substitution.
 template <bool LDL>
-__global__ void __launch_bounds__(256, 4) k_solve_persistent(SolveParams p)
+__device__ void leaf_forward(const SolveParams &p, int s)
+{
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, N = f.k + f.r;
+    const int lane = threadIdx.x & 31;
+    const double *P = p.L + f.lp;
+    double *x1 = p.xp + f.c0;
+    double y[SL_K];
+#pragma unroll
+    for (int j = 0; j < SL_K; ++j) {
+        y[j] = 0.0;
+        if (j < k) {
+            double t = x1[j];
+#pragma unroll
+            for (int q = 0; q < j; ++q) t = fma(-P[(int64_t)q * N + j], y[q], t);
+            if (!LDL) t = t / P[(int64_t)j * N + j];
+            y[j] = t;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < SL_K; ++j) if (j < k) x1[j] = y[j];
+    }
+    if (lane >= k && lane < N) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < SL_K; ++j) if (j < k) acc = fma(P[(int64_t)j * N + lane], y[j], acc);
+        p.uvec[f.rowp + lane - k] = -acc;          // a leaf has no children: its update vector starts from zero
+    }
+}
+
+template <bool LDL>
+__device__ void leaf_backward(const SolveParams &p, int s)
+{
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, N = f.k + f.r;
+    const int lane = threadIdx.x & 31;
+    const double *P = p.L + f.lp;
+    double *x1 = p.xp + f.c0;
+    const double xv = (lane >= k && lane < N) ? p.xp[p.row_idx[f.rowp + lane - k]] : 0.0;
+    double w[SL_K];
+#pragma unroll
+    for (int j = 0; j < SL_K; ++j) {
+        double part = (j < k && lane >= k && lane < N) ? P[(int64_t)j * N + lane] * xv : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        double yj = (j < k) ? x1[j] : 0.0;
+        if (LDL && j < k) yj = yj / P[(int64_t)j * N + j];
+        w[j] = yj - part;
+    }
+#pragma unroll
+    for (int j = SL_K - 1; j >= 0; --j) {
+        if (j < k) {
+            double t = w[j];
+#pragma unroll
+            for (int q = j + 1; q < SL_K; ++q) if (q < k) t = fma(-P[(int64_t)j * N + q], w[q], t);
+            if (!LDL) t = t / P[(int64_t)j * N + j];
+            w[j] = t;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < SL_K; ++j) if (j < k) x1[j] = w[j];
+    }
+}
+
+template <bool LDL>
+__global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double smem[NB * LDS + NB + XR_MAX];
@@ -621,11 +768,19 @@ __global__ void __launch_bounds__(256, 4) k_solve_persistent(SolveParams p)
     for (int64_t i = gtid; i < p.n; i += gsz) p.xp[i] = p.b_in[p.perm[i]];
     for (int64_t i = gtid; i < p.n_u; i += gsz) p.uvec[i] = 0.0;
     grid.sync();
+    const int32_t *leaves = p.sched + p.leaf_off;
+    const int n_leaf_groups = (p.n_leaf + 7) / 8;
     for (int l = 0; l < p.n_levels; ++l) {
         const int32_t *fr = p.sched + p.lvl[2 * l];
         const int nf = (int)p.lvl[2 * l + 1];
-        for (int t = blockIdx.x; t < nf; t += gridDim.x) {
-            front_forward<LDL>(p, fr[t], smem);
+        const int extra = (l == 0) ? n_leaf_groups : 0;      // small leaves ride along with level 0
+        for (int t = blockIdx.x; t < nf + extra; t += gridDim.x) {
+            if (t < extra) {
+                const int li = t * 8 + (threadIdx.x >> 5);
+                if (li < p.n_leaf) leaf_forward<LDL>(p, leaves[li]);
+            } else {
+                front_forward<LDL>(p, fr[t - extra], smem);
+            }
             __syncthreads();
         }
         grid.sync();
@@ -633,8 +788,14 @@ __global__ void __launch_bounds__(256, 4) k_solve_persistent(SolveParams p)
     for (int l = p.n_levels - 1; l >= 0; --l) {
         const int32_t *fr = p.sched + p.lvl[2 * l];
         const int nf = (int)p.lvl[2 * l + 1];
-        for (int t = blockIdx.x; t < nf; t += gridDim.x) {
-            front_backward<LDL>(p, fr[t], smem);
+        const int extra = (l == 0) ? n_leaf_groups : 0;
+        for (int t = blockIdx.x; t < nf + extra; t += gridDim.x) {
+            if (t < extra) {
+                const int li = t * 8 + (threadIdx.x >> 5);
+                if (li < p.n_leaf) leaf_backward<LDL>(p, leaves[li]);
+            } else {
+                front_backward<LDL>(p, fr[t - extra], smem);
+            }
             __syncthreads();
         }
         grid.sync();
@@ -676,11 +837,15 @@ int ls_device_setup(Handle *h)
     std::vector<int64_t> phases, lvl;
     std::vector<int64_t> wp((size_t)ns + 1, 0), dinv_off((size_t)ns + 1, 0);
     std::vector<FrontInfo> finfo((size_t)std::max(ns, 1));
+    std::vector<char> small((size_t)std::max(ns, 1), 0);
+    const bool use_leaf = std::getenv("MIPM_NO_LEAF") == nullptr;
     for (int s = 0; s < ns; ++s) {
         int64_t k = S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s];
         int64_t r = S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s];
-        wp[(size_t)s + 1] = wp[(size_t)s] + (S.kind == MIPM_LDL ? (k + r) * NB : 0);
-        dinv_off[(size_t)s + 1] = dinv_off[(size_t)s] + (k + NB - 1) / NB;
+        small[(size_t)s] = use_leaf && S.child_ptr[(size_t)s + 1] == S.child_ptr[(size_t)s] && k <= SL_K && k + r <= SL_N;
+        // small leaves need neither the LDL^T scratch panel nor inverted diagonal blocks
+        wp[(size_t)s + 1] = wp[(size_t)s] + ((S.kind == MIPM_LDL && !small[(size_t)s]) ? (k + r) * NB : 0);
+        dinv_off[(size_t)s + 1] = dinv_off[(size_t)s] + (small[(size_t)s] ? 0 : (k + NB - 1) / NB);
         FrontInfo &f = finfo[(size_t)s];
         f.k = (int32_t)k; f.r = (int32_t)r; f.c0 = S.sn_ptr[(size_t)s];
         f.nchild = (int32_t)(S.child_ptr[(size_t)s + 1] - S.child_ptr[(size_t)s]);
@@ -692,16 +857,29 @@ int ls_device_setup(Handle *h)
         int64_t d[8] = {type, jb, n_tasks, off_tasks, 0, 0, 0, 0};
         phases.insert(phases.end(), d, d + 8);
     };
+    int64_t leaf_off = 0;
+    int n_leaf = 0;
     for (int l = 0; l < S.n_levels; ++l) {
         const int64_t f0 = S.level_ptr[(size_t)l], f1 = S.level_ptr[(size_t)l + 1];
+        if (l == 0) {            // small leaf fronts: their own list, one PH_LEAF phase, one warp each
+            leaf_off = (int64_t)sched.size();
+            for (int64_t t = f0; t < f1; ++t) {
+                int s = S.level_sn[(size_t)t];
+                if (small[(size_t)s]) { sched.push_back(s); n_leaf++; }
+            }
+            if (n_leaf) push_phase(PH_LEAF, n_leaf, (n_leaf + 7) / 8, leaf_off);
+        }
         lvl.push_back((int64_t)sched.size());
-        lvl.push_back(f1 - f0);
+        int64_t n_reg = 0;
         int kmax = 0;
         for (int64_t t = f0; t < f1; ++t) {
             int s = S.level_sn[(size_t)t];
+            if (small[(size_t)s]) continue;
             sched.push_back(s);
+            n_reg++;
             kmax = std::max(kmax, S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s]);
         }
+        lvl.push_back(n_reg);
         // extend-add: per-child column ranges first, then the task records that point at them
         std::vector<int32_t> ea;
         for (int64_t t = f0; t < f1; ++t) {
@@ -738,7 +916,7 @@ int ls_device_setup(Handle *h)
             for (int64_t t = f0; t < f1; ++t) {
                 int s = S.level_sn[(size_t)t];
                 const FrontInfo &f = finfo[(size_t)s];
-                if (f.k <= jb) continue;
+                if (f.k <= jb || small[(size_t)s]) continue;
                 td.push_back(s);
                 int nb = std::min(NB, f.k - jb), j1 = jb + nb, N = f.k + f.r;
                 int ntr = (N - j1 + TILE - 1) / TILE;
@@ -765,6 +943,8 @@ int ls_device_setup(Handle *h)
             }
         }
     }
+    h->leaf_off = leaf_off;
+    h->n_leaf = n_leaf;
     h->n_phases = (int)(phases.size() / 8);
     h->n_launch_factor = 2;   // scatter + persistent kernel (plus three memsets)
     // ---- cooperative grid sizes
@@ -879,6 +1059,7 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     SolveParams p;
     p.fi = (const FrontInfo *)h->d_finfo.p; p.child_idx = h->d_child_idx.p; p.rel_idx = h->d_rel_idx.p; p.row_idx = h->d_row_idx.p;
     p.perm = h->d_perm.p; p.sched = h->d_sched.p; p.lvl = h->d_lvl.p; p.n_levels = S.n_levels;
+    p.leaf_off = h->leaf_off; p.n_leaf = h->n_leaf;
     p.n = S.n; p.n_u = S.row_ptr[(size_t)S.ns];
     p.L = h->d_L.p; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
     p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
@@ -948,8 +1129,9 @@ extern "C" int mipm_ls_factorize_profile(mipm_handle hh, const double *d_nzval, 
     for (int i = 0; i < h->n_phases; ++i) {
         int type = (int)ph[(size_t)i * 8];
         double t = (double)ns[(size_t)i] * 1e-6;
-        ms[type + 1] += t;
-        launches[type + 1] += 1;
+        const int cls = (type == PH_LEAF) ? 2 : type + 1;     // small-leaf fronts are counted with the diagonal-block class
+        ms[cls] += t;
+        launches[cls] += 1;
         inside += t;
         if (logf) std::fprintf(logf, "%d,%d,%d,%lld,%.2f\n", i, type, (int)ph[(size_t)i * 8 + 1], (long long)ph[(size_t)i * 8 + 2], t * 1e3);
     }
