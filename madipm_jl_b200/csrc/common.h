@@ -78,6 +78,8 @@ struct Handle {
     bool u_prezeroed = false;
     DBuf<int32_t> d_sched;           // schedule arrays (front lists, task prefixes, extend-add triples)
     DBuf<int64_t> d_phases, d_lvl, d_dinv_off;
+    DBuf<int32_t> d_ea_first, d_ea_count;
+    DBuf<int> d_work_counter;
     struct FI64 { char b[64]; };
     DBuf<FI64> d_finfo;              // FrontInfo records (64 bytes each, see factor.cu)
     DBuf<double> d_Dinv;             // inverted 64 x 64 diagonal blocks

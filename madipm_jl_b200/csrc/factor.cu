@@ -41,7 +41,7 @@ constexpr int XS = 68;          // smem row stride of staged operands (68 % 16 =
 constexpr int SMEM_DOUBLES = 2 * TILE * XS;
 static_assert(2 * NB * LDS + 4 * NB <= SMEM_DOUBLES, "diag task: S + scratch + Sinv must fit the tile buffers");
 constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;   // 69,632 B
-enum { PH_EA = 0, PH_DIAG = 1, PH_TRSM = 2, PH_UPDATE = 3, PH_LEAF = 4 };
+enum { PH_EA = 0, PH_DIAG = 1, PH_TRSM = 2, PH_UPDATE = 3, PH_LEAF = 4, PH_FRONT = 5 };
 constexpr int SL_K = 8;         // small leaf front: no children, at most SL_K columns ...
 constexpr int SL_N = 32;        // ... and at most SL_N rows: one warp does the whole front in registers
 
@@ -64,6 +64,9 @@ struct FactorParams {
     int n_phases;
     double *L, *U, *W, *Dinv;
     int *info;
+    const int32_t *ea_first;        // per front: first extend-add task record of its own (PH_FRONT levels), count
+    const int32_t *ea_count;
+    int *work_counter;              // one dynamic task counter per phase (PH_FRONT phases)
     unsigned long long *phase_ns;   // device-side time of every phase (one entry per phase)
     long long *dbg;                 // optional: clock64 stamps of the last diag task (debug)
     double piv_tol;
@@ -481,6 +484,31 @@ __device__ void task_update(const FactorParams &p, int s, int lt, int jb, double
     });
 }
 
+// Whole-front task for levels with many more fronts than CTAs: one CTA assembles the front from its
+// children and runs every block step of its partial factorization with CTA-local barriers only. A level
+// then is ONE phase instead of 1 + 3 x (block steps), no CTA idles at grid barriers while another
+// front's serial diagonal block finishes, and the front stays hot in L2.
+template <bool LDL>
+__device__ void task_front(const FactorParams &p, int s, double *smem)
+{
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, r = f.r, N = f.k + f.r;
+    const int n_ea = p.ea_count[s];
+    const int32_t *ea = p.sched + p.ea_first[s];
+    for (int t = 0; t < n_ea; ++t) task_extend_add(p, ea, t);     // ends with a CTA barrier per child
+    __syncthreads();
+    for (int jb = 0; jb < k; jb += NB) {
+        const int nb = min(NB, k - jb), j1 = jb + nb;
+        task_diag<LDL>(p, s, jb, smem);
+        __syncthreads();
+        const int ntr = (N - j1 + TILE - 1) / TILE;
+        for (int lc = 0; lc < ntr; ++lc) { task_trsm<LDL>(p, s, lc, jb, smem); __syncthreads(); }
+        const int nt1 = (k > j1) ? (k - j1 + TILE - 1) / TILE : 0, nt2 = (r + TILE - 1) / TILE;
+        const int nup = (nt1 + nt2) * (nt1 + nt2 + 1) / 2;
+        for (int lt = 0; lt < nup; ++lt) { task_update<LDL>(p, s, lt, jb, smem); __syncthreads(); }
+    }
+}
+
 template <bool LDL>
 __global__ void __launch_bounds__(256, 3) k_factor_persistent(FactorParams p)
 {
@@ -493,6 +521,19 @@ __global__ void __launch_bounds__(256, 3) k_factor_persistent(FactorParams p)
         const int64_t *d = p.phases + 8 * (int64_t)ph;
         const int type = (int)d[0], jb = (int)d[1], n_tasks = (int)d[2];
         const int32_t *A = p.sched + d[3];
+        if (type == PH_FRONT) {
+            // dynamic distribution (fronts are sorted by decreasing work on the host)
+            __shared__ int next_task;
+            for (;;) {
+                if (threadIdx.x == 0) next_task = atomicAdd(&p.work_counter[ph], 1);
+                __syncthreads();
+                const int task = next_task;
+                __syncthreads();
+                if (task >= n_tasks) break;
+                task_front<LDL>(p, A[task], smem);
+                __syncthreads();
+            }
+        } else
         for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
             if (type == PH_LEAF) {
                 const int li = task * 8 + (threadIdx.x >> 5);       // one warp per leaf front
@@ -859,6 +900,18 @@ int ls_device_setup(Handle *h)
     };
     int64_t leaf_off = 0;
     int n_leaf = 0;
+    // grid size is needed to decide which levels run whole-front tasks
+    int fuse_min = 1 << 30;
+    {
+        cudaDeviceProp prop0;
+        MIPM_CUDA(h, cudaGetDeviceProperties(&prop0, h->device));
+        // Measured on B200 (tools/sweep_fuse.py): per-CTA tile latency, not the grid barriers, bounds
+        // the wide levels, so whole-front tasks are neutral on C2 and slower on C3's small fronts.
+        // Off by default; MIPM_FRONT_FUSE_MIN=<n> enables them for levels with at least n fronts.
+        (void)prop0;
+        if (const char *e = std::getenv("MIPM_FRONT_FUSE_MIN")) fuse_min = std::max(1, atoi(e));
+    }
+    std::vector<int32_t> ea_first((size_t)std::max(ns, 1), 0), ea_count((size_t)std::max(ns, 1), 0);
     for (int l = 0; l < S.n_levels; ++l) {
         const int64_t f0 = S.level_ptr[(size_t)l], f1 = S.level_ptr[(size_t)l + 1];
         if (l == 0) {            // small leaf fronts: their own list, one PH_LEAF phase, one warp each
@@ -880,6 +933,7 @@ int ls_device_setup(Handle *h)
             kmax = std::max(kmax, S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s]);
         }
         lvl.push_back(n_reg);
+        const bool fuse_level = n_reg >= fuse_min;
         // extend-add: per-child column ranges first, then the task records that point at them
         std::vector<int32_t> ea;
         for (int64_t t = f0; t < f1; ++t) {
@@ -887,6 +941,7 @@ int ls_device_setup(Handle *h)
             const FrontInfo &f = finfo[(size_t)s];
             if (f.nchild == 0) continue;
             int N = f.k + f.r;
+            ea_first[(size_t)s] = (int32_t)(ea.size() / 4);            // index inside this level's record array
             for (int q0 = 0; q0 < N; q0 += EA_COLS) {
                 int q1 = std::min(N, q0 + EA_COLS);
                 int64_t off_r = (int64_t)sched.size();
@@ -904,12 +959,34 @@ int ls_device_setup(Handle *h)
                 if (!any) { sched.resize((size_t)off_r); continue; }
                 if (off_r > INT32_MAX) return fail(h, MIPM_ERR_ARG, "schedule too large");
                 ea.push_back(s); ea.push_back(q0); ea.push_back(q1); ea.push_back((int32_t)off_r);
+                ea_count[(size_t)s]++;
             }
         }
         if (!ea.empty()) {
             align4();
-            push_phase(PH_EA, 0, (int64_t)ea.size() / 4, (int64_t)sched.size());
+            const int64_t off_ea = (int64_t)sched.size();
+            if (!fuse_level) push_phase(PH_EA, 0, (int64_t)ea.size() / 4, off_ea);
             sched.insert(sched.end(), ea.begin(), ea.end());
+            for (int64_t t = f0; t < f1; ++t) {       // turn per-level record indices into offsets into sched
+                int s = S.level_sn[(size_t)t];
+                if (ea_count[(size_t)s]) ea_first[(size_t)s] = (int32_t)(off_ea + 4 * (int64_t)ea_first[(size_t)s]);
+            }
+        }
+        if (fuse_level) {
+            std::vector<int32_t> fr;
+            for (int64_t t = f0; t < f1; ++t) {
+                int s = S.level_sn[(size_t)t];
+                if (!small[(size_t)s]) fr.push_back(s);
+            }
+            std::stable_sort(fr.begin(), fr.end(), [&](int32_t a, int32_t b) {
+                const FrontInfo &fa = finfo[(size_t)a], &fb = finfo[(size_t)b];
+                double wa = (double)fa.k * (fa.k + fa.r) * (fa.k + fa.r), wb = (double)fb.k * (fb.k + fb.r) * (fb.k + fb.r);
+                return wa > wb;
+            });
+            align4();
+            push_phase(PH_FRONT, 0, (int64_t)fr.size(), (int64_t)sched.size());
+            sched.insert(sched.end(), fr.begin(), fr.end());
+            continue;
         }
         for (int jb = 0; jb < kmax; jb += NB) {
             std::vector<int32_t> td, tt, tu;
@@ -971,6 +1048,9 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, h->d_finfo.alloc(finfo.size()));
     MIPM_CUDA(h, cudaMemcpyAsync(h->d_finfo.p, finfo.data(), finfo.size() * sizeof(FrontInfo), cudaMemcpyHostToDevice, st));
     MIPM_CUDA(h, h->d_phases.upload(phases, st));
+    MIPM_CUDA(h, h->d_ea_first.upload(ea_first, st));
+    MIPM_CUDA(h, h->d_ea_count.upload(ea_count, st));
+    MIPM_CUDA(h, h->d_work_counter.alloc((size_t)h->n_phases + 8));
     MIPM_CUDA(h, h->d_lvl.upload(lvl, st));
     MIPM_CUDA(h, h->d_sn_ptr.upload(S.sn_ptr, st));
     MIPM_CUDA(h, h->d_sn_parent.upload(S.sn_parent, st));
@@ -1024,6 +1104,7 @@ int ls_factorize_impl(Handle *h, const double *d_nzval)
         MIPM_CUDA(h, cudaMemsetAsync(h->d_U.p, 0, (size_t)std::max<int64_t>(S.update_doubles, 1) * sizeof(double), st));
     }
     MIPM_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, 4 * sizeof(int), st));
+    MIPM_CUDA(h, cudaMemsetAsync(h->d_work_counter.p, 0, ((size_t)h->n_phases + 8) * sizeof(int), st));
     if (S.nnz_a > 0) {
         k_scatter_a<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.nnz_a, h->d_a2l.p, d_nzval, h->d_L.p);
         MIPM_CHECK_LAUNCH(h);
@@ -1034,6 +1115,7 @@ int ls_factorize_impl(Handle *h, const double *d_nzval)
         p.sched = h->d_sched.p; p.phases = h->d_phases.p; p.n_phases = h->n_phases;
         p.L = h->d_L.p; p.U = h->d_U.p; p.W = h->d_W.p; p.Dinv = h->d_Dinv.p; p.info = h->d_info.p;
         p.phase_ns = h->d_phase_ns.p;
+        p.ea_first = h->d_ea_first.p; p.ea_count = h->d_ea_count.p; p.work_counter = h->d_work_counter.p;
         p.dbg = std::getenv("MIPM_DIAG_DBG") ? (long long *)(h->d_phase_ns.p + h->n_phases) : nullptr;
         p.piv_tol = 1e-13;   // LDL^T: absolute floor on |pivot|
         void *args[] = {&p};
@@ -1129,7 +1211,8 @@ extern "C" int mipm_ls_factorize_profile(mipm_handle hh, const double *d_nzval, 
     for (int i = 0; i < h->n_phases; ++i) {
         int type = (int)ph[(size_t)i * 8];
         double t = (double)ns[(size_t)i] * 1e-6;
-        const int cls = (type == PH_LEAF) ? 2 : type + 1;     // small-leaf fronts are counted with the diagonal-block class
+        // small-leaf fronts are counted with the diagonal-block class, whole-front phases with the update class
+        const int cls = (type == PH_LEAF) ? 2 : ((type == PH_FRONT) ? 4 : type + 1);
         ms[cls] += t;
         launches[cls] += 1;
         inside += t;

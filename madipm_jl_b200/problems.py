@@ -193,3 +193,41 @@ def config_c3(seed=3, scale=1.0):
 
 def config_c5(index, seed=5):
     return random_sparse_lp(500, 2_000, 5, seed * 100_003 + index, structure="uniform")
+
+
+def mixed_bounds_lp(m, n, k, seed):
+    """Small LP exercising every bound / constraint kind the reference handles: equality, range,
+    upper-only and lower-only rows (-> slack variables), and variables that are lower-bounded,
+    boxed, upper-only or free. Feasible (built around x*) and bounded (c = A_eq' y* + z*, z* > 0 on
+    the variables with an infinite upper bound, free variables get exactly A_eq' y*)."""
+    rng = np.random.default_rng(seed)
+    rows, cols = _sparsity(rng, m, n, k, "uniform", 0)
+    vals = rng.standard_normal(len(rows))
+    xs = rng.uniform(0.5, 1.5, n)
+    b = np.zeros(m)
+    np.add.at(b, rows, vals * xs[cols])
+    kind = rng.integers(0, 4, m)                 # 0 equality, 1 range, 2 upper-only, 3 lower-only
+    kind[: max(1, m // 3)] = 0
+    lcon = np.where(kind == 0, b, np.where(kind == 1, b - 1.0, np.where(kind == 2, -np.inf, b - 0.5)))
+    ucon = np.where(kind == 0, b, np.where(kind == 1, b + 1.0, np.where(kind == 2, b + 0.5, np.inf)))
+    vk = rng.integers(0, 4, n)                   # 0 x>=0, 1 boxed, 2 upper-only, 3 free
+    vk[rng.random(n) < 0.5] = 0
+    lvar = np.where(vk == 0, 0.0, np.where(vk == 1, -2.0, -np.inf))
+    uvar = np.where(vk == 0, np.inf, np.where(vk == 1, 3.0, np.where(vk == 2, 2.5, np.inf)))
+    ys = np.where(kind == 0, rng.standard_normal(m), 0.0)
+    c = np.zeros(n)
+    np.add.at(c, cols, vals * ys[rows])
+    zs = rng.uniform(0.1, 1.0, n)
+    c += np.where(vk == 0, zs, np.where(vk == 2, -zs, np.where(vk == 1, rng.standard_normal(n), 0.0)))
+    return QuadraticModel(c=c, Hrows=[], Hcols=[], Hvals=[], Arows=rows, Acols=cols, Avals=vals, lcon=lcon, ucon=ucon,
+                          lvar=lvar, uvar=uvar, x0=np.zeros(n), name=f"mixed_lp_m{m}_n{n}_s{seed}")
+
+
+def bound_constrained_qp(n, seed):
+    """Convex QP with bounds only (m = 0), like MadNLPTests.DenseDummyQP(x0; m=0) in test/runtests.jl:64."""
+    rng = np.random.default_rng(seed)
+    Q = rng.standard_normal((n, n))
+    Q = Q @ Q.T + np.eye(n)
+    rows, cols = np.tril_indices(n)
+    return QuadraticModel(c=rng.standard_normal(n), Hrows=rows, Hcols=cols, Hvals=Q[rows, cols], Arows=[], Acols=[], Avals=[],
+                          lcon=[], ucon=[], lvar=np.zeros(n), uvar=np.full(n, 2.0), x0=np.ones(n), name=f"boxqp_n{n}_s{seed}")

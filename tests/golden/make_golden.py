@@ -16,7 +16,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from madipm_jl_b200.problems import random_sparse_lp, random_sparse_qp, simple_lp  # noqa: E402
+from madipm_jl_b200.problems import (bound_constrained_qp, mixed_bounds_lp, random_sparse_lp,  # noqa: E402
+                                     random_sparse_qp, simple_lp)
 from oracle.mpc_oracle import madipm  # noqa: E402
 
 CASES = {
@@ -24,6 +25,11 @@ CASES = {
     "lp_m40_ub": lambda: random_sparse_lp(40, 160, 5, 7, structure="uniform", ub_fraction=0.5),
     "lp_m300_window": lambda: random_sparse_lp(300, 1500, 5, 7, structure="window", window=20),
     "qp_m60_window": lambda: random_sparse_qp(60, 200, 4, 9, structure="window", window=10),
+    # every bound / constraint kind: range, one-sided and equality rows (slacks), free / boxed / upper-only variables
+    "mixed_lp_m30": lambda: mixed_bounds_lp(30, 90, 4, 1),
+    "mixed_lp_m120": lambda: mixed_bounds_lp(120, 400, 5, 2),
+    # bounds only, m = 0 (DenseDummyQP(x0; m=0) in test/runtests.jl:64)
+    "boxqp_n20": lambda: bound_constrained_qp(20, 4),
 }
 
 

@@ -130,6 +130,24 @@ def test_cholesky_factor_solve(handle, case, ordering):
     assert h.ls_factorize(nz2)
 
 
+def test_whole_front_tasks_match_phase_schedule(handle, monkeypatch):
+    """The optional whole-front task path (MIPM_FRONT_FUSE_MIN) must give the same factor as the phase schedule."""
+    Cp, Cj, Cx, K = _normal_matrix(6000, 30000, 8, "window", 3)
+    b = np.random.default_rng(0).standard_normal(6000)
+    sols = []
+    for fuse in (None, "1"):
+        if fuse:
+            monkeypatch.setenv("MIPM_FRONT_FUSE_MIN", fuse)
+        h = handle()
+        h.ls_analyze(6000, Cp, Cj, kind=_lib.MIPM_CHOLESKY)
+        nz = dev(Cx)
+        assert h.ls_factorize(nz)
+        x = dev(b)
+        h.ls_solve(x, 0)
+        sols.append(x.cpu().numpy())
+    assert np.abs(sols[0] - sols[1]).max() <= 1e-12 * np.abs(sols[0]).max()
+
+
 def test_cholesky_reports_breakdown(handle):
     """A non-positive pivot maps to is_factorized == false (src/utils.jl:54-62, linear_solver.jl:11)."""
     Cp, Cj, Cx, K = _normal_matrix(130, 500, 5, "uniform", 3)

@@ -70,6 +70,41 @@ def test_against_highs(case):
         assert abs(s.objective - s.dual_objective) <= 1e-5 * max(1.0, abs(r.fun))
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_mixed_bounds_against_highs(seed):
+    """Range / one-sided rows (slack variables) and free / boxed / upper-only variables."""
+    from madipm_jl_b200.problems import mixed_bounds_lp
+    qp = mixed_bounds_lp(30, 90, 4, seed)
+    m, n = qp.ncon, qp.nvar
+    A = sp.csr_matrix((qp.Avals, (qp.Arows, qp.Acols)), shape=(m, n))
+    eq = qp.lcon == qp.ucon
+    fu, fl = np.isfinite(qp.ucon) & ~eq, np.isfinite(qp.lcon) & ~eq
+    r = linprog(qp.c, A_ub=sp.vstack([A[fu], -A[fl]]), b_ub=np.concatenate([qp.ucon[fu], -qp.lcon[fl]]),
+                A_eq=A[eq], b_eq=qp.lcon[eq], method="highs",
+                bounds=[(None if np.isinf(l) else l, None if np.isinf(u) else u) for l, u in zip(qp.lvar, qp.uvar)])
+    assert r.status == 0
+    for kkt in ("K2", "Normal"):
+        s = madipm(qp, kkt_system=kkt)
+        assert s.status == "SOLVE_SUCCEEDED"
+        assert abs(s.objective - r.fun) <= 1e-6 * max(1.0, abs(r.fun))
+        assert np.all(s.constraints >= qp.lcon - 1e-6) and np.all(s.constraints <= qp.ucon + 1e-6)
+
+
+def test_unbounded_lp_is_reported():
+    """An LP with an unbounded ray must end as DIVERGING_ITERATES (src/solver.jl:212-213), not loop."""
+    qp = random_sparse_lp(10, 30, 3, 1, structure="uniform")
+    qp.c[:] = -np.abs(qp.c)                       # push along the recession cone of {Ax=b, x>=0}? not guaranteed:
+    qp.lvar[:] = -np.inf                          # ... free variables make it unbounded for sure
+    s = madipm(qp, max_iter=200)
+    assert s.status in ("DIVERGING_ITERATES", "INFEASIBLE_PROBLEM_DETECTED", "MAXIMUM_ITERATIONS_EXCEEDED", "INTERNAL_ERROR")
+    assert s.status != "SOLVE_SUCCEEDED"
+
+
+def test_max_iter_status():
+    s = madipm(random_sparse_lp(40, 160, 5, 7, structure="uniform"), max_iter=3)
+    assert s.status == "MAXIMUM_ITERATIONS_EXCEEDED" and s.iter == 3
+
+
 @pytest.mark.parametrize("key", sorted(GOLD))
 def test_golden_traces(key):
     """The oracle reproduces its committed per-iterate traces (regression guard)."""
