@@ -384,7 +384,10 @@ int mipm_spmv(mipm_handle hh, int trans, double alpha, const double *d_Ax, const
     Handle *h = (Handle *)hh;
     MIPM_NEED_DEVICE(h);
     if (!h->has_spmv) return fail(h, MIPM_ERR_STATE, "mipm_spmv_setup has not been called");
-    if ((!d_Ax && h->sp_nnz > 0) || !d_x || !d_y) return fail(h, MIPM_ERR_ARG, "null argument");
+    {
+        const int64_t xlen = trans == 0 ? h->sp_n : h->sp_m, ylen = trans == 0 ? h->sp_m : h->sp_n;
+        if ((!d_Ax && h->sp_nnz > 0) || (!d_x && xlen > 0) || (!d_y && ylen > 0)) return fail(h, MIPM_ERR_ARG, "null argument");
+    }
     if (trans == 0) {
         if (h->sp_m > 0) {
             k_spmv_csr<<<grid_for(h->sp_m * 32, 256), 256, 0, h->stream>>>(h->sp_m, h->d_sp_rowptr.p, h->d_sp_col.p, d_Ax, d_x,

@@ -894,8 +894,12 @@ int mipm_mpc_set_model(mipm_handle hh, const mipm_mpc_model *md)
 {
     Handle *h = (Handle *)hh;
     MIPM_NEED_DEVICE(h);
-    if (!md || (md->kkt_kind != 0 && md->kkt_kind != 1) || !md->d_ATx || !md->d_cvec || !md->d_aug_nz || !md->d_buffer_n ||
-        !md->d_buffer_m || (md->kkt_kind == 1 && !md->d_aug_raw_V))
+    if (!h->bound) return fail(h, MIPM_ERR_STATE, "mipm_mpc_bind has not been called");
+    if (!h->has_spmv) return fail(h, MIPM_ERR_STATE, "mipm_spmv_setup has not been called");
+    // zero-size pieces (no constraints, empty Jacobian) legitimately come with null pointers
+    if (!md || (md->kkt_kind != 0 && md->kkt_kind != 1) || (!md->d_ATx && h->sp_nnz > 0) || (!md->d_cvec && h->v.n > 0) ||
+        !md->d_aug_nz || (!md->d_buffer_n && h->v.n > 0) || (!md->d_buffer_m && h->v.m > 0) ||
+        (md->kkt_kind == 1 && !md->d_aug_raw_V))
         return fail(h, MIPM_ERR_ARG, "bad model");
     if (md->d_Hx && !h->has_hess) return fail(h, MIPM_ERR_STATE, "Hessian values given but mipm_hess_setup not called");
     MIPM_CUDA(h, cudaSetDevice(h->device));

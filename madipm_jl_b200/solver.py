@@ -271,8 +271,11 @@ class MPCSolver:
         md.d_buffer_n, md.d_buffer_m = P(self.buffer_n), P(self.buffer_m)
         self._md = md
         self.h.mpc_set_model(md)
+        # a variable with no finite bound keeps pr_diag = del_w (1e-10): the KKT system is then badly
+        # conditioned from the first iteration on, so the fused path refines every solve from the start
+        self._has_free = (nlb + nub > 0 or n > 0) and bool(np.any(~np.isfinite(lfull) & ~np.isfinite(ufull)))
         self._fused_started = False
-        self._fused_ir = opt.ir_steps
+        self._fused_ir = max(opt.ir_steps, 1 if self._has_free else 0)
         # ---- scalars (structure.jl:62-76)
         self.obj_val = 0.0
         self.inf_pr = self.inf_du = self.inf_compl = 0.0
@@ -503,7 +506,7 @@ class MPCSolver:
         self.status = REGULAR
         self.jtprod(self.jacl, self.y)
         self._fused_started = False
-        self._fused_ir = self.opt.ir_steps
+        self._fused_ir = max(self.opt.ir_steps, 1 if self._has_free else 0)
 
     def init_starting_point(self):
         """src/solver.jl:6-125."""
