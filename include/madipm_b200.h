@@ -137,6 +137,24 @@ int mipm_ls_stats(mipm_handle h, mipm_ls_stats_t *out);
 int mipm_ls_symbolic(mipm_handle h, int32_t **perm, int64_t *n_sn, int32_t **sn_ptr,
                      int32_t **sn_parent, int64_t **row_ptr, int32_t **row_idx);
 
+/* ---- distributed (block-angular) solves: SURVEY 8e, config C4. New functionality (the reference has no
+ * multi-GPU code). Each rank analyses and factors ITS OWN sub-matrix [interior blocks of its commodities; border]
+ * whose last n_border rows/columns (the linking constraints) are kept last as one dense root supernode:
+ *   mipm_ls_analyze_border           host analysis with that constraint
+ *   mipm_ls_factorize_stage(.., 0)   assembly + every front below the root: the root panel then holds this rank's
+ *                                    Schur contribution (the last extend-add wrote straight into it)
+ *   [caller: all-reduce (sum) of the n_root x n_root root panel over NCCL]
+ *   mipm_ls_factorize_stage(.., 1)   factorization of the (now global) root front, redundantly on every rank
+ *   mipm_ls_solve_stage(x, 0)        forward sweep below the root; the root segment of the permuted RHS is partial
+ *   [caller: all-reduce (sum) of the n_root root RHS entries]
+ *   mipm_ls_solve_stage(x, 1)        root solve + backward sweep; x then holds this rank's part of the solution
+ *   mipm_ls_root_info                device pointers to the root panel (column-major, ld = n_root) and root RHS. */
+int mipm_ls_analyze_border(mipm_handle h, int64_t n, const int32_t *colptr, const int32_t *rowval,
+                           int index_base, int kind, int64_t n_border);
+int mipm_ls_factorize_stage(mipm_handle h, const double *d_nzval, int stage);
+int mipm_ls_solve_stage(mipm_handle h, double *d_x, int stage);
+int mipm_ls_root_info(mipm_handle h, double **d_root_panel, int64_t *n_root, double **d_root_rhs);
+
 /* ------------------------------------------------------------------ SpMV ----------- */
 /* Replaces MadIPMOperator / cuSPARSE SpMV on AT (cuda_wrapper.jl:43-94; normalkkt.jl:177,
  * 208,214,228-229): CSR of A (m x n) registered once (host arrays), then
@@ -231,6 +249,10 @@ int mipm_copy(mipm_handle h, int64_t n, const double *d_src, double *d_dst);
  * `kkt.AT.nzVal .= kkt.A.V[kkt.A_csr_map]` (cuda_wrapper.jl:39). map is Int64 like Julia's Vector{Int}. */
 int mipm_gather(mipm_handle h, int64_t n, const double *d_src, const int64_t *d_map, int index_base,
                 double *d_dst);
+/* dst[map[i] - index_base] = src[i], i < n (map entries must be distinct): used to place a rank's part of a
+ * distributed solution into the global vector. */
+int mipm_scatter(mipm_handle h, int64_t n, const double *d_src, const int64_t *d_map, int index_base,
+                 double *d_dst);
 /* dot(x, y) with a deterministic two-level reduction (used for obj = c'x + x'Qx/2). */
 int mipm_dot(mipm_handle h, int64_t n, const double *d_x, const double *d_y, double *out);
 

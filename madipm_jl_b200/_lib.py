@@ -60,13 +60,14 @@ SYMBOLS = [
     "mipm_k2_symbolic", "mipm_k2_transfer",
     "mipm_ls_analyze", "mipm_ls_factorize", "mipm_ls_factorize_async", "mipm_ls_status", "mipm_ls_solve",
     "mipm_ls_inertia", "mipm_ls_stats", "mipm_ls_symbolic",
+    "mipm_ls_analyze_border", "mipm_ls_factorize_stage", "mipm_ls_solve_stage", "mipm_ls_root_info",
     "mipm_spmv_setup", "mipm_spmv", "mipm_hess_setup", "mipm_hess_spmv",
     "mipm_mpc_set_model", "mipm_mpc_iter_begin", "mipm_mpc_refactor", "mipm_mpc_iter_rest",
     "mipm_mpc_bind", "mipm_set_aug_diagonal_reg", "mipm_set_predictive_rhs", "mipm_set_correction_rhs",
     "mipm_get_correction", "mipm_set_extra_correction", "mipm_get_complementarity_measure",
     "mipm_get_affine_complementarity_measure", "mipm_get_alpha_max", "mipm_termination_measures",
     "mipm_apply_step", "mipm_reduce_rhs", "mipm_finish_aug_solve", "mipm_normal_solve_stage", "mipm_kktmul",
-    "mipm_residual_norms", "mipm_init_point_stage", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_gather", "mipm_dot",
+    "mipm_residual_norms", "mipm_init_point_stage", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_gather", "mipm_scatter", "mipm_dot",
     "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk",
 ]
 
@@ -163,6 +164,26 @@ class Handle:
         up = None if user_perm is None else np.ascontiguousarray(user_perm, dtype=np.int32)
         self.check(self.lib.mipm_ls_analyze(self.h, C.c_int64(n), _ptr(colptr), _ptr(rowval), C.c_int(index_base),
                                             C.c_int(kind), C.c_int(ordering), _ptr(up)))
+
+    def ls_analyze_border(self, n, colptr, rowval, n_border, kind=MIPM_CHOLESKY, index_base=0):
+        colptr = np.ascontiguousarray(colptr, dtype=np.int32)
+        rowval = np.ascontiguousarray(rowval, dtype=np.int32)
+        self.check(self.lib.mipm_ls_analyze_border(self.h, C.c_int64(n), _ptr(colptr), _ptr(rowval), C.c_int(index_base),
+                                                   C.c_int(kind), C.c_int64(n_border)))
+
+    def ls_factorize_stage(self, nzval, stage):
+        if stage == 0:
+            self._nz_ref = nzval
+        self.check(self.lib.mipm_ls_factorize_stage(self.h, _ptr(nzval), C.c_int(stage)))
+
+    def ls_solve_stage(self, x, stage):
+        self.check(self.lib.mipm_ls_solve_stage(self.h, _ptr(x), C.c_int(stage)))
+
+    def ls_root_info(self):
+        """(device pointer of the root panel, n_root, device pointer of the root RHS segment)."""
+        pp, pr, nr = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self.check(self.lib.mipm_ls_root_info(self.h, C.byref(pp), C.byref(nr), C.byref(pr)))
+        return pp.value, nr.value, pr.value
 
     def ls_stats(self):
         st = LsStats()
@@ -323,6 +344,9 @@ class Handle:
 
     def gather(self, n, src, map_, dst, index_base=0):
         self.check(self.lib.mipm_gather(self.h, C.c_int64(n), _ptr(src), _ptr(map_), C.c_int(index_base), _ptr(dst)))
+
+    def scatter(self, n, src, map_, dst, index_base=0):
+        self.check(self.lib.mipm_scatter(self.h, C.c_int64(n), _ptr(src), _ptr(map_), C.c_int(index_base), _ptr(dst)))
 
     def dot(self, n, x, y):
         out = C.c_double()

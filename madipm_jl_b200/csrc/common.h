@@ -71,6 +71,7 @@ struct Handle {
     LsSymbolic sym;
     bool has_ls = false, factorized = false;
     int n_phases = 0, grid_factor = 0, grid_solve = 0;
+    int root_phase_begin = -1;       // first phase of the border (root) front's own factorization, -1 = no border
     int64_t leaf_off = 0;            // small leaf fronts (one warp each) in d_sched
     int n_leaf = 0;
     cudaStream_t side = nullptr;     // zero-fill of the update matrices for the next factorization
@@ -147,5 +148,7 @@ inline int fail(Handle *h, int code, const std::string &msg) {
 int ls_device_setup(Handle *h);
 int ls_factorize_impl(Handle *h, const double *d_nzval);
 int ls_solve_impl(Handle *h, double *d_x, int ir_steps);
+int ls_factorize_staged(Handle *h, const double *d_nzval, int stage);
+int ls_solve_staged(Handle *h, double *d_x, int stage);
 
 }  // namespace mipm

@@ -61,7 +61,8 @@ struct FactorParams {
     const int32_t *child_idx, *rel_idx;
     const int32_t *sched;
     const int64_t *phases;      // 8 x int64 per phase: type, jb, n_tasks, off_tasks, 0, 0, 0, 0
-    int n_phases;
+    int n_phases;               // phases [phase_begin, n_phases) are executed by this launch
+    int phase_begin;
     double *L, *U, *W, *Dinv;
     int *info;
     const int32_t *ea_first;        // per front: first extend-add task record of its own (PH_FRONT levels), count
@@ -76,6 +77,9 @@ struct SolveParams {
     const FrontInfo *fi;
     const int32_t *child_idx, *rel_idx, *row_idx, *perm;
     const int32_t *sched;
+    int fwd_begin, fwd_end;     // forward sweep over levels [fwd_begin, fwd_end)
+    int do_gather, do_backward; // stage control (distributed solves pause before the root level)
+    int root_mode;              // front_forward mode for the last level (0 unless staged)
     const int64_t *lvl;         // 2 x int64 per level: off_all, n_all (level 0: regular fronts only)
     int64_t leaf_off;           // small leaf fronts (level 0), one warp each
     int n_leaf;
@@ -517,7 +521,7 @@ __global__ void __launch_bounds__(256, 3) k_factor_persistent(FactorParams p)
     unsigned long long t0 = 0;
     const bool timer = (blockIdx.x == 0 && threadIdx.x == 0);
     if (timer) t0 = globaltimer_ns();
-    for (int ph = 0; ph < p.n_phases; ++ph) {
+    for (int ph = p.phase_begin; ph < p.n_phases; ++ph) {
         const int64_t *d = p.phases + 8 * (int64_t)ph;
         const int type = (int)d[0], jb = (int)d[1], n_tasks = (int)d[2];
         const int32_t *A = p.sched + d[3];
@@ -596,8 +600,10 @@ k_bench_syrk(int n, int kdim, double *__restrict__ C, int64_t ldc, const double 
 // through their stored inverses (mat-vec), so nothing in a front is sequential.
 constexpr int XR_MAX = 1536;    // ancestor entries of x cached in shared memory by the backward sweep
 
+// mode 0: whole front; 1: only fold the children's update vectors in (distributed solves: the root
+// segment is all-reduced after this); 2: skip that part (it was done in the previous stage)
 template <bool LDL>
-__device__ void front_forward(const SolveParams &p, int s, double *smem)
+__device__ void front_forward(const SolveParams &p, int s, double *smem, int mode)
 {
     double *xb = smem, *yb = smem + NB;
     const FrontInfo f = p.fi[s];
@@ -606,7 +612,7 @@ __device__ void front_forward(const SolveParams &p, int s, double *smem)
     double *x1 = p.xp + f.c0;
     double *u = p.uvec + f.rowp;
     const int tid = threadIdx.x;
-    for (int ci = 0; ci < f.nchild; ++ci) {
+    for (int ci = 0; ci < f.nchild && mode != 2; ++ci) {
         const int c = p.child_idx[f.childp + ci];
         const FrontInfo fc = p.fi[c];
         const int32_t *rel = p.rel_idx + fc.rowp;
@@ -617,6 +623,7 @@ __device__ void front_forward(const SolveParams &p, int s, double *smem)
         }
         __syncthreads();
     }
+    if (mode == 1) return;
     for (int jb = 0; jb < k; jb += NB) {
         const int nb = min(NB, k - jb);
         const double *Dv = p.Dinv + (f.dinv + (jb >> 6)) * (int64_t)(NB * NB);
@@ -806,12 +813,14 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
     cg::grid_group grid = cg::this_grid();
     __shared__ double smem[NB * LDS + NB + XR_MAX];
     const int64_t gtid = (int64_t)blockIdx.x * 256 + threadIdx.x, gsz = (int64_t)gridDim.x * 256;
-    for (int64_t i = gtid; i < p.n; i += gsz) p.xp[i] = p.b_in[p.perm[i]];
-    for (int64_t i = gtid; i < p.n_u; i += gsz) p.uvec[i] = 0.0;
-    grid.sync();
+    if (p.do_gather) {
+        for (int64_t i = gtid; i < p.n; i += gsz) p.xp[i] = p.b_in[p.perm[i]];
+        for (int64_t i = gtid; i < p.n_u; i += gsz) p.uvec[i] = 0.0;
+        grid.sync();
+    }
     const int32_t *leaves = p.sched + p.leaf_off;
     const int n_leaf_groups = (p.n_leaf + 7) / 8;
-    for (int l = 0; l < p.n_levels; ++l) {
+    for (int l = p.fwd_begin; l < p.fwd_end; ++l) {
         const int32_t *fr = p.sched + p.lvl[2 * l];
         const int nf = (int)p.lvl[2 * l + 1];
         const int extra = (l == 0) ? n_leaf_groups : 0;      // small leaves ride along with level 0
@@ -820,12 +829,13 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
                 const int li = t * 8 + (threadIdx.x >> 5);
                 if (li < p.n_leaf) leaf_forward<LDL>(p, leaves[li]);
             } else {
-                front_forward<LDL>(p, fr[t - extra], smem);
+                front_forward<LDL>(p, fr[t - extra], smem, (l == p.n_levels - 1) ? p.root_mode : 0);
             }
             __syncthreads();
         }
         grid.sync();
     }
+    if (!p.do_backward) return;
     for (int l = p.n_levels - 1; l >= 0; --l) {
         const int32_t *fr = p.sched + p.lvl[2 * l];
         const int nf = (int)p.lvl[2 * l + 1];
@@ -900,6 +910,7 @@ int ls_device_setup(Handle *h)
     };
     int64_t leaf_off = 0;
     int n_leaf = 0;
+    int root_phase_begin = -1;
     // grid size is needed to decide which levels run whole-front tasks
     int fuse_min = 1 << 30;
     {
@@ -933,7 +944,8 @@ int ls_device_setup(Handle *h)
             kmax = std::max(kmax, S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s]);
         }
         lvl.push_back(n_reg);
-        const bool fuse_level = n_reg >= fuse_min;
+        const bool fuse_level = n_reg >= fuse_min && !(S.root_sn >= 0 && l == S.n_levels - 1);
+        if (S.root_sn >= 0 && l == S.n_levels - 1) root_phase_begin = (int)(phases.size() / 8);   // moved past the EA phase below
         // extend-add: per-child column ranges first, then the task records that point at them
         std::vector<int32_t> ea;
         for (int64_t t = f0; t < f1; ++t) {
@@ -966,6 +978,7 @@ int ls_device_setup(Handle *h)
             align4();
             const int64_t off_ea = (int64_t)sched.size();
             if (!fuse_level) push_phase(PH_EA, 0, (int64_t)ea.size() / 4, off_ea);
+            if (S.root_sn >= 0 && l == S.n_levels - 1) root_phase_begin = (int)(phases.size() / 8);
             sched.insert(sched.end(), ea.begin(), ea.end());
             for (int64_t t = f0; t < f1; ++t) {       // turn per-level record indices into offsets into sched
                 int s = S.level_sn[(size_t)t];
@@ -1022,6 +1035,7 @@ int ls_device_setup(Handle *h)
     }
     h->leaf_off = leaf_off;
     h->n_leaf = n_leaf;
+    h->root_phase_begin = root_phase_begin;
     h->n_phases = (int)(phases.size() / 8);
     h->n_launch_factor = 2;   // scatter + persistent kernel (plus three memsets)
     // ---- cooperative grid sizes
@@ -1090,11 +1104,17 @@ int ls_device_setup(Handle *h)
     return MIPM_OK;
 }
 
-int ls_factorize_impl(Handle *h, const double *d_nzval)
+// stage -1: everything; stage 0: assembly + all phases below the root (border) front, leaving the local
+// Schur contribution in the root panel; stage 1: the root front's own factorization (after the all-reduce).
+int ls_factorize_staged(Handle *h, const double *d_nzval, int stage)
 {
     const LsSymbolic &S = h->sym;
     cudaStream_t st = h->stream;
     MIPM_CUDA(h, cudaSetDevice(h->device));
+    if (stage >= 0 && h->root_phase_begin < 0) return fail(h, MIPM_ERR_STATE, "staged factorization needs mipm_ls_analyze_border");
+    const int ph0 = (stage == 1) ? h->root_phase_begin : 0;
+    const int ph1 = (stage == 0) ? h->root_phase_begin : h->n_phases;
+    if (stage != 1) {
     MIPM_CUDA(h, cudaMemsetAsync(h->d_L.p, 0, (size_t)std::max<int64_t>(S.nnz_l, 1) * sizeof(double), st));
     // The update matrices are only live inside the factorization kernel, so their zero-fill for the
     // NEXT factorization runs on a side stream behind this one (it overlaps the latency-bound solves).
@@ -1109,10 +1129,11 @@ int ls_factorize_impl(Handle *h, const double *d_nzval)
         k_scatter_a<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.nnz_a, h->d_a2l.p, d_nzval, h->d_L.p);
         MIPM_CHECK_LAUNCH(h);
     }
-    if (h->n_phases > 0) {
+    }
+    if (ph1 > ph0) {
         FactorParams p;
         p.fi = (const FrontInfo *)h->d_finfo.p; p.child_idx = h->d_child_idx.p; p.rel_idx = h->d_rel_idx.p;
-        p.sched = h->d_sched.p; p.phases = h->d_phases.p; p.n_phases = h->n_phases;
+        p.sched = h->d_sched.p; p.phases = h->d_phases.p; p.n_phases = ph1; p.phase_begin = ph0;
         p.L = h->d_L.p; p.U = h->d_U.p; p.W = h->d_W.p; p.Dinv = h->d_Dinv.p; p.info = h->d_info.p;
         p.phase_ns = h->d_phase_ns.p;
         p.ea_first = h->d_ea_first.p; p.ea_count = h->d_ea_count.p; p.work_counter = h->d_work_counter.p;
@@ -1123,6 +1144,7 @@ int ls_factorize_impl(Handle *h, const double *d_nzval)
         MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)h->grid_factor), dim3(256), args, SMEM_BYTES, st));
         h->launches++;
     }
+    if (stage == 0) { h->d_nzval = d_nzval; return MIPM_OK; }
     if (h->side) {
         MIPM_CUDA(h, cudaEventRecord(h->ev_factor_done, st));
         MIPM_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_factor_done, 0));
@@ -1130,12 +1152,15 @@ int ls_factorize_impl(Handle *h, const double *d_nzval)
         MIPM_CUDA(h, cudaEventRecord(h->ev_u_zero, h->side));
         h->u_prezeroed = true;
     }
-    h->d_nzval = d_nzval;
+    if (stage != 1) h->d_nzval = d_nzval;
     h->factorized = true;
     return MIPM_OK;
 }
 
-static int solve_once(Handle *h, const double *b_in, double *x_out, int accumulate)
+int ls_factorize_impl(Handle *h, const double *d_nzval) { return ls_factorize_staged(h, d_nzval, -1); }
+
+// stage -1: whole solve; 0: gather + forward sweep below the root level; 1: root level forward, backward sweep, scatter
+static int solve_once(Handle *h, const double *b_in, double *x_out, int accumulate, int stage = -1)
 {
     const LsSymbolic &S = h->sym;
     SolveParams p;
@@ -1145,6 +1170,11 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     p.n = S.n; p.n_u = S.row_ptr[(size_t)S.ns];
     p.L = h->d_L.p; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
     p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
+    p.do_gather = (stage != 1);
+    p.fwd_begin = (stage == 1) ? S.n_levels - 1 : 0;
+    p.fwd_end = S.n_levels;
+    p.root_mode = (stage == 0) ? 1 : ((stage == 1) ? 2 : 0);
+    p.do_backward = (stage != 0);
     void *args[] = {&p};
     const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_solve_persistent<true> : (const void *)k_solve_persistent<false>;
     MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)h->grid_solve), dim3(256), args, 0, h->stream));
@@ -1174,7 +1204,81 @@ int ls_solve_impl(Handle *h, double *d_x, int ir_steps)
     return MIPM_OK;
 }
 
+int ls_solve_staged(Handle *h, double *d_x, int stage)
+{
+    const LsSymbolic &S = h->sym;
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    if (h->root_phase_begin < 0) return fail(h, MIPM_ERR_STATE, "staged solve needs mipm_ls_analyze_border");
+    if (S.n == 0) return MIPM_OK;
+    if (stage == 0) {
+        MIPM_CUDA(h, cudaMemcpyAsync(h->d_b.p, d_x, (size_t)S.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        return solve_once(h, h->d_b.p, d_x, 0, 0);
+    }
+    return solve_once(h, h->d_b.p, d_x, 0, 1);
+}
+
 }  // namespace mipm
+
+extern "C" int mipm_ls_analyze_border(mipm_handle hh, int64_t n, const int32_t *colptr, const int32_t *rowval, int index_base,
+                                      int kind, int64_t n_border)
+{
+    using namespace mipm;
+    Handle *h = (Handle *)hh;
+    if (!h || n < 0 || !colptr || n_border < 1 || n_border > n || (kind != MIPM_CHOLESKY && kind != MIPM_LDL))
+        return fail(h, MIPM_ERR_ARG, "bad argument");
+    int64_t nnz = colptr[n] - index_base;
+    std::vector<int32_t> cp((size_t)n + 1), ri((size_t)std::max<int64_t>(nnz, 0));
+    for (int64_t j = 0; j <= n; ++j) cp[(size_t)j] = colptr[j] - index_base;
+    for (int64_t q = 0; q < nnz; ++q) ri[(size_t)q] = rowval[q] - index_base;
+    LsOptions opt;
+    opt.kind = kind;
+    opt.ordering = MIPM_ORDER_ND;
+    opt.n_border = n_border;
+    if (const char *s = std::getenv("MIPM_ND_LEAF")) opt.nd_leaf = std::max(1, atoi(s));
+    h->has_ls = false;
+    h->factorized = false;
+    std::string e = ls_analyze(n, cp.data(), ri.data(), opt, nullptr, h->sym);
+    if (!e.empty()) return fail(h, MIPM_ERR_ARG, e);
+    h->has_ls = true;
+    if (!h->host_only) return ls_device_setup(h);
+    return MIPM_OK;
+}
+
+extern "C" int mipm_ls_factorize_stage(mipm_handle hh, const double *d_nzval, int stage)
+{
+    using namespace mipm;
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_ls) return fail(h, MIPM_ERR_STATE, "mipm_ls_analyze_border has not been called");
+    if (stage != 0 && stage != 1) return fail(h, MIPM_ERR_ARG, "stage must be 0 or 1");
+    if (stage == 0 && !d_nzval && h->sym.nnz_a > 0) return fail(h, MIPM_ERR_ARG, "null values");
+    return ls_factorize_staged(h, d_nzval, stage);
+}
+
+extern "C" int mipm_ls_solve_stage(mipm_handle hh, double *d_x, int stage)
+{
+    using namespace mipm;
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_ls || !h->factorized) return fail(h, MIPM_ERR_STATE, "solve before factorize");
+    if (stage != 0 && stage != 1) return fail(h, MIPM_ERR_ARG, "stage must be 0 or 1");
+    if (!d_x && h->sym.n > 0) return fail(h, MIPM_ERR_ARG, "null argument");
+    return ls_solve_staged(h, d_x, stage);
+}
+
+extern "C" int mipm_ls_root_info(mipm_handle hh, double **d_root_panel, int64_t *n_root, double **d_root_rhs)
+{
+    using namespace mipm;
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_ls || h->sym.root_sn < 0) return fail(h, MIPM_ERR_STATE, "mipm_ls_analyze_border has not been called");
+    const LsSymbolic &S = h->sym;
+    const int rs = S.root_sn;
+    if (d_root_panel) *d_root_panel = h->d_L.p + S.lp[(size_t)rs];
+    if (n_root) *n_root = S.sn_ptr[(size_t)rs + 1] - S.sn_ptr[(size_t)rs];
+    if (d_root_rhs) *d_root_rhs = h->d_xp.p + S.sn_ptr[(size_t)rs];
+    return MIPM_OK;
+}
 
 extern "C" int mipm_ls_factorize_profile(mipm_handle hh, const double *d_nzval, double *ms, double *work, int64_t *launches)
 {

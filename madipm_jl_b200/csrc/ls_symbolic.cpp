@@ -250,6 +250,19 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
     } else if (opt.ordering == 1 /*NATURAL*/) {
         perm0.resize((size_t)n);
         std::iota(perm0.begin(), perm0.end(), 0);
+    } else if (opt.n_border > 0) {
+        // nested dissection of the interior subgraph only; border vertices stay last in natural order
+        const int64_t ni = n - opt.n_border;
+        if (ni < 0) return "border larger than the matrix";
+        std::vector<int64_t> xi((size_t)ni + 1, 0);
+        std::vector<int32_t> ai;
+        for (int64_t v = 0; v < ni; ++v) {
+            for (int64_t p = xadj[(size_t)v]; p < xadj[(size_t)v + 1]; ++p)
+                if (adj[(size_t)p] < ni) ai.push_back(adj[(size_t)p]);
+            xi[(size_t)v + 1] = (int64_t)ai.size();
+        }
+        order_nested_dissection(ni, xi, ai, opt.nd_leaf, perm0);
+        for (int64_t v = ni; v < n; ++v) perm0.push_back((int32_t)v);
     } else {
         order_nested_dissection(n, xadj, adj, opt.nd_leaf, perm0);
     }
@@ -343,6 +356,14 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
             }
         }
     }
+    if (opt.n_border > 0) {
+        // treat the border block as structurally dense: a chain in the elimination tree with the column
+        // counts of a dense trailing block (a superset of the true structure, filled with explicit zeros)
+        for (int64_t j = n - opt.n_border; j < n; ++j) {
+            parent[(size_t)j] = (j + 1 < n) ? (int32_t)(j + 1) : -1;
+            cnt[(size_t)j] = n - 1 - j;
+        }
+    }
     // ---- postorder (children by ascending count so a supernode-forming child comes last)
     std::vector<int32_t> post((size_t)n);  // post[newpos] = node (in perm0 numbering)
     {
@@ -397,7 +418,8 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
     // ---- fundamental supernodes
     std::vector<int32_t> sn0;  // start columns
     for (int64_t j = 0; j < n; ++j) {
-        bool cont = j > 0 && par[(size_t)j - 1] == j && cc[(size_t)j - 1] == cc[(size_t)j] + 1 &&
+        const bool at_border = opt.n_border > 0 && j == n - opt.n_border;       // the border is its own supernode
+        bool cont = j > 0 && !at_border && par[(size_t)j - 1] == j && cc[(size_t)j - 1] == cc[(size_t)j] + 1 &&
                     (j - sn0.back()) < opt.max_sn_cols;
         if (!cont) sn0.push_back((int32_t)j);
     }
@@ -422,6 +444,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
             if (pv.c1 != x.c0 || pc < x.c0 || pc >= x.c1) break;
             int64_t k = (int64_t)(x.c1 - pv.c0);
             if (k > opt.max_sn_cols) break;
+            if (opt.n_border > 0 && x.c1 > n - opt.n_border && pv.c0 < n - opt.n_border) break;   // interior | border
             int64_t merged = trap(k, x.r);
             int64_t tru = pv.nnz_true + x.nnz_true;
             double z = (double)(merged - tru) / (double)merged;
@@ -442,6 +465,13 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
     S.col2sn.resize((size_t)n);
     for (int32_t s = 0; s < ns; ++s)
         for (int32_t j = S.sn_ptr[(size_t)s]; j < S.sn_ptr[(size_t)s + 1]; ++j) S.col2sn[(size_t)j] = s;
+    if (opt.n_border > 0 && n > 0) {
+        S.root_sn = S.col2sn[(size_t)n - 1];
+        if (S.sn_ptr[(size_t)S.root_sn] != n - opt.n_border || S.sn_ptr[(size_t)S.root_sn + 1] != n)
+            return "border did not end up as one final supernode (internal error)";
+        for (int64_t j = n - opt.n_border; j < n; ++j)
+            if (S.perm[(size_t)j] != (int32_t)j) return "border vertices were reordered (internal error)";
+    }
 
     // ---- strictly-lower column structure of the permuted matrix: below[c] = {r > c}
     std::vector<int64_t> bptr((size_t)n + 1, 0);
@@ -535,6 +565,10 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
         S.max_front_rows = std::max<int32_t>(S.max_front_rows, (int32_t)(k + r));
         for (int32_t c : kids[(size_t)s]) S.sn_level[(size_t)s] = std::max(S.sn_level[(size_t)s], S.sn_level[(size_t)c] + 1);
         S.n_levels = std::max(S.n_levels, S.sn_level[(size_t)s] + 1);
+    }
+    if (S.root_sn >= 0) {       // the border front sits alone on its own top level (staged factorization / solve)
+        S.sn_level[(size_t)S.root_sn] = S.n_levels;
+        S.n_levels += 1;
     }
     S.nnz_l = S.lp[(size_t)ns];
     S.update_doubles = S.up[(size_t)ns];

@@ -23,6 +23,9 @@ struct LsOptions {
     // LDL^T on K2: eliminate every dual vertex after ALL of its primal neighbours (true) or after the
     // first one (false). 'All' is the numerically safe choice for tiny |delta_c| (quirk A.9 v).
     bool ldl_delay_all = true;
+    // Distributed (block-angular) use: the last n_border vertices are kept last, in their given order, and form
+    // ONE final dense supernode (the root separator whose Schur block is all-reduced across GPUs).
+    int64_t n_border = 0;
 };
 
 struct LsSymbolic {
@@ -52,6 +55,7 @@ struct LsSymbolic {
     int64_t nnz_l = 0, nnz_l_exact = 0, update_doubles = 0;
     double flops = 0.0;
     int32_t n_levels = 0, max_front_cols = 0, max_front_rows = 0;
+    int32_t root_sn = -1;                      // the border supernode when n_border > 0
 };
 
 // colptr/rowval: lower-triangular CSC, 0-based. Returns "" on success or an error message.

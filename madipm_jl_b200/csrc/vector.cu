@@ -561,6 +561,10 @@ __global__ void __launch_bounds__(TB) k_gather(int64_t n, const double *src, con
 {
     GRID_STRIDE(i, n) dst[i] = src[map[i] - base];
 }
+__global__ void __launch_bounds__(TB) k_scatter(int64_t n, const double *src, const int64_t *map, int base, double *dst)
+{
+    GRID_STRIDE(i, n) dst[map[i] - base] = src[i];
+}
 __global__ void __launch_bounds__(TB) k_dot(int64_t n, const double *x, const double *y, double *partials, unsigned int *counter, double *out)
 {
     double acc[1] = {0.0};
@@ -865,6 +869,17 @@ int mipm_gather(mipm_handle hh, int64_t n, const double *d_src, const int64_t *d
     if (n < 0 || (n > 0 && (!d_src || !d_map || !d_dst))) return fail(h, MIPM_ERR_ARG, "bad argument");
     if (n == 0) return MIPM_OK;
     k_gather<<<red_grid(h, n), TB, 0, h->stream>>>(n, d_src, d_map, index_base, d_dst);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_scatter(mipm_handle hh, int64_t n, const double *d_src, const int64_t *d_map, int index_base, double *d_dst)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (n < 0 || (n > 0 && (!d_src || !d_map || !d_dst))) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (n == 0) return MIPM_OK;
+    k_scatter<<<red_grid(h, n), TB, 0, h->stream>>>(n, d_src, d_map, index_base, d_dst);
     MIPM_CHECK_LAUNCH(h);
     return MIPM_OK;
 }

@@ -231,3 +231,53 @@ def bound_constrained_qp(n, seed):
     rows, cols = np.tril_indices(n)
     return QuadraticModel(c=rng.standard_normal(n), Hrows=rows, Hcols=cols, Hvals=Q[rows, cols], Arows=[], Acols=[], Avals=[],
                           lcon=[], ucon=[], lvar=np.zeros(n), uvar=np.full(n, 2.0), x0=np.ones(n), name=f"boxqp_n{n}_s{seed}")
+
+
+def block_angular_lp(K, grid_w, grid_h, n_link, seed):
+    """Multicommodity-flow LP (config C4): K commodities on one directed grid graph
+    (V = grid_w*grid_h nodes, 4-neighbour arcs in both directions). Per commodity N' x_k = b_k with N the
+    node-arc incidence matrix minus one node row (the rows sum to zero and the normal path has no dual
+    regularization); n_link linking rows sum_k x_k[e] + s_e = cap_e with explicit slack columns, placed LAST.
+    Rows: [commodity 0 | ... | commodity K-1 | linking]; columns: [arcs of commodity 0 | ... | slacks]."""
+    rng = np.random.default_rng(seed)
+    V = grid_w * grid_h
+    idx = np.arange(V).reshape(grid_h, grid_w)
+    tail = np.concatenate([idx[:, :-1].ravel(), idx[:, 1:].ravel(), idx[:-1, :].ravel(), idx[1:, :].ravel()])
+    head = np.concatenate([idx[:, 1:].ravel(), idx[:, :-1].ravel(), idx[1:, :].ravel(), idx[:-1, :].ravel()])
+    E = len(tail)
+    link = np.sort(rng.choice(E, size=min(n_link, E), replace=False))
+    n_link = len(link)
+    mrow = V - 1                                        # node V-1 dropped
+    rows, cols, vals = [], [], []
+    b = np.zeros(K * mrow + n_link)
+    for kc in range(K):
+        r0, c0 = kc * mrow, kc * E
+        keep_t, keep_h = tail < mrow, head < mrow
+        rows += [r0 + tail[keep_t], r0 + head[keep_h]]
+        cols += [c0 + np.flatnonzero(keep_t), c0 + np.flatnonzero(keep_h)]
+        vals += [np.ones(keep_t.sum()), -np.ones(keep_h.sum())]
+        src, dst = rng.choice(V, size=2, replace=False)
+        if src < mrow:
+            b[r0 + src] += 1.0
+        if dst < mrow:
+            b[r0 + dst] -= 1.0
+        rows.append(K * mrow + np.arange(n_link))
+        cols.append(c0 + link)
+        vals.append(np.ones(n_link))
+    rows.append(K * mrow + np.arange(n_link))
+    cols.append(K * E + np.arange(n_link))
+    vals.append(np.ones(n_link))
+    b[K * mrow:] = 0.5 * K                              # generous capacities: feasible
+    n = K * E + n_link
+    c = np.concatenate([rng.uniform(1.0, 2.0, K * E), np.zeros(n_link)])
+    return QuadraticModel(c=c, Hrows=[], Hcols=[], Hvals=[], Arows=np.concatenate(rows), Acols=np.concatenate(cols),
+                          Avals=np.concatenate(vals), lcon=b, ucon=b.copy(), lvar=np.zeros(n), uvar=np.full(n, np.inf),
+                          x0=np.zeros(n), name=f"mcf_K{K}_{grid_w}x{grid_h}_L{n_link}_s{seed}",
+                          meta=dict(K=K, V=V, E=E, n_link=n_link, n_border=n_link))
+
+
+def config_c4(seed=4, scale=1.0):
+    """m ~ 2e6: K = 64 commodities on a 176 x 176 grid (V = 30 976, E = 123 200), 2 048 linking rows."""
+    K = max(2, int(round(64 * scale)))
+    side = max(6, int(round(176 * np.sqrt(min(1.0, scale)))))
+    return block_angular_lp(K, side, side, max(8, int(2048 * min(1.0, scale))), seed)

@@ -104,6 +104,10 @@ class IPMOptions:
     # device (mipm_mpc_iter_begin / mipm_mpc_iter_rest). Used for the default options (no Gondzio corrections,
     # Adaptive / Conservative step rule); otherwise the fine-grained host-driven sequence runs.
     fused: bool = True
+    # "b200": the single-GPU supernodal solver; "distributed": block-angular normal matrix whose last n_border
+    # rows are the linking constraints, factored over the ranks of the default process group (distributed.py)
+    linear_solver: str = "b200"
+    n_border: int = 0
     exact_assembly_order: bool = False
     device: int = 0
 
@@ -229,8 +233,16 @@ class MPCSolver:
             self.pr_diag, self.du_diag = z(n), z(m)
             Cp, Cj = self.h.normal_symbolic(m, n, Ap, Aj)
             self.aug_colptr, self.aug_rowval = Cp, Cj
-            self.aug_nz = z(len(Cj))
-            self.linear_solver = B200Solver(self.h, m, Cp, Cj, self.aug_nz, _lib.MIPM_CHOLESKY, opt.ordering, opt.ir_steps)
+            if opt.linear_solver == "distributed":
+                from .distributed import DistributedB200Solver
+                if not (0 < opt.n_border <= m):
+                    raise ValueError("linear_solver='distributed' needs n_border = number of linking rows (placed last)")
+                self._aug_nz_ext = z(len(Cj) + 1)                 # one trailing zero slot for the rank-local gather
+                self.aug_nz = self._aug_nz_ext[:len(Cj)]
+                self.linear_solver = DistributedB200Solver(m, Cp, Cj, self._aug_nz_ext, opt.n_border, opt.device, stream)
+            else:
+                self.aug_nz = z(len(Cj))
+                self.linear_solver = B200Solver(self.h, m, Cp, Cj, self.aug_nz, _lib.MIPM_CHOLESKY, opt.ordering, opt.ir_steps)
         elif opt.kkt_system == "K2":
             # MadNLP.SparseKKTSystem: COO values [pr_diag; hess; jac(+slack); du_diag], lower triangular
             nnzh, nnzj = qp.nnzh, len(I)
@@ -687,6 +699,7 @@ class MPCSolver:
 
     def _use_fused(self):
         return (self.opt.fused and self.opt.max_ncorr <= 0 and not self.opt.check_residual
+                and self.opt.linear_solver == "b200"
                 and isinstance(self.opt.step_rule, (AdaptiveStep, ConservativeStep)))
 
     def _mpc_iteration_fused(self):

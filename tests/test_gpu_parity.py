@@ -357,3 +357,17 @@ def test_c1_full_size(built):
     assert abs(got.objective - got.dual_objective) <= 1e-6 * max(1.0, abs(got.objective))
     ref = oracle_madipm(qp, kkt_system="Normal", linear_solver="splu")
     _check_trace(got, ref.trace, ref.iter, ref.status)
+
+
+def test_distributed_solver_single_rank_matches_oracle(built):
+    """Config C4's solver path with one rank (no process group): staged factorization / solve through the
+    border root must reproduce the oracle's iterates on a block-angular LP. The 2-GPU run of the same code
+    is tools/run_distributed.py (needs torchrun, recorded under profiles/)."""
+    from madipm_jl_b200.problems import block_angular_lp
+    from madipm_jl_b200.solver import madipm
+    qp = block_angular_lp(4, 7, 6, 10, 2)
+    ref = oracle_madipm(qp, kkt_system="Normal")
+    got = madipm(qp, kkt_system="Normal", linear_solver="distributed", n_border=qp.meta["n_border"])
+    _check_trace(got, ref.trace, ref.iter, ref.status)
+    plain = madipm(qp, kkt_system="Normal")
+    _check_trace(plain, ref.trace, ref.iter, ref.status)
