@@ -250,24 +250,27 @@ def block_angular_lp(K, grid_w, grid_h, n_link, seed):
     mrow = V - 1                                        # node V-1 dropped
     rows, cols, vals = [], [], []
     b = np.zeros(K * mrow + n_link)
+    link_load = np.zeros(n_link)
     for kc in range(K):
         r0, c0 = kc * mrow, kc * E
         keep_t, keep_h = tail < mrow, head < mrow
         rows += [r0 + tail[keep_t], r0 + head[keep_h]]
         cols += [c0 + np.flatnonzero(keep_t), c0 + np.flatnonzero(keep_h)]
         vals += [np.ones(keep_t.sum()), -np.ones(keep_h.sum())]
-        src, dst = rng.choice(V, size=2, replace=False)
-        if src < mrow:
-            b[r0 + src] += 1.0
-        if dst < mrow:
-            b[r0 + dst] -= 1.0
+        # feasible by construction: supplies are the divergence of a strictly positive flow x*_k, so they are
+        # generic (a unit source/sink pair makes the optimal tree solution massively primal degenerate, and the
+        # normal equations of a degenerate LP break down near the solution)
+        xs = rng.uniform(0.5, 1.5, E)
+        np.add.at(b, r0 + tail[keep_t], xs[keep_t])
+        np.add.at(b, r0 + head[keep_h], -xs[keep_h])
+        link_load += xs[link]
         rows.append(K * mrow + np.arange(n_link))
         cols.append(c0 + link)
         vals.append(np.ones(n_link))
     rows.append(K * mrow + np.arange(n_link))
     cols.append(K * E + np.arange(n_link))
     vals.append(np.ones(n_link))
-    b[K * mrow:] = 0.5 * K                              # generous capacities: feasible
+    b[K * mrow:] = link_load + rng.uniform(0.1, 1.0, n_link)     # cap_e = sum_k x*_k[e] + s*_e
     n = K * E + n_link
     c = np.concatenate([rng.uniform(1.0, 2.0, K * E), np.zeros(n_link)])
     return QuadraticModel(c=c, Hrows=[], Hcols=[], Hvals=[], Arows=np.concatenate(rows), Acols=np.concatenate(cols),
