@@ -212,7 +212,7 @@ def main():
     t_e2e = time.perf_counter() - t1
     iters_total = res.iter
     n, m = solver.n, solver.m
-    h2d = 8 * (5 * n + 2 * m + len(solver.Aj))
+    h2d = solver.h2d_bytes_per_solve          # pinned problem data uploaded by every solve (solver._stage_problem)
     d2h = 8 * (3 * n + m)
     if world > 1:
         tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)

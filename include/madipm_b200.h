@@ -240,6 +240,16 @@ int mipm_residual_norms(mipm_handle h, const double *d_w, const double *d_p, dou
  * sum(x_lr-xl_r), sum(xu_r-x_ur)); stage 2: shifts by (delta_x2, delta_s2) + projection with kappa,
  * returns out[4] = interior check mins (min zl_r, min zu_r, min(x_lr-xl_r), min(xu_r-x_ur)). */
 int mipm_init_point_stage(mipm_handle h, int stage, double a, double b, double kappa, double *out);
+/* MadNLP.initialize! bound handling (called from MadIPM.initialize!, src/solver.jl:127-140), in place
+ * on device vectors of length n that hold the raw values on entry:
+ *   xl -= max(1,|xl|)*tol;  xu += max(1,|xu|)*tol                                  (bound_relax_factor)
+ *   x   = projection of x strictly inside [xl, xu] with bound_push / bound_fac     (initialize_variables!)
+ * Infinite bounds stay infinite. Products and sums are rounded separately (no FMA) so the result is
+ * bit-identical to the reference's broadcast statements. */
+int mipm_init_bounds(mipm_handle h, int64_t n, double tol, double bound_push, double bound_fac,
+                     double *d_x, double *d_xl, double *d_xu);
+/* out = max_i |x_i| (0 for n = 0): norm(x, Inf) as used for norm_b / norm_c and the gradient scaling. */
+int mipm_amax(mipm_handle h, int64_t n, const double *d_x, double *out);
 /* Plain fused helpers used by the host loop in place of broadcast statements:
  * y[i] = alpha*x[i] + beta*y[i];  fill; copy. */
 int mipm_axpby(mipm_handle h, int64_t n, double alpha, const double *d_x, double beta, double *d_y);

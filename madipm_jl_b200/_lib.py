@@ -67,7 +67,7 @@ SYMBOLS = [
     "mipm_get_correction", "mipm_set_extra_correction", "mipm_get_complementarity_measure",
     "mipm_get_affine_complementarity_measure", "mipm_get_alpha_max", "mipm_termination_measures",
     "mipm_apply_step", "mipm_reduce_rhs", "mipm_finish_aug_solve", "mipm_normal_solve_stage", "mipm_kktmul",
-    "mipm_residual_norms", "mipm_init_point_stage", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_gather", "mipm_scatter", "mipm_dot",
+    "mipm_residual_norms", "mipm_init_point_stage", "mipm_init_bounds", "mipm_amax", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_gather", "mipm_scatter", "mipm_dot",
     "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk",
 ]
 
@@ -332,6 +332,15 @@ class Handle:
         out = (C.c_double * 8)()
         self.check(self.lib.mipm_init_point_stage(self.h, C.c_int(stage), C.c_double(a), C.c_double(b), C.c_double(kappa), out))
         return list(out)
+
+    def init_bounds(self, n, tol, bound_push, bound_fac, x, xl, xu):
+        self.check(self.lib.mipm_init_bounds(self.h, C.c_int64(n), C.c_double(tol), C.c_double(bound_push), C.c_double(bound_fac),
+                                             _ptr(x), _ptr(xl), _ptr(xu)))
+
+    def amax(self, n, x):
+        out = C.c_double(0.0)
+        self.check(self.lib.mipm_amax(self.h, C.c_int64(n), _ptr(x), C.byref(out)))
+        return out.value
 
     def axpby(self, n, alpha, x, beta, y):
         self.check(self.lib.mipm_axpby(self.h, C.c_int64(n), C.c_double(alpha), _ptr(x), C.c_double(beta), _ptr(y)))

@@ -99,38 +99,49 @@ k_k2_transfer(int64_t nslots, const int64_t *__restrict__ slot_ptr, const int64_
 }
 
 // ---------------------------------------------------------------- SpMV
-// y = alpha * A x + beta * y, CSR, one warp per row.
+// y = alpha * A x + beta * y, CSR, G lanes per row.
+template <int G>
 __global__ void __launch_bounds__(256)
 k_spmv_csr(int64_t m, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
            const double *__restrict__ val, const double *__restrict__ x, double alpha, double beta,
            double *__restrict__ y)
 {
-    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (row >= m) return;
+    // G lanes per row (G = power of two chosen from the average row length at setup)
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    int lane = threadIdx.x & (G - 1);
     double acc = 0.0;
-    for (int32_t p = rowptr[row] + lane; p < rowptr[row + 1]; p += 32) acc = fma(val[p], __ldg(x + col[p]), acc);
+    if (row < m)
+        for (int32_t p = rowptr[row] + lane; p < rowptr[row + 1]; p += G) acc = fma(val[p], __ldg(x + col[p]), acc);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) y[row] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[row];
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (row < m && lane == 0) y[row] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[row];
 }
 
 // y = alpha * A' x + beta * y through the CSC index (colptr, row, pos into the CSR values):
-// 8 lanes per column (columns of A are short: k nnz/col).
+// G lanes per column (columns of A are short: k nnz/col).
+template <int G>
 __global__ void __launch_bounds__(256)
 k_spmv_csc(int64_t n, const int32_t *__restrict__ colptr, const int32_t *__restrict__ row,
            const int32_t *__restrict__ pos, const double *__restrict__ val, const double *__restrict__ x,
            double alpha, double beta, double *__restrict__ y)
 {
-    int64_t colj = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    int sub = threadIdx.x & 7;
+    int64_t colj = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    int sub = threadIdx.x & (G - 1);
     double acc = 0.0;
     if (colj < n)
-        for (int32_t p = colptr[colj] + sub; p < colptr[colj + 1]; p += 8) acc = fma(__ldg(val + pos[p]), __ldg(x + row[p]), acc);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        for (int32_t p = colptr[colj] + sub; p < colptr[colj + 1]; p += G) acc = fma(__ldg(val + pos[p]), __ldg(x + row[p]), acc);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (colj < n && sub == 0) y[colj] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[colj];
+}
+
+// lanes per row / column: the power of two nearest above the average length, within [2, 32]
+inline int spmv_group(int64_t nnz, int64_t rows)
+{
+    double avg = rows > 0 ? (double)nnz / (double)rows : 1.0;
+    int g = 2;
+    while (g < 32 && g < avg) g *= 2;
+    return g;
 }
 
 inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)std::max<int64_t>(1, (n + per_block - 1) / per_block); }
@@ -390,14 +401,28 @@ int mipm_spmv(mipm_handle hh, int trans, double alpha, const double *d_Ax, const
     }
     if (trans == 0) {
         if (h->sp_m > 0) {
-            k_spmv_csr<<<grid_for(h->sp_m * 32, 256), 256, 0, h->stream>>>(h->sp_m, h->d_sp_rowptr.p, h->d_sp_col.p, d_Ax, d_x,
-                                                                        alpha, beta, d_y);
+#define MIPM_SPMV_CSR(G) k_spmv_csr<G><<<grid_for(h->sp_m * G, 256), 256, 0, h->stream>>>(h->sp_m, h->d_sp_rowptr.p, h->d_sp_col.p, d_Ax, d_x, alpha, beta, d_y)
+            switch (spmv_group(h->sp_nnz, h->sp_m)) {
+            case 2: MIPM_SPMV_CSR(2); break;
+            case 4: MIPM_SPMV_CSR(4); break;
+            case 8: MIPM_SPMV_CSR(8); break;
+            case 16: MIPM_SPMV_CSR(16); break;
+            default: MIPM_SPMV_CSR(32); break;
+            }
+#undef MIPM_SPMV_CSR
             MIPM_CHECK_LAUNCH(h);
         }
     } else {
         if (h->sp_n > 0) {
-            k_spmv_csc<<<grid_for(h->sp_n * 8, 256), 256, 0, h->stream>>>(h->sp_n, h->d_sp_colptr.p, h->d_sp_row.p, h->d_sp_pos.p,
-                                                                       d_Ax, d_x, alpha, beta, d_y);
+#define MIPM_SPMV_CSC(G) k_spmv_csc<G><<<grid_for(h->sp_n * G, 256), 256, 0, h->stream>>>(h->sp_n, h->d_sp_colptr.p, h->d_sp_row.p, h->d_sp_pos.p, d_Ax, d_x, alpha, beta, d_y)
+            switch (spmv_group(h->sp_nnz, h->sp_n)) {
+            case 2: MIPM_SPMV_CSC(2); break;
+            case 4: MIPM_SPMV_CSC(4); break;
+            case 8: MIPM_SPMV_CSC(8); break;
+            case 16: MIPM_SPMV_CSC(16); break;
+            default: MIPM_SPMV_CSC(32); break;
+            }
+#undef MIPM_SPMV_CSC
             MIPM_CHECK_LAUNCH(h);
         }
     }
@@ -433,8 +458,15 @@ int mipm_hess_spmv(mipm_handle hh, double alpha, const double *d_Hx, const doubl
     if (!h->has_hess) return fail(h, MIPM_ERR_STATE, "mipm_hess_setup has not been called");
     if ((!d_Hx && h->hs_nnz > 0) || !d_x || !d_y) return fail(h, MIPM_ERR_ARG, "null argument");
     if (h->hs_n > 0) {
-        k_spmv_csr<<<grid_for(h->hs_n * 32, 256), 256, 0, h->stream>>>(h->hs_n, h->d_hs_rowptr.p, h->d_hs_col.p, d_Hx, d_x,
-                                                                     alpha, beta, d_y);
+#define MIPM_SPMV_H(G) k_spmv_csr<G><<<grid_for(h->hs_n * G, 256), 256, 0, h->stream>>>(h->hs_n, h->d_hs_rowptr.p, h->d_hs_col.p, d_Hx, d_x, alpha, beta, d_y)
+        switch (spmv_group(h->hs_nnz, h->hs_n)) {
+        case 2: MIPM_SPMV_H(2); break;
+        case 4: MIPM_SPMV_H(4); break;
+        case 8: MIPM_SPMV_H(8); break;
+        case 16: MIPM_SPMV_H(16); break;
+        default: MIPM_SPMV_H(32); break;
+        }
+#undef MIPM_SPMV_H
         MIPM_CHECK_LAUNCH(h);
     }
     return MIPM_OK;

@@ -573,6 +573,37 @@ __global__ void __launch_bounds__(TB) k_dot(int64_t n, const double *x, const do
     grid_reduce_vals<1>(acc, op, partials, counter, out);
 }
 
+__global__ void __launch_bounds__(TB) k_amax(int64_t n, const double *x, double *partials, unsigned int *counter, double *out)
+{
+    double acc[1] = {0.0};
+    GRID_STRIDE(i, n) acc[0] = comb(acc[0], fabs(x[i]), OP_MAX);
+    const int op[1] = {OP_MAX};
+    grid_reduce_vals<1>(acc, op, partials, counter, out);
+}
+// MadNLP bound relaxation + initialize_variables! push (App. B). Every product / sum is rounded on its own
+// (__dmul_rn / __dadd_rn are never contracted) so the values match the reference's broadcasts bit for bit.
+__global__ void __launch_bounds__(TB) k_init_bounds(int64_t n, double tol, double bp, double bf, double *x, double *xl, double *xu)
+{
+    GRID_STRIDE(i, n) {
+        const double l = __dadd_rn(xl[i], -__dmul_rn(fmax(1.0, fabs(xl[i])), tol));
+        const double u = __dadd_rn(xu[i], __dmul_rn(fmax(1.0, fabs(xu[i])), tol));
+        xl[i] = l; xu[i] = u;
+        const bool fl = isfinite(l), fu = isfinite(u);
+        double xi = x[i];
+        if (fl && fu) {
+            const double w = __dmul_rn(bf, __dadd_rn(u, -l));
+            const double pl = fmin(__dmul_rn(bp, fmax(1.0, fabs(l))), w);
+            const double pu = fmin(__dmul_rn(bp, fmax(1.0, fabs(u))), w);
+            xi = fmax(__dadd_rn(l, pl), fmin(__dadd_rn(u, -pu), xi));
+        } else if (fl) {
+            xi = fmax(__dadd_rn(l, __dmul_rn(bp, fmax(1.0, fabs(l)))), xi);
+        } else if (fu) {
+            xi = fmin(__dadd_rn(u, -__dmul_rn(bp, fmax(1.0, fabs(u)))), xi);
+        }
+        x[i] = xi;
+    }
+}
+
 }  // namespace
 
 static unsigned red_grid(Handle *h, int64_t len)
@@ -895,6 +926,28 @@ int mipm_dot(mipm_handle hh, int64_t n, const double *d_x, const double *d_y, do
     return fetch_scalars(h, 1, out);
 }
 
+int mipm_amax(mipm_handle hh, int64_t n, const double *d_x, double *out)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (n < 0 || !out || (n > 0 && !d_x)) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (n == 0) { *out = 0.0; return MIPM_OK; }
+    k_amax<<<red_grid(h, n), TB, 0, h->stream>>>(n, d_x, h->d_partials.p, h->d_counter.p, h->d_scal.p);
+    MIPM_CHECK_LAUNCH(h);
+    return fetch_scalars(h, 1, out);
+}
+
+int mipm_init_bounds(mipm_handle hh, int64_t n, double tol, double bound_push, double bound_fac,
+                     double *d_x, double *d_xl, double *d_xu)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (n < 0 || (n > 0 && (!d_x || !d_xl || !d_xu))) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (n == 0) return MIPM_OK;
+    k_init_bounds<<<red_grid(h, n), TB, 0, h->stream>>>(n, tol, bound_push, bound_fac, d_x, d_xl, d_xu);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
 
 // ---------------------------------------------------------------- fused iteration
 static int fused_ready(Handle *h)

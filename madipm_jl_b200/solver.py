@@ -225,6 +225,7 @@ class MPCSolver:
             self.H_full_host = fv[Hmap]
             self.Hx = z(len(Hj))
         self.cvec = z(n)
+        self._stage_problem()
         # ---- KKT system
         self.buffer_n, self.buffer_m = z(n), z(m)
         self.l_diag, self.u_diag, self.l_lower, self.u_lower = z(nlb), z(nub), z(nlb), z(nub)
@@ -331,9 +332,8 @@ class MPCSolver:
 
     # ------------------------------------------------------------------ KKT system
     def compress_jacobian(self):
-        """normalkkt.jl:163-172 / cuda_wrapper.jl:32-41: AT.nzVal = A.V[A_csr_map] (+ slack = -1)."""
-        V = self.A_V_host if self._unit_con_scale else self.A_V_host * self.con_scale[self.A_I]
-        self.A_V.copy_(torch.from_numpy(V))                                   # jac_coord! result, H2D
+        """normalkkt.jl:163-172 / cuda_wrapper.jl:32-41: AT.nzVal = A.V[A_csr_map] (+ slack = -1); A.V (the jac_coord!
+        result, scaled by con_scale) was placed on the device by _madnlp_initialize."""
         self.h.gather(len(self.Aj), self.A_V, self.d_A_csr_map, self.AT_x)     # AT.nzVal .= A.V[A_csr_map]
         if self.opt.kkt_system == "Normal":
             self.h.normal_set_jacobian(self.AT_x)
@@ -341,10 +341,11 @@ class MPCSolver:
             self.h.copy(len(self.Aj), self.A_V, self.jac)
 
     def compress_hessian(self):
-        if self.qp.nnzh > 0:
-            self.Hx.copy_(torch.from_numpy(self.obj_scale * self.H_full_host))
+        """hess_coord! values times obj_scale (the raw values were uploaded by _madnlp_initialize)."""
+        if self.qp.nnzh > 0 and self.obj_scale != 1.0:
+            self.h.axpby(self.Hx.numel(), self.obj_scale, self.Hx, 0.0, self.Hx)
             if self.opt.kkt_system == "K2":
-                self.hess.copy_(torch.from_numpy(self.obj_scale * self.qp.Hvals))
+                self.h.axpby(self.hess.numel(), self.obj_scale, self.hess, 0.0, self.hess)
 
     def build_kkt(self):
         """build_kkt!: normalkkt.jl:180-194 (Normal) / MadNLP.transfer! (K2)."""
@@ -445,55 +446,60 @@ class MPCSolver:
             raise TypeError(r)
 
     # ------------------------------------------------------------------ initialization
+    def _stage_problem(self):
+        """Pinned host copies of the numeric problem data (the host side of `convert(QuadraticModel{T, CuVector}, qp)`,
+        README.md:77): every solve() uploads them again, so a timed solve includes its host->device traffic."""
+        qp, nx, ns, m = self.qp, self.nx, self.ns, self.m
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
+        zs = np.zeros(ns)
+        self._host = dict(
+            x0=pin(np.concatenate([qp.x0, zs])), c=pin(np.concatenate([qp.c, zs])), y0=pin(qp.y0),
+            xl=pin(np.concatenate([qp.lvar, qp.lcon[self.ind_ineq]])), xu=pin(np.concatenate([qp.uvar, qp.ucon[self.ind_ineq]])),
+            rhs=pin(np.where(qp.lcon == qp.ucon, qp.lcon, 0.0)), A_V=pin(self.A_V_host))
+        if qp.nnzh > 0:
+            self._host["H_full"] = pin(self.H_full_host)
+            self._host["H_tril"] = pin(qp.Hvals)
+        self._amax_A = float(np.abs(self.A_V_host).max()) if len(self.A_V_host) else 0.0
+        self.h2d_bytes_per_solve = int(sum(t.numel() * 8 for t in self._host.values()))
+
     def _madnlp_initialize(self):
-        """MadNLP.initialize!(cb, ...) + set_scaling! (App. B): one-time host preprocessing."""
-        qp, opt, nx, n, m = self.qp, self.opt, self.nx, self.n, self.m
-        x = np.zeros(n)
-        x[:nx] = qp.x0
-        xl = np.concatenate([qp.lvar, qp.lcon[self.ind_ineq]])
-        xu = np.concatenate([qp.uvar, qp.ucon[self.ind_ineq]])
-        rhs = np.where(qp.lcon == qp.ucon, qp.lcon, 0.0)
-        tol = opt.bound_relax_factor
-        xl = xl - np.maximum(1.0, np.abs(xl)) * tol
-        xu = xu + np.maximum(1.0, np.abs(xu)) * tol
-        bp, bf = opt.bound_push, opt.bound_fac
-        fl, fu = np.isfinite(xl), np.isfinite(xu)
-        both, lo, up = fl & fu, fl & ~fu, ~fl & fu
-        with np.errstate(invalid="ignore"):
-            pl = np.minimum(bp * np.maximum(1.0, np.abs(xl)), bf * (xu - xl))
-            pu = np.minimum(bp * np.maximum(1.0, np.abs(xu)), bf * (xu - xl))
-            x[both] = np.maximum(xl + pl, np.minimum(xu - pu, x))[both]
-            x[lo] = np.maximum(xl + bp * np.maximum(1.0, np.abs(xl)), x)[lo]
-            x[up] = np.minimum(xu - bp * np.maximum(1.0, np.abs(xu)), x)[up]
+        """MadNLP.initialize!(cb, ...) + set_scaling! (App. B) on the device; inputs come from pinned host memory."""
+        qp, opt, nx, n, m, h = self.qp, self.opt, self.nx, self.n, self.m, self.h
+        H = self._host
+        up_ = lambda t, a: t.copy_(a, non_blocking=True)
+        up_(self.x, H["x0"]), up_(self.xl, H["xl"]), up_(self.xu, H["xu"]), up_(self.rhs, H["rhs"]), up_(self.cvec, H["c"])
+        up_(self.y, H["y0"]), up_(self.A_V, H["A_V"])
+        if qp.nnzh > 0:
+            up_(self.Hx, H["H_full"])
+            if opt.kkt_system == "K2":
+                up_(self.hess, H["H_tril"])
+        h.init_bounds(n, opt.bound_relax_factor, opt.bound_push, opt.bound_fac, self.x, self.xl, self.xu)
         self.con_scale = np.ones(m)
         self.obj_scale = 1.0
         if opt.scaling:
-            # con_scale_i = min(1, 100 / max_j |A_ij|) is identically 1 when max |A_ij| <= 100, which one
-            # pass over the values decides; only otherwise are the per-row maxima needed (CSR order)
-            amax = float(np.abs(self.A_V_host).max()) if len(self.A_V_host) else 0.0
-            if amax > 100.0:
+            # con_scale_i = min(1, 100 / max_j |A_ij|) is identically 1 when max |A_ij| <= 100 (the usual case, decided
+            # once from the values); only otherwise are the per-row maxima needed (host, CSR order)
+            if self._amax_A > 100.0:
                 absv = np.abs(self.A_V_host)[self.A_csr_map]
                 rowmax = np.zeros(m)
                 nz = np.flatnonzero(np.diff(self.Ap) > 0)
                 rowmax[nz] = np.maximum.reduceat(absv, self.Ap[:-1][nz])
                 self.con_scale = np.minimum(1.0, 100.0 / np.maximum(rowmax, 1e-300))
-            rhs = rhs * self.con_scale
-            g = np.zeros(n)
-            g[:nx] = qp.c
+                self.rhs.copy_(torch.from_numpy(H["rhs"].numpy() * self.con_scale))
+                self.A_V.copy_(torch.from_numpy(self.A_V_host * self.con_scale[self.A_I]))
+            # obj_scale = min(1, 100 / ||grad f(x0)||_inf) with grad f = c + H x0
             if qp.nnzh > 0:
-                import scipy.sparse as sp
-                Hl = sp.csr_matrix((qp.Hvals, (qp.Hrows, qp.Hcols)), shape=(nx, nx))
-                g[:nx] += (Hl + sp.tril(Hl, -1).T) @ x[:nx]
-            gn = np.linalg.norm(g, np.inf)
+                h.copy(n, self.cvec, self.f)
+                h.hess_spmv(1.0, self.Hx, self.x, 1.0, self.f)
+                gn = h.amax(n, self.f)
+            else:
+                gn = h.amax(n, self.cvec)
             self.obj_scale = min(1.0, 100.0 / gn) if gn > 0 else 1.0
-        self._unit_con_scale = bool(np.all(self.con_scale == 1.0))
-        cv = np.zeros(n)
-        cv[:nx] = self.obj_scale * qp.c
-        up_ = lambda t, a: t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
-        up_(self.x, x), up_(self.xl, xl), up_(self.xu, xu), up_(self.rhs, rhs), up_(self.cvec, cv)
-        up_(self.y, qp.y0)
+        self._unit_con_scale = bool(np.all(self.con_scale == 1.0)) if self._amax_A > 100.0 else True
+        if self.obj_scale != 1.0:
+            h.axpby(n, self.obj_scale, self.cvec, 0.0, self.cvec)
         self.zl.zero_(), self.zu.zero_()
-        self.norm_b = float(np.linalg.norm(rhs, np.inf)) if m else 0.0
+        self.norm_b = h.amax(m, self.rhs)
 
     def initialize(self):
         """src/solver.jl:127-189."""

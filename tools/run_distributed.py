@@ -48,6 +48,32 @@ def main():
                           "components": s.linear_solver.n_components, "status": r.status, "iterations": r.iter, "objective": r.objective,
                           "solve_s": float(tt.item()), "iters_per_s": r.iter / float(tt.item()), "setup_s": t_setup,
                           "local_symbolic": {k: st[k] for k in ("n", "nnz_l", "flops", "n_supernodes", "n_levels", "max_front_cols")}}), flush=True)
+    if os.environ.get("MIPM_DIST_PROFILE"):
+        # coarse per-stage wall times (synchronised; perturbs the run, so it is done after the timed solve)
+        ls = s.linear_solver
+        acc = {}
+        def timed(name, fn):
+            def w(*a, **k):
+                torch.cuda.synchronize(); t = time.perf_counter()
+                out = fn(*a, **k)
+                torch.cuda.synchronize(); acc[name] = acc.get(name, 0.0) + time.perf_counter() - t
+                acc[name + "_n"] = acc.get(name + "_n", 0) + 1
+                return out
+            return w
+        h = ls.h
+        orig_stage, orig_sstage, orig_ar = h.ls_factorize_stage, h.ls_solve_stage, ls._allreduce
+        h.ls_factorize_stage = lambda nz, st: timed("factor_stage%d" % st, orig_stage)(nz, st)
+        h.ls_solve_stage = lambda b, st: timed("solve_stage%d" % st, orig_sstage)(b, st)
+        ls._allreduce = lambda t, op=None: timed("allreduce_%d" % t.numel(), orig_ar)(t, op)
+        ls.factorize = timed("factorize_total", ls.factorize)
+        ls.solve = timed("ls_solve_total", ls.solve)
+        s.k = 0; s.trace = []
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        r = s.solve()
+        torch.cuda.synchronize(); acc["solve_s"] = time.perf_counter() - t1
+        if rank == 0:
+            print(json.dumps({"profile": {k: (round(v, 5) if isinstance(v, float) else v) for k, v in sorted(acc.items())},
+                              "iterations": r.iter, "ranks": world}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
