@@ -71,6 +71,8 @@ struct FactorParams {
     unsigned long long *phase_ns;   // device-side time of every phase (one entry per phase)
     long long *dbg;                 // optional: clock64 stamps of the last diag task (debug)
     double piv_tol;
+    const int *vmap;                // virtual CTA id per blockIdx.x (see build_cta_map), or null
+    int *probe;                     // non-null: write %smid per block and return (setup-time placement probe)
 };
 
 struct SolveParams {
@@ -90,7 +92,16 @@ struct SolveParams {
     const double *b_in;         // gathered through perm at the start
     double *x_out;              // scattered through perm at the end
     int accumulate;             // x_out[perm] += xp instead of =
+    const int *vmap;            // virtual CTA id per blockIdx.x, or null
+    int *probe;                 // non-null: placement probe only
 };
+
+__device__ __forceinline__ int read_smid()
+{
+    unsigned s;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+    return (int)s;
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
@@ -519,6 +530,11 @@ __global__ void __launch_bounds__(256, 3) k_factor_persistent(FactorParams p)
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double smem[];
     unsigned long long t0 = 0;
+    if (p.probe) { if (threadIdx.x == 0) p.probe[blockIdx.x] = read_smid(); return; }
+    // Tasks are dealt to VIRTUAL CTA ids: ids 0..#SM-1 sit on distinct SMs, the next #SM ids are each SM's second
+    // resident CTA, and so on, so a phase with few latency-bound tasks (diag) gets one SM per task. The hardware
+    // places the first blockIdx values three to an SM (tools/smid_map.cu), which doubled those phases.
+    const int vid = p.vmap ? p.vmap[blockIdx.x] : (int)blockIdx.x;
     const bool timer = (blockIdx.x == 0 && threadIdx.x == 0);
     if (timer) t0 = globaltimer_ns();
     for (int ph = p.phase_begin; ph < p.n_phases; ++ph) {
@@ -538,7 +554,7 @@ __global__ void __launch_bounds__(256, 3) k_factor_persistent(FactorParams p)
                 __syncthreads();
             }
         } else
-        for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        for (int task = vid; task < n_tasks; task += gridDim.x) {
             if (type == PH_LEAF) {
                 const int li = task * 8 + (threadIdx.x >> 5);       // one warp per leaf front
                 if (li < jb) leaf_factor<LDL>(p, A[li]);             // jb carries the number of leaves
@@ -812,6 +828,8 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double smem[NB * LDS + NB + XR_MAX];
+    if (p.probe) { if (threadIdx.x == 0) p.probe[blockIdx.x] = read_smid(); return; }
+    const int vid = p.vmap ? p.vmap[blockIdx.x] : (int)blockIdx.x;
     const int64_t gtid = (int64_t)blockIdx.x * 256 + threadIdx.x, gsz = (int64_t)gridDim.x * 256;
     if (p.do_gather) {
         for (int64_t i = gtid; i < p.n; i += gsz) p.xp[i] = p.b_in[p.perm[i]];
@@ -824,7 +842,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
         const int32_t *fr = p.sched + p.lvl[2 * l];
         const int nf = (int)p.lvl[2 * l + 1];
         const int extra = (l == 0) ? n_leaf_groups : 0;      // small leaves ride along with level 0
-        for (int t = blockIdx.x; t < nf + extra; t += gridDim.x) {
+        for (int t = vid; t < nf + extra; t += gridDim.x) {
             if (t < extra) {
                 const int li = t * 8 + (threadIdx.x >> 5);
                 if (li < p.n_leaf) leaf_forward<LDL>(p, leaves[li]);
@@ -840,7 +858,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
         const int32_t *fr = p.sched + p.lvl[2 * l];
         const int nf = (int)p.lvl[2 * l + 1];
         const int extra = (l == 0) ? n_leaf_groups : 0;
-        for (int t = blockIdx.x; t < nf + extra; t += gridDim.x) {
+        for (int t = vid; t < nf + extra; t += gridDim.x) {
             if (t < extra) {
                 const int li = t * 8 + (threadIdx.x >> 5);
                 if (li < p.n_leaf) leaf_backward<LDL>(p, leaves[li]);
@@ -876,6 +894,60 @@ inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)std::max<i
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
+// Placement probe: launch the persistent kernel in probe mode (same function, block size, shared memory and grid
+// as the real launches, so the block scheduler places it the same way), read back the SM of every block and number
+// the blocks so that ids [0, #SM) are the first resident CTA of each SM, [#SM, 2 #SM) the second, ...
+// The map is a permutation of the block indices whatever the probe returns, so it can only affect speed.
+static int build_cta_map(Handle *h, bool factor)
+{
+    const int grid = factor ? h->grid_factor : h->grid_solve;
+    DBuf<int> &dmap = factor ? h->d_vmap_factor : h->d_vmap_solve;
+    if (std::getenv("MIPM_NO_VMAP")) { dmap.release(); return MIPM_OK; }
+    DBuf<int> d_probe;
+    MIPM_CUDA(h, d_probe.alloc((size_t)grid));
+    MIPM_CUDA(h, cudaMemsetAsync(d_probe.p, 0xff, (size_t)grid * sizeof(int), h->stream));
+    const bool ldl = (h->sym.kind == MIPM_LDL);
+    if (factor) {
+        FactorParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.probe = d_probe.p;
+        void *args[] = {&p};
+        const void *fn = ldl ? (const void *)k_factor_persistent<true> : (const void *)k_factor_persistent<false>;
+        MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), args, SMEM_BYTES, h->stream));
+    } else {
+        SolveParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.probe = d_probe.p;
+        void *args[] = {&p};
+        const void *fn = ldl ? (const void *)k_solve_persistent<true> : (const void *)k_solve_persistent<false>;
+        MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), args, 0, h->stream));
+    }
+    std::vector<int> smid((size_t)grid);
+    MIPM_CUDA(h, cudaMemcpyAsync(smid.data(), d_probe.p, (size_t)grid * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    // slot of each block on its SM (in block order), then sort by (slot, smid, block)
+    std::vector<int> slot((size_t)grid), order((size_t)grid), vmap((size_t)grid);
+    {
+        std::vector<std::pair<int, int>> seen;      // (smid, count), tiny
+        for (int b = 0; b < grid; ++b) {
+            int c = -1;
+            for (auto &e : seen) if (e.first == smid[(size_t)b]) { c = e.second++; break; }
+            if (c < 0) { seen.push_back({smid[(size_t)b], 1}); c = 0; }
+            slot[(size_t)b] = c;
+        }
+    }
+    for (int b = 0; b < grid; ++b) order[(size_t)b] = b;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (slot[(size_t)a] != slot[(size_t)b]) return slot[(size_t)a] < slot[(size_t)b];
+        if (smid[(size_t)a] != smid[(size_t)b]) return smid[(size_t)a] < smid[(size_t)b];
+        return a < b;
+    });
+    for (int v = 0; v < grid; ++v) vmap[(size_t)order[(size_t)v]] = v;
+    MIPM_CUDA(h, dmap.upload(vmap, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MIPM_OK;
+}
+
 int ls_device_setup(Handle *h)
 {
     const LsSymbolic &S = h->sym;
@@ -1092,6 +1164,11 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, h->d_r.alloc((size_t)std::max<int64_t>(S.n, 1)));
     MIPM_CUDA(h, h->d_phase_ns.alloc((size_t)h->n_phases + 8));
     MIPM_CUDA(h, cudaStreamSynchronize(st));
+    {
+        int rc = build_cta_map(h, true);
+        if (rc == MIPM_OK) rc = build_cta_map(h, false);
+        if (rc != MIPM_OK) return rc;
+    }
     if (!h->side) {
         MIPM_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
         MIPM_CUDA(h, cudaEventCreateWithFlags(&h->ev_factor_done, cudaEventDisableTiming));
@@ -1139,6 +1216,7 @@ int ls_factorize_staged(Handle *h, const double *d_nzval, int stage)
         p.ea_first = h->d_ea_first.p; p.ea_count = h->d_ea_count.p; p.work_counter = h->d_work_counter.p;
         p.dbg = std::getenv("MIPM_DIAG_DBG") ? (long long *)(h->d_phase_ns.p + h->n_phases) : nullptr;
         p.piv_tol = 1e-13;   // LDL^T: absolute floor on |pivot|
+        p.vmap = h->d_vmap_factor.p; p.probe = nullptr;
         void *args[] = {&p};
         const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_factor_persistent<true> : (const void *)k_factor_persistent<false>;
         MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)h->grid_factor), dim3(256), args, SMEM_BYTES, st));
@@ -1170,6 +1248,7 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     p.n = S.n; p.n_u = S.row_ptr[(size_t)S.ns];
     p.L = h->d_L.p; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
     p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
+    p.vmap = h->d_vmap_solve.p; p.probe = nullptr;
     p.do_gather = (stage != 1);
     p.fwd_begin = (stage == 1) ? S.n_levels - 1 : 0;
     p.fwd_end = S.n_levels;
