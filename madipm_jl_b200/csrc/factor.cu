@@ -26,6 +26,7 @@
 #include <cstring>
 
 #include "common.h"
+#include "diag_block.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -40,6 +41,7 @@ constexpr int TILE = 64;        // GEMM tile
 constexpr int XS = 68;          // smem row stride of staged operands (68 % 16 == 4: conflict-free DMMA loads)
 constexpr int SMEM_DOUBLES = 2 * TILE * XS;
 static_assert(2 * NB * LDS + 4 * NB <= SMEM_DOUBLES, "diag task: S + scratch + Sinv must fit the tile buffers");
+static_assert(NB == mipm_diag::DB && LDS == mipm_diag::DLD, "diag_block.cuh is written for 64 x 64 blocks, ld 65");
 constexpr int SMEM_BYTES = SMEM_DOUBLES * 8;   // 69,632 B
 enum { PH_EA = 0, PH_DIAG = 1, PH_TRSM = 2, PH_UPDATE = 3, PH_LEAF = 4, PH_FRONT = 5 };
 constexpr int SL_K = 8;         // small leaf front: no children, at most SL_K columns ...
@@ -285,138 +287,20 @@ __device__ void leaf_factor(const FactorParams &p, int s)
     }
 }
 
-// Diagonal block: factor the nb x nb block at column jb (register-tiled right-looking, one
-// barrier per column), then invert the triangular factor; both are written out.
+// Diagonal block: factor the nb x nb block at column jb and invert the triangular factor (diag_block.cuh:
+// panel-blocked, one warp on the 16 x 16 serial part, everything else CTA-wide); both are written out.
 // Cholesky: a non-positive pivot sets info[0] and is replaced by 1 so the run stays finite (the
 // host then retries with more regularization like src/linear_solver.jl:6-17).
 // LDL^T: unit-lower L11 with D on the diagonal; |pivot| < piv_tol is replaced by +-piv_tol.
 template <bool LDL>
 __device__ void task_diag(const FactorParams &p, int s, int jb, double *smem)
 {
-    double *S = smem;                      // L11, col-major, ld LDS
-    double *colbuf = smem + NB * LDS;      // 2 x 64 column buffers, then invd and dv (4160 + 4*64 <= 4352... see static_assert)
-    double *invd = colbuf + 2 * NB;        // reciprocals of the pivots of L11 (1/L_jj, or 1/D_j for LDL^T)
-    double *Sinv = smem + NB * LDS + 4 * NB;   // inv(L11), col-major, ld LDS
     const FrontInfo f = p.fi[s];
     const int k = f.k, N = f.k + f.r;
     const int nb = min(NB, k - jb);
     double *P = p.L + f.lp + (int64_t)jb * N + jb;
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    long long c0 = clock64();
-    double a[4][4];
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int rr = 4 * ty + i, cc = 4 * tx + jj;
-            a[i][jj] = (rr < nb && cc < nb && rr >= cc) ? P[(int64_t)cc * N + rr] : ((rr == cc) ? 1.0 : 0.0);
-        }
-    long long c1 = clock64();
-    // Square-root-free right-looking elimination (L unit-lower, pivots d_j): the only
-    // serial floating-point chain per column is one reciprocal, one multiply and one FMA.
-    // For Cholesky the columns are scaled by sqrt(d_j) afterwards, off the critical path.
-    double *dv = colbuf + 3 * NB;          // pivots d_j
-    int nbad = 0, ntiny = 0;
-    for (int j4 = 0; j4 < NB / 4; ++j4) {
-#pragma unroll
-        for (int js = 0; js < 4; ++js) {
-            const int j = 4 * j4 + js;
-            double *cb = colbuf + (j & 1) * NB;
-            // The 16 owners of column j publish it with the rows <= j zeroed, so every thread can
-            // use the buffer for both its row and its column multipliers without any masking;
-            // the pivot itself goes to dv[j].
-            if (tx == j4) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int rr = 4 * ty + i;
-                    cb[rr] = (rr > j) ? a[i][js] : 0.0;
-                    if (rr == j) dv[j] = a[i][js];
-                }
-            }
-            __syncthreads();
-            double d = dv[j];
-            if (!LDL) {
-                if (!(d > 0.0) || !(d < 1.0e300)) { nbad++; d = 1.0; }
-            } else {
-                if (!(fabs(d) <= 1.0e300)) { nbad++; d = 1.0; }
-                else if (fabs(d) < p.piv_tol) { ntiny++; d = (d < 0.0) ? -p.piv_tol : p.piv_tol; }
-            }
-            const double scale = 1.0 / d;
-            double lr[4], lc[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) lr[i] = cb[4 * ty + i] * scale;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) lc[jj] = cb[4 * tx + jj];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) a[i][jj] = fma(-lr[i], lc[jj], a[i][jj]);
-            if (tx == j4) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int rr = 4 * ty + i;
-                    if (rr > j) a[i][js] = lr[i];
-                    else if (rr == j) a[i][js] = d;
-                }
-                if (4 * ty <= j && j < 4 * ty + 4) dv[j] = d;    // keep a perturbed pivot consistent
-            }
-        }
-    }
-    long long c2 = clock64();
-    __syncthreads();
-    if (tid < NB) {
-        // invd = reciprocal of the diagonal of the stored factor: 1/sqrt(d) (Cholesky) or unused (LDL^T)
-        double d = dv[tid];
-        double sq = LDL ? d : sqrt(d);
-        dv[tid] = sq;
-        invd[tid] = LDL ? 1.0 : 1.0 / sq;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int rr = 4 * ty + i, cc = 4 * tx + jj;
-            if (rr >= cc) {
-                double v = a[i][jj];
-                if (!LDL) v = (rr == cc) ? dv[cc] : v * dv[cc];     // L = L_unit * sqrt(D)
-                S[cc * LDS + rr] = v;
-                if (rr < nb && cc < nb) P[(int64_t)cc * N + rr] = v;
-            }
-        }
-    __syncthreads();
-    long long c3 = clock64();
-    // inverse of the triangular factor: column c by the 4 threads (c, q), rows i = 4t + q
-    {
-        const int c = tid >> 2, q = tid & 3, lane = tid & 31;
-        double res[16];
-#pragma unroll
-        for (int t = 0; t < 16; ++t) res[t] = (4 * t + q == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int rr = 0; rr < NB; ++rr) {
-            double xr = __shfl_sync(0xffffffffu, res[rr >> 2], (lane & ~3) | (rr & 3));
-            if (!LDL) xr = xr * invd[rr];
-            if (q == (rr & 3)) Sinv[c * LDS + rr] = xr;
-#pragma unroll
-            for (int t = rr >> 2; t < 16; ++t)
-                if (4 * t + q > rr) res[t] = fma(-S[rr * LDS + 4 * t + q], xr, res[t]);
-        }
-    }
-    __syncthreads();
-    long long c4 = clock64();
     double *Dv = p.Dinv + (f.dinv + (jb >> 6)) * (int64_t)(NB * NB);
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        int rr = idx & 63, cc = idx >> 6;
-        Dv[idx] = (rr >= cc) ? Sinv[cc * LDS + rr] : 0.0;
-    }
-    if (p.dbg && tid == 0 && blockIdx.x == 0) {
-        p.dbg[0] = c1 - c0; p.dbg[1] = c2 - c1; p.dbg[2] = c3 - c2; p.dbg[3] = c4 - c3; p.dbg[4] = clock64() - c4;
-    }
-    if (LDL && tid < nb && S[tid * LDS + tid] < 0.0) atomicAdd(&p.info[1], 1);
-    if (tid == 0) {
-        if (nbad) atomicMax(&p.info[0], 1);
-        if (ntiny) atomicAdd(&p.info[2], ntiny);
-    }
+    mipm_diag::diag_block<LDL>(P, N, nb, Dv, p.piv_tol, p.info, smem);
 }
 
 // Panel TRSM as a tile GEMM with the inverted diagonal block: X = R * inv(L11)'  (64 rows per task).
@@ -1402,11 +1286,6 @@ extern "C" int mipm_ls_factorize_profile(mipm_handle hh, const double *d_nzval, 
         if (logf) std::fprintf(logf, "%d,%d,%d,%lld,%.2f\n", i, type, (int)ph[(size_t)i * 8 + 1], (long long)ph[(size_t)i * 8 + 2], t * 1e3);
     }
     if (logf) std::fclose(logf);
-    if (std::getenv("MIPM_DIAG_DBG")) {
-        long long dbg[5];
-        MIPM_CUDA(h, cudaMemcpy(dbg, h->d_phase_ns.p + h->n_phases, sizeof(dbg), cudaMemcpyDeviceToHost));
-        std::fprintf(stderr, "diag task cycles: load %lld potrf %lld scale %lld inverse %lld store %lld\n", dbg[0], dbg[1], dbg[2], dbg[3], dbg[4]);
-    }
     ms[0] = std::max(0.0, (double)total - inside);
     launches[0] = 4;
     work[0] = 8.0 * (double)(S.nnz_l + S.update_doubles) + 24.0 * (double)S.nnz_a;
