@@ -164,6 +164,11 @@ int mipm_spmv_setup(mipm_handle h, int64_t m, int64_t n, const int32_t *Ap, cons
                     int index_base);
 int mipm_spmv(mipm_handle h, int trans, double alpha, const double *d_Ax, const double *d_x,
               double beta, double *d_y);
+/* Tells the library that the CSR values at d_Ax stay unchanged until the next call of this function (in MadIPM
+ * compress_jacobian!, normalkkt.jl:163-172, is their only writer): a column-ordered copy is kept so that
+ * mul!(y, AT', x) streams its values instead of gathering them through the position map. mipm_spmv uses the copy
+ * only when it is called with the same d_Ax; d_Ax = NULL drops the copy. */
+int mipm_spmv_cache_values(mipm_handle h, const double *d_Ax);
 
 /* Hessian operator for obj / grad / the (1,1) block of mul!: replaces MadIPMOperator(H; symmetric=true),
  * cuda_wrapper.jl:62-68 (H expanded to its full symmetric CSR by the caller, as `tril(A,-1) + A'` does):

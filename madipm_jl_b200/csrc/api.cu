@@ -117,22 +117,68 @@ k_spmv_csr(int64_t m, const int32_t *__restrict__ rowptr, const int32_t *__restr
     if (row < m && lane == 0) y[row] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[row];
 }
 
-// y = alpha * A' x + beta * y through the CSC index (colptr, row, pos into the CSR values):
-// G lanes per column (columns of A are short: k nnz/col).
-template <int G>
+// Streaming SpMV ("CSR-stream", Greathouse & Daga): a block owns a run of consecutive rows with at most SPMV_CAP
+// nonzeros. Step 1: all threads form the products val * x[idx] with coalesced loads (8 independent loads in flight
+// per thread) into shared memory; step 2: one thread per row adds its products in storage order (deterministic).
+// A row longer than SPMV_CAP is a block of its own and is reduced CTA-wide. The same kernel serves A x (rows of the
+// CSR index) and A' y (columns of the CSC index; POS = values reached through the position map when no
+// column-ordered copy of the values has been cached).
+constexpr int SPMV_CAP = 2048;
+template <bool POS>
 __global__ void __launch_bounds__(256)
-k_spmv_csc(int64_t n, const int32_t *__restrict__ colptr, const int32_t *__restrict__ row,
-           const int32_t *__restrict__ pos, const double *__restrict__ val, const double *__restrict__ x,
-           double alpha, double beta, double *__restrict__ y)
+k_spmv_stream(const int32_t *__restrict__ blk, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
+              const int32_t *__restrict__ pos, const double *__restrict__ val, const double *__restrict__ x,
+              double alpha, double beta, double *__restrict__ y)
 {
-    int64_t colj = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    int sub = threadIdx.x & (G - 1);
-    double acc = 0.0;
-    if (colj < n)
-        for (int32_t p = colptr[colj] + sub; p < colptr[colj + 1]; p += G) acc = fma(__ldg(val + pos[p]), __ldg(x + row[p]), acc);
+    __shared__ double prod[SPMV_CAP];
+    __shared__ double red[8];
+    const int r0 = blk[blockIdx.x], r1 = blk[blockIdx.x + 1];
+    const int p0 = ptr[r0], p1 = ptr[r1];
+    const int tid = threadIdx.x;
+    if (p1 - p0 > SPMV_CAP) {               // one long row
+        double acc = 0.0;
+        for (int p = p0 + tid; p < p1; p += 256) acc = fma(POS ? __ldg(val + pos[p]) : val[p], __ldg(x + idx[p]), acc);
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (colj < n && sub == 0) y[colj] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[colj];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((tid & 31) == 0) red[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += red[w];
+            y[r0] = (beta == 0.0) ? alpha * t : alpha * t + beta * y[r0];
+        }
+        return;
+    }
+    for (int p = p0 + tid; p < p1; p += 256) prod[p - p0] = (POS ? __ldg(val + pos[p]) : val[p]) * __ldg(x + idx[p]);
+    __syncthreads();
+    for (int row = r0 + tid; row < r1; row += 256) {
+        const int a = ptr[row] - p0, b = ptr[row + 1] - p0;
+        double acc = 0.0;
+        for (int q = a; q < b; ++q) acc += prod[q];
+        y[row] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[row];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather32(int64_t n, const double *__restrict__ src, const int32_t *__restrict__ map, double *__restrict__ dst)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[map[i]];
+}
+
+// Row runs for k_spmv_stream: consecutive rows, at most SPMV_CAP nonzeros and 256 rows per block.
+static std::vector<int32_t> spmv_blocks(const std::vector<int32_t> &ptr)
+{
+    const int64_t nrows = (int64_t)ptr.size() - 1;
+    std::vector<int32_t> blk;
+    blk.push_back(0);
+    int64_t r = 0;
+    while (r < nrows) {
+        int64_t e = r + 1;      // at least one row (a long row stands alone)
+        while (e < nrows && e - r < 256 && ptr[(size_t)e + 1] - ptr[(size_t)r] <= SPMV_CAP) ++e;
+        blk.push_back((int32_t)e);
+        r = e;
+    }
+    return blk;
 }
 
 // lanes per row / column: the power of two nearest above the average length, within [2, 32]
@@ -382,6 +428,15 @@ int mipm_spmv_setup(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap, con
     MIPM_CUDA(h, h->d_sp_colptr.upload(cp, h->stream));
     MIPM_CUDA(h, h->d_sp_row.upload(ri, h->stream));
     MIPM_CUDA(h, h->d_sp_pos.upload(pos, h->stream));
+    {
+        std::vector<int32_t> br = spmv_blocks(rp), bc = spmv_blocks(cp);
+        h->sp_nblk_rows = (int64_t)br.size() - 1;
+        h->sp_nblk_cols = (int64_t)bc.size() - 1;
+        MIPM_CUDA(h, h->d_sp_blk_rows.upload(br, h->stream));
+        MIPM_CUDA(h, h->d_sp_blk_cols.upload(bc, h->stream));
+    }
+    MIPM_CUDA(h, h->d_sp_valT.alloc((size_t)nnz));
+    h->sp_valT_src = nullptr;
     MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->sp_m = m;
     h->sp_n = n;
@@ -401,31 +456,34 @@ int mipm_spmv(mipm_handle hh, int trans, double alpha, const double *d_Ax, const
     }
     if (trans == 0) {
         if (h->sp_m > 0) {
-#define MIPM_SPMV_CSR(G) k_spmv_csr<G><<<grid_for(h->sp_m * G, 256), 256, 0, h->stream>>>(h->sp_m, h->d_sp_rowptr.p, h->d_sp_col.p, d_Ax, d_x, alpha, beta, d_y)
-            switch (spmv_group(h->sp_nnz, h->sp_m)) {
-            case 2: MIPM_SPMV_CSR(2); break;
-            case 4: MIPM_SPMV_CSR(4); break;
-            case 8: MIPM_SPMV_CSR(8); break;
-            case 16: MIPM_SPMV_CSR(16); break;
-            default: MIPM_SPMV_CSR(32); break;
-            }
-#undef MIPM_SPMV_CSR
+            k_spmv_stream<false><<<(unsigned)h->sp_nblk_rows, 256, 0, h->stream>>>(h->d_sp_blk_rows.p, h->d_sp_rowptr.p, h->d_sp_col.p,
+                                                                                  nullptr, d_Ax, d_x, alpha, beta, d_y);
             MIPM_CHECK_LAUNCH(h);
         }
     } else {
         if (h->sp_n > 0) {
-#define MIPM_SPMV_CSC(G) k_spmv_csc<G><<<grid_for(h->sp_n * G, 256), 256, 0, h->stream>>>(h->sp_n, h->d_sp_colptr.p, h->d_sp_row.p, h->d_sp_pos.p, d_Ax, d_x, alpha, beta, d_y)
-            switch (spmv_group(h->sp_nnz, h->sp_n)) {
-            case 2: MIPM_SPMV_CSC(2); break;
-            case 4: MIPM_SPMV_CSC(4); break;
-            case 8: MIPM_SPMV_CSC(8); break;
-            case 16: MIPM_SPMV_CSC(16); break;
-            default: MIPM_SPMV_CSC(32); break;
-            }
-#undef MIPM_SPMV_CSC
+            if (h->sp_valT_src == d_Ax && d_Ax)      // column-ordered copy cached by mipm_spmv_cache_values
+                k_spmv_stream<false><<<(unsigned)h->sp_nblk_cols, 256, 0, h->stream>>>(h->d_sp_blk_cols.p, h->d_sp_colptr.p, h->d_sp_row.p,
+                                                                                      nullptr, h->d_sp_valT.p, d_x, alpha, beta, d_y);
+            else
+                k_spmv_stream<true><<<(unsigned)h->sp_nblk_cols, 256, 0, h->stream>>>(h->d_sp_blk_cols.p, h->d_sp_colptr.p, h->d_sp_row.p,
+                                                                                     h->d_sp_pos.p, d_Ax, d_x, alpha, beta, d_y);
             MIPM_CHECK_LAUNCH(h);
         }
     }
+    return MIPM_OK;
+}
+
+int mipm_spmv_cache_values(mipm_handle hh, const double *d_Ax)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_spmv) return fail(h, MIPM_ERR_STATE, "mipm_spmv_setup has not been called");
+    h->sp_valT_src = nullptr;
+    if (!d_Ax || h->sp_nnz == 0) return MIPM_OK;       // null: drop the cache
+    k_gather32<<<(unsigned)std::min<int64_t>(grid_for(h->sp_nnz, 256), 148 * 16), 256, 0, h->stream>>>(h->sp_nnz, d_Ax, h->d_sp_pos.p, h->d_sp_valT.p);
+    MIPM_CHECK_LAUNCH(h);
+    h->sp_valT_src = d_Ax;
     return MIPM_OK;
 }
 

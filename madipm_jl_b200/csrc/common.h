@@ -97,6 +97,10 @@ struct Handle {
     bool has_spmv = false;
     int64_t sp_m = 0, sp_n = 0, sp_nnz = 0;
     DBuf<int32_t> d_sp_rowptr, d_sp_col, d_sp_colptr, d_sp_row, d_sp_pos;
+    DBuf<int32_t> d_sp_blk_rows, d_sp_blk_cols;     // row / column runs of the streaming SpMV
+    int64_t sp_nblk_rows = 0, sp_nblk_cols = 0;
+    DBuf<double> d_sp_valT;                         // column-ordered copy of the values (mipm_spmv_cache_values)
+    const double *sp_valT_src = nullptr;            // the caller's value array the copy was taken from
 
     // ---- Hessian operator (full symmetric CSR), the MadIPMOperator(H; symmetric=true) analogue
     bool has_hess = false;

@@ -96,6 +96,7 @@ struct SolveParams {
     int accumulate;             // x_out[perm] += xp instead of =
     const int *vmap;            // virtual CTA id per blockIdx.x, or null
     int *probe;                 // non-null: placement probe only
+    unsigned long long *lvl_ns; // optional (MIPM_SOLVE_LOG): device time of gather, every forward level, every backward level
 };
 
 __device__ __forceinline__ int read_smid()
@@ -720,6 +721,10 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
         for (int64_t i = gtid; i < p.n_u; i += gsz) p.uvec[i] = 0.0;
         grid.sync();
     }
+    const bool timer = (p.lvl_ns != nullptr && blockIdx.x == 0 && threadIdx.x == 0);
+    unsigned long long tprev = 0;
+    int tslot = 0;
+    if (timer) tprev = globaltimer_ns();
     const int32_t *leaves = p.sched + p.leaf_off;
     const int n_leaf_groups = (p.n_leaf + 7) / 8;
     for (int l = p.fwd_begin; l < p.fwd_end; ++l) {
@@ -736,6 +741,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
             __syncthreads();
         }
         grid.sync();
+        if (timer) { unsigned long long t1 = globaltimer_ns(); p.lvl_ns[tslot++] = t1 - tprev; tprev = t1; }
     }
     if (!p.do_backward) return;
     for (int l = p.n_levels - 1; l >= 0; --l) {
@@ -752,6 +758,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
             __syncthreads();
         }
         grid.sync();
+        if (timer) { unsigned long long t1 = globaltimer_ns(); p.lvl_ns[tslot++] = t1 - tprev; tprev = t1; }
     }
     if (p.accumulate) { for (int64_t i = gtid; i < p.n; i += gsz) p.x_out[p.perm[i]] += p.xp[i]; }
     else { for (int64_t i = gtid; i < p.n; i += gsz) p.x_out[p.perm[i]] = p.xp[i]; }
@@ -1133,6 +1140,14 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     p.L = h->d_L.p; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
     p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
     p.vmap = h->d_vmap_solve.p; p.probe = nullptr;
+    static const bool solve_log = std::getenv("MIPM_SOLVE_LOG") != nullptr;
+    DBuf<unsigned long long> d_lvl_ns;
+    p.lvl_ns = nullptr;
+    if (solve_log) {
+        MIPM_CUDA(h, d_lvl_ns.alloc((size_t)2 * S.n_levels + 2));
+        MIPM_CUDA(h, cudaMemsetAsync(d_lvl_ns.p, 0, ((size_t)2 * S.n_levels + 2) * sizeof(unsigned long long), h->stream));
+        p.lvl_ns = d_lvl_ns.p;
+    }
     p.do_gather = (stage != 1);
     p.fwd_begin = (stage == 1) ? S.n_levels - 1 : 0;
     p.fwd_end = S.n_levels;
@@ -1142,6 +1157,19 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_solve_persistent<true> : (const void *)k_solve_persistent<false>;
     MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)h->grid_solve), dim3(256), args, 0, h->stream));
     h->launches++;
+    if (solve_log) {        // diagnostic only: synchronises
+        std::vector<unsigned long long> ns((size_t)2 * S.n_levels + 2);
+        MIPM_CUDA(h, cudaMemcpyAsync(ns.data(), d_lvl_ns.p, ns.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+        std::fprintf(stderr, "solve levels (us): fwd");
+        int slot = 0;
+        for (int l = p.fwd_begin; l < p.fwd_end; ++l) std::fprintf(stderr, " %d:%lld[%lld]", l, (long long)(ns[(size_t)slot++] / 1000), (long long)S.level_ptr[(size_t)l + 1] - (long long)S.level_ptr[(size_t)l]);
+        if (p.do_backward) {
+            std::fprintf(stderr, " | bwd");
+            for (int l = S.n_levels - 1; l >= 0; --l) std::fprintf(stderr, " %d:%lld", l, (long long)(ns[(size_t)slot++] / 1000));
+        }
+        std::fprintf(stderr, "\n");
+    }
     return MIPM_OK;
 }
 

@@ -335,6 +335,7 @@ class MPCSolver:
         """normalkkt.jl:163-172 / cuda_wrapper.jl:32-41: AT.nzVal = A.V[A_csr_map] (+ slack = -1); A.V (the jac_coord!
         result, scaled by con_scale) was placed on the device by _madnlp_initialize."""
         self.h.gather(len(self.Aj), self.A_V, self.d_A_csr_map, self.AT_x)     # AT.nzVal .= A.V[A_csr_map]
+        self.h.spmv_cache_values(self.AT_x)       # the values stay fixed until the next compress_jacobian!
         if self.opt.kkt_system == "Normal":
             self.h.normal_set_jacobian(self.AT_x)
         else:

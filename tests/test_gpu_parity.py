@@ -90,6 +90,40 @@ def test_spmv(handle):
     h.spmv(1, -1.0, dA, dev(v), 1.0, w)
     assert np.abs(y.cpu().numpy() - (1.5 * (A @ x) - 0.5 * y0)).max() < 1e-12
     assert np.abs(w.cpu().numpy() - (-(A.T @ v) + w0)).max() < 1e-12
+    # the same products with the column-ordered value cache (what the solver uses between compress_jacobian! calls)
+    h.spmv_cache_values(dA)
+    w = dev(w0)
+    h.spmv(1, -1.0, dA, dev(v), 1.0, w)
+    assert np.abs(w.cpu().numpy() - (-(A.T @ v) + w0)).max() < 1e-12
+    dB = dev(2.0 * A.data)                      # a different value array must not hit the cache
+    w = dev(w0)
+    h.spmv(1, -1.0, dB, dev(v), 1.0, w)
+    assert np.abs(w.cpu().numpy() - (-2.0 * (A.T @ v) + w0)).max() < 1e-12
+
+
+def test_spmv_ragged(handle):
+    """Empty rows / columns, one row and one column longer than a block's capacity (2048 products), beta = 0."""
+    rng = np.random.default_rng(3)
+    m, n = 300, 5000
+    rows = [np.full(3000, 7), rng.integers(0, m, 4000), rng.integers(0, m, 2500)]
+    cols = [rng.choice(n, 3000, replace=False), rng.integers(0, n, 4000), np.full(2500, 11)]
+    A = sp.coo_matrix((rng.standard_normal(9500), (np.concatenate(rows), np.concatenate(cols))), shape=(m, n)).tocsr()
+    A.sum_duplicates()
+    A = sp.vstack([A, sp.csr_matrix((5, n))]).tocsr()           # trailing empty rows
+    m = A.shape[0]
+    h = handle()
+    h.spmv_setup(m, n, A.indptr.astype(np.int32), A.indices.astype(np.int32))
+    x, v = rng.standard_normal(n), rng.standard_normal(m)
+    dA = dev(A.data)
+    y, w = dev(np.full(m, np.nan)), dev(np.full(n, np.nan))     # beta = 0 must overwrite, not scale
+    h.spmv(0, 2.0, dA, dev(x), 0.0, y)
+    h.spmv(1, 1.0, dA, dev(v), 0.0, w)
+    assert np.abs(y.cpu().numpy() - 2.0 * (A @ x)).max() < 1e-11
+    assert np.abs(w.cpu().numpy() - (A.T @ v)).max() < 1e-11
+    h.spmv_cache_values(dA)
+    w = dev(np.full(n, np.nan))
+    h.spmv(1, 1.0, dA, dev(v), 0.0, w)
+    assert np.abs(w.cpu().numpy() - (A.T @ v)).max() < 1e-11
 
 
 # ------------------------------------------------------------------ linear solver (a9, a11, a21)
