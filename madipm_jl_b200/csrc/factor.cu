@@ -96,6 +96,7 @@ struct SolveParams {
     int accumulate;             // x_out[perm] += xp instead of =
     const int *vmap;            // virtual CTA id per blockIdx.x, or null
     int *probe;                 // non-null: placement probe only
+    int prefetch;               // L2 prefetch of upcoming fronts (MIPM_NO_PREFETCH=1 turns it off)
     unsigned long long *lvl_ns; // optional (MIPM_SOLVE_LOG): device time of gather, every forward level, every backward level
 };
 
@@ -501,6 +502,24 @@ k_bench_syrk(int n, int kdim, double *__restrict__ C, int64_t ldc, const double 
 // through their stored inverses (mat-vec), so nothing in a front is sequential.
 constexpr int XR_MAX = 1536;    // ancestor entries of x cached in shared memory by the backward sweep
 
+// L2 prefetch of a front's panel and inverted diagonal blocks. The solves are latency-bound: a front is a chain of
+// dependent global loads, and the factor (hundreds of MB) does not stay in L2. CTAs with no task at a level fetch the
+// next level's fronts when that level is small (near the root; prefetching a wide level only thrashes L2), so the
+// dependent loads hit L2 instead of HBM.
+constexpr int PREFETCH_MAX_FRONTS = 128;
+__device__ __forceinline__ void prefetch_front(const SolveParams &p, int s)
+{
+    const FrontInfo f = p.fi[s];
+    const char *base = reinterpret_cast<const char *>(p.L + f.lp);
+    const int64_t bytes = (int64_t)(f.k + f.r) * f.k * 8;
+    for (int64_t off = (int64_t)threadIdx.x * 128; off < bytes; off += 256 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    const char *dv = reinterpret_cast<const char *>(p.Dinv + f.dinv * (int64_t)(NB * NB));
+    const int64_t bytes2 = (int64_t)((f.k + NB - 1) / NB) * NB * NB * 8;
+    for (int64_t off = (int64_t)threadIdx.x * 128; off < bytes2; off += 256 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(dv + off));
+}
+
 // mode 0: whole front; 1: only fold the children's update vectors in (distributed solves: the root
 // segment is all-reduced after this); 2: skip that part (it was done in the previous stage)
 template <bool LDL>
@@ -731,6 +750,11 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
         const int32_t *fr = p.sched + p.lvl[2 * l];
         const int nf = (int)p.lvl[2 * l + 1];
         const int extra = (l == 0) ? n_leaf_groups : 0;      // small leaves ride along with level 0
+        if (p.prefetch && l + 1 < p.fwd_end && vid >= nf + extra && (int)p.lvl[2 * (l + 1) + 1] <= PREFETCH_MAX_FRONTS) {
+            const int32_t *nx = p.sched + p.lvl[2 * (l + 1)];
+            const int nnx = (int)p.lvl[2 * (l + 1) + 1], idle = (int)gridDim.x - (nf + extra);
+            for (int j = vid - (nf + extra); j < nnx; j += idle) prefetch_front(p, nx[j]);
+        }
         for (int t = vid; t < nf + extra; t += gridDim.x) {
             if (t < extra) {
                 const int li = t * 8 + (threadIdx.x >> 5);
@@ -748,6 +772,11 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
         const int32_t *fr = p.sched + p.lvl[2 * l];
         const int nf = (int)p.lvl[2 * l + 1];
         const int extra = (l == 0) ? n_leaf_groups : 0;
+        if (p.prefetch && l > 0 && vid >= nf + extra && (int)p.lvl[2 * (l - 1) + 1] <= PREFETCH_MAX_FRONTS) {
+            const int32_t *nx = p.sched + p.lvl[2 * (l - 1)];
+            const int nnx = (int)p.lvl[2 * (l - 1) + 1], idle = (int)gridDim.x - (nf + extra);
+            for (int j = vid - (nf + extra); j < nnx; j += idle) prefetch_front(p, nx[j]);
+        }
         for (int t = vid; t < nf + extra; t += gridDim.x) {
             if (t < extra) {
                 const int li = t * 8 + (threadIdx.x >> 5);
@@ -1141,6 +1170,8 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
     p.vmap = h->d_vmap_solve.p; p.probe = nullptr;
     static const bool solve_log = std::getenv("MIPM_SOLVE_LOG") != nullptr;
+    static const bool no_prefetch = std::getenv("MIPM_NO_PREFETCH") != nullptr;
+    p.prefetch = no_prefetch ? 0 : 1;
     DBuf<unsigned long long> d_lvl_ns;
     p.lvl_ns = nullptr;
     if (solve_log) {
