@@ -211,7 +211,17 @@ __device__ void task_extend_add(const FactorParams &p, const int32_t *tasks, int
             const int tb = rel[b];
             const double *src = Uc + (int64_t)b * rc;
             double *dst = (tb < k) ? (P + (int64_t)tb * N) : (Us + (int64_t)(tb - k) * r - k);
-            for (int a = b + (threadIdx.x & 31); a < rc; a += 32) dst[rel[a]] += src[a];
+            // rows of one child column land on distinct parent rows: four independent read-modify-writes in flight
+            // per lane (the plain loop is a chain of dependent global round trips, the compiler cannot prove
+            // the destinations distinct)
+            int a = b + (threadIdx.x & 31);
+            for (; a + 96 < rc; a += 128) {
+                const int r0 = rel[a], r1 = rel[a + 32], r2 = rel[a + 64], r3 = rel[a + 96];
+                const double s0 = src[a], s1 = src[a + 32], s2 = src[a + 64], s3 = src[a + 96];
+                const double d0 = dst[r0], d1 = dst[r1], d2 = dst[r2], d3 = dst[r3];
+                dst[r0] = d0 + s0; dst[r1] = d1 + s1; dst[r2] = d2 + s2; dst[r3] = d3 + s3;
+            }
+            for (; a < rc; a += 32) dst[rel[a]] += src[a];
         }
         __syncthreads();
     }
