@@ -387,12 +387,33 @@ __device__ void task_update(const FactorParams &p, int s, int lt, int jb, double
     int64_t ldc;
     if (col0 < k) { C = P + (int64_t)col0 * N + row0; ldc = N; }
     else { C = p.U + f.up + (int64_t)(col0 - k) * r + (row0 - k); ldc = r; }
-    acc_foreach(acc, [&](int rr, int cc, double val) {
-        if (rr < nrow && cc < ncol && (row0 + rr) >= (col0 + cc)) {
-            double *q = C + (int64_t)cc * ldc + rr;
-            *q -= val;
-        }
-    });
+    // read all 16 destination entries first, then subtract and store: as read-modify-writes in sequence they are a
+    // chain of dependent global round trips (the compiler must assume the stores alias the next load)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, l3 = lane & 3;
+        double cv[4][2][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int rr = wm * 32 + mi * 8 + g, cc = wn * 16 + ni * 8 + l3 * 2 + e;
+                    const bool on = rr < nrow && cc < ncol && (row0 + rr) >= (col0 + cc);
+                    cv[mi][ni][e] = on ? C[(int64_t)cc * ldc + rr] : 0.0;
+                }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int rr = wm * 32 + mi * 8 + g, cc = wn * 16 + ni * 8 + l3 * 2 + e;
+                    const bool on = rr < nrow && cc < ncol && (row0 + rr) >= (col0 + cc);
+                    if (on) C[(int64_t)cc * ldc + rr] = cv[mi][ni][e] - acc[mi][ni][e];
+                }
+    }
 }
 
 // Whole-front task for levels with many more fronts than CTAs: one CTA assembles the front from its
