@@ -92,9 +92,18 @@ __device__ __forceinline__ void diag_block(double *__restrict__ P, int N, int nb
 
     long long tq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
 #define DIAG_STAMP(i) do { if (DBG && dbg) { long long now_ = clock64(); tq[i] += now_ - tc; tc = now_; } } while (0)
-    for (int idx = tid; idx < DB * DB; idx += 256) {
-        const int rr = idx & 63, cc = idx >> 6;
-        S[cc * DLD + rr] = (rr < nb && cc < nb && rr >= cc) ? P[(int64_t)cc * N + rr] : ((rr == cc) ? 1.0 : 0.0);
+    {
+        double v[DB * DB / 256];            // all 16 global loads in flight before the first shared store
+#pragma unroll
+        for (int t = 0; t < DB * DB / 256; ++t) {
+            const int idx = tid + 256 * t, rr = idx & 63, cc = idx >> 6;
+            v[t] = (rr < nb && cc < nb && rr >= cc) ? P[(int64_t)cc * N + rr] : ((rr == cc) ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int t = 0; t < DB * DB / 256; ++t) {
+            const int idx = tid + 256 * t;
+            S[(idx >> 6) * DLD + (idx & 63)] = v[t];
+        }
     }
     __syncthreads();
     DIAG_STAMP(0);

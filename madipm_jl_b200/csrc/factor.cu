@@ -135,11 +135,37 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 // Stage a (nrows x ncols) column-major block into smem k-major: dst[kk * XS + rr], zero padded to 64 x 64.
 __device__ __forceinline__ void stage_tile(double *dst, const double *__restrict__ src, int64_t ld, int nrows, int ncols)
 {
+    double v[(TILE * TILE) / 256];          // all 16 global loads in flight before the first shared store
 #pragma unroll
     for (int i = 0; i < (TILE * TILE) / 256; ++i) {
         int idx = threadIdx.x + i * 256;
         int rr = idx & 63, kk = idx >> 6;
-        dst[kk * XS + rr] = (rr < nrows && kk < ncols) ? src[(int64_t)kk * ld + rr] : 0.0;
+        v[i] = (rr < nrows && kk < ncols) ? src[(int64_t)kk * ld + rr] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < (TILE * TILE) / 256; ++i) {
+        int idx = threadIdx.x + i * 256;
+        dst[(idx >> 6) * XS + (idx & 63)] = v[i];
+    }
+}
+
+// Two operand tiles at once: 32 loads in flight per thread (one global round trip instead of two).
+__device__ __forceinline__ void stage_two(double *dx, const double *__restrict__ sx, int64_t ldx, int nrx, int ncx,
+                                          double *dy, const double *__restrict__ sy, int64_t ldy, int nry, int ncy)
+{
+    double v[(TILE * TILE) / 256], w[(TILE * TILE) / 256];
+#pragma unroll
+    for (int i = 0; i < (TILE * TILE) / 256; ++i) {
+        int idx = threadIdx.x + i * 256;
+        int rr = idx & 63, kk = idx >> 6;
+        v[i] = (rr < nrx && kk < ncx) ? sx[(int64_t)kk * ldx + rr] : 0.0;
+        w[i] = (rr < nry && kk < ncy) ? sy[(int64_t)kk * ldy + rr] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < (TILE * TILE) / 256; ++i) {
+        int idx = threadIdx.x + i * 256;
+        dx[(idx >> 6) * XS + (idx & 63)] = v[i];
+        dy[(idx >> 6) * XS + (idx & 63)] = w[i];
     }
 }
 
@@ -328,8 +354,7 @@ __device__ void task_trsm(const FactorParams &p, int s, int lc, int jb, double *
     double *P = p.L + f.lp;
     double *R = P + (int64_t)jb * N + row0;
     const double *Dv = p.Dinv + (f.dinv + (jb >> 6)) * (int64_t)(NB * NB);
-    stage_tile(Xs, R, N, nrow, nb);
-    stage_tile(Ys, Dv, NB, NB, nb);
+    stage_two(Xs, R, N, nrow, nb, Ys, Dv, NB, NB, nb);
     __syncthreads();
     double acc[4][2][2];
 #pragma unroll
@@ -374,8 +399,8 @@ __device__ void task_update(const FactorParams &p, int s, int lt, int jb, double
     double *P = p.L + f.lp;
     const double *Y = P + (int64_t)jb * N + col0;
     const double *X = LDL ? (p.W + f.wp + row0) : (P + (int64_t)jb * N + row0);
-    stage_tile(Xs, X, N, nrow, nb);
-    if (LDL || tr != tc) stage_tile(Ys, Y, N, ncol, nb); else Ys = Xs;
+    if (LDL || tr != tc) stage_two(Xs, X, N, nrow, nb, Ys, Y, N, ncol, nb);
+    else { stage_tile(Xs, X, N, nrow, nb); Ys = Xs; }
     __syncthreads();
     double acc[4][2][2];
 #pragma unroll
@@ -583,8 +608,11 @@ __device__ void front_forward(const SolveParams &p, int s, double *smem, int mod
         {   // y = inv(L11 block) * xb : row rr by the 4 threads (rr, q), columns pp = q, q+4, ...
             const int rr = tid >> 2, q = tid & 3;
             double acc = 0.0;
-#pragma unroll 4
-            for (int pp = q; pp <= rr; pp += 4) acc = fma(Dv[pp * NB + rr], xb[pp], acc);
+            double dvv[NB / 4];                  // the 16 loads of this row first (entries above the diagonal are stored zeros)
+#pragma unroll
+            for (int t = 0; t < NB / 4; ++t) dvv[t] = Dv[(q + 4 * t) * NB + rr];
+#pragma unroll
+            for (int t = 0; t < NB / 4; ++t) acc = fma(dvv[t], xb[q + 4 * t], acc);
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
             if (q == 0) { yb[rr] = acc; if (rr < nb) x1[jb + rr] = acc; }
