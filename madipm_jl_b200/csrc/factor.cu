@@ -354,7 +354,8 @@ __device__ void task_trsm(const FactorParams &p, int s, int lc, int jb, double *
     double *P = p.L + f.lp;
     double *R = P + (int64_t)jb * N + row0;
     const double *Dv = p.Dinv + (f.dinv + (jb >> 6)) * (int64_t)(NB * NB);
-    stage_two(Xs, R, N, nrow, nb, Ys, Dv, NB, NB, nb);
+    stage_tile(Xs, R, N, nrow, nb);
+    stage_tile(Ys, Dv, NB, NB, nb);
     __syncthreads();
     double acc[4][2][2];
 #pragma unroll
