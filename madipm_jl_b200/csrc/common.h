@@ -88,6 +88,9 @@ struct Handle {
     DBuf<int32_t> d_sn_ptr, d_sn_parent, d_row_idx, d_rel_idx, d_perm, d_child_idx, d_full_col;
     DBuf<int64_t> d_row_ptr, d_lp, d_up, d_child_ptr, d_a2l, d_full_ptr, d_full_val, d_wp;
     DBuf<double> d_L, d_U, d_W, d_xp, d_uvec, d_b, d_r;
+    DBuf<double> d_L2;               // second factor buffer: the idle one is zero-filled on the side stream (not in border mode)
+    double *L_cur = nullptr;         // buffer holding the current factor
+    bool l_prezeroed = false;
     DBuf<int> d_vmap_factor, d_vmap_solve;   // virtual CTA ids of the persistent kernels (placement probe)
     DBuf<int> d_info;                // [0]=first failed column+1 (0 = ok), [1]=#neg pivots, [2]=#zero pivots
     const double *d_nzval = nullptr;

@@ -1135,6 +1135,12 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, h->d_full_col.upload(S.full_col, st));
     MIPM_CUDA(h, h->d_full_val.upload(S.full_val, st));
     MIPM_CUDA(h, h->d_L.alloc((size_t)std::max<int64_t>(S.nnz_l, 1)));
+    h->L_cur = h->d_L.p;
+    h->l_prezeroed = false;
+    h->d_L2.release();
+    if (S.root_sn < 0 && S.nnz_l > 0 && (size_t)S.nnz_l * sizeof(double) <= ((size_t)16 << 30) && !std::getenv("MIPM_SINGLE_L")) {
+        if (h->d_L2.alloc((size_t)S.nnz_l) != cudaSuccess) { h->d_L2.release(); (void)cudaGetLastError(); }   // optional
+    }
     MIPM_CUDA(h, h->d_U.alloc((size_t)std::max<int64_t>(S.update_doubles, 1)));
     MIPM_CUDA(h, h->d_W.alloc((size_t)std::max<int64_t>(wp[(size_t)ns], 1)));
     MIPM_CUDA(h, h->d_Dinv.alloc((size_t)std::max<int64_t>(dinv_off[(size_t)ns], 1) * NB * NB));
@@ -1172,7 +1178,15 @@ int ls_factorize_staged(Handle *h, const double *d_nzval, int stage)
     const int ph0 = (stage == 1) ? h->root_phase_begin : 0;
     const int ph1 = (stage == 0) ? h->root_phase_begin : h->n_phases;
     if (stage != 1) {
-    MIPM_CUDA(h, cudaMemsetAsync(h->d_L.p, 0, (size_t)std::max<int64_t>(S.nnz_l, 1) * sizeof(double), st));
+    if (h->d_L2.p) {
+        // two factor buffers: this factorization writes the one the previous solves did not use; it was zero-filled on
+        // the side stream while they ran
+        h->L_cur = (h->L_cur == h->d_L.p) ? h->d_L2.p : h->d_L.p;
+        if (h->l_prezeroed) { MIPM_CUDA(h, cudaStreamWaitEvent(st, h->ev_u_zero, 0)); }
+        else { MIPM_CUDA(h, cudaMemsetAsync(h->L_cur, 0, (size_t)S.nnz_l * sizeof(double), st)); }
+    } else {
+        MIPM_CUDA(h, cudaMemsetAsync(h->d_L.p, 0, (size_t)std::max<int64_t>(S.nnz_l, 1) * sizeof(double), st));
+    }
     // The update matrices are only live inside the factorization kernel, so their zero-fill for the
     // NEXT factorization runs on a side stream behind this one (it overlaps the latency-bound solves).
     if (h->u_prezeroed) {
@@ -1183,7 +1197,7 @@ int ls_factorize_staged(Handle *h, const double *d_nzval, int stage)
     MIPM_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, 4 * sizeof(int), st));
     MIPM_CUDA(h, cudaMemsetAsync(h->d_work_counter.p, 0, ((size_t)h->n_phases + 8) * sizeof(int), st));
     if (S.nnz_a > 0) {
-        k_scatter_a<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.nnz_a, h->d_a2l.p, d_nzval, h->d_L.p);
+        k_scatter_a<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.nnz_a, h->d_a2l.p, d_nzval, h->L_cur);
         MIPM_CHECK_LAUNCH(h);
     }
     }
@@ -1191,7 +1205,7 @@ int ls_factorize_staged(Handle *h, const double *d_nzval, int stage)
         FactorParams p;
         p.fi = (const FrontInfo *)h->d_finfo.p; p.child_idx = h->d_child_idx.p; p.rel_idx = h->d_rel_idx.p;
         p.sched = h->d_sched.p; p.phases = h->d_phases.p; p.n_phases = ph1; p.phase_begin = ph0;
-        p.L = h->d_L.p; p.U = h->d_U.p; p.W = h->d_W.p; p.Dinv = h->d_Dinv.p; p.info = h->d_info.p;
+        p.L = h->L_cur; p.U = h->d_U.p; p.W = h->d_W.p; p.Dinv = h->d_Dinv.p; p.info = h->d_info.p;
         p.phase_ns = h->d_phase_ns.p;
         p.ea_first = h->d_ea_first.p; p.ea_count = h->d_ea_count.p; p.work_counter = h->d_work_counter.p;
         p.dbg = std::getenv("MIPM_DIAG_DBG") ? (long long *)(h->d_phase_ns.p + h->n_phases) : nullptr;
@@ -1207,6 +1221,11 @@ int ls_factorize_staged(Handle *h, const double *d_nzval, int stage)
         MIPM_CUDA(h, cudaEventRecord(h->ev_factor_done, st));
         MIPM_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_factor_done, 0));
         MIPM_CUDA(h, cudaMemsetAsync(h->d_U.p, 0, (size_t)std::max<int64_t>(S.update_doubles, 1) * sizeof(double), h->side));
+        if (h->d_L2.p) {     // the buffer of the PREVIOUS factor: every solve that read it precedes ev_factor_done in stream order
+            double *idle = (h->L_cur == h->d_L.p) ? h->d_L2.p : h->d_L.p;
+            MIPM_CUDA(h, cudaMemsetAsync(idle, 0, (size_t)S.nnz_l * sizeof(double), h->side));
+            h->l_prezeroed = true;
+        }
         MIPM_CUDA(h, cudaEventRecord(h->ev_u_zero, h->side));
         h->u_prezeroed = true;
     }
@@ -1226,7 +1245,7 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     p.perm = h->d_perm.p; p.sched = h->d_sched.p; p.lvl = h->d_lvl.p; p.n_levels = S.n_levels;
     p.leaf_off = h->leaf_off; p.n_leaf = h->n_leaf;
     p.n = S.n; p.n_u = S.row_ptr[(size_t)S.ns];
-    p.L = h->d_L.p; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
+    p.L = h->L_cur; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
     p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
     p.vmap = h->d_vmap_solve.p; p.probe = nullptr;
     static const bool solve_log = std::getenv("MIPM_SOLVE_LOG") != nullptr;
