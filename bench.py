@@ -30,11 +30,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_factor_persistent launch from `ncu --set full`
-# (profiles/ncu_factor_persistent_r01_raw.csv), keyed by --scale; None when not captured for that size
+# (profiles/ncu_factor_persistent_r01_final_raw.csv), keyed by --scale; None when not captured for that size
 TRAFFIC_BYTES = {}
 try:
-    TRAFFIC_BYTES = {float(k): v for k, v in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)),
-                                                                    "profiles", "factor_traffic_r01.json"))).items()}
+    for _k, _v in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "factor_traffic_r01.json"))).items():
+        try:
+            TRAFFIC_BYTES[float(_k)] = float(_v)
+        except (TypeError, ValueError):
+            pass            # descriptive entries (source, capture details)
 except Exception:
     pass
 
