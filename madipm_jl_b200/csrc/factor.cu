@@ -965,13 +965,14 @@ int ls_device_setup(Handle *h)
     int root_phase_begin = -1;
     // grid size is needed to decide which levels run whole-front tasks
     int fuse_min = 1 << 30;
+    int grid_estimate = 444;
     {
         cudaDeviceProp prop0;
         MIPM_CUDA(h, cudaGetDeviceProperties(&prop0, h->device));
         // Measured on B200 (tools/sweep_fuse.py): per-CTA tile latency, not the grid barriers, bounds
         // the wide levels, so whole-front tasks are neutral on C2 and slower on C3's small fronts.
         // Off by default; MIPM_FRONT_FUSE_MIN=<n> enables them for levels with at least n fronts.
-        (void)prop0;
+        grid_estimate = prop0.multiProcessorCount * 3;       // __launch_bounds__(256, 3)
         if (const char *e = std::getenv("MIPM_FRONT_FUSE_MIN")) fuse_min = std::max(1, atoi(e));
     }
     std::vector<int32_t> ea_first((size_t)std::max(ns, 1), 0), ea_count((size_t)std::max(ns, 1), 0);
@@ -1000,14 +1001,26 @@ int ls_device_setup(Handle *h)
         if (S.root_sn >= 0 && l == S.n_levels - 1) root_phase_begin = (int)(phases.size() / 8);   // moved past the EA phase below
         // extend-add: per-child column ranges first, then the task records that point at them
         std::vector<int32_t> ea;
+        // columns per task: EA_COLS, narrower near the root where a level has fewer tasks than CTAs (an extend-add
+        // task is a chain of dependent global round trips, so the level costs one task's latency)
+        int ea_cols = EA_COLS;
+        for (;;) {
+            int64_t nt = 0;
+            for (int64_t t = f0; t < f1; ++t) {
+                const FrontInfo &f = finfo[(size_t)S.level_sn[(size_t)t]];
+                if (f.nchild > 0) nt += (f.k + f.r + ea_cols / 2 - 1) / (ea_cols / 2);
+            }
+            if (ea_cols <= 8 || nt > grid_estimate) break;
+            ea_cols /= 2;
+        }
         for (int64_t t = f0; t < f1; ++t) {
             int s = S.level_sn[(size_t)t];
             const FrontInfo &f = finfo[(size_t)s];
             if (f.nchild == 0) continue;
             int N = f.k + f.r;
             ea_first[(size_t)s] = (int32_t)(ea.size() / 4);            // index inside this level's record array
-            for (int q0 = 0; q0 < N; q0 += EA_COLS) {
-                int q1 = std::min(N, q0 + EA_COLS);
+            for (int q0 = 0; q0 < N; q0 += ea_cols) {
+                int q1 = std::min(N, q0 + ea_cols);
                 int64_t off_r = (int64_t)sched.size();
                 bool any = false;
                 for (int ci = 0; ci < f.nchild; ++ci) {
