@@ -3,8 +3,20 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 constexpr int PW = 16;
+// branch-free reciprocal (normal, finite, non-zero argument): MUFU seed (2^-23) + two Newton steps
+__device__ __forceinline__ double fast_rcp(double d)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
 // V bit0: no reciprocal (multiply instead)   bit1: no shared-memory exchange (use own register)
 // V bit2: no pivot test                       bit3: no next-pivot shuffle (use own value)
+// V bit4: branch-free reciprocal (fast_rcp) instead of __drcp_rn
 template <int V>
 __global__ void k(const double *A, double *out, long long *cyc, int reps)
 {
@@ -23,7 +35,7 @@ __global__ void k(const double *A, double *out, long long *cyc, int reps)
 #pragma unroll
         for (int kk = 0; kk < PW; ++kk) a[kk] = fac ? S[kk * 17 + i] : ((kk == i) ? 1.0 : 0.0);
         double d = __shfl_sync(FULL, a[0], 0);
-        double inv = (V & 1) ? d * 0.01 : __drcp_rn(d);
+        double inv = (V & 1) ? d * 0.01 : ((V & 16) ? fast_rcp(d) : __drcp_rn(d));
 #pragma unroll
         for (int j = 0; j < PW; ++j) {
             const double aj = a[j];
@@ -34,7 +46,7 @@ __global__ void k(const double *A, double *out, long long *cyc, int reps)
             if (j + 1 < PW) {
                 const double own = fma(-lij, aj, a[j + 1]);
                 d_n = (V & 8) ? own : __shfl_sync(FULL, own, j + 1);
-                inv_n = (V & 1) ? d_n * 0.01 : __drcp_rn(d_n);
+                inv_n = (V & 1) ? d_n * 0.01 : ((V & 16) ? fast_rcp(d_n) : __drcp_rn(d_n));
             }
             if (!(V & 2)) __syncwarp();
 #pragma unroll
@@ -75,6 +87,8 @@ int main()
     run<4>("no pivot test", A, out, cyc);
     run<8>("no pivot shuffle", A, out, cyc);
     run<15>("none of them (DFMA work only)", A, out, cyc);
+    run<16>("fast_rcp", A, out, cyc);
+    run<20>("fast_rcp, no pivot test", A, out, cyc);
     run<3>("no rcp, no exchange", A, out, cyc);
     run<6>("no exchange, no test", A, out, cyc);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
