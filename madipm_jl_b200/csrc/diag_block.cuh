@@ -23,6 +23,20 @@ constexpr int DB = 64;          // block size
 constexpr int DLD = 65;         // shared-memory leading dimension
 constexpr int PW = 16;          // panel width
 
+// Branch-free reciprocal for a normal, finite, non-zero argument: MUFU seed (relative error 2^-23) and two Newton steps.
+// (__drcp_rn ends in a slow-path branch that keeps ptxas from overlapping it with independent work.) Arguments outside
+// that range are caught by pivot_bad and recomputed by the careful pass.
+__device__ __forceinline__ double fast_rcp(double d)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+
 template <bool LDL>
 __device__ __forceinline__ bool pivot_bad(double d, double piv_tol)
 {
@@ -36,6 +50,42 @@ __device__ __forceinline__ void pivot_fix(double &d, double piv_tol, int &nbad, 
 {
     if (LDL && fabs(d) <= 1.0e300) { ntiny++; d = (d < 0.0) ? -piv_tol : piv_tol; }
     else { nbad++; d = 1.0; }
+}
+
+// Careful version of the warp-level 16 x 16 panel factorization (same layout as the fast pass in diag_block): pivots are
+// tested and fixed one by one. Kept out of line so its registers do not weigh on the fast pass.
+template <bool LDL>
+__device__ __noinline__ void careful_panel(double *S, double *Sinv, double *dv, double *invd, int pc, double piv_tol,
+                                           int &nbad, int &ntiny)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, i = lane & 15;
+    const bool fac = lane < PW;
+    double a[PW];
+#pragma unroll
+    for (int k = 0; k < PW; ++k) a[k] = fac ? S[(pc + k) * DLD + pc + i] : ((k == i) ? 1.0 : 0.0);
+#pragma unroll
+    for (int j = 0; j < PW; ++j) {
+        double d = __shfl_sync(FULL, a[j], j);
+        if (pivot_bad<LDL>(d, piv_tol)) pivot_fix<LDL>(d, piv_tol, nbad, ntiny);
+        const double inv = 1.0 / d;
+        const double aj = a[j];
+        const double lij = aj * inv;
+#pragma unroll
+        for (int k = j + 1; k < PW; ++k) a[k] = fma(-lij, __shfl_sync(FULL, aj, k), a[k]);
+        if (fac) {
+            if (i > j) a[j] = lij;
+            else if (i == j) a[j] = d;
+        }
+        if (lane == j) { dv[pc + j] = d; invd[pc + j] = inv; }
+    }
+    if (fac) {
+#pragma unroll
+        for (int k = 0; k < PW; ++k) if (k <= i) S[(pc + k) * DLD + pc + i] = a[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < PW; ++k) Sinv[(pc + i) * DLD + pc + k] = a[k];
+    }
 }
 
 // Rank-16 update of the trailing block (8 NCOL rows / columns). Lane = row (two halves of 32), warp w = columns
@@ -123,43 +173,46 @@ __device__ __forceinline__ void diag_block(double *__restrict__ P, int N, int nb
 #pragma unroll
             for (int k = 0; k < PW; ++k) a[k] = fac ? S[(pc + k) * DLD + pc + i] : ((k == i) ? 1.0 : 0.0);
             // Serial chain per column: multiply -> FMA (lane j+1's own next pivot) -> shuffle -> reciprocal. The other
-            // updates of column j are issued while the reciprocal of pivot j+1 is in flight; the pivot test sits at the
-            // end of the iteration so its branch never blocks them.
-            double d = __shfl_sync(FULL, a[0], 0);
-            double inv = __drcp_rn(d);
-            if (pivot_bad<LDL>(d, piv_tol)) { pivot_fix<LDL>(d, piv_tol, nbad, ntiny); inv = 1.0 / d; }
+            // updates of column j are issued while the reciprocal of pivot j+1 is in flight. The fast pass has no
+            // branch at all (ptxas does not move instructions across one, and a branch per column cost 40 cycles of
+            // the chain: tools/panel16_bench.cu): pivot tests only accumulate a flag, and a panel that saw a bad
+            // pivot is redone from shared memory by the careful pass (rare: it means the factorization broke down
+            // or LDL^T needed a perturbation).
+            bool redo = false;
+            {
+                double d = __shfl_sync(FULL, a[0], 0);
+                double inv = fast_rcp(d);
+                redo = pivot_bad<LDL>(d, piv_tol);
 #pragma unroll
-            for (int j = 0; j < PW; ++j) {
-                const double aj = a[j];                          // A(i, j) before scaling
-                const double lij = aj * inv;
-                // column j goes through shared memory (one store, broadcast loads): a 64-bit shuffle is two
-                // instructions per operand and this warp is issue-bound
-                double *cj = cbuf + (j & 1) * PW;
-                if (fac) cj[i] = aj;
-                double d_n = 1.0, inv_n = 1.0;
-                if (j + 1 < PW) {
-                    const double own = fma(-lij, aj, a[j + 1]);  // exact for lane j+1: its updated diagonal entry
-                    d_n = __shfl_sync(FULL, own, j + 1);
-                    inv_n = __drcp_rn(d_n);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int k = j + 1; k < PW; ++k) a[k] = fma(-lij, cj[k], a[k]);
-                if (fac) {
-                    if (i > j) a[j] = lij;
-                    else if (i == j) a[j] = d;
-                }
-                if (lane == j) { dv[pc + j] = d; invd[pc + j] = inv; }
-                if (j + 1 < PW) {
-                    if (pivot_bad<LDL>(d_n, piv_tol)) {          // warp-uniform, rare
-                        pivot_fix<LDL>(d_n, piv_tol, nbad, ntiny);
-                        inv_n = 1.0 / d_n;
-                        if (lane == j + 1) a[j + 1] = d_n;       // keep the perturbed pivot consistent
+                for (int j = 0; j < PW; ++j) {
+                    const double aj = a[j];                          // A(i, j) before scaling
+                    const double lij = aj * inv;
+                    // column j goes through shared memory (one store, broadcast loads): a 64-bit shuffle is two
+                    // instructions per operand and this warp is issue-bound
+                    double *cj = cbuf + (j & 1) * PW;
+                    if (fac) cj[i] = aj;
+                    double d_n = 1.0, inv_n = 1.0;
+                    if (j + 1 < PW) {
+                        const double own = fma(-lij, aj, a[j + 1]);  // exact for lane j+1: its updated diagonal entry
+                        d_n = __shfl_sync(FULL, own, j + 1);
+                        inv_n = fast_rcp(d_n);
+                        redo = redo || pivot_bad<LDL>(d_n, piv_tol);
                     }
+                    __syncwarp();
+#pragma unroll
+                    for (int k = j + 1; k < PW; ++k) a[k] = fma(-lij, cj[k], a[k]);
+                    if (fac) {
+                        if (i > j) a[j] = lij;
+                        else if (i == j) a[j] = d;
+                    }
+                    if (lane == j) { dv[pc + j] = d; invd[pc + j] = inv; }
                     d = d_n; inv = inv_n;
                 }
             }
-            if (fac) {
+            if (redo) {                                              // warp-uniform, rare
+                __syncwarp();
+                careful_panel<LDL>(S, Sinv, dv, invd, pc, piv_tol, nbad, ntiny);
+            } else if (fac) {
 #pragma unroll
                 for (int k = 0; k < PW; ++k) if (k <= i) S[(pc + k) * DLD + pc + i] = a[k];
             } else {

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256, 3) k(double *A, int N, int nb, double *Di
 }
 
 template <bool LDL>
-static int run(int nblk, int nb, bool check)
+static int run(int nblk, int nb, bool check, int special = 0)
 {
     const int N = 96;
     std::vector<double> h((size_t)nblk * N * NB, 0.0), ref;
@@ -35,6 +35,10 @@ static int run(int nblk, int nb, bool check)
                 double v = (double)rand() / RAND_MAX - 0.5;
                 M[c * N + r] = (r == c) ? (LDL && (c % 3 == 1) ? -(8.0 + v) : 8.0 + v) : v * 0.5;
             }
+    }
+    if (special == 1) h[20 * N + 20] = -3.0;                      // Cholesky breakdown: flagged, run stays finite
+    if (special == 2) {                                           // LDL^T: exact zero pivot -> perturbed to 1e-13
+        for (int c = 0; c < nb; ++c) for (int r = c; r < nb; ++r) if (r == 7 || c == 7) h[c * N + r] = 0.0;
     }
     ref = h;
     double *A, *Dinv; int *info; long long *cyc;
@@ -90,6 +94,7 @@ static int run(int nblk, int nb, bool check)
 int main()
 {
     run<false>(1, 64, true); run<false>(1, 37, true); run<true>(1, 64, true); run<true>(1, 50, true);
+    run<false>(1, 64, false, 1); run<true>(1, 64, true, 2);
     run<false>(1, 64, false); run<false>(1, 64, false); run<false>(148, 64, false); run<false>(444, 64, false); run<false>(888, 64, false);
     return 0;
 }
