@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 from madipm_jl_b200 import _lib  # noqa: E402
-from madipm_jl_b200.problems import config_c1, random_sparse_lp, random_sparse_qp, simple_lp  # noqa: E402
+from madipm_jl_b200.problems import config_c1, mixed_bounds_lp, random_sparse_lp, random_sparse_qp, simple_lp  # noqa: E402
 from oracle import sparse_ref  # noqa: E402
 from oracle.mpc_oracle import MPCOracle, madipm as oracle_madipm  # noqa: E402
 
@@ -246,6 +246,50 @@ def _cmp(t, a, tol=1e-12):
     if fin.any():
         scale = max(1.0, np.abs(a[fin]).max())
         assert np.abs(got[fin] - a[fin]).max() <= tol * scale
+
+
+def test_init_bounds_bit_exact(handle):
+    """mipm_init_bounds == MadNLP's bound relaxation + initial-point push as restated by the oracle (App. B), bit for
+    bit, on every bound kind (both / lower only / upper only / free, wide and degenerate-narrow boxes); mipm_amax."""
+    from oracle.mpc_oracle import MPCOracle
+    qp = mixed_bounds_lp(40, 160, 4, 7)
+    o = MPCOracle(qp, kkt_system="K2")
+    o._madnlp_initialize()
+    rng = np.random.default_rng(0)
+    n = o.n
+    xl = np.concatenate([qp.lvar, qp.lcon[o.ind_ineq]])
+    xu = np.concatenate([qp.uvar, qp.ucon[o.ind_ineq]])
+    x0 = np.concatenate([qp.x0, np.zeros(n - qp.nvar)])
+    h = handle()
+    dx, dl, du = dev(x0), dev(xl), dev(xu)
+    h.init_bounds(n, o.opt.bound_relax_factor, o.opt.bound_push, o.opt.bound_fac, dx, dl, du)
+    assert np.array_equal(dl.cpu().numpy(), o.xl)
+    assert np.array_equal(du.cpu().numpy(), o.xu)
+    assert np.array_equal(dx.cpu().numpy(), o.x)
+    # a hand-made vector with every branch, including a box narrower than the push and huge magnitudes
+    xl = np.array([0.0, -np.inf, -np.inf, 1.0, -1e6, 2.0, -3.0, 5e8])
+    xu = np.array([np.inf, 4.0, np.inf, 1.0 + 1e-3, 1e6, 2.5, -2.99999, np.inf])
+    x0 = np.array([-7.0, 9.0, 0.3, 0.0, 1e9, 2.25, -10.0, 0.0])
+    tol, bp, bf = 1e-8, 1e-2, 1e-2
+    rl = xl - np.maximum(1.0, np.abs(xl)) * tol
+    ru = xu + np.maximum(1.0, np.abs(xu)) * tol
+    fl, fu = np.isfinite(rl), np.isfinite(ru)
+    want = x0.copy()
+    with np.errstate(invalid="ignore"):
+        pl = np.minimum(bp * np.maximum(1.0, np.abs(rl)), bf * (ru - rl))
+        pu = np.minimum(bp * np.maximum(1.0, np.abs(ru)), bf * (ru - rl))
+        both, lo, up = fl & fu, fl & ~fu, ~fl & fu
+        want[both] = np.maximum(rl + pl, np.minimum(ru - pu, x0))[both]
+        want[lo] = np.maximum(rl + bp * np.maximum(1.0, np.abs(rl)), x0)[lo]
+        want[up] = np.minimum(ru - bp * np.maximum(1.0, np.abs(ru)), x0)[up]
+    dx, dl, du = dev(x0), dev(xl), dev(xu)
+    h.init_bounds(len(x0), tol, bp, bf, dx, dl, du)
+    assert np.array_equal(dl.cpu().numpy(), rl) and np.array_equal(du.cpu().numpy(), ru)
+    assert np.array_equal(dx.cpu().numpy(), want)
+    v = rng.standard_normal(100003)
+    v[777] = -123.5
+    assert h.amax(len(v), dev(v)) == 123.5
+    assert h.amax(0, None) == 0.0
 
 
 @pytest.mark.parametrize("kkt", ["Normal", "K2"])
