@@ -91,6 +91,8 @@ struct Handle {
     DBuf<double> d_L2;               // second factor buffer: the idle one is zero-filled on the side stream (not in border mode)
     double *L_cur = nullptr;         // buffer holding the current factor
     bool l_prezeroed = false;
+    DBuf<int64_t> d_gat_off;         // transposed child maps of the forward solve (fronts with many children)
+    DBuf<int32_t> d_gat_ptr, d_gat_src;
     DBuf<int> d_vmap_factor, d_vmap_solve;   // virtual CTA ids of the persistent kernels (placement probe)
     DBuf<int> d_info;                // [0]=first failed column+1 (0 = ok), [1]=#neg pivots, [2]=#zero pivots
     const double *d_nzval = nullptr;

@@ -97,6 +97,12 @@ struct SolveParams {
     const int *vmap;            // virtual CTA id per blockIdx.x, or null
     int *probe;                 // non-null: placement probe only
     int prefetch;               // L2 prefetch of upcoming fronts (MIPM_NO_PREFETCH=1 turns it off)
+    // fronts with many children (K2: one tiny leaf child per primal variable) fold their children's update vectors in
+    // through a transposed map: per destination row of the front, the update-vector slots that land on it, in child
+    // order. gat_off[2 s] = offset of the front's N + 1 pointers in gat_ptr (-1: walk the children instead),
+    // gat_off[2 s + 1] = offset of its source list in gat_src.
+    const int64_t *gat_off;
+    const int32_t *gat_ptr, *gat_src;
     unsigned long long *lvl_ns; // optional (MIPM_SOLVE_LOG): device time of gather, every forward level, every backward level
 };
 
@@ -223,10 +229,12 @@ __device__ void task_extend_add(const FactorParams &p, const int32_t *tasks, int
     const int k = f.k, r = f.r, N = f.k + f.r;
     double *P = p.L + f.lp;
     double *Us = p.U + f.up;
+    // per task: the number of children that reach this column range, then (child position, b0, b1) for each of them
+    // (a front of a K2 system can have thousands of tiny leaf children, almost all of them outside any one range)
     const int32_t *ranges = p.sched + t4.w;
-    for (int ci = 0; ci < f.nchild; ++ci) {
-        const int b0 = ranges[2 * ci], b1 = ranges[2 * ci + 1];
-        if (b0 >= b1) continue;                      // uniform across the CTA
+    const int nrel = ranges[0];
+    for (int e = 0; e < nrel; ++e) {
+        const int ci = ranges[1 + 3 * e], b0 = ranges[2 + 3 * e], b1 = ranges[3 + 3 * e];
         const int c = p.child_idx[f.childp + ci];
         const FrontInfo fc = p.fi[c];
         const int rc = fc.r;
@@ -589,7 +597,21 @@ __device__ void front_forward(const SolveParams &p, int s, double *smem, int mod
     double *x1 = p.xp + f.c0;
     double *u = p.uvec + f.rowp;
     const int tid = threadIdx.x;
-    for (int ci = 0; ci < f.nchild && mode != 2; ++ci) {
+    const int64_t go = p.gat_off[2 * (int64_t)s];
+    if (go >= 0 && mode != 2) {
+        const int32_t *gp = p.gat_ptr + go;
+        const int32_t *gs = p.gat_src + p.gat_off[2 * (int64_t)s + 1];
+        for (int t = tid; t < N; t += 256) {
+            const int q0 = gp[t], q1 = gp[t + 1];
+            if (q1 > q0) {
+                double acc = 0.0;
+                for (int q = q0; q < q1; ++q) acc += p.uvec[gs[q]];
+                if (t < k) x1[t] += acc; else u[t - k] += acc;
+            }
+        }
+        __syncthreads();
+    }
+    for (int ci = 0; ci < f.nchild && mode != 2 && go < 0; ++ci) {
         const int c = p.child_idx[f.childp + ci];
         const FrontInfo fc = p.fi[c];
         const int32_t *rel = p.rel_idx + fc.rowp;
@@ -1022,18 +1044,23 @@ int ls_device_setup(Handle *h)
             for (int q0 = 0; q0 < N; q0 += ea_cols) {
                 int q1 = std::min(N, q0 + ea_cols);
                 int64_t off_r = (int64_t)sched.size();
-                bool any = false;
+                sched.push_back(0);                                    // count, patched below
+                int nrel = 0;
                 for (int ci = 0; ci < f.nchild; ++ci) {
                     int c = S.child_idx[(size_t)(f.childp + ci)];
                     const int32_t *rel = S.rel_idx.data() + S.row_ptr[(size_t)c];
                     int rc = finfo[(size_t)c].r;
                     int b0 = (int)(std::lower_bound(rel, rel + rc, q0) - rel);
                     int b1 = (int)(std::lower_bound(rel, rel + rc, q1) - rel);
-                    sched.push_back(b0);
-                    sched.push_back(b1);
-                    any = any || (b1 > b0);
+                    if (b1 > b0) {
+                        sched.push_back(ci);
+                        sched.push_back(b0);
+                        sched.push_back(b1);
+                        ++nrel;
+                    }
                 }
-                if (!any) { sched.resize((size_t)off_r); continue; }
+                if (nrel == 0) { sched.resize((size_t)off_r); continue; }
+                sched[(size_t)off_r] = nrel;
                 if (off_r > INT32_MAX) return fail(h, MIPM_ERR_ARG, "schedule too large");
                 ea.push_back(s); ea.push_back(q0); ea.push_back(q1); ea.push_back((int32_t)off_r);
                 ea_count[(size_t)s]++;
@@ -1162,6 +1189,40 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, h->d_b.alloc((size_t)std::max<int64_t>(S.n, 1)));
     MIPM_CUDA(h, h->d_r.alloc((size_t)std::max<int64_t>(S.n, 1)));
     MIPM_CUDA(h, h->d_phase_ns.alloc((size_t)h->n_phases + 8));
+    {
+        // transposed child maps for the forward solve (fronts with more than GATHER_MIN_CHILDREN children)
+        constexpr int GATHER_MIN_CHILDREN = 4;
+        std::vector<int64_t> gat_off((size_t)2 * std::max(ns, 1), -1);
+        std::vector<int32_t> gat_ptr, gat_src, cnt;
+        const bool slots_fit = S.row_ptr[(size_t)ns] < (int64_t)INT32_MAX;
+        for (int s = 0; s < ns && slots_fit; ++s) {
+            const FrontInfo &f = finfo[(size_t)s];
+            if (f.nchild <= GATHER_MIN_CHILDREN) continue;
+            const int N = f.k + f.r;
+            cnt.assign((size_t)N + 1, 0);
+            for (int ci = 0; ci < f.nchild; ++ci) {
+                const int c = S.child_idx[(size_t)(f.childp + ci)];
+                const int32_t *rel = S.rel_idx.data() + S.row_ptr[(size_t)c];
+                for (int a = 0; a < finfo[(size_t)c].r; ++a) cnt[(size_t)rel[a] + 1]++;
+            }
+            for (int t = 0; t < N; ++t) cnt[(size_t)t + 1] += cnt[(size_t)t];
+            gat_off[(size_t)2 * s] = (int64_t)gat_ptr.size();
+            gat_off[(size_t)2 * s + 1] = (int64_t)gat_src.size();
+            gat_ptr.insert(gat_ptr.end(), cnt.begin(), cnt.end());
+            const size_t base = gat_src.size();
+            gat_src.resize(base + (size_t)cnt[(size_t)N]);
+            for (int ci = 0; ci < f.nchild; ++ci) {             // child order, then row order: the summation order
+                const int c = S.child_idx[(size_t)(f.childp + ci)];
+                const int64_t rp = S.row_ptr[(size_t)c];
+                const int32_t *rel = S.rel_idx.data() + rp;
+                for (int a = 0; a < finfo[(size_t)c].r; ++a) gat_src[base + (size_t)cnt[(size_t)rel[a]]++] = (int32_t)(rp + a);
+            }
+        }
+        if (gat_ptr.empty()) { gat_ptr.push_back(0); gat_src.push_back(0); }
+        MIPM_CUDA(h, h->d_gat_off.upload(gat_off, st));
+        MIPM_CUDA(h, h->d_gat_ptr.upload(gat_ptr, st));
+        MIPM_CUDA(h, h->d_gat_src.upload(gat_src, st));
+    }
     MIPM_CUDA(h, cudaStreamSynchronize(st));
     {
         int rc = build_cta_map(h, true);
@@ -1261,6 +1322,7 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     p.L = h->L_cur; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
     p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
     p.vmap = h->d_vmap_solve.p; p.probe = nullptr;
+    p.gat_off = h->d_gat_off.p; p.gat_ptr = h->d_gat_ptr.p; p.gat_src = h->d_gat_src.p;
     static const bool solve_log = std::getenv("MIPM_SOLVE_LOG") != nullptr;
     static const bool no_prefetch = std::getenv("MIPM_NO_PREFETCH") != nullptr;
     p.prefetch = no_prefetch ? 0 : 1;

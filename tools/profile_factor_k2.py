@@ -1,11 +1,12 @@
-"""ncu / phase-log driver for the K2 (LDL^T) system of config C3. Usage: python tools/profile_factor_k2.py [scale]"""
+"""ncu / phase-log driver for the K2 (LDL^T) system of config C3 (or C1 with `c1` as second argument).
+Usage: python tools/profile_factor_k2.py [scale] [c1]"""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from madipm_jl_b200 import _lib
-from madipm_jl_b200.problems import config_c3
+from madipm_jl_b200.problems import config_c1, config_c3
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-qp = config_c3(scale=scale)
+qp = config_c1() if (len(sys.argv) > 2 and sys.argv[2] == 'c1') else config_c3(scale=scale)
 n, m = qp.nvar, qp.ncon
 I = np.concatenate([np.arange(n), qp.Hrows, n + qp.Arows, n + np.arange(m)]).astype(np.int32)
 J = np.concatenate([np.arange(n), qp.Hcols, qp.Acols, n + np.arange(m)]).astype(np.int32)
