@@ -233,22 +233,34 @@ __device__ void task_extend_add(const FactorParams &p, const int32_t *tasks, int
     // (a front of a K2 system can have thousands of tiny leaf children, almost all of them outside any one range)
     const int32_t *ranges = p.sched + t4.w;
     const int nrel = ranges[0];
+    // Each warp owns a slice of the task's parent columns and walks ALL children for it, in order: destinations of
+    // different warps are disjoint, so no CTA barrier separates the children (with hundreds of tiny leaf children per
+    // task the barriers were most of the time) and the summation order per entry is still the child order.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cw = (t4.z - t4.y + 7) >> 3;
+    const int lo = t4.y + warp * cw, hi = min(t4.z, lo + cw);
+    if (lo >= hi) return;
     for (int e = 0; e < nrel; ++e) {
-        const int ci = ranges[1 + 3 * e], b0 = ranges[2 + 3 * e], b1 = ranges[3 + 3 * e];
+        const int ci = ranges[1 + 3 * e], b0 = ranges[2 + 3 * e], b1 = ranges[3 + 3 * e];   // b1 - b0 <= 32
         const int c = p.child_idx[f.childp + ci];
         const FrontInfo fc = p.fi[c];
         const int rc = fc.r;
         const int32_t *rel = p.rel_idx + fc.rowp;
         const double *Uc = p.U + fc.up;
-        // one warp per child column (8 columns in flight), lanes over the rows of that column
-        for (int b = b0 + (threadIdx.x >> 5); b < b1; b += 8) {
-            const int tb = rel[b];
+        // rel is increasing: the child columns that land in [lo, hi) are a contiguous run of [b0, b1)
+        const int bl = b0 + lane;
+        const int tl = (bl < b1) ? rel[bl] : -1;
+        const unsigned mine = __ballot_sync(0xffffffffu, tl >= lo && tl < hi);
+        if (mine == 0u) continue;
+        const int bfirst = b0 + __ffs(mine) - 1, bend = bfirst + __popc(mine);
+        for (int b = bfirst; b < bend; ++b) {
+            const int tb = __shfl_sync(0xffffffffu, tl, b - b0);
             const double *src = Uc + (int64_t)b * rc;
             double *dst = (tb < k) ? (P + (int64_t)tb * N) : (Us + (int64_t)(tb - k) * r - k);
             // rows of one child column land on distinct parent rows: four independent read-modify-writes in flight
             // per lane (the plain loop is a chain of dependent global round trips, the compiler cannot prove
             // the destinations distinct)
-            int a = b + (threadIdx.x & 31);
+            int a = b + lane;
             for (; a + 96 < rc; a += 128) {
                 const int r0 = rel[a], r1 = rel[a + 32], r2 = rel[a + 64], r3 = rel[a + 96];
                 const double s0 = src[a], s1 = src[a + 32], s2 = src[a + 64], s3 = src[a + 96];
@@ -257,7 +269,6 @@ __device__ void task_extend_add(const FactorParams &p, const int32_t *tasks, int
             }
             for (; a < rc; a += 32) dst[rel[a]] += src[a];
         }
-        __syncthreads();
     }
 }
 
