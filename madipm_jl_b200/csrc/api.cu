@@ -32,41 +32,9 @@ __global__ void k_recip(int64_t n, const double *__restrict__ x, double *__restr
     if (i < n) y[i] = __ddiv_rn(1.0, x[i]);   // D .= 1.0 ./ pr_diag  (normalkkt.jl:191)
 }
 
-// One thread per stored entry c of tril(A D A'): Cx[c] = sum_t w[t] * D[k[t]] over its segment.
-// Segments longer than LONG_SEG (the diagonal entries: one term per nonzero of the row) are left
-// to k_normal_assemble_long so a warp's trip count is not set by its one long lane.
-constexpr int LONG_SEG = 12;
-__global__ void __launch_bounds__(256)
-k_normal_assemble_fast(int64_t nnzC, const int32_t *__restrict__ term_ptr, const int32_t *__restrict__ term_k,
-                       const double *__restrict__ w, const double *__restrict__ D, double *__restrict__ Cx)
-{
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nnzC) return;
-    int32_t t0 = term_ptr[c], t1 = term_ptr[c + 1];
-    if (t1 - t0 > LONG_SEG) return;
-    double acc = 0.0;
-    for (int32_t t = t0; t < t1; ++t) acc = fma(w[t], __ldg(D + term_k[t]), acc);
-    Cx[c] = acc;
-}
-
-// Long segments: one warp per listed entry, lanes stride over the terms in order; the partial
-// sums are folded in a fixed order (deterministic).
-__global__ void __launch_bounds__(256)
-k_normal_assemble_long(int64_t nlong, const int32_t *__restrict__ long_c, const int32_t *__restrict__ term_ptr,
-                       const int32_t *__restrict__ term_k, const double *__restrict__ w, const double *__restrict__ D,
-                       double *__restrict__ Cx)
-{
-    int64_t wi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (wi >= nlong) return;
-    const int32_t c = long_c[wi];
-    const int32_t t0 = term_ptr[c], t1 = term_ptr[c + 1];
-    double acc = 0.0;
-    for (int32_t t = t0 + lane; t < t1; t += 32) acc = fma(w[t], __ldg(D + term_k[t]), acc);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) Cx[c] = acc;
-}
+// The fast assembly Cx[c] = sum_t w[t] * D[k[t]] over the term segment of every stored entry c of tril(A D A') is a
+// sparse matrix-vector product (rows = stored entries, nonzeros = product terms, x = D) and runs through
+// k_spmv_stream below: coalesced term loads, per-entry sums in storage order (deterministic).
 
 // Same, reproducing the reference CPU loop's operation order (src/utils.jl:288-301):
 // buffer[k] = A[i,k]*D[k]; Cx[c] += buffer[k]*A[j,k] in row-j order, mul and add unfused.
@@ -221,7 +189,7 @@ int mipm_create(mipm_handle *out, int device, void *stream)
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return MIPM_ERR_CUDA; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return MIPM_ERR_CUDA; }
-    h->red_blocks = prop.multiProcessorCount * 4;
+    h->red_blocks = prop.multiProcessorCount * 8;      // every block of a reduction kernel resident at once (8 x 256 threads / SM)
     if (h->d_partials.alloc((size_t)h->red_blocks * 16) != cudaSuccess ||
         h->d_scal.alloc(64) != cudaSuccess || h->d_counter.alloc(4) != cudaSuccess ||
         cudaMallocHost((void **)&h->h_scal, 64 * sizeof(double)) != cudaSuccess ||
@@ -306,11 +274,9 @@ int mipm_normal_symbolic(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap
         MIPM_CUDA(h, h->d_term_k.upload(h->nsym.term_k, h->stream));
         MIPM_CUDA(h, h->d_term_w.alloc((size_t)h->nsym.n_terms));
         {
-            std::vector<int32_t> lc;
-            for (int64_t c = 0; c < h->nsym.nnz_c; ++c)
-                if (h->nsym.term_ptr[(size_t)c + 1] - h->nsym.term_ptr[(size_t)c] > LONG_SEG) lc.push_back((int32_t)c);
-            h->n_long = (int64_t)lc.size();
-            MIPM_CUDA(h, h->d_long_c.upload(lc, h->stream));
+            std::vector<int32_t> blk = spmv_blocks(h->nsym.term_ptr);       // runs of stored entries, <= 2048 terms each
+            h->asm_nblk = (int64_t)blk.size() - 1;
+            MIPM_CUDA(h, h->d_asm_blk.upload(blk, h->stream));
         }
         MIPM_CUDA(h, h->d_D.alloc((size_t)n));
         MIPM_CUDA(h, cudaStreamSynchronize(h->stream));   // host vectors may be reused
@@ -350,13 +316,8 @@ int mipm_normal_assemble(mipm_handle hh, const double *d_pr_diag, double *d_Cx, 
             k_normal_assemble_exact<<<grid_for(S.nnz_c, 256), 256, 0, h->stream>>>(
                 S.nnz_c, h->d_term_ptr.p, h->d_term_pi.p, h->d_term_pj.p, h->d_term_k.p, h->d_ATx, h->d_D.p, d_Cx);
         else {
-            k_normal_assemble_fast<<<grid_for(S.nnz_c, 256), 256, 0, h->stream>>>(
-                S.nnz_c, h->d_term_ptr.p, h->d_term_k.p, h->d_term_w.p, h->d_D.p, d_Cx);
-            if (h->n_long > 0) {
-                MIPM_CHECK_LAUNCH(h);
-                k_normal_assemble_long<<<grid_for(h->n_long * 32, 256), 256, 0, h->stream>>>(
-                    h->n_long, h->d_long_c.p, h->d_term_ptr.p, h->d_term_k.p, h->d_term_w.p, h->d_D.p, d_Cx);
-            }
+            k_spmv_stream<false><<<(unsigned)h->asm_nblk, 256, 0, h->stream>>>(h->d_asm_blk.p, h->d_term_ptr.p, h->d_term_k.p, nullptr,
+                                                                               h->d_term_w.p, h->d_D.p, 1.0, 0.0, d_Cx);
         }
         MIPM_CHECK_LAUNCH(h);
     }

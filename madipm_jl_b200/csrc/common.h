@@ -57,8 +57,8 @@ struct Handle {
     // ---- normal equations
     NormalSymbolic nsym;
     bool has_normal = false, has_jac = false;
-    DBuf<int32_t> d_term_ptr, d_term_pi, d_term_pj, d_term_k, d_long_c;
-    int64_t n_long = 0;
+    DBuf<int32_t> d_term_ptr, d_term_pi, d_term_pj, d_term_k, d_asm_blk;
+    int64_t asm_nblk = 0;            // runs of stored entries for the streaming assembly
     DBuf<double> d_term_w, d_D;
     const double *d_ATx = nullptr;
 
