@@ -129,6 +129,10 @@ typedef struct {
     int64_t n_launches;      /* kernel launches per numeric factorization                 */
 } mipm_ls_stats_t;
 int mipm_ls_stats(mipm_handle h, mipm_ls_stats_t *out);
+/* Caps the grid of the persistent factorization / solve kernels of this handle (0 = whole GPU, the default). Call before
+ * mipm_ls_analyze. With a small cap several handles on different streams run side by side on one GPU: the batch of small
+ * independent LPs of BASELINE config C5 (the reference solves such batches one after the other). */
+int mipm_set_grid_limit(mipm_handle h, int max_ctas);
 
 /* Symbolic structure export (for parity tests: "GPU library == oracle" on the same
  * deterministic host analysis). All arrays 0-based, library-owned.

@@ -189,6 +189,20 @@ int mipm_create(mipm_handle *out, int device, void *stream)
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return MIPM_ERR_CUDA; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return MIPM_ERR_CUDA; }
+    {
+        // stream-ordered allocations for everything this handle owns; keep freed blocks in the pool instead of returning
+        // them to the driver at every synchronisation
+        int pools = 0;
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && pools &&
+            cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && !std::getenv("MIPM_NO_POOL")) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            h->pool_ok = true;
+        }
+        (void)cudaGetLastError();
+        use_handle(h);
+    }
     h->red_blocks = prop.multiProcessorCount * 8;      // every block of a reduction kernel resident at once (8 x 256 threads / SM)
     if (h->d_partials.alloc((size_t)h->red_blocks * 16) != cudaSuccess ||
         h->d_scal.alloc(64) != cudaSuccess || h->d_counter.alloc(4) != cudaSuccess ||
@@ -257,6 +271,7 @@ int mipm_normal_symbolic(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap
                          int index_base, int32_t **Cp, int32_t **Cj, int64_t *nnzC)
 {
     Handle *h = (Handle *)hh;
+    if (h && !h->host_only) use_handle(h);
     if (!h || !Ap || (!Aj && m > 0 && Ap[m] != index_base) || !Cp || !Cj || !nnzC) return fail(h, MIPM_ERR_ARG, "null argument");
     std::string e = normal_symbolic_host(m, n, Ap, Aj, index_base, h->nsym);
     if (!e.empty()) return fail(h, e.find("duplicate") != std::string::npos ? MIPM_ERR_DUPLICATE : MIPM_ERR_ARG, e);
@@ -328,6 +343,7 @@ int mipm_k2_symbolic(mipm_handle hh, int64_t dim, int64_t nnz_coo, const int32_t
                      int index_base, int32_t **colptr, int32_t **rowval, int64_t **map, int64_t *nnz_csc)
 {
     Handle *h = (Handle *)hh;
+    if (h && !h->host_only) use_handle(h);
     if (!h || (nnz_coo > 0 && (!I || !J)) || !colptr || !rowval || !map || !nnz_csc) return fail(h, MIPM_ERR_ARG, "null argument");
     std::string e = k2_symbolic_host(dim, nnz_coo, I, J, index_base, h->ksym);
     if (!e.empty()) return fail(h, MIPM_ERR_ARG, e);
@@ -435,6 +451,14 @@ int mipm_spmv(mipm_handle hh, int trans, double alpha, const double *d_Ax, const
     return MIPM_OK;
 }
 
+int mipm_set_grid_limit(mipm_handle hh, int max_ctas)
+{
+    Handle *h = (Handle *)hh;
+    if (!h || max_ctas < 0) return fail(h, MIPM_ERR_ARG, "bad argument");
+    h->grid_limit = max_ctas;
+    return MIPM_OK;
+}
+
 int mipm_spmv_cache_values(mipm_handle hh, const double *d_Ax)
 {
     Handle *h = (Handle *)hh;
@@ -496,6 +520,7 @@ int mipm_ls_analyze(mipm_handle hh, int64_t n, const int32_t *colptr, const int3
                     int kind, int ordering, const int32_t *user_perm)
 {
     Handle *h = (Handle *)hh;
+    if (h && !h->host_only) use_handle(h);
     if (!h || n < 0 || !colptr || (kind != MIPM_CHOLESKY && kind != MIPM_LDL)) return fail(h, MIPM_ERR_ARG, "bad argument");
     int64_t nnz = colptr[n] - index_base;
     if (nnz < 0 || (nnz > 0 && !rowval)) return fail(h, MIPM_ERR_ARG, "bad column pointer");

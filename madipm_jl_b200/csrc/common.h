@@ -13,17 +13,28 @@
 
 namespace mipm {
 
+// Stream of the API call the calling thread is in (set by MIPM_NEED_DEVICE / use_handle). Device buffers come from
+// CUDA's stream-ordered memory pool on that stream: cudaMalloc / cudaFree synchronise the whole device, which hurts
+// exactly when many small handles are created and destroyed side by side (batches of independent LPs, config C5).
+inline thread_local cudaStream_t tl_stream = nullptr;
+inline thread_local bool tl_pooled = false;
+
 // Simple owning device buffer.
 template <typename T>
 struct DBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t st = nullptr;       // stream the pooled allocation is ordered on
+    bool pooled = false;
     DBuf() = default;
     DBuf(const DBuf &) = delete;
     DBuf &operator=(const DBuf &) = delete;
     ~DBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pooled) cudaFreeAsync(p, st);
+            else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }
@@ -31,6 +42,12 @@ struct DBuf {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
+        if (tl_pooled) {
+            pooled = true;
+            st = tl_stream;
+            return cudaMallocAsync((void **)&p, count * sizeof(T), st);
+        }
+        pooled = false;
         return cudaMalloc((void **)&p, count * sizeof(T));
     }
     cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {
@@ -43,6 +60,7 @@ struct DBuf {
 struct Handle {
     int device = -1;
     bool host_only = false;
+    bool pool_ok = false;            // device supports stream-ordered allocation (cudaMallocAsync)
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
@@ -71,6 +89,7 @@ struct Handle {
     LsSymbolic sym;
     bool has_ls = false, factorized = false;
     int n_phases = 0, grid_factor = 0, grid_solve = 0;
+    int grid_limit = 0;              // cap on the persistent kernels' grid (0 = whole GPU)
     int root_phase_begin = -1;       // first phase of the border (root) front's own factorization, -1 = no border
     int64_t leaf_off = 0;            // small leaf fronts (one warp each) in d_sched
     int n_leaf = 0;
@@ -152,7 +171,14 @@ inline int fail(Handle *h, int code, const std::string &msg) {
             return mipm::fail((h), MIPM_ERR_CUDA,                                           \
                               "analysis-only handle (device < 0): no device work possible; " \
                               "there is no CPU fallback");                                  \
+        mipm::use_handle(h);                                                                \
     } while (0)
+
+inline void use_handle(const Handle *h)
+{
+    tl_stream = h->stream;
+    tl_pooled = h->pool_ok && !h->host_only;
+}
 
 // implemented in the .cu files
 int ls_device_setup(Handle *h);

@@ -1159,6 +1159,10 @@ int ls_device_setup(Handle *h)
     if (occ_f < 1 || occ_s < 1) return fail(h, MIPM_ERR_CUDA, "persistent kernels do not fit on an SM");
     h->grid_factor = prop.multiProcessorCount * occ_f;
     h->grid_solve = prop.multiProcessorCount * std::min(occ_s, 4);
+    if (h->grid_limit > 0) {        // small systems solved side by side on one GPU (mipm_set_grid_limit)
+        h->grid_factor = std::min(h->grid_factor, h->grid_limit);
+        h->grid_solve = std::min(h->grid_solve, h->grid_limit);
+    }
     // ---- uploads and workspaces
     cudaStream_t st = h->stream;
     MIPM_CUDA(h, h->d_sched.upload(sched, st));
@@ -1411,6 +1415,7 @@ extern "C" int mipm_ls_analyze_border(mipm_handle hh, int64_t n, const int32_t *
 {
     using namespace mipm;
     Handle *h = (Handle *)hh;
+    if (h && !h->host_only) use_handle(h);
     if (!h || n < 0 || !colptr || n_border < 1 || n_border > n || (kind != MIPM_CHOLESKY && kind != MIPM_LDL))
         return fail(h, MIPM_ERR_ARG, "bad argument");
     int64_t nnz = colptr[n] - index_base;

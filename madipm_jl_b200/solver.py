@@ -78,6 +78,7 @@ class IPMOptions:
     tol: float = 1e-8
     kkt_system: str = "K2"
     max_iter: int = 3000
+    grid_limit: int = 0            # cap on the persistent kernels' grid (0 = whole GPU); see batch.solve_batch
     max_wall_time: float = 1e6
     divergence_tol: float = 1e4
     scaling: bool = True
@@ -190,6 +191,8 @@ class MPCSolver:
             raise ValueError("The KKT system NormalKKTSystem supports only linear programs.")  # normalkkt.jl:45-48
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.h = _lib.Handle(device=opt.device, stream=stream)
+        if opt.grid_limit:
+            self.h.set_grid_limit(opt.grid_limit)
         dev = self.device
         z = lambda k: torch.zeros(max(k, 0), dtype=torch.float64, device=dev)
         # ---- iterate and buffers (structure.jl:125-153)
@@ -451,7 +454,10 @@ class MPCSolver:
         """Pinned host copies of the numeric problem data (the host side of `convert(QuadraticModel{T, CuVector}, qp)`,
         README.md:77): every solve() uploads them again, so a timed solve includes its host->device traffic."""
         qp, nx, ns, m = self.qp, self.nx, self.ns, self.m
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
+        # page-locking costs ~0.1 ms per array: only worth it when the array is large enough for the copy to matter
+        def pin(a):
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+            return t.pin_memory() if t.numel() >= 65536 else t
         zs = np.zeros(ns)
         self._host = dict(
             x0=pin(np.concatenate([qp.x0, zs])), c=pin(np.concatenate([qp.c, zs])), y0=pin(qp.y0),

@@ -1,6 +1,6 @@
 """Runs the BASELINE.json configs other than the bench workload through the CUDA path and prints one
 JSON line per config (status, iterations, time, symbolic stats). Usage:
-  python tools/run_configs.py c1 c3 c5 [--c3-scale S] [--c5-units N]
+  python tools/run_configs.py c1 c3 c5 [--c3-scale S] [--c5-units N] [--c5-threads T --c5-grid G]
 Under torchrun, C5 units are sharded across ranks (madipm_jl_b200.batch.solve_batch)."""
 import json
 import os
@@ -39,7 +39,7 @@ def run_one(name, qp, kkt, **kw):
 
 def main():
     args = sys.argv[1:]
-    opt = {"--c3-scale": 1.0, "--c5-units": 32}
+    opt = {"--c3-scale": 1.0, "--c5-units": 32, "--c5-threads": 1, "--c5-grid": 0}
     for k in list(opt):
         if k in args:
             i = args.index(k)
@@ -61,14 +61,22 @@ def main():
         run_one("C3 scale %g" % opt["--c3-scale"], qp, "K2", device=local)
     if "c5" in args:
         n_units = int(opt["--c5-units"])
+        from madipm_jl_b200.batch import shard_range
+        lo, hi = shard_range(n_units, rank, world)
+        models = {i: problems.config_c5(i) for i in range(lo, hi)}      # the synthetic generator is not part of the timing
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = solve_batch(lambda i: problems.config_c5(i), n_units, kkt_system="Normal", device=local)
+        res = solve_batch(lambda i: models[i], n_units, kkt_system="Normal", device=local,
+                          threads=int(opt["--c5-threads"]), grid_limit=int(opt["--c5-grid"]))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if rank == 0:
             ok = sum(r.status == "SOLVE_SUCCEEDED" for r in res)
-            print(json.dumps({"config": "C5", "units": n_units, "ranks": world, "succeeded": ok, "wall_s": dt,
+            print(json.dumps({"config": "C5", "units": n_units, "ranks": world, "threads_per_gpu": int(opt["--c5-threads"]),
+                              "grid_limit": int(opt["--c5-grid"]), "succeeded": ok, "wall_s": dt,
                               "lps_per_s": n_units / dt, "mean_iters": float(np.mean([r.iter for r in res])),
                               "units_per_rank": [sum(r.rank == q for r in res) for q in range(world)]}), flush=True)
     if world > 1:
