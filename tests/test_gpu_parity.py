@@ -437,6 +437,48 @@ def test_c1_full_size(built):
     _check_trace(got, ref.trace, ref.iter, ref.status)
 
 
+def test_c2_full_size_properties(built):
+    """BASELINE config C2 (the bench workload: m=200000, n=1000000, 8 nnz/col) at full size, where the oracle takes
+    minutes: size-independent properties only. Primal feasibility and the duality gap are recomputed on the host from
+    the returned point with scipy, independently of every kernel on the path."""
+    from madipm_jl_b200.problems import config_c2
+    from madipm_jl_b200.solver import madipm
+    qp = config_c2()
+    got = madipm(qp, kkt_system="Normal")
+    assert got.status == "SOLVE_SUCCEEDED" and 10 <= got.iter <= 60
+    A = sp.csr_matrix((qp.Avals, (qp.Arows, qp.Acols)), shape=(qp.ncon, qp.nvar))
+    x, y = got.solution, got.multipliers
+    assert np.abs(A @ x - qp.lcon).max() <= 1e-7 * max(1.0, np.abs(qp.lcon).max())
+    assert x.min() > -1e-8
+    # dual feasibility: reduced costs c + A'y >= 0 (sign convention of the reference: z = c + A'y on x >= 0)
+    z = qp.c + A.T @ y
+    assert z.min() >= -1e-6 * max(1.0, np.abs(qp.c).max())
+    assert abs(float(qp.c @ x) - got.objective) <= 1e-9 * max(1.0, abs(got.objective))
+    assert abs(got.objective - got.dual_objective) <= 1e-6 * max(1.0, abs(got.objective))
+    assert float(x @ z) <= 1e-5 * max(1.0, abs(got.objective))          # complementarity of the returned point
+
+
+def test_c3_full_size_properties(built):
+    """BASELINE config C3 (QP, K2 system of 650000 rows, LDL'): status, feasibility and stationarity of the returned
+    point recomputed on the host."""
+    from madipm_jl_b200.problems import config_c3
+    from madipm_jl_b200.solver import madipm
+    qp = config_c3()
+    got = madipm(qp, kkt_system="K2")
+    assert got.status == "SOLVE_SUCCEEDED" and got.iter <= 60
+    A = sp.csr_matrix((qp.Avals, (qp.Arows, qp.Acols)), shape=(qp.ncon, qp.nvar))
+    Hl = sp.csr_matrix((qp.Hvals, (qp.Hrows, qp.Hcols)), shape=(qp.nvar, qp.nvar))
+    H = Hl + sp.tril(Hl, -1).T
+    x, y = got.solution, got.multipliers
+    assert np.abs(A @ x - qp.lcon).max() <= 1e-7 * max(1.0, np.abs(qp.lcon).max())
+    assert x.min() > -1e-8
+    z = H @ x + qp.c + A.T @ y                                           # = zl >= 0 at a KKT point with x >= 0
+    scale = max(1.0, np.abs(qp.c).max())
+    assert z.min() >= -1e-6 * scale
+    assert float(x @ np.maximum(z, 0.0)) <= 1e-5 * max(1.0, abs(got.objective))
+    assert abs(0.5 * float(x @ (H @ x)) + float(qp.c @ x) + qp.c0 - got.objective) <= 1e-8 * max(1.0, abs(got.objective))
+
+
 def test_distributed_solver_single_rank_matches_oracle(built):
     """Config C4's solver path with one rank (no process group): staged factorization / solve through the
     border root must reproduce the oracle's iterates on a block-angular LP. The 2-GPU run of the same code
