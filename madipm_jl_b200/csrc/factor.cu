@@ -71,7 +71,6 @@ struct FactorParams {
     const int32_t *ea_count;
     int *work_counter;              // one dynamic task counter per phase (PH_FRONT phases)
     unsigned long long *phase_ns;   // device-side time of every phase (one entry per phase)
-    long long *dbg;                 // optional: clock64 stamps of the last diag task (debug)
     double piv_tol;
     const int *vmap;                // virtual CTA id per blockIdx.x (see build_cta_map), or null
     int *probe;                     // non-null: write %smid per block and return (setup-time placement probe)
@@ -1297,7 +1296,6 @@ int ls_factorize_staged(Handle *h, const double *d_nzval, int stage)
         p.L = h->L_cur; p.U = h->d_U.p; p.W = h->d_W.p; p.Dinv = h->d_Dinv.p; p.info = h->d_info.p;
         p.phase_ns = h->d_phase_ns.p;
         p.ea_first = h->d_ea_first.p; p.ea_count = h->d_ea_count.p; p.work_counter = h->d_work_counter.p;
-        p.dbg = std::getenv("MIPM_DIAG_DBG") ? (long long *)(h->d_phase_ns.p + h->n_phases) : nullptr;
         p.piv_tol = 1e-13;   // LDL^T: absolute floor on |pivot|
         p.vmap = h->d_vmap_factor.p; p.probe = nullptr;
         void *args[] = {&p};
