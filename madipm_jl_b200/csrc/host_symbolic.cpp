@@ -5,10 +5,33 @@
 // row i, of the rows j >= i of column k, and the same sweep emits the product-term map.
 #include "host_symbolic.h"
 
+#include <cstdlib>
+#include <functional>
+#include <thread>
+
 #include <algorithm>
 #include <cstring>
 
 namespace mipm {
+
+// Host threads for the one-time symbolic work (MIPM_HOST_THREADS overrides; results never depend on the count).
+int host_threads()
+{
+    if (const char *e = std::getenv("MIPM_HOST_THREADS")) return std::max(1, atoi(e));
+    unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(hc ? hc : 1u, 16u);
+}
+
+void run_host_threads(int nthreads, const std::function<void(int)> &work)
+{
+    if (nthreads <= 1) { work(0); return; }
+    std::vector<std::thread> th;
+    th.reserve((size_t)nthreads - 1);
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+}
+
 
 void coo_to_csr_host(int64_t n_rows, int64_t nnz, const int32_t *Ai, const int32_t *Aj,
                      int32_t *Bp, int32_t *Bj, int64_t *Bmap)
@@ -63,38 +86,70 @@ std::string normal_symbolic_host(int64_t m, int64_t n, const int32_t *Ap_in, con
         for (int64_t d = cptr[(size_t)k] + 1; d < cptr[(size_t)k + 1]; ++d)
             if (crow[(size_t)d] == crow[(size_t)d - 1]) return "duplicate column inside a row of A";
 
+    // Row i of the pattern = sorted union over the columns k of row i of {j >= i : A[j,k] != 0}; the same sweep emits the
+    // product terms (p_i, p_j, k) grouped by destination (i, j) and ordered by p_j inside a group. Rows are independent:
+    // contiguous row chunks go to host threads, each fills its own vectors, and the pieces are concatenated in row
+    // order, so the result does not depend on the thread count.
     struct Term { uint64_t key; int32_t pi; };
-    std::vector<int64_t> start(cptr.begin(), cptr.end() - 1);   // first entry of column k with row >= i
-    std::vector<Term> buf;
-    S.Cp.assign((size_t)m + 1, 0);
-    S.term_ptr.push_back(0);
-    for (int64_t i = 0; i < m; ++i) {
-        buf.clear();
-        for (int32_t p = S.Ap[(size_t)i]; p < S.Ap[(size_t)i + 1]; ++p) {
-            int32_t k = S.Aj[(size_t)p];
-            int64_t &st = start[(size_t)k];
-            while (st < cptr[(size_t)k + 1] && crow[(size_t)st] < i) ++st;
-            for (int64_t d = st; d < cptr[(size_t)k + 1]; ++d)
-                buf.push_back(Term{((uint64_t)(uint32_t)crow[(size_t)d] << 32) | (uint32_t)cpos[(size_t)d], p});
-        }
-        std::sort(buf.begin(), buf.end(), [](const Term &a, const Term &b) { return a.key < b.key; });
-        int32_t lastj = -1;
-        for (const Term &t : buf) {
-            int32_t j = (int32_t)(t.key >> 32);
-            int32_t pj = (int32_t)(t.key & 0xffffffffu);
-            if (j != lastj) {
-                if (lastj >= 0) S.term_ptr.push_back((int32_t)S.term_pi.size());
-                S.Cj.push_back(j);
-                lastj = j;
+    struct Piece {
+        std::vector<int32_t> Cj, term_ptr, term_pi, term_pj, term_k, row_nnz;
+        std::string err;
+    };
+    int nthreads = (int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, m / 4096));
+    std::vector<Piece> pieces((size_t)nthreads);
+    auto work = [&](int t) {
+        Piece &P = pieces[(size_t)t];
+        const int64_t r0 = m * t / nthreads, r1 = m * (t + 1) / nthreads;
+        std::vector<Term> buf;
+        P.row_nnz.reserve((size_t)(r1 - r0));
+        for (int64_t i = r0; i < r1; ++i) {
+            buf.clear();
+            for (int32_t p = S.Ap[(size_t)i]; p < S.Ap[(size_t)i + 1]; ++p) {
+                const int32_t k = S.Aj[(size_t)p];
+                const int32_t *cb = crow.data() + cptr[(size_t)k], *ce = crow.data() + cptr[(size_t)k + 1];
+                int64_t d = cptr[(size_t)k] + (std::lower_bound(cb, ce, (int32_t)i) - cb);      // first entry with row >= i
+                for (; d < cptr[(size_t)k + 1]; ++d)
+                    buf.push_back(Term{((uint64_t)(uint32_t)crow[(size_t)d] << 32) | (uint32_t)cpos[(size_t)d], p});
             }
-            S.term_pi.push_back(t.pi);
-            S.term_pj.push_back(pj);
-            S.term_k.push_back(S.Aj[(size_t)pj]);
-            if (S.term_pi.size() >= (size_t)INT32_MAX) return "too many product terms for 32-bit segment pointers";
+            std::sort(buf.begin(), buf.end(), [](const Term &a, const Term &b) { return a.key < b.key; });
+            int32_t lastj = -1, cnt = 0;
+            for (const Term &tm : buf) {
+                const int32_t j = (int32_t)(tm.key >> 32);
+                const int32_t pj = (int32_t)(tm.key & 0xffffffffu);
+                if (j != lastj) {
+                    P.term_ptr.push_back((int32_t)P.term_pi.size());      // start of the group, relative to the piece
+                    P.Cj.push_back(j);
+                    lastj = j;
+                    ++cnt;
+                }
+                P.term_pi.push_back(tm.pi);
+                P.term_pj.push_back(pj);
+                P.term_k.push_back(S.Aj[(size_t)pj]);
+            }
+            P.row_nnz.push_back(cnt);
         }
-        if (lastj >= 0) S.term_ptr.push_back((int32_t)S.term_pi.size());
-        S.Cp[(size_t)i + 1] = (int32_t)S.Cj.size();
+    };
+    run_host_threads(nthreads, work);
+    int64_t tot_c = 0, tot_t = 0;
+    for (const Piece &P : pieces) { tot_c += (int64_t)P.Cj.size(); tot_t += (int64_t)P.term_pi.size(); }
+    if (tot_t >= (int64_t)INT32_MAX || tot_c >= (int64_t)INT32_MAX) return "too many product terms for 32-bit segment pointers";
+    S.Cp.assign((size_t)m + 1, 0);
+    S.Cj.reserve((size_t)tot_c);
+    S.term_ptr.reserve((size_t)tot_c + 1);
+    S.term_pi.reserve((size_t)tot_t);
+    S.term_pj.reserve((size_t)tot_t);
+    S.term_k.reserve((size_t)tot_t);
+    int64_t row = 0;
+    for (const Piece &P : pieces) {
+        const int32_t toff = (int32_t)S.term_pi.size();
+        for (int32_t v : P.term_ptr) S.term_ptr.push_back(v + toff);
+        S.Cj.insert(S.Cj.end(), P.Cj.begin(), P.Cj.end());
+        S.term_pi.insert(S.term_pi.end(), P.term_pi.begin(), P.term_pi.end());
+        S.term_pj.insert(S.term_pj.end(), P.term_pj.begin(), P.term_pj.end());
+        S.term_k.insert(S.term_k.end(), P.term_k.begin(), P.term_k.end());
+        for (int32_t c : P.row_nnz) { S.Cp[(size_t)row + 1] = S.Cp[(size_t)row] + c; ++row; }
     }
+    S.term_ptr.push_back((int32_t)S.term_pi.size());
     S.nnz_c = (int64_t)S.Cj.size();
     S.n_terms = (int64_t)S.term_pi.size();
     return "";

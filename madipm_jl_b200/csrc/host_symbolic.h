@@ -1,10 +1,15 @@
 // Host-side symbolic builders for the two KKT formulations (pure C++, no CUDA).
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
 namespace mipm {
+
+// Host threads for the one-time symbolic work (env MIPM_HOST_THREADS overrides); work(t) runs for t in [0, nthreads).
+int host_threads();
+void run_host_threads(int nthreads, const std::function<void(int)> &work);
 
 // Replaces MadIPM.coo_to_csr (src/utils.jl:158-207): stable counting sort by row. 0-based.
 void coo_to_csr_host(int64_t n_rows, int64_t nnz, const int32_t *Ai, const int32_t *Aj,

@@ -4,6 +4,15 @@
 // amalgamation); nothing here comes from the reference, whose analysis lives inside the
 // closed cuDSS binary.
 #include "ls_symbolic.h"
+#include "host_symbolic.h"
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include <algorithm>
 #include <cstring>
@@ -63,9 +72,13 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
         it.connected = false;
         stack.push_back(std::move(it));
     }
-    int32_t next_rid = 1, tag = 0;
-    std::vector<int32_t> order, best_order;
-    std::vector<int64_t> lvl, best_lvl;
+    // Sub-graphs are independent once split, so they are dissected by a small pool of host threads. Tasks touch
+    // disjoint entries of region / stamp / perm; region ids and stamp tags come from atomic counters, and a task's
+    // result depends only on its vertex set, so the ordering does not depend on the schedule.
+    std::atomic<int32_t> next_rid{1}, tag_counter{0};
+    std::mutex mu;
+    std::condition_variable cv;
+    int active = 0;
 
     auto order_leaf = [&](const std::vector<int32_t> &order_bfs, int64_t lo) {
         // reverse Cuthill-McKee: BFS order reversed
@@ -73,17 +86,22 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
         for (int64_t t = 0; t < nv; ++t) perm[(size_t)(lo + t)] = order_bfs[(size_t)(nv - 1 - t)];
     };
 
-    while (!stack.empty()) {
-        Item it = std::move(stack.back());
-        stack.pop_back();
+    auto push_items = [&](std::vector<Item> &items) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &c : items) stack.push_back(std::move(c));
+        cv.notify_all();
+    };
+    auto process = [&](Item &it, std::vector<int32_t> &order, std::vector<int32_t> &best_order, std::vector<int64_t> &lvl,
+                       std::vector<int64_t> &best_lvl) {
+        int32_t tag = 0;
         const int64_t nv = (int64_t)it.verts.size();
-        if (nv == 0) continue;
-        const int32_t rid = next_rid++;
+        if (nv == 0) return;
+        const int32_t rid = next_rid.fetch_add(1);
         for (int32_t v : it.verts) region[v] = rid;
 
         if (!it.connected) {
             // split into connected components
-            ++tag;
+            tag = tag_counter.fetch_add(1) + 1;
             int64_t lo = it.lo;
             bool single = true;
             std::vector<Item> comps;
@@ -100,8 +118,8 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
                 comps.push_back(std::move(c));
             }
             if (!single) {
-                for (auto &c : comps) stack.push_back(std::move(c));
-                continue;
+                push_items(comps);
+                return;
             }
         }
 
@@ -116,7 +134,7 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
         }
         int64_t best_h = -1;
         for (int round = 0; round < 6; ++round) {
-            ++tag;
+            tag = tag_counter.fetch_add(1) + 1;
             bfs_levels(xadj, adj, region, rid, root, stamp, tag, order, lvl);
             int64_t h = (int64_t)lvl.size() - 1;
             if (h <= best_h) break;
@@ -134,7 +152,7 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
         const int64_t nlev = best_h;
         if (nv <= leaf_size || nlev < 3) {
             order_leaf(best_order, it.lo);
-            continue;
+            return;
         }
         // choose the separator level: balance the two sides, prefer small separators
         int64_t bestj = 1;
@@ -149,7 +167,7 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
         }
         const int64_t j = bestj;
         // thin the separator: keep only level-j vertices adjacent to level j+1
-        ++tag;  // stamp level j+1 vertices with tag
+        tag = tag_counter.fetch_add(1) + 1;  // stamp level j+1 vertices with tag
         for (int64_t t = best_lvl[(size_t)j + 1]; t < best_lvl[(size_t)j + 2]; ++t)
             stamp[best_order[(size_t)t]] = tag;
         Item A, B;
@@ -171,16 +189,45 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
         B.connected = false;
         int64_t slo = B.lo + (int64_t)B.verts.size();
         for (size_t t = 0; t < S.size(); ++t) perm[(size_t)slo + t] = S[t];
-        stack.push_back(std::move(A));
-        stack.push_back(std::move(B));
-    }
+        std::vector<Item> two;
+        two.push_back(std::move(A));
+        two.push_back(std::move(B));
+        push_items(two);
+    };
+    auto worker = [&](int) {
+        std::vector<int32_t> order, best_order;
+        std::vector<int64_t> lvl, best_lvl;
+        for (;;) {
+            Item it;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !stack.empty() || active == 0; });
+                if (stack.empty()) return;          // nothing queued and nobody working: done
+                it = std::move(stack.back());
+                stack.pop_back();
+                ++active;
+            }
+            process(it, order, best_order, lvl, best_lvl);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                --active;
+                cv.notify_all();
+            }
+        }
+    };
+    run_host_threads((int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, n / 20000)), worker);
 }
+
+
 
 static inline int64_t trap(int64_t k, int64_t r) { return k * (k + 1) / 2 + k * r; }
 
+#define TLOG(name) do { if (tlog) { auto now_ = std::chrono::steady_clock::now(); std::fprintf(stderr, "analyze stage before %s: %.3f s\n", name, std::chrono::duration<double>(now_ - t_prev).count()); t_prev = now_; } } while (0)
 std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
                        const LsOptions &opt, const int32_t *user_perm, LsSymbolic &S)
 {
+    const bool tlog = std::getenv("MIPM_ANALYZE_LOG") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
     S = LsSymbolic();
     S.n = n;
     S.kind = opt.kind;
@@ -237,6 +284,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
                 }
             }
     }
+    TLOG("0");
     // ---- ordering
     std::vector<int32_t> perm0;
     if (opt.ordering == 2 /*USER*/) {
@@ -317,6 +365,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
     std::vector<int32_t> ip0((size_t)n);
     for (int64_t k = 0; k < n; ++k) ip0[(size_t)perm0[(size_t)k]] = (int32_t)k;
 
+    TLOG("1");
     // ---- strictly-lower adjacency in the permuted numbering: lowadj[r] = {c < r}
     auto build_lowadj = [&](const std::vector<int32_t> &ip, std::vector<int64_t> &lptr, std::vector<int32_t> &lidx) {
         lptr.assign((size_t)n + 1, 0);
@@ -342,6 +391,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
     std::vector<int32_t> lidx;
     build_lowadj(ip0, lptr, lidx);
 
+    TLOG("2");
     // ---- elimination tree + off-diagonal column counts (row-subtree traversal)
     std::vector<int32_t> parent((size_t)n, -1), flag((size_t)n);
     std::vector<int64_t> cnt((size_t)n, 0);
@@ -364,6 +414,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
             cnt[(size_t)j] = n - 1 - j;
         }
     }
+    TLOG("3");
     // ---- postorder (children by ascending count so a supernode-forming child comes last)
     std::vector<int32_t> post((size_t)n);  // post[newpos] = node (in perm0 numbering)
     {
@@ -415,6 +466,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
         S.flops += (double)(cc[(size_t)j] + 1) * (double)(cc[(size_t)j] + 1);
     }
 
+    TLOG("4");
     // ---- fundamental supernodes
     std::vector<int32_t> sn0;  // start columns
     for (int64_t j = 0; j < n; ++j) {
@@ -473,6 +525,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
             if (S.perm[(size_t)j] != (int32_t)j) return "border vertices were reordered (internal error)";
     }
 
+    TLOG("5");
     // ---- strictly-lower column structure of the permuted matrix: below[c] = {r > c}
     std::vector<int64_t> bptr((size_t)n + 1, 0);
     std::vector<int32_t> bidx;
@@ -495,6 +548,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
                 bidx[(size_t)pos[(size_t)std::min(a, b)]++] = std::max(a, b);
             }
     }
+    TLOG("6");
     // ---- supernode parents, children, row structures (merge original entries + children)
     S.sn_parent.assign((size_t)ns, -1);
     S.row_ptr.assign((size_t)ns + 1, 0);
@@ -552,6 +606,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
             }
         }
     }
+    TLOG("7");
     // ---- storage offsets, levels, stats
     S.lp.assign((size_t)ns + 1, 0);
     S.up.assign((size_t)ns + 1, 0);
@@ -580,6 +635,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
         std::vector<int64_t> pos(S.level_ptr.begin(), S.level_ptr.end() - 1);
         for (int32_t s = 0; s < ns; ++s) S.level_sn[(size_t)pos[(size_t)S.sn_level[(size_t)s]]++] = s;
     }
+    TLOG("8");
     // ---- scatter map of the input nonzeros into the panels
     S.a2l.resize((size_t)nnz);
     for (int64_t j = 0; j < n; ++j)
