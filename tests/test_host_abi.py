@@ -195,3 +195,26 @@ def test_ls_symbolic_k2_ldl_ordering_is_quasidefinite_safe(built):
     assert np.abs(L @ np.diag(D) @ L.T - Ad).max() < 1e-12 * np.abs(Ad).max()
     assert np.abs(L).max() < 1e3
     assert (D > 0).sum() == n and (D < 0).sum() == m
+
+
+def test_host_analysis_is_independent_of_the_thread_count(built, monkeypatch):
+    """The pattern / product-term sweep and the nested dissection run on a pool of host threads (MIPM_HOST_THREADS);
+    the symbolic structure must be identical for any thread count. Sized so that both really use several threads
+    (row chunks of 4096 rows, one dissection worker per 20000 vertices)."""
+    from madipm_jl_b200.problems import random_sparse_lp
+    m, n = 50_000, 150_000
+    qp = random_sparse_lp(m, n, 4, 21, structure="window", window=40)
+    Bp, Bj, _ = _lib.coo_to_csr(m, n, qp.Arows, qp.Acols)
+    got = {}
+    for nt in (1, 5):
+        monkeypatch.setenv("MIPM_HOST_THREADS", str(nt))
+        h = _lib.Handle(device=-1)
+        Cp, Cj = h.normal_symbolic(m, n, Bp, Bj)
+        h.ls_analyze(m, Cp, Cj)
+        got[nt] = (Cp, Cj, h.ls_symbolic(), h.ls_stats())
+        h.close()
+    a, b = got[1], got[5]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    for key in a[2]:
+        assert np.array_equal(a[2][key], b[2][key]), key
+    assert a[3] == b[3]
