@@ -36,9 +36,9 @@ def _gpu_solve_concurrent(make_model, indices, threads, grid_limit, **kwargs):
     cooperative launches of different units are resident together. A small LP cannot fill a B200 (a 500 x 500 normal
     matrix is 8 block steps of a handful of tiles) and an IPM iteration is a chain of dependent launches, so units are
     overlapped instead. The C library releases the GIL in every call (ctypes).
-    EXPERIMENTAL (round 1): 128 C5 units take 1.2 s with 12-16 threads in most runs (3x the one-at-a-time rate) but 6-8 s
-    in others - concurrent cooperative launches from several streams stall each other in a way not yet understood -
-    so `threads` defaults to 1 and the recorded C5 numbers are the sequential ones."""
+    Measured on one B200 (128 C5 units, tools/run_configs.py): 2.0 s one at a time, 0.50-0.68 s with 12 threads and
+    grid_limit 32 (five runs). Earlier multi-second stalls came from per-handle cudaMallocHost / cudaFreeHost /
+    cudaGetDeviceProperties calls, which synchronise the device; the library now caches those per process."""
     import queue
     import threading
     import torch
@@ -81,7 +81,7 @@ def solve_batch(make_model, n_units, solve_fn=None, threads=1, grid_limit=0, **k
     """Solve units make_model(0..n_units-1), sharded over the ranks of the default process group
     (or alone when torch.distributed is not initialised). Returns the full, index-ordered list
     of UnitResult on every rank. threads > 1 (GPU path only) overlaps that many units per GPU, each on its own
-    stream with its persistent kernels capped at grid_limit CTAs."""
+    stream with its persistent kernels capped at grid_limit CTAs (use e.g. threads=12, grid_limit=32 for small LPs)."""
     import torch.distributed as dist
     solve_fn = solve_fn or _gpu_solve
     if dist.is_available() and dist.is_initialized():

@@ -6,6 +6,8 @@
 
 #include "common.h"
 
+#include <mutex>
+
 using namespace mipm;
 
 namespace {
@@ -162,6 +164,45 @@ inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)std::max<i
 
 }  // namespace
 
+namespace mipm {
+
+int device_info(int device, DeviceInfo &out)
+{
+    static std::mutex mu;
+    static std::vector<std::pair<int, DeviceInfo>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto &e : cache) if (e.first == device) { out = e.second; return MIPM_OK; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MIPM_ERR_CUDA;
+    out.sm_count = prop.multiProcessorCount;
+    out.cooperative = prop.cooperativeLaunch;
+    cache.push_back({device, out});
+    return MIPM_OK;
+}
+
+static std::mutex g_pin_mu;
+static std::vector<double *> g_pin_free;
+
+double *pinned_scalars_acquire()
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (!g_pin_free.empty()) { double *p = g_pin_free.back(); g_pin_free.pop_back(); return p; }
+    }
+    double *p = nullptr;
+    if (cudaMallocHost((void **)&p, 64 * sizeof(double)) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void pinned_scalars_release(double *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_free.push_back(p);
+}
+
+}  // namespace mipm
+
 extern "C" {
 
 int mipm_version(void) { return 100; }
@@ -187,8 +228,8 @@ int mipm_create(mipm_handle *out, int device, void *stream)
         return MIPM_ERR_CUDA;
     }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return MIPM_ERR_CUDA; }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return MIPM_ERR_CUDA; }
+    DeviceInfo prop;
+    if (device_info(device, prop) != MIPM_OK) { delete h; return MIPM_ERR_CUDA; }
     {
         // stream-ordered allocations for everything this handle owns; keep freed blocks in the pool instead of returning
         // them to the driver at every synchronisation
@@ -203,10 +244,10 @@ int mipm_create(mipm_handle *out, int device, void *stream)
         (void)cudaGetLastError();
         use_handle(h);
     }
-    h->red_blocks = prop.multiProcessorCount * 8;      // every block of a reduction kernel resident at once (8 x 256 threads / SM)
+    h->red_blocks = prop.sm_count * 8;      // every block of a reduction kernel resident at once (8 x 256 threads / SM)
     if (h->d_partials.alloc((size_t)h->red_blocks * 16) != cudaSuccess ||
         h->d_scal.alloc(64) != cudaSuccess || h->d_counter.alloc(4) != cudaSuccess ||
-        cudaMallocHost((void **)&h->h_scal, 64 * sizeof(double)) != cudaSuccess ||
+        (h->h_scal = pinned_scalars_acquire()) == nullptr ||
         h->d_info.alloc(4) != cudaSuccess) {
         delete h;
         return MIPM_ERR_ALLOC;
@@ -230,7 +271,7 @@ int mipm_destroy(mipm_handle hh)
             cudaEventDestroy(h->ev_u_zero);
             cudaStreamDestroy(h->side);
         }
-        if (h->h_scal) cudaFreeHost(h->h_scal);
+        pinned_scalars_release(h->h_scal);
     }
     delete h;
     return MIPM_OK;

@@ -174,6 +174,13 @@ inline int fail(Handle *h, int code, const std::string &msg) {
         mipm::use_handle(h);                                                                \
     } while (0)
 
+// Per-process caches of things that are slow or device-synchronising to obtain per handle (they matter when hundreds of
+// small handles are created: BASELINE config C5). Implemented in api.cu.
+struct DeviceInfo { int sm_count = 0; int cooperative = 0; };
+int device_info(int device, DeviceInfo &out);       // cudaGetDeviceProperties once per device
+double *pinned_scalars_acquire();                   // 64 pinned doubles from a free list (never returned to the driver)
+void pinned_scalars_release(double *p);
+
 inline void use_handle(const Handle *h)
 {
     tl_stream = h->stream;

@@ -999,12 +999,12 @@ int ls_device_setup(Handle *h)
     int fuse_min = 1 << 30;
     int grid_estimate = 444;
     {
-        cudaDeviceProp prop0;
-        MIPM_CUDA(h, cudaGetDeviceProperties(&prop0, h->device));
+        DeviceInfo prop0;
+        if (device_info(h->device, prop0) != MIPM_OK) return fail(h, MIPM_ERR_CUDA, "cudaGetDeviceProperties failed");
         // Measured on B200 (tools/sweep_fuse.py): per-CTA tile latency, not the grid barriers, bounds
         // the wide levels, so whole-front tasks are neutral on C2 and slower on C3's small fronts.
         // Off by default; MIPM_FRONT_FUSE_MIN=<n> enables them for levels with at least n fronts.
-        grid_estimate = prop0.multiProcessorCount * 3;       // __launch_bounds__(256, 3)
+        grid_estimate = prop0.sm_count * 3;       // __launch_bounds__(256, 3)
         if (const char *e = std::getenv("MIPM_FRONT_FUSE_MIN")) fuse_min = std::max(1, atoi(e));
     }
     std::vector<int32_t> ea_first((size_t)std::max(ns, 1), 0), ea_count((size_t)std::max(ns, 1), 0);
@@ -1141,9 +1141,9 @@ int ls_device_setup(Handle *h)
     h->n_phases = (int)(phases.size() / 8);
     h->n_launch_factor = 2;   // scatter + persistent kernel (plus three memsets)
     // ---- cooperative grid sizes
-    cudaDeviceProp prop;
-    MIPM_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
-    if (!prop.cooperativeLaunch) return fail(h, MIPM_ERR_CUDA, "device does not support cooperative launch");
+    DeviceInfo prop;
+    if (device_info(h->device, prop) != MIPM_OK) return fail(h, MIPM_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (!prop.cooperative) return fail(h, MIPM_ERR_CUDA, "device does not support cooperative launch");
     MIPM_CUDA(h, cudaFuncSetAttribute(k_factor_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     MIPM_CUDA(h, cudaFuncSetAttribute(k_factor_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     MIPM_CUDA(h, cudaFuncSetAttribute(k_bench_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -1156,8 +1156,8 @@ int ls_device_setup(Handle *h)
         MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_solve_persistent<false>, 256, 0));
     }
     if (occ_f < 1 || occ_s < 1) return fail(h, MIPM_ERR_CUDA, "persistent kernels do not fit on an SM");
-    h->grid_factor = prop.multiProcessorCount * occ_f;
-    h->grid_solve = prop.multiProcessorCount * std::min(occ_s, 4);
+    h->grid_factor = prop.sm_count * occ_f;
+    h->grid_solve = prop.sm_count * std::min(occ_s, 4);
     if (h->grid_limit > 0) {        // small systems solved side by side on one GPU (mipm_set_grid_limit)
         h->grid_factor = std::min(h->grid_factor, h->grid_limit);
         h->grid_solve = std::min(h->grid_solve, h->grid_limit);

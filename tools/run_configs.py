@@ -39,7 +39,7 @@ def run_one(name, qp, kkt, **kw):
 
 def main():
     args = sys.argv[1:]
-    opt = {"--c3-scale": 1.0, "--c5-units": 32, "--c5-threads": 1, "--c5-grid": 0}
+    opt = {"--c3-scale": 1.0, "--c5-units": 32, "--c5-threads": 12, "--c5-grid": 32}
     for k in list(opt):
         if k in args:
             i = args.index(k)
