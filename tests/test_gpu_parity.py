@@ -491,3 +491,18 @@ def test_distributed_solver_single_rank_matches_oracle(built):
     _check_trace(got, ref.trace, ref.iter, ref.status)
     plain = madipm(qp, kkt_system="Normal")
     _check_trace(plain, ref.trace, ref.iter, ref.status)
+
+
+def test_concurrent_batch_matches_sequential(built):
+    """BASELINE config C5 units solved several at a time (own stream per worker, persistent kernels capped with
+    mipm_set_grid_limit) must return exactly what the one-at-a-time path returns, in index order."""
+    from madipm_jl_b200.batch import solve_batch
+    from madipm_jl_b200.problems import config_c5
+    models = {i: config_c5(i) for i in range(10)}
+    seq = solve_batch(lambda i: models[i], 10, kkt_system="Normal")
+    par = solve_batch(lambda i: models[i], 10, kkt_system="Normal", threads=4, grid_limit=32)
+    assert [r.index for r in par] == list(range(10))
+    for a, b in zip(seq, par):
+        assert a.status == b.status == "SOLVE_SUCCEEDED"
+        assert a.iter == b.iter
+        assert a.objective == b.objective          # same kernels, same schedule per unit: bit-identical
