@@ -636,27 +636,36 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
         for (int32_t s = 0; s < ns; ++s) S.level_sn[(size_t)pos[(size_t)S.sn_level[(size_t)s]]++] = s;
     }
     TLOG("8");
-    // ---- scatter map of the input nonzeros into the panels
+    // ---- scatter map of the input nonzeros into the panels (independent per column: host threads over column chunks)
     S.a2l.resize((size_t)nnz);
-    for (int64_t j = 0; j < n; ++j)
-        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-            int32_t a = S.iperm[(size_t)rowval[p]], b = S.iperm[(size_t)j];
-            int32_t r = std::max(a, b), c = std::min(a, b);
-            int32_t s = S.col2sn[(size_t)c];
-            int32_t c0 = S.sn_ptr[(size_t)s], c1 = S.sn_ptr[(size_t)s + 1];
-            int64_t k = c1 - c0;
-            int64_t nr = S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s];
-            int64_t t;
-            if (r < c1) {
-                t = r - c0;
-            } else {
-                const int32_t *rb = S.row_idx.data() + S.row_ptr[(size_t)s];
-                const int32_t *f = std::lower_bound(rb, rb + nr, r);
-                if (f == rb + nr || *f != r) return "input entry outside the symbolic structure (internal error)";
-                t = k + (f - rb);
-            }
-            S.a2l[(size_t)p] = S.lp[(size_t)s] + (int64_t)(c - c0) * (k + nr) + t;
-        }
+    {
+        const int nth = (int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, n / 8192));
+        std::vector<int> bad((size_t)nth, 0);
+        auto work = [&](int t) {
+            const int64_t j0 = n * t / nth, j1 = n * (t + 1) / nth;
+            for (int64_t j = j0; j < j1; ++j)
+                for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                    int32_t a = S.iperm[(size_t)rowval[p]], b = S.iperm[(size_t)j];
+                    int32_t r = std::max(a, b), c = std::min(a, b);
+                    int32_t s = S.col2sn[(size_t)c];
+                    int32_t c0 = S.sn_ptr[(size_t)s], c1 = S.sn_ptr[(size_t)s + 1];
+                    int64_t k = c1 - c0;
+                    int64_t nr = S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s];
+                    int64_t tt;
+                    if (r < c1) {
+                        tt = r - c0;
+                    } else {
+                        const int32_t *rb = S.row_idx.data() + S.row_ptr[(size_t)s];
+                        const int32_t *f = std::lower_bound(rb, rb + nr, r);
+                        if (f == rb + nr || *f != r) { bad[(size_t)t] = 1; return; }
+                        tt = k + (f - rb);
+                    }
+                    S.a2l[(size_t)p] = S.lp[(size_t)s] + (int64_t)(c - c0) * (k + nr) + tt;
+                }
+        };
+        run_host_threads(nth, work);
+        for (int v : bad) if (v) return "input entry outside the symbolic structure (internal error)";
+    }
     return "";
 }
 
