@@ -95,7 +95,7 @@ struct SolveParams {
     int accumulate;             // x_out[perm] += xp instead of =
     const int *vmap;            // virtual CTA id per blockIdx.x, or null
     int *probe;                 // non-null: placement probe only
-    int prefetch;               // L2 prefetch of upcoming fronts (MIPM_NO_PREFETCH=1 turns it off)
+    int prefetch;               // L2 prefetch of the next level's fronts when it has at most this many (0 = off)
     // fronts with many children (K2: one tiny leaf child per primal variable) fold their children's update vectors in
     // through a transposed map: per destination row of the front, the update-vector slots that land on it, in child
     // order. gat_off[2 s] = offset of the front's N + 1 pointers in gat_ptr (-1: walk the children instead),
@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
         const int32_t *fr = p.sched + p.lvl[2 * l];
         const int nf = (int)p.lvl[2 * l + 1];
         const int extra = (l == 0) ? n_leaf_groups : 0;      // small leaves ride along with level 0
-        if (p.prefetch && l + 1 < p.fwd_end && vid >= nf + extra && (int)p.lvl[2 * (l + 1) + 1] <= PREFETCH_MAX_FRONTS) {
+        if (p.prefetch && l + 1 < p.fwd_end && vid >= nf + extra && (int)p.lvl[2 * (l + 1) + 1] <= p.prefetch) {
             const int32_t *nx = p.sched + p.lvl[2 * (l + 1)];
             const int nnx = (int)p.lvl[2 * (l + 1) + 1], idle = (int)gridDim.x - (nf + extra);
             for (int j = vid - (nf + extra); j < nnx; j += idle) prefetch_front(p, nx[j]);
@@ -864,7 +864,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
         const int32_t *fr = p.sched + p.lvl[2 * l];
         const int nf = (int)p.lvl[2 * l + 1];
         const int extra = (l == 0) ? n_leaf_groups : 0;
-        if (p.prefetch && l > 0 && vid >= nf + extra && (int)p.lvl[2 * (l - 1) + 1] <= PREFETCH_MAX_FRONTS) {
+        if (p.prefetch && l > 0 && vid >= nf + extra && (int)p.lvl[2 * (l - 1) + 1] <= p.prefetch) {
             const int32_t *nx = p.sched + p.lvl[2 * (l - 1)];
             const int nnx = (int)p.lvl[2 * (l - 1) + 1], idle = (int)gridDim.x - (nf + extra);
             for (int j = vid - (nf + extra); j < nnx; j += idle) prefetch_front(p, nx[j]);
@@ -1337,8 +1337,9 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     p.vmap = h->d_vmap_solve.p; p.probe = nullptr;
     p.gat_off = h->d_gat_off.p; p.gat_ptr = h->d_gat_ptr.p; p.gat_src = h->d_gat_src.p;
     static const bool solve_log = std::getenv("MIPM_SOLVE_LOG") != nullptr;
-    static const bool no_prefetch = std::getenv("MIPM_NO_PREFETCH") != nullptr;
-    p.prefetch = no_prefetch ? 0 : 1;
+    static const int prefetch_max = std::getenv("MIPM_NO_PREFETCH") ? 0
+                                    : (std::getenv("MIPM_PREFETCH_MAX") ? atoi(std::getenv("MIPM_PREFETCH_MAX")) : PREFETCH_MAX_FRONTS);
+    p.prefetch = prefetch_max;
     DBuf<unsigned long long> d_lvl_ns;
     p.lvl_ns = nullptr;
     if (solve_log) {
