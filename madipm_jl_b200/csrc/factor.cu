@@ -119,17 +119,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-// largest i in [0, n) with prefix[i] <= x  (prefix[0] = 0, prefix[n] = total > x)
-__device__ __forceinline__ int find_segment(const int32_t *prefix, int n, int x)
-{
-    int lo = 0, hi = n;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (prefix[mid] <= x) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -602,7 +591,7 @@ __device__ void front_forward(const SolveParams &p, int s, double *smem, int mod
 {
     double *xb = smem, *yb = smem + NB;
     const FrontInfo f = p.fi[s];
-    const int k = f.k, r = f.r, N = f.k + f.r;
+    const int k = f.k, N = f.k + f.r;
     const double *P = p.L + f.lp;
     double *x1 = p.xp + f.c0;
     double *u = p.uvec + f.rowp;
