@@ -310,10 +310,13 @@ int mipm_mpc_iter_rest(mipm_handle h, double mu_min, int step_rule, double tau_p
 /* ------------------------------------------------------------------ diagnostics ---- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t mipm_launch_count(mipm_handle h);
-/* One numeric factorization with a CUDA-event pair around every launch, summed per kernel class:
- * 0 zero-fill + scatter of the input values, 1 extend-add, 2 diagonal-block factorization,
- * 3 panel TRSM, 4 trailing DMMA update. ms[5] = device milliseconds, work[5] = algorithmic
- * bytes (classes 0-1) or flops (classes 2-4), launches[5] = launch counts. For bench.py's roofline. */
+/* One timed numeric factorization with the task kernel's own per-class accounting (all arrays have 8 entries):
+ * ms[0] zero-fill + scatter of the input values (CUDA-event time minus the kernel span); ms[1..4] extend-add,
+ * diagonal blocks (+ small leaf fronts), panel solves, trailing DMMA updates: %globaltimer busy time of the tasks of
+ * that class summed over all CTAs and divided by the grid size; ms[5] the same for dependency waits; ms[6] the
+ * span of the task kernel (first task start to last task end); ms[7] the grid size. work[] = algorithmic bytes
+ * (classes 0-1) or flops (classes 2-4). MIPM_PHASE_LOG=<file> also writes when each elimination-tree level finished.
+ * For bench.py's roofline. */
 int mipm_ls_factorize_profile(mipm_handle h, const double *d_nzval, double *ms, double *work,
                               int64_t *launches);
 /* Dense FP64 update-kernel micro-benchmark hook: C(n x n, lower tiles) -= X(n x k) X(n x k)'

@@ -371,9 +371,10 @@ class Handle:
     def ls_factorize_profile(self, nzval):
         """Per-class device timing of one factorization: dict class -> (ms, work, launches)."""
         self._nz_ref = nzval
-        ms, work, cnt = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int64 * 5)()
+        ms, work, cnt = (C.c_double * 8)(), (C.c_double * 8)(), (C.c_int64 * 8)()
         self.check(self.lib.mipm_ls_factorize_profile(self.h, _ptr(nzval), ms, work, cnt))
-        names = ["zero_scatter", "extend_add", "diag", "trsm", "update"]
+        # classes 1-5: CTA-busy milliseconds summed over the grid / grid size; "kernel" = span of the task kernel
+        names = ["zero_scatter", "extend_add", "diag", "trsm", "update", "wait", "kernel", "grid"]
         return {nm: dict(ms=ms[i], work=work[i], launches=cnt[i]) for i, nm in enumerate(names)}
 
     def launch_count(self):

@@ -88,31 +88,33 @@ struct Handle {
     // ---- linear solver
     LsSymbolic sym;
     bool has_ls = false, factorized = false;
-    int n_phases = 0, grid_factor = 0, grid_solve = 0;
+    int n_tasks = 0, grid_factor = 0, grid_solve = 0;
     int grid_limit = 0;              // cap on the persistent kernels' grid (0 = whole GPU)
-    int root_phase_begin = -1;       // first phase of the border (root) front's own factorization, -1 = no border
+    int root_task_begin = -1;        // first task of the border (root) front's own factorization, -1 = no border
     int64_t leaf_off = 0;            // small leaf fronts (one warp each) in d_sched
     int n_leaf = 0;
     cudaStream_t side = nullptr;     // zero-fill of the update matrices for the next factorization
     cudaEvent_t ev_factor_done = nullptr, ev_u_zero = nullptr;
     bool u_prezeroed = false;
-    DBuf<int32_t> d_sched;           // schedule arrays (front lists, task prefixes, extend-add triples)
-    DBuf<int64_t> d_phases, d_lvl, d_dinv_off;
-    DBuf<int32_t> d_ea_first, d_ea_count;
-    DBuf<int> d_work_counter;
+    DBuf<int32_t> d_sched;           // schedule arrays (per-level front lists, small-leaf list, extend-add child ranges)
+    DBuf<int64_t> d_lvl;
     struct FI64 { char b[64]; };
-    DBuf<FI64> d_finfo;              // FrontInfo records (64 bytes each, see factor.cu)
+    DBuf<FI64> d_finfo;              // FrontInfo records (64 bytes each, see front.cuh)
+    struct T32 { char b[32]; };
+    DBuf<T32> d_tasks;               // task list of the factorization (32 bytes each, see factor.cu)
+    DBuf<int> d_prog;                // per front: completed tasks; [ns] = ticket counter
+    DBuf<unsigned long long> d_prof, d_front_ns, d_trace;     // per-CTA busy time per task class; per-front completion time (diagnostic)
     DBuf<double> d_Dinv;             // inverted 64 x 64 diagonal blocks
-    DBuf<unsigned long long> d_phase_ns;
-    DBuf<int32_t> d_sn_ptr, d_sn_parent, d_row_idx, d_rel_idx, d_perm, d_child_idx, d_full_col;
-    DBuf<int64_t> d_row_ptr, d_lp, d_up, d_child_ptr, d_a2l, d_full_ptr, d_full_val, d_wp;
-    DBuf<double> d_L, d_U, d_W, d_xp, d_uvec, d_b, d_r;
+    DBuf<double> d_Dg;               // LDL^T pivots by (permuted) column
+    DBuf<int32_t> d_row_idx, d_rel_idx, d_perm, d_child_idx, d_full_col;
+    DBuf<int64_t> d_a2l, d_full_ptr, d_full_val;
+    DBuf<double> d_L, d_U, d_xp, d_uvec, d_b, d_r;
     DBuf<double> d_L2;               // second factor buffer: the idle one is zero-filled on the side stream (not in border mode)
     double *L_cur = nullptr;         // buffer holding the current factor
     bool l_prezeroed = false;
     DBuf<int64_t> d_gat_off;         // transposed child maps of the forward solve (fronts with many children)
     DBuf<int32_t> d_gat_ptr, d_gat_src;
-    DBuf<int> d_vmap_factor, d_vmap_solve;   // virtual CTA ids of the persistent kernels (placement probe)
+    DBuf<int> d_vmap_solve;          // virtual CTA ids of the persistent solve kernel (placement probe)
     DBuf<int> d_info;                // [0]=first failed column+1 (0 = ok), [1]=#neg pivots, [2]=#zero pivots
     const double *d_nzval = nullptr;
     int64_t n_launch_factor = 0;
@@ -183,12 +185,14 @@ void pinned_scalars_release(double *p);
 
 inline void use_handle(const Handle *h)
 {
+    if (!h->host_only) cudaSetDevice(h->device);     // cheap when unchanged; handles on several GPUs in one process
     tl_stream = h->stream;
     tl_pooled = h->pool_ok && !h->host_only;
 }
 
 // implemented in the .cu files
 int ls_device_setup(Handle *h);
+int ls_solve_setup(Handle *h, const void *finfo_host);
 int ls_factorize_impl(Handle *h, const double *d_nzval);
 int ls_solve_impl(Handle *h, double *d_x, int ir_steps);
 int ls_factorize_staged(Handle *h, const double *d_nzval, int stage);

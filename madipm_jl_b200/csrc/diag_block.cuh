@@ -126,11 +126,12 @@ __device__ __forceinline__ void trailing_update(double *S, const double *Ysc, co
 // smem: [0, 64*65) S | [4160, 4160+256) dv, invd, spare | [4416, 4416+4160) Sinv (its upper right corner doubles as
 // the panel scratch during the factorization).  Needs 8576 doubles.
 // P: the block inside the front panel (column-major, leading dimension N); nb <= 64 valid rows / columns.
-// Dv: 64 x 64 column-major output, inverse of the stored factor (identity outside nb).
+// preloaded: S already holds the block (lower triangle inside nb, identity elsewhere); P is then only written.
+// Dv: 64 x 64 column-major output with column stride ldv, inverse of the stored factor (identity outside nb).
 // info[0] = breakdown flag, info[1] = # negative pivots (LDL^T), info[2] = # perturbed pivots.
 template <bool LDL, bool DBG = false>
-__device__ __forceinline__ void diag_block(double *__restrict__ P, int N, int nb, double *__restrict__ Dv,
-                                           double piv_tol, int *info, double *smem, long long *dbg = nullptr)
+__device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv, int ldv,
+                                           double piv_tol, int *info, double *smem, bool preloaded = false, long long *dbg = nullptr)
 {
     double *S = smem;
     double *dv = smem + DB * DLD;           // pivots d_j, later sqrt(d_j)
@@ -142,7 +143,7 @@ __device__ __forceinline__ void diag_block(double *__restrict__ P, int N, int nb
 
     long long tq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
 #define DIAG_STAMP(i) do { if (DBG && dbg) { long long now_ = clock64(); tq[i] += now_ - tc; tc = now_; } } while (0)
-    {
+    if (!preloaded) {                       // (preloaded: the caller already placed the block, identity-padded, in S)
         double v[DB * DB / 256];            // all 16 global loads in flight before the first shared store
 #pragma unroll
         for (int t = 0; t < DB * DB / 256; ++t) {
@@ -331,7 +332,7 @@ __device__ __forceinline__ void diag_block(double *__restrict__ P, int N, int nb
             const double v = S[cc * DLD + rr];
             P[(int64_t)cc * N + rr] = (rr == cc) ? dv[cc] : (LDL ? v : v * dv[cc]);
         }
-        Dv[idx] = (rr >= cc) ? Sinv[cc * DLD + rr] * invd[rr] : 0.0;
+        Dv[cc * ldv + rr] = (rr >= cc) ? Sinv[cc * DLD + rr] * invd[rr] : 0.0;
     }
     DIAG_STAMP(6);
     if (DBG && dbg && tid == 0) for (int i = 0; i < 7; ++i) dbg[i] = tq[i];

@@ -614,7 +614,8 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
     for (int32_t s = 0; s < ns; ++s) {
         int64_t k = S.sn_ptr[(size_t)s + 1] - S.sn_ptr[(size_t)s];
         int64_t r = S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s];
-        S.lp[(size_t)s + 1] = S.lp[(size_t)s] + (k + r) * k;
+        // leading dimension k + r rounded up to even: every panel column starts on a 16-byte boundary (TMA bulk copies)
+        S.lp[(size_t)s + 1] = S.lp[(size_t)s] + ((k + r + 1) & ~(int64_t)1) * k;
         S.up[(size_t)s + 1] = S.up[(size_t)s] + r * r;
         S.max_front_cols = std::max<int32_t>(S.max_front_cols, (int32_t)k);
         S.max_front_rows = std::max<int32_t>(S.max_front_rows, (int32_t)(k + r));
@@ -660,7 +661,7 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
                         if (f == rb + nr || *f != r) { bad[(size_t)t] = 1; return; }
                         tt = k + (f - rb);
                     }
-                    S.a2l[(size_t)p] = S.lp[(size_t)s] + (int64_t)(c - c0) * (k + nr) + tt;
+                    S.a2l[(size_t)p] = S.lp[(size_t)s] + (int64_t)(c - c0) * ((k + nr + 1) & ~(int64_t)1) + tt;
                 }
         };
         run_host_threads(nth, work);

@@ -1,0 +1,575 @@
+// Level-scheduled supernodal triangular solves and iterative refinement. Replaces cuDSS's solve phase as reached
+// through MadNLP.solve!(linear_solver, x) (reference call site: src/KKT/normalkkt.jl:210). The factor comes from factor.cu.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+#include "front.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mipm {
+
+namespace {
+
+struct SolveParams {
+    const FrontInfo *fi;
+    const int32_t *child_idx, *rel_idx, *row_idx, *perm;
+    const int32_t *sched;
+    int fwd_begin, fwd_end;     // forward sweep over levels [fwd_begin, fwd_end)
+    int do_gather, do_backward; // stage control (distributed solves pause before the root level)
+    int root_mode;              // front_forward mode for the last level (0 unless staged)
+    const int64_t *lvl;         // 2 x int64 per level: off_all, n_all (level 0: regular fronts only)
+    int64_t leaf_off;           // small leaf fronts (level 0), one warp each
+    int n_leaf;
+    int n_levels;
+    int64_t n, n_u;
+    const double *L, *Dinv;
+    double *xp, *uvec;
+    const double *b_in;         // gathered through perm at the start
+    double *x_out;              // scattered through perm at the end
+    int accumulate;             // x_out[perm] += xp instead of =
+    const int *vmap;            // virtual CTA id per blockIdx.x, or null
+    int *probe;                 // non-null: placement probe only
+    int prefetch;               // L2 prefetch of the next level's fronts when it has at most this many (0 = off)
+    // fronts with many children (K2: one tiny leaf child per primal variable) fold their children's update vectors in
+    // through a transposed map: per destination row of the front, the update-vector slots that land on it, in child
+    // order. gat_off[2 s] = offset of the front's N + 1 pointers in gat_ptr (-1: walk the children instead),
+    // gat_off[2 s + 1] = offset of its source list in gat_src.
+    const int64_t *gat_off;
+    const int32_t *gat_ptr, *gat_src;
+    unsigned long long *lvl_ns; // optional (MIPM_SOLVE_LOG): device time of gather, every forward level, every backward level
+};
+
+// ------------------------------------------------------------------ triangular solves
+// One persistent cooperative kernel: gather through perm, forward sweep level by level (children's
+// update vectors are summed by the parent in a fixed order), backward sweep from the root down,
+// scatter through perm. One CTA per front per level; the 64 x 64 diagonal blocks are applied
+// through their stored inverses (mat-vec), so nothing in a front is sequential.
+constexpr int XR_MAX = 1536;    // ancestor entries of x cached in shared memory by the backward sweep
+
+// L2 prefetch of a front's panel and inverted diagonal blocks. The solves are latency-bound: a front is a chain of
+// dependent global loads, and the factor (hundreds of MB) does not stay in L2. CTAs with no task at a level fetch the
+// next level's fronts when that level is small (near the root; prefetching a wide level only thrashes L2), so the
+// dependent loads hit L2 instead of HBM.
+constexpr int PREFETCH_MAX_FRONTS = 128;
+__device__ __forceinline__ void prefetch_front(const SolveParams &p, int s)
+{
+    const FrontInfo f = p.fi[s];
+    const char *base = reinterpret_cast<const char *>(p.L + f.lp);
+    const int64_t bytes = (int64_t)front_ld(f.k, f.r) * f.k * 8;
+    for (int64_t off = (int64_t)threadIdx.x * 128; off < bytes; off += 256 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    const char *dv = reinterpret_cast<const char *>(p.Dinv + f.dinv * (int64_t)(NB * XS));
+    const int64_t bytes2 = (int64_t)((f.k + NB - 1) / NB) * NB * XS * 8;
+    for (int64_t off = (int64_t)threadIdx.x * 128; off < bytes2; off += 256 * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(dv + off));
+}
+
+// mode 0: whole front; 1: only fold the children's update vectors in (distributed solves: the root
+// segment is all-reduced after this); 2: skip that part (it was done in the previous stage)
+template <bool LDL>
+__device__ void front_forward(const SolveParams &p, int s, double *smem, int mode)
+{
+    double *xb = smem, *yb = smem + NB;
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, N = f.k + f.r, ld = front_ld(f.k, f.r);
+    const double *P = p.L + f.lp;
+    double *x1 = p.xp + f.c0;
+    double *u = p.uvec + f.rowp;
+    const int tid = threadIdx.x;
+    const int64_t go = p.gat_off[2 * (int64_t)s];
+    if (go >= 0 && mode != 2) {
+        const int32_t *gp = p.gat_ptr + go;
+        const int32_t *gs = p.gat_src + p.gat_off[2 * (int64_t)s + 1];
+        for (int t = tid; t < N; t += 256) {
+            const int q0 = gp[t], q1 = gp[t + 1];
+            if (q1 > q0) {
+                double acc = 0.0;
+                for (int q = q0; q < q1; ++q) acc += p.uvec[gs[q]];
+                if (t < k) x1[t] += acc; else u[t - k] += acc;
+            }
+        }
+        __syncthreads();
+    }
+    for (int ci = 0; ci < f.nchild && mode != 2 && go < 0; ++ci) {
+        const int c = p.child_idx[f.childp + ci];
+        const FrontInfo fc = p.fi[c];
+        const int32_t *rel = p.rel_idx + fc.rowp;
+        const double *uc = p.uvec + fc.rowp;
+        for (int a = tid; a < fc.r; a += 256) {
+            int t = rel[a];
+            if (t < k) x1[t] += uc[a]; else u[t - k] += uc[a];
+        }
+        __syncthreads();
+    }
+    if (mode == 1) return;
+    for (int jb = 0; jb < k; jb += NB) {
+        const int nb = min(NB, k - jb);
+        const double *Dv = p.Dinv + (f.dinv + (jb >> 6)) * (int64_t)(NB * XS);
+        if (tid < NB) xb[tid] = (tid < nb) ? x1[jb + tid] : 0.0;
+        __syncthreads();
+        {   // y = inv(L11 block) * xb : row rr by the 4 threads (rr, q), columns pp = q, q+4, ...
+            const int rr = tid >> 2, q = tid & 3;
+            double acc = 0.0;
+            double dvv[NB / 4];                  // the 16 loads of this row first (entries above the diagonal are stored zeros)
+#pragma unroll
+            for (int t = 0; t < NB / 4; ++t) dvv[t] = Dv[(q + 4 * t) * XS + rr];
+#pragma unroll
+            for (int t = 0; t < NB / 4; ++t) acc = fma(dvv[t], xb[q + 4 * t], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (q == 0) { yb[rr] = acc; if (rr < nb) x1[jb + rr] = acc; }
+        }
+        __syncthreads();
+        for (int i = jb + nb + tid; i < N; i += 256) {
+            // 16 independent loads in flight per thread (the panel lives in HBM: latency-bound otherwise)
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const double *col = P + (int64_t)jb * ld + i;
+            int j = 0;
+            for (; j + 16 <= nb; j += 16) {
+                double v[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) v[t] = col[(int64_t)(j + t) * ld];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) acc[t & 3] = fma(v[t], yb[j + t], acc[t & 3]);
+            }
+            for (; j < nb; ++j) acc[j & 3] = fma(col[(int64_t)j * ld], yb[j], acc[j & 3]);
+            const double tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            if (i < k) x1[i] -= tot; else u[i - k] -= tot;
+        }
+        __syncthreads();
+    }
+}
+
+template <bool LDL>
+__device__ void front_backward(const SolveParams &p, int s, double *smem)
+{
+    double *S = smem;                 // inverse block, col-major ld LDS
+    double *wb = smem + NB * LDS;     // 64
+    double *xr = wb + NB;             // XR_MAX: x at the front's below-diagonal rows
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, r = f.r, N = f.k + f.r, ld = front_ld(f.k, f.r);
+    const double *P = p.L + f.lp;
+    double *x1 = p.xp + f.c0;
+    const int32_t *rows = p.row_idx + f.rowp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool cached = r <= XR_MAX;
+    if (cached) for (int i = tid; i < r; i += 256) xr[i] = p.xp[rows[i]];
+    const int nblk = (k + NB - 1) / NB;
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int jb = b * NB;
+        const int nb = min(NB, k - jb);
+        const double *Dv = p.Dinv + (f.dinv + b) * (int64_t)(NB * XS);
+        for (int idx = tid; idx < NB * NB; idx += 256) S[(idx >> 6) * LDS + (idx & 63)] = Dv[(idx >> 6) * XS + (idx & 63)];
+        if (tid < NB) wb[tid] = 0.0;
+        __syncthreads();
+        // w[q] = y[q] (/ D[q]) - sum_{i >= jb+nb} L[i][q] * xfull[i]; each warp owns 8 consecutive
+        // columns and walks the rows once for all of them (8 independent loads per lane in flight)
+        {
+            const int q0 = warp * 8;
+            if (q0 < nb) {
+                double acc[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+                const double *col = P + (int64_t)(jb + q0) * ld;
+                int i = jb + nb + lane;
+                for (; i + 32 < N; i += 64) {     // two row-chunks per trip: 16 loads in flight per lane
+                    const int i2 = i + 32;
+                    double xv = (i < k) ? x1[i] : (cached ? xr[i - k] : p.xp[rows[i - k]]);
+                    double xw = (i2 < k) ? x1[i2] : (cached ? xr[i2 - k] : p.xp[rows[i2 - k]]);
+                    double v[8], w[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const bool on = q0 + c < nb;
+                        v[c] = on ? col[(int64_t)c * ld + i] : 0.0;
+                        w[c] = on ? col[(int64_t)c * ld + i2] : 0.0;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[c] = fma(w[c], xw, fma(v[c], xv, acc[c]));
+                }
+                for (; i < N; i += 32) {
+                    double xv = (i < k) ? x1[i] : (cached ? xr[i - k] : p.xp[rows[i - k]]);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (q0 + c < nb) acc[c] = fma(col[(int64_t)c * ld + i], xv, acc[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                }
+                if (lane < 8 && q0 + lane < nb) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) if (lane == c) a = acc[c];
+                    double y = x1[jb + q0 + lane];
+                    if (LDL) y = y / col[(int64_t)lane * ld + jb + q0 + lane];
+                    wb[q0 + lane] = y - a;
+                }
+            }
+        }
+        __syncthreads();
+        {   // x = inv(L11 block)' * w : column cc by the 4 threads (cc, q)
+            const int cc = tid >> 2, q = tid & 3;
+            double acc = 0.0;
+            for (int rr = cc + q; rr < NB; rr += 4) acc = fma(S[cc * LDS + rr], wb[rr], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (q == 0 && cc < nb) x1[jb + cc] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// Small leaf fronts in the solves: one warp per front, L11 (k <= SL_K) applied by direct substitution.
+template <bool LDL>
+__device__ void leaf_forward(const SolveParams &p, int s)
+{
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, N = f.k + f.r, ld = front_ld(f.k, f.r);
+    const int lane = threadIdx.x & 31;
+    const double *P = p.L + f.lp;
+    double *x1 = p.xp + f.c0;
+    double y[SL_K];
+#pragma unroll
+    for (int j = 0; j < SL_K; ++j) {
+        y[j] = 0.0;
+        if (j < k) {
+            double t = x1[j];
+#pragma unroll
+            for (int q = 0; q < j; ++q) t = fma(-P[(int64_t)q * ld + j], y[q], t);
+            if (!LDL) t = t / P[(int64_t)j * ld + j];
+            y[j] = t;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < SL_K; ++j) if (j < k) x1[j] = y[j];
+    }
+    if (lane >= k && lane < N) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < SL_K; ++j) if (j < k) acc = fma(P[(int64_t)j * ld + lane], y[j], acc);
+        p.uvec[f.rowp + lane - k] = -acc;          // a leaf has no children: its update vector starts from zero
+    }
+}
+
+template <bool LDL>
+__device__ void leaf_backward(const SolveParams &p, int s)
+{
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, N = f.k + f.r, ld = front_ld(f.k, f.r);
+    const int lane = threadIdx.x & 31;
+    const double *P = p.L + f.lp;
+    double *x1 = p.xp + f.c0;
+    const double xv = (lane >= k && lane < N) ? p.xp[p.row_idx[f.rowp + lane - k]] : 0.0;
+    double w[SL_K];
+#pragma unroll
+    for (int j = 0; j < SL_K; ++j) {
+        double part = (j < k && lane >= k && lane < N) ? P[(int64_t)j * ld + lane] * xv : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        double yj = (j < k) ? x1[j] : 0.0;
+        if (LDL && j < k) yj = yj / P[(int64_t)j * ld + j];
+        w[j] = yj - part;
+    }
+#pragma unroll
+    for (int j = SL_K - 1; j >= 0; --j) {
+        if (j < k) {
+            double t = w[j];
+#pragma unroll
+            for (int q = j + 1; q < SL_K; ++q) if (q < k) t = fma(-P[(int64_t)j * ld + q], w[q], t);
+            if (!LDL) t = t / P[(int64_t)j * ld + j];
+            w[j] = t;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < SL_K; ++j) if (j < k) x1[j] = w[j];
+    }
+}
+
+template <bool LDL>
+__global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double smem[NB * LDS + NB + XR_MAX];
+    if (p.probe) { if (threadIdx.x == 0) p.probe[blockIdx.x] = read_smid(); return; }
+    const int vid = p.vmap ? p.vmap[blockIdx.x] : (int)blockIdx.x;
+    const int64_t gtid = (int64_t)blockIdx.x * 256 + threadIdx.x, gsz = (int64_t)gridDim.x * 256;
+    if (p.do_gather) {
+        for (int64_t i = gtid; i < p.n; i += gsz) p.xp[i] = p.b_in[p.perm[i]];
+        for (int64_t i = gtid; i < p.n_u; i += gsz) p.uvec[i] = 0.0;
+        grid.sync();
+    }
+    const bool timer = (p.lvl_ns != nullptr && blockIdx.x == 0 && threadIdx.x == 0);
+    unsigned long long tprev = 0;
+    int tslot = 0;
+    if (timer) tprev = globaltimer_ns();
+    const int32_t *leaves = p.sched + p.leaf_off;
+    const int n_leaf_groups = (p.n_leaf + 7) / 8;
+    for (int l = p.fwd_begin; l < p.fwd_end; ++l) {
+        const int32_t *fr = p.sched + p.lvl[2 * l];
+        const int nf = (int)p.lvl[2 * l + 1];
+        const int extra = (l == 0) ? n_leaf_groups : 0;      // small leaves ride along with level 0
+        if (p.prefetch && l + 1 < p.fwd_end && vid >= nf + extra && (int)p.lvl[2 * (l + 1) + 1] <= p.prefetch) {
+            const int32_t *nx = p.sched + p.lvl[2 * (l + 1)];
+            const int nnx = (int)p.lvl[2 * (l + 1) + 1], idle = (int)gridDim.x - (nf + extra);
+            for (int j = vid - (nf + extra); j < nnx; j += idle) prefetch_front(p, nx[j]);
+        }
+        for (int t = vid; t < nf + extra; t += gridDim.x) {
+            if (t < extra) {
+                const int li = t * 8 + (threadIdx.x >> 5);
+                if (li < p.n_leaf) leaf_forward<LDL>(p, leaves[li]);
+            } else {
+                front_forward<LDL>(p, fr[t - extra], smem, (l == p.n_levels - 1) ? p.root_mode : 0);
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        if (timer) { unsigned long long t1 = globaltimer_ns(); p.lvl_ns[tslot++] = t1 - tprev; tprev = t1; }
+    }
+    if (!p.do_backward) return;
+    for (int l = p.n_levels - 1; l >= 0; --l) {
+        const int32_t *fr = p.sched + p.lvl[2 * l];
+        const int nf = (int)p.lvl[2 * l + 1];
+        const int extra = (l == 0) ? n_leaf_groups : 0;
+        if (p.prefetch && l > 0 && vid >= nf + extra && (int)p.lvl[2 * (l - 1) + 1] <= p.prefetch) {
+            const int32_t *nx = p.sched + p.lvl[2 * (l - 1)];
+            const int nnx = (int)p.lvl[2 * (l - 1) + 1], idle = (int)gridDim.x - (nf + extra);
+            for (int j = vid - (nf + extra); j < nnx; j += idle) prefetch_front(p, nx[j]);
+        }
+        for (int t = vid; t < nf + extra; t += gridDim.x) {
+            if (t < extra) {
+                const int li = t * 8 + (threadIdx.x >> 5);
+                if (li < p.n_leaf) leaf_backward<LDL>(p, leaves[li]);
+            } else {
+                front_backward<LDL>(p, fr[t - extra], smem);
+            }
+            __syncthreads();
+        }
+        grid.sync();
+        if (timer) { unsigned long long t1 = globaltimer_ns(); p.lvl_ns[tslot++] = t1 - tprev; tprev = t1; }
+    }
+    if (p.accumulate) { for (int64_t i = gtid; i < p.n; i += gsz) p.x_out[p.perm[i]] += p.xp[i]; }
+    else { for (int64_t i = gtid; i < p.n; i += gsz) p.x_out[p.perm[i]] = p.xp[i]; }
+}
+
+// r = b - K x with K symmetric, given by its full CSR index into the caller's lower-CSC values.
+__global__ void __launch_bounds__(256)
+k_sym_residual(int64_t n, const int64_t *__restrict__ ptr, const int32_t *__restrict__ col,
+               const int64_t *__restrict__ vpos, const double *__restrict__ val, const double *__restrict__ x,
+               const double *__restrict__ b, double *__restrict__ rout)
+{
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double acc = 0.0;
+    for (int64_t q = ptr[row] + lane; q < ptr[row + 1]; q += 32) acc = fma(__ldg(val + vpos[q]), __ldg(x + col[q]), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) rout[row] = b[row] - acc;
+}
+
+inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)std::max<int64_t>(1, (n + per_block - 1) / per_block); }
+
+}  // namespace
+
+// Placement probe: launch the persistent kernel in probe mode (same function, block size, shared memory and grid
+// as the real launches, so the block scheduler places it the same way), read back the SM of every block and number
+// the blocks so that ids [0, #SM) are the first resident CTA of each SM, [#SM, 2 #SM) the second, ...
+// The map is a permutation of the block indices whatever the probe returns, so it can only affect speed.
+static int build_cta_map(Handle *h)
+{
+    const int grid = h->grid_solve;
+    DBuf<int> &dmap = h->d_vmap_solve;
+    if (std::getenv("MIPM_NO_VMAP")) { dmap.release(); return MIPM_OK; }
+    DBuf<int> d_probe;
+    MIPM_CUDA(h, d_probe.alloc((size_t)grid));
+    MIPM_CUDA(h, cudaMemsetAsync(d_probe.p, 0xff, (size_t)grid * sizeof(int), h->stream));
+    const bool ldl = (h->sym.kind == MIPM_LDL);
+    SolveParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.probe = d_probe.p;
+    void *args[] = {&p};
+    const void *fn = ldl ? (const void *)k_solve_persistent<true> : (const void *)k_solve_persistent<false>;
+    MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), args, 0, h->stream));
+    std::vector<int> smid((size_t)grid);
+    MIPM_CUDA(h, cudaMemcpyAsync(smid.data(), d_probe.p, (size_t)grid * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    // slot of each block on its SM (in block order), then sort by (slot, smid, block)
+    std::vector<int> slot((size_t)grid), order((size_t)grid), vmap((size_t)grid);
+    {
+        std::vector<std::pair<int, int>> seen;      // (smid, count), tiny
+        for (int b = 0; b < grid; ++b) {
+            int c = -1;
+            for (auto &e : seen) if (e.first == smid[(size_t)b]) { c = e.second++; break; }
+            if (c < 0) { seen.push_back({smid[(size_t)b], 1}); c = 0; }
+            slot[(size_t)b] = c;
+        }
+    }
+    for (int b = 0; b < grid; ++b) order[(size_t)b] = b;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (slot[(size_t)a] != slot[(size_t)b]) return slot[(size_t)a] < slot[(size_t)b];
+        if (smid[(size_t)a] != smid[(size_t)b]) return smid[(size_t)a] < smid[(size_t)b];
+        return a < b;
+    });
+    for (int v = 0; v < grid; ++v) vmap[(size_t)order[(size_t)v]] = v;
+    MIPM_CUDA(h, dmap.upload(vmap, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MIPM_OK;
+}
+
+// Solve-side part of ls_device_setup (factor.cu): grid size, transposed child maps, CTA placement map.
+int ls_solve_setup(Handle *h, const void *finfo_host)
+{
+    const LsSymbolic &S = h->sym;
+    const int ns = S.ns;
+    const FrontInfo *finfo = (const FrontInfo *)finfo_host;
+    cudaStream_t st = h->stream;
+    DeviceInfo prop;
+    if (device_info(h->device, prop) != MIPM_OK) return fail(h, MIPM_ERR_CUDA, "cudaGetDeviceProperties failed");
+    int occ_s = 0;
+    if (S.kind == MIPM_LDL) MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_solve_persistent<true>, 256, 0));
+    else MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_solve_persistent<false>, 256, 0));
+    if (occ_s < 1) return fail(h, MIPM_ERR_CUDA, "solve kernel does not fit on an SM");
+    h->grid_solve = prop.sm_count * std::min(occ_s, 4);
+    if (h->grid_limit > 0) h->grid_solve = std::min(h->grid_solve, h->grid_limit);
+    {
+        // transposed child maps for the forward solve (fronts with more than GATHER_MIN_CHILDREN children)
+        constexpr int GATHER_MIN_CHILDREN = 4;
+        std::vector<int64_t> gat_off((size_t)2 * std::max(ns, 1), -1);
+        std::vector<int32_t> gat_ptr, gat_src, cnt;
+        const bool slots_fit = S.row_ptr[(size_t)ns] < (int64_t)INT32_MAX;
+        for (int s = 0; s < ns && slots_fit; ++s) {
+            const FrontInfo &f = finfo[(size_t)s];
+            if (f.nchild <= GATHER_MIN_CHILDREN) continue;
+            const int N = f.k + f.r;
+            cnt.assign((size_t)N + 1, 0);
+            for (int ci = 0; ci < f.nchild; ++ci) {
+                const int c = S.child_idx[(size_t)(f.childp + ci)];
+                const int32_t *rel = S.rel_idx.data() + S.row_ptr[(size_t)c];
+                for (int a = 0; a < finfo[(size_t)c].r; ++a) cnt[(size_t)rel[a] + 1]++;
+            }
+            for (int t = 0; t < N; ++t) cnt[(size_t)t + 1] += cnt[(size_t)t];
+            gat_off[(size_t)2 * s] = (int64_t)gat_ptr.size();
+            gat_off[(size_t)2 * s + 1] = (int64_t)gat_src.size();
+            gat_ptr.insert(gat_ptr.end(), cnt.begin(), cnt.end());
+            const size_t base = gat_src.size();
+            gat_src.resize(base + (size_t)cnt[(size_t)N]);
+            for (int ci = 0; ci < f.nchild; ++ci) {             // child order, then row order: the summation order
+                const int c = S.child_idx[(size_t)(f.childp + ci)];
+                const int64_t rp = S.row_ptr[(size_t)c];
+                const int32_t *rel = S.rel_idx.data() + rp;
+                for (int a = 0; a < finfo[(size_t)c].r; ++a) gat_src[base + (size_t)cnt[(size_t)rel[a]]++] = (int32_t)(rp + a);
+            }
+        }
+        if (gat_ptr.empty()) { gat_ptr.push_back(0); gat_src.push_back(0); }
+        MIPM_CUDA(h, h->d_gat_off.upload(gat_off, st));
+        MIPM_CUDA(h, h->d_gat_ptr.upload(gat_ptr, st));
+        MIPM_CUDA(h, h->d_gat_src.upload(gat_src, st));
+    }
+    MIPM_CUDA(h, cudaStreamSynchronize(st));
+    return build_cta_map(h);
+}
+
+// stage -1: whole solve; 0: gather + forward sweep below the root level; 1: root level forward, backward sweep, scatter
+static int solve_once(Handle *h, const double *b_in, double *x_out, int accumulate, int stage = -1)
+{
+    const LsSymbolic &S = h->sym;
+    SolveParams p;
+    p.fi = (const FrontInfo *)h->d_finfo.p; p.child_idx = h->d_child_idx.p; p.rel_idx = h->d_rel_idx.p; p.row_idx = h->d_row_idx.p;
+    p.perm = h->d_perm.p; p.sched = h->d_sched.p; p.lvl = h->d_lvl.p; p.n_levels = S.n_levels;
+    p.leaf_off = h->leaf_off; p.n_leaf = h->n_leaf;
+    p.n = S.n; p.n_u = S.row_ptr[(size_t)S.ns];
+    p.L = h->L_cur; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
+    p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
+    p.vmap = h->d_vmap_solve.p; p.probe = nullptr;
+    p.gat_off = h->d_gat_off.p; p.gat_ptr = h->d_gat_ptr.p; p.gat_src = h->d_gat_src.p;
+    static const bool solve_log = std::getenv("MIPM_SOLVE_LOG") != nullptr;
+    static const int prefetch_max = std::getenv("MIPM_NO_PREFETCH") ? 0
+                                    : (std::getenv("MIPM_PREFETCH_MAX") ? atoi(std::getenv("MIPM_PREFETCH_MAX")) : PREFETCH_MAX_FRONTS);
+    p.prefetch = prefetch_max;
+    DBuf<unsigned long long> d_lvl_ns;
+    p.lvl_ns = nullptr;
+    if (solve_log) {
+        MIPM_CUDA(h, d_lvl_ns.alloc((size_t)2 * S.n_levels + 2));
+        MIPM_CUDA(h, cudaMemsetAsync(d_lvl_ns.p, 0, ((size_t)2 * S.n_levels + 2) * sizeof(unsigned long long), h->stream));
+        p.lvl_ns = d_lvl_ns.p;
+    }
+    p.do_gather = (stage != 1);
+    p.fwd_begin = (stage == 1) ? S.n_levels - 1 : 0;
+    p.fwd_end = S.n_levels;
+    p.root_mode = (stage == 0) ? 1 : ((stage == 1) ? 2 : 0);
+    p.do_backward = (stage != 0);
+    void *args[] = {&p};
+    const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_solve_persistent<true> : (const void *)k_solve_persistent<false>;
+    MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)h->grid_solve), dim3(256), args, 0, h->stream));
+    h->launches++;
+    if (solve_log) {        // diagnostic only: synchronises
+        std::vector<unsigned long long> ns((size_t)2 * S.n_levels + 2);
+        MIPM_CUDA(h, cudaMemcpyAsync(ns.data(), d_lvl_ns.p, ns.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+        std::fprintf(stderr, "solve levels (us): fwd");
+        int slot = 0;
+        for (int l = p.fwd_begin; l < p.fwd_end; ++l) std::fprintf(stderr, " %d:%lld[%lld]", l, (long long)(ns[(size_t)slot++] / 1000), (long long)S.level_ptr[(size_t)l + 1] - (long long)S.level_ptr[(size_t)l]);
+        if (p.do_backward) {
+            std::fprintf(stderr, " | bwd");
+            for (int l = S.n_levels - 1; l >= 0; --l) std::fprintf(stderr, " %d:%lld", l, (long long)(ns[(size_t)slot++] / 1000));
+        }
+        std::fprintf(stderr, "\n");
+    }
+    return MIPM_OK;
+}
+int ls_solve_impl(Handle *h, double *d_x, int ir_steps)
+{
+    const LsSymbolic &S = h->sym;
+    cudaStream_t st = h->stream;
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    const int64_t n = S.n;
+    if (n == 0) return MIPM_OK;
+    // b is needed after x is overwritten (refinement) and the solve reads b through perm while
+    // writing x through perm: always work from a copy of the right-hand side
+    MIPM_CUDA(h, cudaMemcpyAsync(h->d_b.p, d_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    int rc = solve_once(h, h->d_b.p, d_x, 0);
+    if (rc != MIPM_OK) return rc;
+    for (int it = 0; it < ir_steps; ++it) {
+        k_sym_residual<<<grid_for(n * 32, 256), 256, 0, st>>>(n, h->d_full_ptr.p, h->d_full_col.p, h->d_full_val.p, h->d_nzval,
+                                                            d_x, h->d_b.p, h->d_r.p);
+        MIPM_CHECK_LAUNCH(h);
+        rc = solve_once(h, h->d_r.p, d_x, 1);
+        if (rc != MIPM_OK) return rc;
+    }
+    return MIPM_OK;
+}
+int ls_solve_staged(Handle *h, double *d_x, int stage)
+{
+    const LsSymbolic &S = h->sym;
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    if (h->root_task_begin < 0) return fail(h, MIPM_ERR_STATE, "staged solve needs mipm_ls_analyze_border");
+    if (S.n == 0) return MIPM_OK;
+    if (stage == 0) {
+        MIPM_CUDA(h, cudaMemcpyAsync(h->d_b.p, d_x, (size_t)S.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        return solve_once(h, h->d_b.p, d_x, 0, 0);
+    }
+    return solve_once(h, h->d_b.p, d_x, 0, 1);
+}
+
+}  // namespace mipm
+
+extern "C" int mipm_ls_solve_stage(mipm_handle hh, double *d_x, int stage)
+{
+    using namespace mipm;
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_ls || !h->factorized) return fail(h, MIPM_ERR_STATE, "solve before factorize");
+    if (stage != 0 && stage != 1) return fail(h, MIPM_ERR_ARG, "stage must be 0 or 1");
+    if (!d_x && h->sym.n > 0) return fail(h, MIPM_ERR_ARG, "null argument");
+    return ls_solve_staged(h, d_x, stage);
+}

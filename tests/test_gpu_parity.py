@@ -479,6 +479,68 @@ def test_c3_full_size_properties(built):
     assert abs(0.5 * float(x @ (H @ x)) + float(qp.c @ x) + qp.c0 - got.objective) <= 1e-8 * max(1.0, abs(got.objective))
 
 
+# ------------------------------------------------------------------ full-size configs against oracle traces (N1)
+_FULL_PATH = os.path.join(os.path.dirname(__file__), "golden", "traces_full.json")
+FULL = json.load(open(_FULL_PATH)) if os.path.exists(_FULL_PATH) else {}
+
+
+def _full(key):
+    if key not in FULL:
+        pytest.skip("tests/golden/traces_full.json has no %s (run tests/golden/make_golden_full.py)" % key)
+    return FULL[key]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_c2_full_size_matches_oracle_trace(built, fused):
+    """The bench workload (BASELINE configs[1], m=200000, n=1000000): every iterate of the CUDA path against the
+    committed trace of the CPU oracle on the same instance -- objective, dual objective, inf_pr, inf_du, inf_compl at
+    1e-8 (scale max(1,|v|)), iteration count +-2 -- for both host sequencings (north_star: "same iterates")."""
+    from madipm_jl_b200.problems import config_c2
+    from madipm_jl_b200.solver import madipm
+    g = _full("c2_full/Normal")
+    got = madipm(config_c2(), kkt_system="Normal", fused=fused)
+    _check_trace(got, g["trace"], g["iter"], g["status"])
+    assert close(got.objective, g["objective"])
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_c3_full_size_matches_oracle_trace(built, fused):
+    """BASELINE configs[2] (QP, K2 system of 650000 rows, LDL'): per-iterate parity with the oracle (SuperLU solves)."""
+    from madipm_jl_b200.problems import config_c3
+    from madipm_jl_b200.solver import madipm
+    g = _full("c3_full/K2")
+    got = madipm(config_c3(), kkt_system="K2", fused=fused)
+    _check_trace(got, g["trace"], g["iter"], g["status"])
+    assert close(got.objective, g["objective"])
+
+
+@pytest.mark.parametrize("solver", ["b200", "distributed"])
+def test_c4_scaled_matches_oracle_trace(built, solver):
+    """BASELINE configs[3] at the scale the oracle can finish (make_golden_full.py: c4_s15), through the single-GPU solver
+    and through the distributed (border-root, staged) solver on one rank."""
+    from madipm_jl_b200.problems import config_c4
+    from madipm_jl_b200.solver import madipm
+    g = _full("c4_s15/Normal")
+    qp = config_c4(scale=0.15)
+    kw = dict(linear_solver="distributed", n_border=qp.meta["n_border"]) if solver == "distributed" else {}
+    got = madipm(qp, kkt_system="Normal", **kw)
+    _check_trace(got, g["trace"], g["iter"], g["status"])
+    assert close(got.objective, g["objective"])
+
+
+def test_c5_units_match_oracle_traces(built):
+    """BASELINE configs[4]: the first 8 units of the batch, solved concurrently (own stream per worker), each compared
+    with its oracle trace."""
+    from madipm_jl_b200.batch import _gpu_solve_concurrent
+    from madipm_jl_b200.problems import config_c5
+    keys = ["c5_u%d/Normal" % i for i in range(8)]
+    gs = [_full(k) for k in keys]
+    res = _gpu_solve_concurrent(config_c5, list(range(8)), threads=4, grid_limit=32, kkt_system="Normal")
+    for (i, st), g in zip(res, gs):
+        _check_trace(st, g["trace"], g["iter"], g["status"])
+        assert close(st.objective, g["objective"])
+
+
 def test_distributed_solver_single_rank_matches_oracle(built):
     """Config C4's solver path with one rank (no process group): staged factorization / solve through the
     border root must reproduce the oracle's iterates on a block-angular LP. The 2-GPU run of the same code

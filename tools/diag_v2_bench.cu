@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256, 3) k(double *A, int N, int nb, double *Di
     double *P = A + (size_t)blockIdx.x * N * NB;
     long long c0 = clock64();
     for (int r = 0; r < reps; ++r) {
-        mipm_diag::diag_block<LDL, true>(P, N, nb, Dinv + (size_t)blockIdx.x * NB * NB, 1e-13, info, smem, (blockIdx.x == 0 && gridDim.x == 1) ? cyc + 8 : nullptr);
+        mipm_diag::diag_block<LDL, true>(P, N, nb, Dinv + (size_t)blockIdx.x * NB * NB, NB, 1e-13, info, smem, false, (blockIdx.x == 0 && gridDim.x == 1) ? cyc + 8 : nullptr);
         __syncthreads();
     }
     if (threadIdx.x == 0) cyc[blockIdx.x] = clock64() - c0;

@@ -37,7 +37,28 @@ def main():
     h.ls_factorize(Cx)
     torch.cuda.synchronize()
     print("factor ms", 1e3 * (time.perf_counter() - t))
-    print(h.ls_factorize_profile(Cx))
+    for _ in range(3):
+        pr_ = h.ls_factorize_profile(Cx)
+        print({k_: round(v["ms"], 4) for k_, v in pr_.items()})
+    out = os.environ.get("PROFILE_OUT")
+    if out:
+        os.environ["MIPM_TASK_TRACE"] = out + "_trace.csv"
+        os.environ["MIPM_PHASE_LOG"] = out + "_levels.csv"
+        print(h.ls_factorize_profile(Cx))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        h.ls_factorize_async(Cx)
+    e1.record()
+    torch.cuda.synchronize()
+    print("factorize (events, avg of 5) ms", e0.elapsed_time(e1) / 5)
+    e0.record()
+    for _ in range(5):
+        x = b.clone()
+        h.ls_solve(x, 0)
+    e1.record()
+    torch.cuda.synchronize()
+    print("solve (events, avg of 5, incl. clone) ms", e0.elapsed_time(e1) / 5)
 
 
 if __name__ == "__main__":
