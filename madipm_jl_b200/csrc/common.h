@@ -114,7 +114,10 @@ struct Handle {
     bool l_prezeroed = false;
     DBuf<int64_t> d_gat_off;         // transposed child maps of the forward solve (fronts with many children)
     DBuf<int32_t> d_gat_ptr, d_gat_src;
-    DBuf<int> d_vmap_solve;          // virtual CTA ids of the persistent solve kernel (placement probe)
+    struct I2 { int x, y; };
+    DBuf<I2> d_solve_tasks;          // task list of the solves (kind, id), see solve.cu
+    DBuf<int> d_solve_prog;          // per front: forward children done | backward done; [2 ns] = ticket counter
+    int n_solve_fwd = 0, n_solve_tasks = 0;
     DBuf<int> d_info;                // [0]=first failed column+1 (0 = ok), [1]=#neg pivots, [2]=#zero pivots
     const double *d_nzval = nullptr;
     int64_t n_launch_factor = 0;
@@ -192,7 +195,7 @@ inline void use_handle(const Handle *h)
 
 // implemented in the .cu files
 int ls_device_setup(Handle *h);
-int ls_solve_setup(Handle *h, const void *finfo_host);
+int ls_solve_setup(Handle *h, const void *finfo_host, const char *small_leaf);
 int ls_factorize_impl(Handle *h, const double *d_nzval);
 int ls_solve_impl(Handle *h, double *d_x, int ir_steps);
 int ls_factorize_staged(Handle *h, const double *d_nzval, int stage);

@@ -869,7 +869,7 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, cudaMemsetAsync(h->d_L.p + std::max<int64_t>(S.nnz_l, 1), 0, 64 * sizeof(double), st));
     if (h->d_L2.p) MIPM_CUDA(h, cudaMemsetAsync(h->d_L2.p + S.nnz_l, 0, 64 * sizeof(double), st));
     {
-        int rc = ls_solve_setup(h, finfo.data());
+        int rc = ls_solve_setup(h, finfo.data(), small.data());
         if (rc != MIPM_OK) return rc;
     }
     MIPM_CUDA(h, cudaStreamSynchronize(st));

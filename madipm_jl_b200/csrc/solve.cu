@@ -1,7 +1,5 @@
 // Level-scheduled supernodal triangular solves and iterative refinement. Replaces cuDSS's solve phase as reached
 // through MadNLP.solve!(linear_solver, x) (reference call site: src/KKT/normalkkt.jl:210). The factor comes from factor.cu.
-#include <cooperative_groups.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -11,8 +9,6 @@
 #include "common.h"
 #include "front.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace mipm {
 
 namespace {
@@ -20,44 +16,41 @@ namespace {
 struct SolveParams {
     const FrontInfo *fi;
     const int32_t *child_idx, *rel_idx, *row_idx, *perm;
-    const int32_t *sched;
-    int fwd_begin, fwd_end;     // forward sweep over levels [fwd_begin, fwd_end)
-    int do_gather, do_backward; // stage control (distributed solves pause before the root level)
-    int root_mode;              // front_forward mode for the last level (0 unless staged)
-    const int64_t *lvl;         // 2 x int64 per level: off_all, n_all (level 0: regular fronts only)
-    int64_t leaf_off;           // small leaf fronts (level 0), one warp each
+    const int32_t *leaves;      // small leaf fronts, one warp each
     int n_leaf;
-    int n_levels;
-    int64_t n, n_u;
+    const int2 *tasks;          // (kind, id): 0 forward front, 1 forward leaf group, 2 backward front, 3 backward leaf group
+    int task_begin, task_end;
+    int root_sn, root_mode;     // staged (distributed) solves: front_forward mode of the border root (0 unless staged)
+    int *fprog;                 // per front: children whose forward step is complete
+    int *bdone;                 // per front: backward step complete
+    int *ticket;
     const double *L, *Dinv;
     double *xp, *uvec;
-    const double *b_in;         // gathered through perm at the start
-    double *x_out;              // scattered through perm at the end
-    int accumulate;             // x_out[perm] += xp instead of =
-    const int *vmap;            // virtual CTA id per blockIdx.x, or null
-    int *probe;                 // non-null: placement probe only
-    int prefetch;               // L2 prefetch of the next level's fronts when it has at most this many (0 = off)
+    const double *b_in;         // right-hand side (original numbering), read through perm by the front that owns the entry
+    double *x_out;              // solution (original numbering), written through perm by the front that owns the entry
+    int accumulate;             // x_out[perm] += x instead of =
     // fronts with many children (K2: one tiny leaf child per primal variable) fold their children's update vectors in
     // through a transposed map: per destination row of the front, the update-vector slots that land on it, in child
     // order. gat_off[2 s] = offset of the front's N + 1 pointers in gat_ptr (-1: walk the children instead),
     // gat_off[2 s + 1] = offset of its source list in gat_src.
     const int64_t *gat_off;
     const int32_t *gat_ptr, *gat_src;
-    unsigned long long *lvl_ns; // optional (MIPM_SOLVE_LOG): device time of gather, every forward level, every backward level
 };
 
 // ------------------------------------------------------------------ triangular solves
-// One persistent cooperative kernel: gather through perm, forward sweep level by level (children's
-// update vectors are summed by the parent in a fixed order), backward sweep from the root down,
-// scatter through perm. One CTA per front per level; the 64 x 64 diagonal blocks are applied
-// through their stored inverses (mat-vec), so nothing in a front is sequential.
+// One persistent launch that executes a task list: one task per front and sweep, forward tasks in elimination-tree
+// level order, then backward tasks from the root down. CTAs draw tasks in list order from a ticket counter; a forward
+// task waits until all children of its front have signalled (per-front counter), a backward task until its parent has
+// (per-front flag). No grid-wide barrier anywhere (the round-1 kernel had one per level and sweep), and a CTA that
+// waits first prefetches its front's panel into L2. A front reads its part of the right-hand side through perm and
+// writes its part of the solution through perm itself. The 64 x 64 diagonal blocks are applied through their stored
+// inverses (mat-vec), so nothing in a front is sequential; children's update vectors are summed by the parent in a
+// fixed order (deterministic).
 constexpr int XR_MAX = 1536;    // ancestor entries of x cached in shared memory by the backward sweep
 
-// L2 prefetch of a front's panel and inverted diagonal blocks. The solves are latency-bound: a front is a chain of
-// dependent global loads, and the factor (hundreds of MB) does not stay in L2. CTAs with no task at a level fetch the
-// next level's fronts when that level is small (near the root; prefetching a wide level only thrashes L2), so the
-// dependent loads hit L2 instead of HBM.
-constexpr int PREFETCH_MAX_FRONTS = 128;
+// L2 prefetch of a front's panel and inverted diagonal blocks. The solves are latency-bound near the root: a front is
+// a chain of dependent global loads, and the factor (hundreds of MB) does not stay in L2. A CTA whose front still waits
+// for its children (or its parent) fetches the panel first, so the dependent loads hit L2 instead of HBM.
 __device__ __forceinline__ void prefetch_front(const SolveParams &p, int s)
 {
     const FrontInfo f = p.fi[s];
@@ -84,6 +77,12 @@ __device__ void front_forward(const SolveParams &p, int s, double *smem, int mod
     double *u = p.uvec + f.rowp;
     const int tid = threadIdx.x;
     const int64_t go = p.gat_off[2 * (int64_t)s];
+    if (mode != 2) {            // this front owns x1 and u: right-hand side through perm, empty update vector
+        for (int t = tid; t < N; t += 256) {
+            if (t < k) x1[t] = p.b_in[p.perm[f.c0 + t]]; else u[t - k] = 0.0;
+        }
+        __syncthreads();
+    }
     if (go >= 0 && mode != 2) {
         const int32_t *gp = p.gat_ptr + go;
         const int32_t *gs = p.gat_src + p.gat_off[2 * (int64_t)s + 1];
@@ -221,7 +220,11 @@ __device__ void front_backward(const SolveParams &p, int s, double *smem)
             for (int rr = cc + q; rr < NB; rr += 4) acc = fma(S[cc * LDS + rr], wb[rr], acc);
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if (q == 0 && cc < nb) x1[jb + cc] = acc;
+            if (q == 0 && cc < nb) {
+                x1[jb + cc] = acc;
+                double *o = p.x_out + p.perm[f.c0 + jb + cc];
+                *o = p.accumulate ? *o + acc : acc;
+            }
         }
         __syncthreads();
     }
@@ -241,7 +244,7 @@ __device__ void leaf_forward(const SolveParams &p, int s)
     for (int j = 0; j < SL_K; ++j) {
         y[j] = 0.0;
         if (j < k) {
-            double t = x1[j];
+            double t = p.b_in[p.perm[f.c0 + j]];
 #pragma unroll
             for (int q = 0; q < j; ++q) t = fma(-P[(int64_t)q * ld + j], y[q], t);
             if (!LDL) t = t / P[(int64_t)j * ld + j];
@@ -291,74 +294,88 @@ __device__ void leaf_backward(const SolveParams &p, int s)
     }
     if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < SL_K; ++j) if (j < k) x1[j] = w[j];
+        for (int j = 0; j < SL_K; ++j)
+            if (j < k) {
+                x1[j] = w[j];
+                double *o = p.x_out + p.perm[f.c0 + j];
+                *o = p.accumulate ? *o + w[j] : w[j];
+            }
     }
 }
 
-template <bool LDL>
-__global__ void __launch_bounds__(256, 3) k_solve_persistent(SolveParams p)
+__device__ __forceinline__ int ld_acquire_s(const int *p)
 {
-    cg::grid_group grid = cg::this_grid();
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool LDL>
+__global__ void __launch_bounds__(256, 3) k_solve_tasks(SolveParams p)
+{
     __shared__ double smem[NB * LDS + NB + XR_MAX];
-    if (p.probe) { if (threadIdx.x == 0) p.probe[blockIdx.x] = read_smid(); return; }
-    const int vid = p.vmap ? p.vmap[blockIdx.x] : (int)blockIdx.x;
-    const int64_t gtid = (int64_t)blockIdx.x * 256 + threadIdx.x, gsz = (int64_t)gridDim.x * 256;
-    if (p.do_gather) {
-        for (int64_t i = gtid; i < p.n; i += gsz) p.xp[i] = p.b_in[p.perm[i]];
-        for (int64_t i = gtid; i < p.n_u; i += gsz) p.uvec[i] = 0.0;
-        grid.sync();
-    }
-    const bool timer = (p.lvl_ns != nullptr && blockIdx.x == 0 && threadIdx.x == 0);
-    unsigned long long tprev = 0;
-    int tslot = 0;
-    if (timer) tprev = globaltimer_ns();
-    const int32_t *leaves = p.sched + p.leaf_off;
-    const int n_leaf_groups = (p.n_leaf + 7) / 8;
-    for (int l = p.fwd_begin; l < p.fwd_end; ++l) {
-        const int32_t *fr = p.sched + p.lvl[2 * l];
-        const int nf = (int)p.lvl[2 * l + 1];
-        const int extra = (l == 0) ? n_leaf_groups : 0;      // small leaves ride along with level 0
-        if (p.prefetch && l + 1 < p.fwd_end && vid >= nf + extra && (int)p.lvl[2 * (l + 1) + 1] <= p.prefetch) {
-            const int32_t *nx = p.sched + p.lvl[2 * (l + 1)];
-            const int nnx = (int)p.lvl[2 * (l + 1) + 1], idle = (int)gridDim.x - (nf + extra);
-            for (int j = vid - (nf + extra); j < nnx; j += idle) prefetch_front(p, nx[j]);
-        }
-        for (int t = vid; t < nf + extra; t += gridDim.x) {
-            if (t < extra) {
-                const int li = t * 8 + (threadIdx.x >> 5);
-                if (li < p.n_leaf) leaf_forward<LDL>(p, leaves[li]);
-            } else {
-                front_forward<LDL>(p, fr[t - extra], smem, (l == p.n_levels - 1) ? p.root_mode : 0);
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_ticket = p.task_begin + atomicAdd(p.ticket, 1);
+    __syncthreads();
+    for (;;) {
+        const int t = s_ticket;
+        if (t >= p.task_end) break;
+        const int2 tk = p.tasks[t];
+        int next = 0;
+        if (tk.x == 0 || tk.x == 2) {
+            const int s = tk.y;
+            const FrontInfo f = p.fi[s];
+            const bool fwd = (tk.x == 0);
+            const int mode = (fwd && s == p.root_sn) ? p.root_mode : 0;
+            // a root's backward step follows its own forward step (another task): that one bumps fprog[s] once more
+            const bool may_wait = fwd ? (f.nchild > 0 && mode != 2) : true;
+            if (may_wait) prefetch_front(p, s);
+            if (tid == 0) {
+                if (may_wait) {
+                    if (fwd) { while (ld_acquire_s(p.fprog + s) < f.nchild) __nanosleep(40); }
+                    else if (f.parent >= 0) { while (ld_acquire_s(p.bdone + f.parent) == 0) __nanosleep(40); }
+                    else { while (ld_acquire_s(p.fprog + s) <= f.nchild) __nanosleep(40); }
+                }
+                next = p.task_begin + atomicAdd(p.ticket, 1);
             }
             __syncthreads();
-        }
-        grid.sync();
-        if (timer) { unsigned long long t1 = globaltimer_ns(); p.lvl_ns[tslot++] = t1 - tprev; tprev = t1; }
-    }
-    if (!p.do_backward) return;
-    for (int l = p.n_levels - 1; l >= 0; --l) {
-        const int32_t *fr = p.sched + p.lvl[2 * l];
-        const int nf = (int)p.lvl[2 * l + 1];
-        const int extra = (l == 0) ? n_leaf_groups : 0;
-        if (p.prefetch && l > 0 && vid >= nf + extra && (int)p.lvl[2 * (l - 1) + 1] <= p.prefetch) {
-            const int32_t *nx = p.sched + p.lvl[2 * (l - 1)];
-            const int nnx = (int)p.lvl[2 * (l - 1) + 1], idle = (int)gridDim.x - (nf + extra);
-            for (int j = vid - (nf + extra); j < nnx; j += idle) prefetch_front(p, nx[j]);
-        }
-        for (int t = vid; t < nf + extra; t += gridDim.x) {
-            if (t < extra) {
-                const int li = t * 8 + (threadIdx.x >> 5);
-                if (li < p.n_leaf) leaf_backward<LDL>(p, leaves[li]);
-            } else {
-                front_backward<LDL>(p, fr[t - extra], smem);
-            }
+            if (fwd) front_forward<LDL>(p, s, smem, mode);
+            else front_backward<LDL>(p, s, smem);
             __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                if (fwd) { if (mode != 1) atomicAdd(p.fprog + (f.parent >= 0 ? f.parent : s), 1); }
+                else atomicExch(p.bdone + s, 1);
+            }
+        } else {
+            if (tid == 0) next = p.task_begin + atomicAdd(p.ticket, 1);
+            const int li = tk.y + (tid >> 5);
+            if (li < p.n_leaf) {
+                const int s = p.leaves[li];
+                if (tk.x == 1) {
+                    leaf_forward<LDL>(p, s);
+                    __syncwarp();
+                    if ((tid & 31) == 0) {
+                        const int par = p.fi[s].parent;
+                        __threadfence();
+                        atomicAdd(p.fprog + (par >= 0 ? par : s), 1);
+                    }
+                } else {
+                    const int par = p.fi[s].parent;
+                    if ((tid & 31) == 0) {
+                        if (par >= 0) { while (ld_acquire_s(p.bdone + par) == 0) __nanosleep(40); }
+                        else { while (ld_acquire_s(p.fprog + s) == 0) __nanosleep(40); }
+                    }
+                    __syncwarp();
+                    leaf_backward<LDL>(p, s);
+                }
+            }
         }
-        grid.sync();
-        if (timer) { unsigned long long t1 = globaltimer_ns(); p.lvl_ns[tslot++] = t1 - tprev; tprev = t1; }
+        __syncthreads();
+        if (tid == 0) s_ticket = next;
+        __syncthreads();
     }
-    if (p.accumulate) { for (int64_t i = gtid; i < p.n; i += gsz) p.x_out[p.perm[i]] += p.xp[i]; }
-    else { for (int64_t i = gtid; i < p.n; i += gsz) p.x_out[p.perm[i]] = p.xp[i]; }
 }
 
 // r = b - K x with K symmetric, given by its full CSR index into the caller's lower-CSC values.
@@ -381,53 +398,8 @@ inline unsigned grid_for(int64_t n, int per_block) { return (unsigned)std::max<i
 
 }  // namespace
 
-// Placement probe: launch the persistent kernel in probe mode (same function, block size, shared memory and grid
-// as the real launches, so the block scheduler places it the same way), read back the SM of every block and number
-// the blocks so that ids [0, #SM) are the first resident CTA of each SM, [#SM, 2 #SM) the second, ...
-// The map is a permutation of the block indices whatever the probe returns, so it can only affect speed.
-static int build_cta_map(Handle *h)
-{
-    const int grid = h->grid_solve;
-    DBuf<int> &dmap = h->d_vmap_solve;
-    if (std::getenv("MIPM_NO_VMAP")) { dmap.release(); return MIPM_OK; }
-    DBuf<int> d_probe;
-    MIPM_CUDA(h, d_probe.alloc((size_t)grid));
-    MIPM_CUDA(h, cudaMemsetAsync(d_probe.p, 0xff, (size_t)grid * sizeof(int), h->stream));
-    const bool ldl = (h->sym.kind == MIPM_LDL);
-    SolveParams p;
-    std::memset(&p, 0, sizeof(p));
-    p.probe = d_probe.p;
-    void *args[] = {&p};
-    const void *fn = ldl ? (const void *)k_solve_persistent<true> : (const void *)k_solve_persistent<false>;
-    MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), args, 0, h->stream));
-    std::vector<int> smid((size_t)grid);
-    MIPM_CUDA(h, cudaMemcpyAsync(smid.data(), d_probe.p, (size_t)grid * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
-    // slot of each block on its SM (in block order), then sort by (slot, smid, block)
-    std::vector<int> slot((size_t)grid), order((size_t)grid), vmap((size_t)grid);
-    {
-        std::vector<std::pair<int, int>> seen;      // (smid, count), tiny
-        for (int b = 0; b < grid; ++b) {
-            int c = -1;
-            for (auto &e : seen) if (e.first == smid[(size_t)b]) { c = e.second++; break; }
-            if (c < 0) { seen.push_back({smid[(size_t)b], 1}); c = 0; }
-            slot[(size_t)b] = c;
-        }
-    }
-    for (int b = 0; b < grid; ++b) order[(size_t)b] = b;
-    std::sort(order.begin(), order.end(), [&](int a, int b) {
-        if (slot[(size_t)a] != slot[(size_t)b]) return slot[(size_t)a] < slot[(size_t)b];
-        if (smid[(size_t)a] != smid[(size_t)b]) return smid[(size_t)a] < smid[(size_t)b];
-        return a < b;
-    });
-    for (int v = 0; v < grid; ++v) vmap[(size_t)order[(size_t)v]] = v;
-    MIPM_CUDA(h, dmap.upload(vmap, h->stream));
-    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
-    return MIPM_OK;
-}
-
-// Solve-side part of ls_device_setup (factor.cu): grid size, transposed child maps, CTA placement map.
-int ls_solve_setup(Handle *h, const void *finfo_host)
+// Solve-side part of ls_device_setup (factor.cu): task list, grid size, transposed child maps.
+int ls_solve_setup(Handle *h, const void *finfo_host, const char *small)
 {
     const LsSymbolic &S = h->sym;
     const int ns = S.ns;
@@ -436,11 +408,32 @@ int ls_solve_setup(Handle *h, const void *finfo_host)
     DeviceInfo prop;
     if (device_info(h->device, prop) != MIPM_OK) return fail(h, MIPM_ERR_CUDA, "cudaGetDeviceProperties failed");
     int occ_s = 0;
-    if (S.kind == MIPM_LDL) MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_solve_persistent<true>, 256, 0));
-    else MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_solve_persistent<false>, 256, 0));
+    if (S.kind == MIPM_LDL) MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_solve_tasks<true>, 256, 0));
+    else MIPM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_solve_tasks<false>, 256, 0));
     if (occ_s < 1) return fail(h, MIPM_ERR_CUDA, "solve kernel does not fit on an SM");
     h->grid_solve = prop.sm_count * std::min(occ_s, 4);
     if (h->grid_limit > 0) h->grid_solve = std::min(h->grid_solve, h->grid_limit);
+    // ---- task list: forward by level (small leaves first, eight per task), then backward from the root down
+    std::vector<int2> tasks;
+    const int n_leaf = h->n_leaf;
+    for (int i = 0; i < n_leaf; i += 8) tasks.push_back(make_int2(1, i));
+    for (int l = 0; l < S.n_levels; ++l)
+        for (int64_t t = S.level_ptr[(size_t)l]; t < S.level_ptr[(size_t)l + 1]; ++t) {
+            const int s2 = S.level_sn[(size_t)t];
+            if (!small[(size_t)s2]) tasks.push_back(make_int2(0, s2));
+        }
+    h->n_solve_fwd = (int)tasks.size();
+    for (int l = S.n_levels - 1; l >= 0; --l)
+        for (int64_t t = S.level_ptr[(size_t)l]; t < S.level_ptr[(size_t)l + 1]; ++t) {
+            const int s2 = S.level_sn[(size_t)t];
+            if (!small[(size_t)s2]) tasks.push_back(make_int2(2, s2));
+        }
+    for (int i = 0; i < n_leaf; i += 8) tasks.push_back(make_int2(3, i));
+    h->n_solve_tasks = (int)tasks.size();
+    h->grid_solve = std::max(1, std::min(h->grid_solve, h->n_solve_tasks));
+    MIPM_CUDA(h, h->d_solve_tasks.alloc(std::max<size_t>(tasks.size(), 1)));
+    if (!tasks.empty()) MIPM_CUDA(h, cudaMemcpyAsync(h->d_solve_tasks.p, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    MIPM_CUDA(h, h->d_solve_prog.alloc((size_t)2 * std::max(ns, 1) + 4));
     {
         // transposed child maps for the forward solve (fronts with more than GATHER_MIN_CHILDREN children)
         constexpr int GATHER_MIN_CHILDREN = 4;
@@ -476,57 +469,38 @@ int ls_solve_setup(Handle *h, const void *finfo_host)
         MIPM_CUDA(h, h->d_gat_src.upload(gat_src, st));
     }
     MIPM_CUDA(h, cudaStreamSynchronize(st));
-    return build_cta_map(h);
+    return MIPM_OK;
 }
 
-// stage -1: whole solve; 0: gather + forward sweep below the root level; 1: root level forward, backward sweep, scatter
+// stage -1: whole solve; 0: forward sweep below the root, the root only folds its children's contributions in;
+// 1: the root's own forward step, backward sweep
 static int solve_once(Handle *h, const double *b_in, double *x_out, int accumulate, int stage = -1)
 {
     const LsSymbolic &S = h->sym;
+    const int ns = S.ns;
     SolveParams p;
     p.fi = (const FrontInfo *)h->d_finfo.p; p.child_idx = h->d_child_idx.p; p.rel_idx = h->d_rel_idx.p; p.row_idx = h->d_row_idx.p;
-    p.perm = h->d_perm.p; p.sched = h->d_sched.p; p.lvl = h->d_lvl.p; p.n_levels = S.n_levels;
-    p.leaf_off = h->leaf_off; p.n_leaf = h->n_leaf;
-    p.n = S.n; p.n_u = S.row_ptr[(size_t)S.ns];
+    p.perm = h->d_perm.p; p.leaves = h->d_sched.p + h->leaf_off; p.n_leaf = h->n_leaf;
+    p.tasks = (const int2 *)h->d_solve_tasks.p;
+    p.task_begin = (stage == 1) ? h->n_solve_fwd - 1 : 0;
+    p.task_end = (stage == 0) ? h->n_solve_fwd : h->n_solve_tasks;
+    p.root_sn = (stage >= 0) ? S.root_sn : -1;
+    p.root_mode = (stage == 0) ? 1 : ((stage == 1) ? 2 : 0);
+    p.fprog = h->d_solve_prog.p; p.bdone = h->d_solve_prog.p + ns; p.ticket = h->d_solve_prog.p + 2 * (size_t)ns;
     p.L = h->L_cur; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
     p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
-    p.vmap = h->d_vmap_solve.p; p.probe = nullptr;
     p.gat_off = h->d_gat_off.p; p.gat_ptr = h->d_gat_ptr.p; p.gat_src = h->d_gat_src.p;
-    static const bool solve_log = std::getenv("MIPM_SOLVE_LOG") != nullptr;
-    static const int prefetch_max = std::getenv("MIPM_NO_PREFETCH") ? 0
-                                    : (std::getenv("MIPM_PREFETCH_MAX") ? atoi(std::getenv("MIPM_PREFETCH_MAX")) : PREFETCH_MAX_FRONTS);
-    p.prefetch = prefetch_max;
-    DBuf<unsigned long long> d_lvl_ns;
-    p.lvl_ns = nullptr;
-    if (solve_log) {
-        MIPM_CUDA(h, d_lvl_ns.alloc((size_t)2 * S.n_levels + 2));
-        MIPM_CUDA(h, cudaMemsetAsync(d_lvl_ns.p, 0, ((size_t)2 * S.n_levels + 2) * sizeof(unsigned long long), h->stream));
-        p.lvl_ns = d_lvl_ns.p;
-    }
-    p.do_gather = (stage != 1);
-    p.fwd_begin = (stage == 1) ? S.n_levels - 1 : 0;
-    p.fwd_end = S.n_levels;
-    p.root_mode = (stage == 0) ? 1 : ((stage == 1) ? 2 : 0);
-    p.do_backward = (stage != 0);
+    if (stage == 1) { MIPM_CUDA(h, cudaMemsetAsync(h->d_solve_prog.p + 2 * (size_t)ns, 0, sizeof(int), h->stream)); }   // ticket only
+    else { MIPM_CUDA(h, cudaMemsetAsync(h->d_solve_prog.p, 0, ((size_t)2 * ns + 4) * sizeof(int), h->stream)); }
+    if (p.task_end <= p.task_begin) return MIPM_OK;
     void *args[] = {&p};
-    const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_solve_persistent<true> : (const void *)k_solve_persistent<false>;
+    const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_solve_tasks<true> : (const void *)k_solve_tasks<false>;
+    // cooperative launch: every CTA is resident, which the dependency spins rely on
     MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)h->grid_solve), dim3(256), args, 0, h->stream));
     h->launches++;
-    if (solve_log) {        // diagnostic only: synchronises
-        std::vector<unsigned long long> ns((size_t)2 * S.n_levels + 2);
-        MIPM_CUDA(h, cudaMemcpyAsync(ns.data(), d_lvl_ns.p, ns.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-        MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
-        std::fprintf(stderr, "solve levels (us): fwd");
-        int slot = 0;
-        for (int l = p.fwd_begin; l < p.fwd_end; ++l) std::fprintf(stderr, " %d:%lld[%lld]", l, (long long)(ns[(size_t)slot++] / 1000), (long long)S.level_ptr[(size_t)l + 1] - (long long)S.level_ptr[(size_t)l]);
-        if (p.do_backward) {
-            std::fprintf(stderr, " | bwd");
-            for (int l = S.n_levels - 1; l >= 0; --l) std::fprintf(stderr, " %d:%lld", l, (long long)(ns[(size_t)slot++] / 1000));
-        }
-        std::fprintf(stderr, "\n");
-    }
     return MIPM_OK;
 }
+
 int ls_solve_impl(Handle *h, double *d_x, int ir_steps)
 {
     const LsSymbolic &S = h->sym;
