@@ -35,6 +35,7 @@ struct SolveParams {
     // gat_off[2 s + 1] = offset of its source list in gat_src.
     const int64_t *gat_off;
     const int32_t *gat_ptr, *gat_src;
+    unsigned long long *trace;  // optional (MIPM_SOLVE_TRACE): 3 per task: wait start, start, end
 };
 
 // ------------------------------------------------------------------ triangular solves
@@ -323,6 +324,8 @@ __global__ void __launch_bounds__(256, 3) k_solve_tasks(SolveParams p)
         if (t >= p.task_end) break;
         const int2 tk = p.tasks[t];
         int next = 0;
+        unsigned long long tr0 = 0, tr1 = 0;
+        if (p.trace && tid == 0) tr0 = tr1 = globaltimer_ns();
         if (tk.x == 0 || tk.x == 2) {
             const int s = tk.y;
             const FrontInfo f = p.fi[s];
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_tasks(SolveParams p)
                     else if (f.parent >= 0) { while (ld_acquire_s(p.bdone + f.parent) == 0) __nanosleep(40); }
                     else { while (ld_acquire_s(p.fprog + s) <= f.nchild) __nanosleep(40); }
                 }
+                if (p.trace) tr1 = globaltimer_ns();
                 next = p.task_begin + atomicAdd(p.ticket, 1);
             }
             __syncthreads();
@@ -373,7 +377,10 @@ __global__ void __launch_bounds__(256, 3) k_solve_tasks(SolveParams p)
             }
         }
         __syncthreads();
-        if (tid == 0) s_ticket = next;
+        if (tid == 0) {
+            s_ticket = next;
+            if (p.trace) { p.trace[3 * (size_t)t] = tr0; p.trace[3 * (size_t)t + 1] = tr1; p.trace[3 * (size_t)t + 2] = globaltimer_ns(); }
+        }
         __syncthreads();
     }
 }
@@ -493,11 +500,41 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     if (stage == 1) { MIPM_CUDA(h, cudaMemsetAsync(h->d_solve_prog.p + 2 * (size_t)ns, 0, sizeof(int), h->stream)); }   // ticket only
     else { MIPM_CUDA(h, cudaMemsetAsync(h->d_solve_prog.p, 0, ((size_t)2 * ns + 4) * sizeof(int), h->stream)); }
     if (p.task_end <= p.task_begin) return MIPM_OK;
+    const char *trace_path = std::getenv("MIPM_SOLVE_TRACE");      // diagnostic only: synchronises
+    DBuf<unsigned long long> d_trace;
+    p.trace = nullptr;
+    if (trace_path) {
+        MIPM_CUDA(h, d_trace.alloc((size_t)3 * h->n_solve_tasks));
+        MIPM_CUDA(h, cudaMemsetAsync(d_trace.p, 0, (size_t)3 * h->n_solve_tasks * sizeof(unsigned long long), h->stream));
+        p.trace = d_trace.p;
+    }
     void *args[] = {&p};
     const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_solve_tasks<true> : (const void *)k_solve_tasks<false>;
     // cooperative launch: every CTA is resident, which the dependency spins rely on
     MIPM_CUDA(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)h->grid_solve), dim3(256), args, 0, h->stream));
     h->launches++;
+    if (trace_path) {
+        std::vector<unsigned long long> tr((size_t)3 * h->n_solve_tasks);
+        std::vector<int2> tk((size_t)h->n_solve_tasks);
+        MIPM_CUDA(h, cudaMemcpyAsync(tr.data(), d_trace.p, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        MIPM_CUDA(h, cudaMemcpyAsync(tk.data(), h->d_solve_tasks.p, tk.size() * sizeof(int2), cudaMemcpyDeviceToHost, h->stream));
+        MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+        unsigned long long t0 = ~0ull;
+        for (size_t i = 0; i < tk.size(); ++i) if (tr[3 * i]) t0 = std::min(t0, tr[3 * i]);
+        if (FILE *tf = std::fopen(trace_path, "w")) {
+            std::fprintf(tf, "task,kind,id,level,k,r,wait_us,start_us,end_us\n");
+            for (size_t i = 0; i < tk.size(); ++i) {
+                if (!tr[3 * i]) continue;
+                const bool front = (tk[i].x == 0 || tk[i].x == 2);
+                const int s2 = tk[i].y;
+                std::fprintf(tf, "%zu,%d,%d,%d,%d,%d,%.2f,%.2f,%.2f\n", i, tk[i].x, s2, front ? S.sn_level[(size_t)s2] : 0,
+                             front ? S.sn_ptr[(size_t)s2 + 1] - S.sn_ptr[(size_t)s2] : 0,
+                             front ? (int)(S.row_ptr[(size_t)s2 + 1] - S.row_ptr[(size_t)s2]) : 0,
+                             (double)(tr[3 * i] - t0) * 1e-3, (double)(tr[3 * i + 1] - t0) * 1e-3, (double)(tr[3 * i + 2] - t0) * 1e-3);
+            }
+            std::fclose(tf);
+        }
+    }
     return MIPM_OK;
 }
 

@@ -223,6 +223,17 @@ def mixed_bounds_lp(m, n, k, seed):
                           lvar=lvar, uvar=uvar, x0=np.zeros(n), name=f"mixed_lp_m{m}_n{n}_s{seed}")
 
 
+def badly_scaled_lp(m, n, k, seed):
+    """mixed_bounds_lp with a third of the rows (inequality rows among them) multiplied by 1e3: max |A_ij| > 100 on those rows,
+    so MadNLP's constraint scaling (con_scale_i = 100 / max_j |A_ij|) is active, on slack rows too."""
+    qp = mixed_bounds_lp(m, n, k, seed)
+    big = np.zeros(m, dtype=bool)
+    big[::3] = True
+    f = np.where(big, 1.0e3, 1.0)
+    return QuadraticModel(c=qp.c, Hrows=[], Hcols=[], Hvals=[], Arows=qp.Arows, Acols=qp.Acols, Avals=qp.Avals * f[qp.Arows],
+                          lcon=qp.lcon * f, ucon=qp.ucon * f, lvar=qp.lvar, uvar=qp.uvar, x0=qp.x0, name=f"badscale_lp_m{m}_n{n}_s{seed}")
+
+
 def bound_constrained_qp(n, seed):
     """Convex QP with bounds only (m = 0), like MadNLPTests.DenseDummyQP(x0; m=0) in test/runtests.jl:64."""
     rng = np.random.default_rng(seed)

@@ -111,6 +111,9 @@ class IPMOptions:
     n_border: int = 0
     exact_assembly_order: bool = False
     device: int = 0
+    # 0: C / Python conventions. 1: every index array crosses the C ABI exactly as the Julia glue passes it (1-based
+    # Int32 patterns, 1-based Int64 value maps and bound indices, `index_base = 1` in every call): ext/MadIPMB200Ext
+    index_base: int = 0
 
 
 @dataclass
@@ -140,10 +143,10 @@ class B200Solver:
     inertia / introduce), replacing MadNLPGPU.CUDSSSolver. Works on the lower-triangular CSC
     `aug_com` handed over by the KKT system."""
 
-    def __init__(self, handle, n, colptr, rowval, nzval, kind, ordering, ir_steps):
+    def __init__(self, handle, n, colptr, rowval, nzval, kind, ordering, ir_steps, index_base=0):
         self.h, self.nzval, self.ir_steps = handle, nzval, ir_steps
         self.kind = kind
-        handle.ls_analyze(n, colptr, rowval, kind=kind, ordering=ordering)
+        handle.ls_analyze(n, colptr, rowval, kind=kind, ordering=ordering, index_base=index_base)
         self.stats = handle.ls_stats()
 
     def factorize(self):
@@ -177,6 +180,8 @@ class MPCSolver:
         lvar, uvar, lcon, ucon = qp.lvar, qp.uvar, qp.lcon, qp.ucon
         if np.any(lvar == uvar):
             raise NotImplementedError("fixed variables (MadNLP.MakeParameter) are outside the hot-path scope")
+        if not qp.minimize:
+            raise NotImplementedError("maximization models (MadNLP obj_sign = -1) are outside the hot-path scope: negate c, H, c0")
         self.ind_ineq = np.flatnonzero(lcon != ucon)
         nx, ns = qp.nvar, len(self.ind_ineq)
         lfull = np.concatenate([lvar, lcon[self.ind_ineq]])
@@ -201,19 +206,21 @@ class MPCSolver:
         N = n + m + nlb + nub
         self.d, self.p, self._w1, self._w2 = z(N), z(N), z(N), z(N)
         self.correction_lb, self.correction_ub = z(nlb), z(nub)
-        self.d_ind_lb = _dev(self.ind_lb, dev, torch.int64)
-        self.d_ind_ub = _dev(self.ind_ub, dev, torch.int64)
+        ib = int(opt.index_base)
+        self.d_ind_lb = _dev(self.ind_lb + ib, dev, torch.int64)
+        self.d_ind_ub = _dev(self.ind_ub + ib, dev, torch.int64)
         # ---- Jacobian with slack columns (normalkkt.jl:70-79) in CSR through coo_to_csr
         I = np.concatenate([qp.Arows, self.ind_ineq]).astype(np.int32)
         J = np.concatenate([qp.Acols, nx + np.arange(ns)]).astype(np.int32)
         self.A_I, self.A_J = I, J
         self.A_V_host = np.concatenate([qp.Avals, -np.ones(ns)])
-        Ap, Aj, Amap = _lib.coo_to_csr(m, n, I, J)
-        self.Ap, self.Aj, self.A_csr_map = Ap, Aj, Amap
-        self.h.spmv_setup(m, n, Ap, Aj)
+        Ap, Aj, Amap = _lib.coo_to_csr(m, n, I + ib, J + ib, index_base=ib)      # in index_base like the inputs
+        self.h.spmv_setup(m, n, Ap, Aj, index_base=ib)
+        self._Ap_abi, self._Aj_abi = Ap, Aj
+        self.Ap, self.Aj, self.A_csr_map = Ap - ib, Aj - ib, Amap - ib            # 0-based copies for the host logic
         self.AT_x = z(len(Aj))                      # AT.nzVal: CSR-ordered values of A
         self.A_V = z(len(Aj))                       # A.V: COO-ordered values (jac + slack), like kkt.A.V
-        self.d_A_csr_map = _dev(Amap, dev, torch.int64)
+        self.d_A_csr_map = _dev(Amap, dev, torch.int64)                            # as returned (index_base)
         # ---- Hessian operator (MadIPMOperator symmetric=true, cuda_wrapper.jl:62-68)
         self.hH = None
         if qp.nnzh > 0:
@@ -222,10 +229,10 @@ class MPCSolver:
             fr = np.concatenate([hr, hc[off]]).astype(np.int32)
             fc = np.concatenate([hc, hr[off]]).astype(np.int32)
             fv = np.concatenate([hv, hv[off]])
-            Hp, Hj, Hmap = _lib.coo_to_csr(nx, nx, fr, fc)
+            Hp, Hj, Hmap = _lib.coo_to_csr(nx, nx, fr + ib, fc + ib, index_base=ib)
             self.hH = self.h
-            self.h.hess_setup(nx, Hp, Hj)
-            self.H_full_host = fv[Hmap]
+            self.h.hess_setup(nx, Hp, Hj, index_base=ib)
+            self.H_full_host = fv[Hmap - ib]
             self.Hx = z(len(Hj))
         self.cvec = z(n)
         self._stage_problem()
@@ -235,7 +242,7 @@ class MPCSolver:
         self.reg = z(n)
         if opt.kkt_system == "Normal":
             self.pr_diag, self.du_diag = z(n), z(m)
-            Cp, Cj = self.h.normal_symbolic(m, n, Ap, Aj)
+            Cp, Cj = self.h.normal_symbolic(m, n, self._Ap_abi, self._Aj_abi, index_base=ib)
             self.aug_colptr, self.aug_rowval = Cp, Cj
             if opt.linear_solver == "distributed":
                 from .distributed import DistributedB200Solver
@@ -243,16 +250,16 @@ class MPCSolver:
                     raise ValueError("linear_solver='distributed' needs n_border = number of linking rows (placed last)")
                 self._aug_nz_ext = z(len(Cj) + 1)                 # one trailing zero slot for the rank-local gather
                 self.aug_nz = self._aug_nz_ext[:len(Cj)]
-                self.linear_solver = DistributedB200Solver(m, Cp, Cj, self._aug_nz_ext, opt.n_border, opt.device, stream)
+                self.linear_solver = DistributedB200Solver(m, Cp - ib, Cj - ib, self._aug_nz_ext, opt.n_border, opt.device, stream)
             else:
                 self.aug_nz = z(len(Cj))
-                self.linear_solver = B200Solver(self.h, m, Cp, Cj, self.aug_nz, _lib.MIPM_CHOLESKY, opt.ordering, opt.ir_steps)
+                self.linear_solver = B200Solver(self.h, m, Cp, Cj, self.aug_nz, _lib.MIPM_CHOLESKY, opt.ordering, opt.ir_steps, ib)
         elif opt.kkt_system == "K2":
             # MadNLP.SparseKKTSystem: COO values [pr_diag; hess; jac(+slack); du_diag], lower triangular
             nnzh, nnzj = qp.nnzh, len(I)
             KI = np.concatenate([np.arange(n), qp.Hrows, n + I, n + np.arange(m)]).astype(np.int32)
             KJ = np.concatenate([np.arange(n), qp.Hcols, J, n + np.arange(m)]).astype(np.int32)
-            colptr, rowval, kmap = self.h.k2_symbolic(n + m, KI, KJ)
+            colptr, rowval, kmap = self.h.k2_symbolic(n + m, KI + ib, KJ + ib, index_base=ib)
             self.aug_colptr, self.aug_rowval, self.aug_csc_map = colptr, rowval, kmap
             self.aug_raw_V = z(n + nnzh + nnzj + m)
             self.pr_diag = self.aug_raw_V[:n]                       # views, like MadNLP's _madnlp_unsafe_wrap
@@ -260,12 +267,12 @@ class MPCSolver:
             self.jac = self.aug_raw_V[n + nnzh:n + nnzh + nnzj]
             self.du_diag = self.aug_raw_V[n + nnzh + nnzj:]
             self.aug_nz = z(len(rowval))
-            self.linear_solver = B200Solver(self.h, n + m, colptr, rowval, self.aug_nz, _lib.MIPM_LDL, opt.ordering, opt.ir_steps)
+            self.linear_solver = B200Solver(self.h, n + m, colptr, rowval, self.aug_nz, _lib.MIPM_LDL, opt.ordering, opt.ir_steps, ib)
         else:
             raise ValueError(opt.kkt_system)
         # ---- bind the device vectors once
         mv = MpcVectors()
-        mv.n, mv.m, mv.nlb, mv.nub, mv.index_base = n, m, nlb, nub, 0
+        mv.n, mv.m, mv.nlb, mv.nub, mv.index_base = n, m, nlb, nub, ib
         P = lambda t: t.data_ptr() if t.numel() > 0 else None
         mv.d_ind_lb, mv.d_ind_ub = P(self.d_ind_lb), P(self.d_ind_ub)
         for name, t in [("d_x", self.x), ("d_xl", self.xl), ("d_xu", self.xu), ("d_zl", self.zl), ("d_zu", self.zu),
@@ -337,7 +344,7 @@ class MPCSolver:
     def compress_jacobian(self):
         """normalkkt.jl:163-172 / cuda_wrapper.jl:32-41: AT.nzVal = A.V[A_csr_map] (+ slack = -1); A.V (the jac_coord!
         result, scaled by con_scale) was placed on the device by _madnlp_initialize."""
-        self.h.gather(len(self.Aj), self.A_V, self.d_A_csr_map, self.AT_x)     # AT.nzVal .= A.V[A_csr_map]
+        self.h.gather(len(self.Aj), self.A_V, self.d_A_csr_map, self.AT_x, index_base=self.opt.index_base)     # AT.nzVal .= A.V[A_csr_map] (slack entries are -1)
         self.h.spmv_cache_values(self.AT_x)       # the values stay fixed until the next compress_jacobian!
         if self.opt.kkt_system == "Normal":
             self.h.normal_set_jacobian(self.AT_x)
@@ -492,8 +499,18 @@ class MPCSolver:
                 nz = np.flatnonzero(np.diff(self.Ap) > 0)
                 rowmax[nz] = np.maximum.reduceat(absv, self.Ap[:-1][nz])
                 self.con_scale = np.minimum(1.0, 100.0 / np.maximum(rowmax, 1e-300))
+                # MadNLP.set_scaling! (MadNLP 0.8): rhs .*= con_scale; y0 ./= con_scale; slack(x), slack(xl), slack(xu)
+                # .*= con_scale[ind_ineq]; the Jacobian entries of the model are scaled by row, the slack entries stay
+                # -1 (compress_jacobian!, normalkkt.jl:163-172). Rare path (some |A_ij| > 100): host arithmetic.
                 self.rhs.copy_(torch.from_numpy(H["rhs"].numpy() * self.con_scale))
-                self.A_V.copy_(torch.from_numpy(self.A_V_host * self.con_scale[self.A_I]))
+                self.y.copy_(torch.from_numpy(H["y0"].numpy() / self.con_scale))
+                csv = np.concatenate([self.con_scale[self.A_I[:qp.nnzj]], np.ones(self.ns)])
+                self.A_V.copy_(torch.from_numpy(self.A_V_host * csv))
+                if self.ns:
+                    cs = torch.from_numpy(self.con_scale[self.ind_ineq]).to(self.device)
+                    self.x[nx:] *= cs
+                    self.xl[nx:] *= cs
+                    self.xu[nx:] *= cs
             # obj_scale = min(1, 100 / ||grad f(x0)||_inf) with grad f = c + H x0
             if qp.nnzh > 0:
                 h.copy(n, self.cvec, self.f)
@@ -817,12 +834,12 @@ class MPCSolver:
         x = self.x.cpu().numpy()
         # stats.constraints = A0 x (unscaled, without the slack columns): device SpMV, then undo both
         self.h.spmv(0, 1.0, self.AT_x, self.x, 0.0, self.buffer_m)
-        cons = self.buffer_m.cpu().numpy() / self.con_scale
+        cons = self.buffer_m.cpu().numpy()
         if self.ns:
-            cons[self.ind_ineq] += x[self.nx:]
-        sign = 1.0 if self.qp.minimize else -1.0
+            cons[self.ind_ineq] += x[self.nx:]         # the (scaled) slack columns are -1
+        cons = cons / self.con_scale
         return ExecutionStats(
-            status=self.status, iter=self.k, objective=sign * self.obj_val / self.obj_scale,
+            status=self.status, iter=self.k, objective=self.obj_val / self.obj_scale,
             dual_objective=getattr(self, "dobj", float("nan")) / self.obj_scale,
             solution=x[: self.nx].copy(), constraints=cons,
             multipliers=self.y.cpu().numpy() * self.con_scale / self.obj_scale,

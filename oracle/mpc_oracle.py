@@ -186,6 +186,7 @@ class MPCOracle:
         V = np.concatenate([qp.Avals, -np.ones(self.ns)])
         self.A_I, self.A_J, self.A_V = I, J, V
         self.A = sp.csr_matrix((V, (I, J)), shape=(m, n))
+        self.As = self.A                # scaled Jacobian (set_scaling!); identical while con_scale == 1
         Hl = sp.csr_matrix((qp.Hvals, (qp.Hrows, qp.Hcols)), shape=(nx, nx))
         self.Hfull = (Hl + sp.tril(Hl, -1).T).tocsr()
         self.cvec = np.concatenate([qp.c, np.zeros(self.ns)])
@@ -200,15 +201,21 @@ class MPCOracle:
         g[: self.nx] = self.obj_scale * (self.Hfull @ xv + self.qp.c)
         return g
 
+    def _scaled_jacobian(self):
+        """Jacobian with MadNLP's constraint scaling: the model entries of row i times con_scale[i]; the slack entries
+        stay -1 (normalkkt.jl:163-172 / MadNLP.set_scaling!: the slack VARIABLES are scaled instead)."""
+        cs = np.concatenate([self.con_scale[self.A_I[:len(self.qp.Avals)]], np.ones(self.ns)])
+        return self.A_V * cs
+
     def _eval_cons(self, x):
         """c(x) = A x - s - rhs with the slack columns inside self.A (App. A)."""
-        return self.con_scale * (self.A @ x) - self.rhs
+        return self.As @ x - self.rhs
 
     def _jtprod(self, y):
-        return self.A.T @ (self.con_scale * y)
+        return self.As.T @ y
 
     def _jprod(self, x):
-        return self.con_scale * (self.A @ x)
+        return self.As @ x
 
     # ---------------------------------------------------------------- KKT systems
     def _create_kkt_system(self):
@@ -252,7 +259,7 @@ class MPCOracle:
 
     def _compress_jacobian(self):
         """normalkkt.jl:163-172 (Normal); values scaled by con_scale like MadNLP's jac callback."""
-        V = self.A_V * self.con_scale[self.A_I]
+        V = self._scaled_jacobian()
         self.jac_V = V
         if self.opt.kkt_system == "Normal":
             self.AT_x = V[self.A_csr_map]
@@ -416,7 +423,15 @@ class MPCOracle:
         rowmax = np.zeros(self.m)
         np.maximum.at(rowmax, self.A_I, np.abs(self.A_V))
         self.con_scale = np.minimum(1.0, maxg / np.maximum(rowmax, 1e-300))
+        # MadNLP.set_scaling! (MadNLP 0.8, un-vendored): y0 ./= con_scale; rhs .*= con_scale; slack(x), slack(xl),
+        # slack(xu) .*= con_scale[ind_ineq] (the slack columns of the Jacobian stay -1)
+        self.y /= self.con_scale
         self.rhs *= self.con_scale
+        cs = self.con_scale[self.ind_ineq]
+        self.x[self.nx:] *= cs
+        self.xl[self.nx:] *= cs
+        self.xu[self.nx:] *= cs
+        self.As = sp.csr_matrix((self._scaled_jacobian(), (self.A_I, self.A_J)), shape=(self.m, self.n))
         self.obj_scale = 1.0
         g = np.linalg.norm(self._eval_grad(self.x), np.inf)
         self.obj_scale = min(1.0, maxg / g) if g > 0 else 1.0

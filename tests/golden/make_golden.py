@@ -16,7 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from madipm_jl_b200.problems import (bound_constrained_qp, mixed_bounds_lp, random_sparse_lp,  # noqa: E402
+from madipm_jl_b200.problems import (badly_scaled_lp, bound_constrained_qp, mixed_bounds_lp, random_sparse_lp,  # noqa: E402
                                      random_sparse_qp, simple_lp)
 from oracle.mpc_oracle import madipm  # noqa: E402
 
@@ -28,6 +28,8 @@ CASES = {
     # every bound / constraint kind: range, one-sided and equality rows (slacks), free / boxed / upper-only variables
     "mixed_lp_m30": lambda: mixed_bounds_lp(30, 90, 4, 1),
     "mixed_lp_m120": lambda: mixed_bounds_lp(120, 400, 5, 2),
+    # |A_ij| > 100 on a third of the rows, inequality rows included: MadNLP's con_scale path (scaled slacks, y0, rhs)
+    "badscale_lp_m30": lambda: badly_scaled_lp(30, 90, 4, 1),
     # bounds only, m = 0 (DenseDummyQP(x0; m=0) in test/runtests.jl:64)
     "boxqp_n20": lambda: bound_constrained_qp(20, 4),
 }

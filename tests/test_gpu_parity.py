@@ -391,6 +391,26 @@ def test_end_to_end_matches_golden_traces(built, key, fused):
     assert close(got.objective, g["objective"], tol)
 
 
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("key", ["lp_m300_window/Normal", "lp_m300_window/K2", "qp_m60_window/K2", "mixed_lp_m120/Normal",
+                                 "mixed_lp_m120/K2", "badscale_lp_m30/Normal", "boxqp_n20/K2"])
+def test_julia_calling_convention(built, key, fused):
+    """The C ABI driven the way ext/MadIPMB200Ext drives it from Julia: 1-based Int32 patterns into
+    mipm_coo_to_csr / mipm_normal_symbolic / mipm_k2_symbolic / mipm_ls_analyze / mipm_spmv_setup / mipm_hess_setup,
+    1-based Int64 value maps into mipm_gather, 1-based Int64 bound indices into mipm_mpc_bind, index_base = 1 in every
+    call, library-owned host arrays released with mipm_free, one handle per KKT system shared by its linear solver
+    (INTEGRATION.md). Iterates must be the oracle's."""
+    from madipm_jl_b200.solver import madipm
+    from tests.golden.make_golden import CASES
+    name, kkt = key.split("/")
+    qp = CASES[name]()
+    got = madipm(qp, kkt_system=kkt, fused=fused, index_base=1)
+    g = GOLD[key]
+    free = bool(np.any(~np.isfinite(qp.lvar) & ~np.isfinite(qp.uvar)))
+    tol = 5e-5 if (free and kkt == "Normal") else TOL
+    _check_trace(got, g["trace"], g["iter"], g["status"], tol=tol)
+
+
 def test_simple_lp_reference_pin_on_gpu(built):
     """test/test_gpu.jl:4-22 + runtests.jl:144-198: status only in the reference; we also pin objective 1.0."""
     from madipm_jl_b200.solver import madipm
@@ -515,13 +535,15 @@ def test_c3_full_size_matches_oracle_trace(built, fused):
 
 
 @pytest.mark.parametrize("solver", ["b200", "distributed"])
-def test_c4_scaled_matches_oracle_trace(built, solver):
-    """BASELINE configs[3] at the scale the oracle can finish (make_golden_full.py: c4_s15), through the single-GPU solver
-    and through the distributed (border-root, staged) solver on one rank."""
+@pytest.mark.parametrize("scale", [15, 25])
+def test_c4_scaled_matches_oracle_trace(built, solver, scale):
+    """BASELINE configs[3] at the scales the oracle can finish (make_golden_full.py: c4_s15 in 3 minutes, c4_s25 =
+    16 commodities on an 88 x 88 grid, m = 124 400, in 40 minutes), through the single-GPU solver and through the
+    distributed (border-root, staged) solver on one rank."""
     from madipm_jl_b200.problems import config_c4
     from madipm_jl_b200.solver import madipm
-    g = _full("c4_s15/Normal")
-    qp = config_c4(scale=0.15)
+    g = _full("c4_s%d/Normal" % scale)
+    qp = config_c4(scale=scale / 100.0)
     kw = dict(linear_solver="distributed", n_border=qp.meta["n_border"]) if solver == "distributed" else {}
     got = madipm(qp, kkt_system="Normal", **kw)
     _check_trace(got, g["trace"], g["iter"], g["status"])

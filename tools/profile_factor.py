@@ -59,6 +59,12 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     print("solve (events, avg of 5, incl. clone) ms", e0.elapsed_time(e1) / 5)
+    if out:
+        os.environ["MIPM_SOLVE_TRACE"] = out + "_solve_trace.csv"
+        x = b.clone()
+        h.ls_solve(x, 0)
+        torch.cuda.synchronize()
+        del os.environ["MIPM_SOLVE_TRACE"]
 
 
 if __name__ == "__main__":
