@@ -218,6 +218,11 @@ int mipm_get_affine_complementarity_measure(mipm_handle h, double alpha_p, doubl
  * reference's strict '<' reduction. get_fraction_to_boundary_step (kernels.jl:274-289) is
  * min(alpha[0],alpha[1]), min(alpha[2],alpha[3]). */
 int mipm_get_alpha_max(mipm_handle h, double tau, double *alpha, int64_t *idx);
+/* update_step!(::MehrotraAdaptiveStep), src/kernels.jl:309-358 (Mehrotra's GTSF heuristic), entirely on the device: the
+ * four ratio tests with tau = 1, the affine complementarity measure at (alpha_p^max, alpha_d^max) and the element reads
+ * at the blocking indices, which the reference does by scalar indexing into device arrays from the host.
+ * alpha[2] = (alpha_p, alpha_d). One synchronisation (none through mipm_mpc_iter_rest with step_rule = 2). */
+int mipm_mehrotra_adaptive_step(mipm_handle h, double gamma_f, double *alpha);
 /* dual_objective (kernels.jl:408-417), get_inf_pr / get_inf_du / get_optimality_gap
  * (solver.jl:196-204, kernels.jl:419-430) and ||primal(d)||_inf (structure.jl:193) in one
  * launch. out[5] = (dobj, ||c||_inf, ||f - zl + zu + jacl||_inf, max compl, ||dx||_inf). */
@@ -288,7 +293,8 @@ int mipm_dot(mipm_handle h, int64_t n, const double *d_x, const double *d_y, dou
  *                        where entries 5.. describe the PREVIOUS iteration's step. *status as mipm_ls_factorize.
  *   mipm_mpc_refactor  : the retry of factorize_regularized_system! with new (del_w, del_c).
  *   mipm_mpc_iter_rest : prediction_step! + mehrotra_correction_direction! + update_step_size!
- *                        (step_rule 0 = AdaptiveStep(tau_param), 1 = ConservativeStep(tau_param)) +
+ *                        (step_rule 0 = AdaptiveStep(tau_param), 1 = ConservativeStep(tau_param),
+ *                        2 = MehrotraAdaptiveStep(gamma_f = tau_param)) +
  *                        apply_step! + evaluate_model!; nothing is read back. */
 typedef struct {
     int kkt_kind;                 /* 0 Normal, 1 K2 */

@@ -68,7 +68,7 @@ SYMBOLS = [
     "mipm_get_affine_complementarity_measure", "mipm_get_alpha_max", "mipm_termination_measures",
     "mipm_apply_step", "mipm_reduce_rhs", "mipm_finish_aug_solve", "mipm_normal_solve_stage", "mipm_kktmul",
     "mipm_residual_norms", "mipm_init_point_stage", "mipm_init_bounds", "mipm_amax", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_gather", "mipm_scatter", "mipm_dot",
-    "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk",
+    "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk", "mipm_mehrotra_adaptive_step",
 ]
 
 _lib = None
@@ -308,6 +308,11 @@ class Handle:
         i = (C.c_int64 * 4)()
         self.check(self.lib.mipm_get_alpha_max(self.h, C.c_double(tau), a, i))
         return list(a), list(i)
+
+    def mehrotra_adaptive_step(self, gamma_f):
+        out = (C.c_double * 2)()
+        self.check(self.lib.mipm_mehrotra_adaptive_step(self.h, C.c_double(gamma_f), out))
+        return out[0], out[1]
 
     def termination_measures(self):
         out = (C.c_double * 5)()

@@ -260,8 +260,9 @@ __global__ void __launch_bounds__(TB) k_set_extra_correction(V v, double ap, dou
 
 // src/kernels.jl:155-208: out[0] = sum_l, out[1] = sum_u (affine == 0: current point)
 __global__ void __launch_bounds__(TB) k_compl_measure(V v, int affine, double ap, double ad, double *partials,
-                                                      unsigned int *counter, double *out)
+                                                      unsigned int *counter, double *out, const double *sc_in = nullptr)
 {
+    if (sc_in) { ap = sc_in[SC_ALPHA_P]; ad = sc_in[SC_ALPHA_D]; }     // step lengths left on the device by k_alpha_max
     const double *dx = v.d, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
     double acc[2] = {0.0, 0.0};
     GRID_STRIDE(i, v.n) {
@@ -355,6 +356,64 @@ __global__ void __launch_bounds__(TB) k_alpha_max(V v, double tau, double *parti
         sc_out[SC_ALPHA_D] = fmin(out[2], out[3]);
         sc_out[SC_TAU] = tau;
     }
+}
+
+// update_step!(::MehrotraAdaptiveStep), src/kernels.jl:309-358, after k_alpha_max(tau = 1) left the four ratio tests and
+// their arg-min positions in sc[SC_ALPHA..] and k_compl_measure(affine, alpha_max) left the two complementarity sums in
+// sc[SC_SUMS..]: the reference reads single elements of device arrays from the host (scalar indexing, "CUDA.@allowscalar"
+// in its comment); here one thread does it on the device and leaves (alpha_p, alpha_d) in the scalar block.
+__global__ void k_mehrotra_step(V v, const int64_t *ind_lb, const int64_t *ind_ub, int base, double gamma_f, double *sc)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double *dx = v.d, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
+    const double gamma_a = 1.0 / (1.0 - gamma_f);
+    const double axl = sc[SC_ALPHA + 0], axu = sc[SC_ALPHA + 1], azl = sc[SC_ALPHA + 2], azu = sc[SC_ALPHA + 3];
+    const int64_t ixl = (int64_t)sc[SC_ALPHA + 4], ixu = (int64_t)sc[SC_ALPHA + 5];
+    const int64_t izl = (int64_t)sc[SC_ALPHA + 6], izu = (int64_t)sc[SC_ALPHA + 7];
+    const double max_ap = fmin(axl, axu), max_ad = fmin(azl, azu);
+    const double cnt = (double)(v.nlb + v.nub);
+    double mu_full = (cnt > 0) ? (sc[SC_SUMS + 0] + sc[SC_SUMS + 1]) / cnt : 0.0;
+    mu_full /= gamma_a;
+    double ap = 1.0, ad = 1.0;
+    if (max_ap < 1.0) {
+        if (axl <= axu) {
+            const int64_t j = ixl - 1, i = ind_lb[j] - base;
+            const double tmp = mu_full / (v.zl[i] + max_ad * dzl[j]);
+            ap = (v.x[i] - v.xl[i] - tmp) / (-dx[i]);
+        } else {
+            const int64_t j = ixu - 1, i = ind_ub[j] - base;
+            const double tmp = mu_full / (v.zu[i] + max_ad * dzu[j]);
+            ap = (v.xu[i] - v.x[i] - tmp) / (dx[i]);
+        }
+    }
+    if (max_ad < 1.0) {
+        if (azl <= azu) {
+            const int64_t j = izl - 1, i = ind_lb[j] - base;
+            const double tmp = mu_full / (v.x[i] + max_ap * dx[i] - v.xl[i]);
+            ad = -(v.zl[i] - tmp) / dzl[j];
+        } else {
+            const int64_t j = izu - 1, i = ind_ub[j] - base;
+            const double tmp = mu_full / (v.xu[i] - v.x[i] - max_ap * dx[i]);
+            ad = -(v.zu[i] - tmp) / dzu[j];
+        }
+    }
+    sc[SC_ALPHA_P] = fmax(ap, gamma_f * max_ap);
+    sc[SC_ALPHA_D] = fmax(ad, gamma_f * max_ad);
+    sc[SC_TAU] = 1.0;
+}
+
+// The three launches of the rule; leaves alpha_p / alpha_d in sc (device).
+static int mehrotra_step_launch(Handle *h, const V &v, unsigned g, double gamma_f, double *sc)
+{
+    k_alpha_max<<<g, TB, 0, h->stream>>>(v, 1.0, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, nullptr, 0.0, sc);
+    MIPM_CHECK_LAUNCH(h);
+    if (v.nlb + v.nub > 0) {
+        k_compl_measure<<<g, TB, 0, h->stream>>>(v, 1, 0.0, 0.0, h->d_partials.p, h->d_counter.p, sc + SC_SUMS, sc);
+        MIPM_CHECK_LAUNCH(h);
+    }
+    k_mehrotra_step<<<1, 32, 0, h->stream>>>(v, h->v.d_ind_lb, h->v.d_ind_ub, h->v.index_base, gamma_f, sc);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
 }
 
 // src/solver.jl:194-205 + src/kernels.jl:408-430 + src/structure.jl:193
@@ -761,6 +820,24 @@ int mipm_get_alpha_max(mipm_handle hh, double tau, double *alpha, int64_t *idx)
     return MIPM_OK;
 }
 
+int mipm_mehrotra_adaptive_step(mipm_handle hh, double gamma_f, double *alpha)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!alpha || !(gamma_f > 0.0 && gamma_f < 1.0)) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (!h->d_sc.p) {
+        MIPM_CUDA(h, h->d_sc.alloc(SC_COUNT));
+        MIPM_CUDA(h, cudaMemsetAsync(h->d_sc.p, 0, SC_COUNT * sizeof(double), h->stream));
+    }
+    int rc = mehrotra_step_launch(h, v, red_grid(h, nmax), gamma_f, h->d_sc.p);
+    if (rc != MIPM_OK) return rc;
+    MIPM_CUDA(h, cudaMemcpyAsync(h->h_scal, h->d_sc.p + SC_ALPHA_P, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    alpha[0] = h->h_scal[0];
+    alpha[1] = h->h_scal[1];
+    return MIPM_OK;
+}
+
 int mipm_termination_measures(mipm_handle hh, double *out)
 {
     Handle *h = (Handle *)hh;
@@ -1100,7 +1177,7 @@ int mipm_mpc_iter_rest(mipm_handle hh, double mu_min, int step_rule, double tau_
     MIPM_NEED_DEVICE(h);
     int rc = fused_ready(h);
     if (rc != MIPM_OK) return rc;
-    if (step_rule != 0 && step_rule != 1) return fail(h, MIPM_ERR_ARG, "step_rule must be 0 (adaptive) or 1 (conservative)");
+    if (step_rule < 0 || step_rule > 2) return fail(h, MIPM_ERR_ARG, "step_rule must be 0 (adaptive), 1 (conservative) or 2 (Mehrotra adaptive)");
     MIPM_CUDA(h, cudaSetDevice(h->device));
     V v = make_view(h, inv_lb_buf(h).p, inv_ub_buf(h).p);
     const mipm_mpc_model &md = h->model;
@@ -1120,9 +1197,13 @@ int mipm_mpc_iter_rest(mipm_handle hh, double mu_min, int step_rule, double tau_
     MIPM_CHECK_LAUNCH(h);
     if ((rc = fused_solve_system(h, ir_steps, 1)) != MIPM_OK) return rc;
     // update_step_size! (kernels.jl:291-305)
-    if (step_rule == 0) k_alpha_max<<<g, TB, 0, h->stream>>>(v, 0.0, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, sc, tau_param, sc);
-    else k_alpha_max<<<g, TB, 0, h->stream>>>(v, tau_param, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, nullptr, 0.0, sc);
-    MIPM_CHECK_LAUNCH(h);
+    if (step_rule == 2) {
+        if ((rc = mehrotra_step_launch(h, v, g, tau_param, sc)) != MIPM_OK) return rc;      // tau_param carries gamma_f
+    } else {
+        if (step_rule == 0) k_alpha_max<<<g, TB, 0, h->stream>>>(v, 0.0, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, sc, tau_param, sc);
+        else k_alpha_max<<<g, TB, 0, h->stream>>>(v, tau_param, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, nullptr, 0.0, sc);
+        MIPM_CHECK_LAUNCH(h);
+    }
     // apply_step! (solver.jl:308-317)
     k_apply_step<<<g, TB, 0, h->stream>>>(v, 0.0, 0.0, 0.0, pow(DBL_EPSILON, 0.75), sc);
     MIPM_CHECK_LAUNCH(h);

@@ -671,42 +671,9 @@ class MPCSolver:
             raise TypeError(rule)
 
     def _mehrotra_adaptive_step(self, rule):
-        """src/kernels.jl:309-358; the reference's scalar indexing into device arrays becomes
-        four single-element device->host reads."""
-        n, m, nlb = self.n, self.m, self.nlb
-        gamma_a = 1.0 / (1.0 - rule.gamma_f)
-        a, idx = self.h.get_alpha_max(1.0)
-        axl, axu, azl, azu = a
-        i_xl, i_xu, i_zl, i_zu = idx
-        max_ap, max_ad = min(axl, axu), min(azl, azu)
-        mu_full = self.h.get_affine_complementarity_measure(max_ap, max_ad) / gamma_a
-        ap, ad = 1.0, 1.0
-        dx, dzl, dzu = self.d[:n], self.d[n + m:n + m + nlb], self.d[n + m + nlb:]
-        g = lambda t, i: float(t[i].item())
-        if max_ap < 1.0:
-            if axl <= axu:
-                j = i_xl - 1
-                i = int(self.ind_lb[j])
-                tmp = mu_full / (g(self.zl, i) + max_ad * g(dzl, j))
-                ap = (g(self.x, i) - g(self.xl, i) - tmp) / (-g(dx, i))
-            else:
-                j = i_xu - 1
-                i = int(self.ind_ub[j])
-                tmp = mu_full / (g(self.zu, i) + max_ad * g(dzu, j))
-                ap = (g(self.xu, i) - g(self.x, i) - tmp) / (g(dx, i))
-        if max_ad < 1.0:
-            if azl <= azu:
-                j = i_zl - 1
-                i = int(self.ind_lb[j])
-                tmp = mu_full / (g(self.x, i) + max_ap * g(dx, i) - g(self.xl, i))
-                ad = -(g(self.zl, i) - tmp) / g(dzl, j)
-            else:
-                j = i_zu - 1
-                i = int(self.ind_ub[j])
-                tmp = mu_full / (g(self.xu, i) - g(self.x, i) - max_ap * g(dx, i))
-                ad = -(g(self.zu, i) - tmp) / g(dzu, j)
-        self.alpha_p = max(ap, rule.gamma_f * max_ap)
-        self.alpha_d = max(ad, rule.gamma_f * max_ad)
+        """src/kernels.jl:309-358 on the device (mipm_mehrotra_adaptive_step): the reference's scalar indexing into device
+        arrays from the host is done by one device thread."""
+        self.alpha_p, self.alpha_d = self.h.mehrotra_adaptive_step(rule.gamma_f)
 
     def apply_step(self):
         """src/solver.jl:308-317."""
@@ -730,7 +697,7 @@ class MPCSolver:
     def _use_fused(self):
         return (self.opt.fused and self.opt.max_ncorr <= 0 and not self.opt.check_residual
                 and self.opt.linear_solver == "b200"
-                and isinstance(self.opt.step_rule, (AdaptiveStep, ConservativeStep)))
+                and isinstance(self.opt.step_rule, (AdaptiveStep, ConservativeStep, MehrotraAdaptiveStep)))
 
     def _mpc_iteration_fused(self):
         """The same loop body through mipm_mpc_iter_begin / mipm_mpc_iter_rest: one host sync."""
@@ -780,6 +747,8 @@ class MPCSolver:
         rule = opt.step_rule
         if isinstance(rule, AdaptiveStep):
             self.h.mpc_iter_rest(opt.mu_min, 0, rule.tau_min, self._fused_ir)
+        elif isinstance(rule, MehrotraAdaptiveStep):
+            self.h.mpc_iter_rest(opt.mu_min, 2, rule.gamma_f, self._fused_ir)
         else:
             self.h.mpc_iter_rest(opt.mu_min, 1, rule.tau, self._fused_ir)
         self.cnt["solves"] += 2

@@ -437,8 +437,9 @@ def test_options_parity(built, opts):
                                   "none": S.NoRegularization}[r[0]](*r[1:])
     for kkt in ("Normal", "K2"):
         ref = oracle_madipm(qp, kkt_system=kkt, **opts)
-        got = S.madipm(qp, kkt_system=kkt, **conv)
-        _check_trace(got, ref.trace, ref.iter, ref.status, tol=1e-7)
+        for fused in (True, False):     # MehrotraAdaptiveStep runs on the device in both sequencings (mipm_mehrotra_adaptive_step)
+            got = S.madipm(qp, kkt_system=kkt, fused=fused, **conv)
+            _check_trace(got, ref.trace, ref.iter, ref.status, tol=1e-7)
 
 
 def test_c1_full_size(built):
