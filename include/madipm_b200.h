@@ -201,6 +201,22 @@ int mipm_mpc_bind(mipm_handle h, const mipm_mpc_vectors *v);
 
 /* set_aug_diagonal_reg!, src/kernels.jl:124-136 (one fused launch instead of eight). */
 int mipm_set_aug_diagonal_reg(mipm_handle h, double del_w, double del_c);
+/* K2.5 = MadNLP.ScaledSparseKKTSystem (test/runtests.jl:107-120, test/test_gpu.jl:9): the K2 system scaled symmetrically by
+ * S = diag(sqrt((x - xl)(xu - x))) (absent bounds count as 1) so that its diagonal stays bounded as bounds become active.
+ *   mipm_set_aug_diagonal_reg_scaled  set_aug_diagonal_reg!(::ScaledSparseKKTSystem), src/kernels.jl:139-149 +
+ *                                     MadNLP._set_aug_diagonal!: l_diag = x - xl, u_diag = xu - x (sign flipped against K2),
+ *                                     pr_diag = zu (x - xl) + zl (xu - x) + reg S^2, d_scaling_factor = S (length n)
+ *   mipm_k25_scale_values             build_kkt!: hess_out = hess_raw * S_i S_j, jac_out = jac_raw * S_col (device index arrays)
+ *   mipm_reduce_rhs_scaled / mipm_finish_aug_solve_scaled   solve!: reduce_rhs! with the positive diagonals, primal block
+ *                                     times S before and after the linear solve, then the bound duals
+ *   mipm_kktmul_scaled                _kktmul! for the residual check on the unscaled unreduced system */
+int mipm_set_aug_diagonal_reg_scaled(mipm_handle h, double del_w, double del_c, double *d_scaling_factor);
+int mipm_k25_scale_values(mipm_handle h, int64_t nnzh, const int32_t *d_hess_i, const int32_t *d_hess_j,
+                          const double *d_hess_raw, double *d_hess_out, int64_t nnzj, const int32_t *d_jac_j,
+                          const double *d_jac_raw, double *d_jac_out, int index_base, const double *d_scaling_factor);
+int mipm_reduce_rhs_scaled(mipm_handle h, double *d_w, const double *d_scaling_factor);
+int mipm_finish_aug_solve_scaled(mipm_handle h, double *d_w, const double *d_scaling_factor);
+int mipm_kktmul_scaled(mipm_handle h, double *d_w, const double *d_v, double alpha, double beta);
 /* set_predictive_rhs! / set_correction_rhs!, src/kernels.jl:21-58. */
 int mipm_set_predictive_rhs(mipm_handle h);
 int mipm_set_correction_rhs(mipm_handle h, double mu);

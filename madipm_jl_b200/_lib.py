@@ -68,7 +68,8 @@ SYMBOLS = [
     "mipm_get_affine_complementarity_measure", "mipm_get_alpha_max", "mipm_termination_measures",
     "mipm_apply_step", "mipm_reduce_rhs", "mipm_finish_aug_solve", "mipm_normal_solve_stage", "mipm_kktmul",
     "mipm_residual_norms", "mipm_init_point_stage", "mipm_init_bounds", "mipm_amax", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_gather", "mipm_scatter", "mipm_dot",
-    "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk", "mipm_mehrotra_adaptive_step",
+    "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk", "mipm_mehrotra_adaptive_step", "mipm_set_aug_diagonal_reg_scaled", "mipm_k25_scale_values",
+    "mipm_reduce_rhs_scaled", "mipm_finish_aug_solve_scaled", "mipm_kktmul_scaled",
 ]
 
 _lib = None
@@ -279,6 +280,22 @@ class Handle:
 
     def set_aug_diagonal_reg(self, del_w, del_c):
         self.check(self.lib.mipm_set_aug_diagonal_reg(self.h, C.c_double(del_w), C.c_double(del_c)))
+
+    def set_aug_diagonal_reg_scaled(self, del_w, del_c, sf):
+        self.check(self.lib.mipm_set_aug_diagonal_reg_scaled(self.h, C.c_double(del_w), C.c_double(del_c), _ptr(sf)))
+
+    def k25_scale_values(self, hi, hj, hraw, hout, jj, jraw, jout, sf, index_base=0):
+        self.check(self.lib.mipm_k25_scale_values(self.h, C.c_int64(hraw.numel()), _ptr(hi), _ptr(hj), _ptr(hraw), _ptr(hout),
+                                                  C.c_int64(jraw.numel()), _ptr(jj), _ptr(jraw), _ptr(jout), C.c_int(index_base), _ptr(sf)))
+
+    def reduce_rhs_scaled(self, w, sf):
+        self.check(self.lib.mipm_reduce_rhs_scaled(self.h, _ptr(w), _ptr(sf)))
+
+    def finish_aug_solve_scaled(self, w, sf):
+        self.check(self.lib.mipm_finish_aug_solve_scaled(self.h, _ptr(w), _ptr(sf)))
+
+    def kktmul_scaled(self, w, v, alpha, beta):
+        self.check(self.lib.mipm_kktmul_scaled(self.h, _ptr(w), _ptr(v), C.c_double(alpha), C.c_double(beta)))
 
     def set_predictive_rhs(self):
         self.check(self.lib.mipm_set_predictive_rhs(self.h))

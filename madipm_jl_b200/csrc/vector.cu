@@ -417,6 +417,79 @@ static int mehrotra_step_launch(Handle *h, const V &v, unsigned g, double gamma_
 }
 
 // src/solver.jl:194-205 + src/kernels.jl:408-430 + src/structure.jl:193
+// K2.5 (MadNLP.ScaledSparseKKTSystem): src/kernels.jl:139-149 + MadNLP._set_aug_diagonal! (un-vendored, restated from the
+// symmetric scaling K2.5 = S K2 S with S = diag(sqrt((x - xl)(xu - x))), absent factors = 1): l_diag = x - xl and
+// u_diag = xu - x are POSITIVE here (sign flipped against K2), pr_diag = zu (x - xl) + zl (xu - x) + reg S^2.
+__global__ void __launch_bounds__(TB) k_set_aug_diag_scaled(V v, double del_w, double del_c, double *sf)
+{
+    GRID_STRIDE(i, v.n) {
+        v.reg[i] = del_w;
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        double xlzu = 0.0, xuzl = 0.0, s = 1.0;
+        double ld = 1.0, ud = 1.0;
+        if (jl >= 0) { ld = v.x[i] - v.xl[i]; v.l_diag[jl] = ld; v.l_lower[jl] = v.zl[i]; xuzl = v.zl[i]; s *= sqrt(ld); }
+        if (ju >= 0) { ud = v.xu[i] - v.x[i]; v.u_diag[ju] = ud; v.u_lower[ju] = v.zu[i]; xlzu = v.zu[i]; s *= sqrt(ud); }
+        if (jl >= 0) xlzu *= ld;        // (X - Xl) zu   (zero without an upper bound)
+        if (ju >= 0) xuzl *= ud;        // (Xu - X) zl   (zero without a lower bound)
+        sf[i] = s;
+        v.pr_diag[i] = (xlzu + xuzl) + del_w * (s * s);
+    }
+    GRID_STRIDE(i, v.m) v.du_diag[i] = del_c;
+}
+
+// K2.5 build_kkt!: Hessian entries times S_i S_j, Jacobian entries (slack columns included) times S_col.
+__global__ void __launch_bounds__(TB) k_k25_scale(int64_t nnzh, const int32_t *hi, const int32_t *hj, const double *hraw, double *hout,
+                                                  int64_t nnzj, const int32_t *jj, const double *jraw, double *jout, int base,
+                                                  const double *sf)
+{
+    GRID_STRIDE(q, nnzh) hout[q] = hraw[q] * sf[hi[q] - base] * sf[hj[q] - base];
+    GRID_STRIDE(q, nnzj) jout[q] = jraw[q] * sf[jj[q] - base];
+}
+
+// K2.5 reduce_rhs! (positive diagonals) followed by the scaling of the primal block; finish: unscale, then the bound duals.
+__global__ void __launch_bounds__(TB) k_reduce_rhs_scaled(V v, double *w, const double *sf)
+{
+    double *wx = w, *wzl = w + v.n + v.m, *wzu = w + v.n + v.m + v.nlb;
+    GRID_STRIDE(i, v.n) {
+        double t = wx[i];
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) t = t + wzl[jl] / v.l_diag[jl];
+        if (ju >= 0) t = t + wzu[ju] / v.u_diag[ju];
+        wx[i] = t * sf[i];
+    }
+}
+__global__ void __launch_bounds__(TB) k_finish_aug_scaled(V v, double *w, const double *sf)
+{
+    double *wx = w, *wzl = w + v.n + v.m, *wzu = w + v.n + v.m + v.nlb;
+    GRID_STRIDE(i, v.n) {
+        const double t = wx[i] * sf[i];
+        wx[i] = t;
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) wzl[jl] = (wzl[jl] - v.l_lower[jl] * t) / v.l_diag[jl];
+        if (ju >= 0) wzu[ju] = (-wzu[ju] + v.u_lower[ju] * t) / v.u_diag[ju];
+    }
+}
+// _kktmul! on the UNSCALED unreduced system with the positive K2.5 diagonals (l_diag = -(xl - x), u_diag = -(x - xu)).
+__global__ void __launch_bounds__(TB) k_kktmul_scaled(V v, double *w, const double *vv, double alpha, double beta)
+{
+    double *wx = w, *wy = w + v.n, *wzl = w + v.n + v.m, *wzu = w + v.n + v.m + v.nlb;
+    const double *vx = vv, *vy = vv + v.n, *vzl = vv + v.n + v.m, *vzu = vv + v.n + v.m + v.nlb;
+    GRID_STRIDE(i, v.n) {
+        double t = wx[i] + alpha * v.reg[i] * vx[i];
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) {
+            t = t - alpha * vzl[jl];
+            wzl[jl] = beta * wzl[jl] + alpha * (vx[i] * v.l_lower[jl] + vzl[jl] * v.l_diag[jl]);
+        }
+        if (ju >= 0) {
+            t = t + alpha * vzu[ju];
+            wzu[ju] = beta * wzu[ju] + alpha * (vx[i] * v.u_lower[ju] - vzu[ju] * v.u_diag[ju]);
+        }
+        wx[i] = t;
+    }
+    GRID_STRIDE(i, v.m) wy[i] = wy[i] + alpha * v.du_diag[i] * vy[i];
+}
+
 // out = (-y.rhs, zl_r.xl_r, zu_r.xu_r, ||c||inf, ||f-zl+zu+jacl||inf, max compl, ||dx||inf)
 __global__ void __launch_bounds__(TB) k_termination(V v, double *partials, unsigned int *counter, double *out)
 {
@@ -742,6 +815,62 @@ int mipm_set_aug_diagonal_reg(mipm_handle hh, double del_w, double del_c)
     Handle *h = (Handle *)hh;
     VIEW_OR_FAIL(h);
     k_set_aug_diag<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, del_w, del_c);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_set_aug_diagonal_reg_scaled(mipm_handle hh, double del_w, double del_c, double *d_scaling_factor)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!d_scaling_factor && v.n > 0) return fail(h, MIPM_ERR_ARG, "null argument");
+    k_set_aug_diag_scaled<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, del_w, del_c, d_scaling_factor);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_k25_scale_values(mipm_handle hh, int64_t nnzh, const int32_t *d_hess_i, const int32_t *d_hess_j, const double *d_hess_raw,
+                          double *d_hess_out, int64_t nnzj, const int32_t *d_jac_j, const double *d_jac_raw, double *d_jac_out,
+                          int index_base, const double *d_scaling_factor)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (nnzh < 0 || nnzj < 0 || (nnzh > 0 && (!d_hess_i || !d_hess_j || !d_hess_raw || !d_hess_out)) ||
+        (nnzj > 0 && (!d_jac_j || !d_jac_raw || !d_jac_out)) || !d_scaling_factor)
+        return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (nnzh + nnzj == 0) return MIPM_OK;
+    k_k25_scale<<<red_grid(h, std::max(nnzh, nnzj)), TB, 0, h->stream>>>(nnzh, d_hess_i, d_hess_j, d_hess_raw, d_hess_out, nnzj, d_jac_j,
+                                                                        d_jac_raw, d_jac_out, index_base, d_scaling_factor);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_reduce_rhs_scaled(mipm_handle hh, double *d_w, const double *d_scaling_factor)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!d_w || !d_scaling_factor) return fail(h, MIPM_ERR_ARG, "null argument");
+    k_reduce_rhs_scaled<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, d_w, d_scaling_factor);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_finish_aug_solve_scaled(mipm_handle hh, double *d_w, const double *d_scaling_factor)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!d_w || !d_scaling_factor) return fail(h, MIPM_ERR_ARG, "null argument");
+    k_finish_aug_scaled<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, d_w, d_scaling_factor);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_kktmul_scaled(mipm_handle hh, double *d_w, const double *d_v, double alpha, double beta)
+{
+    Handle *h = (Handle *)hh;
+    VIEW_OR_FAIL(h);
+    if (!d_w || !d_v) return fail(h, MIPM_ERR_ARG, "null argument");
+    k_kktmul_scaled<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, d_w, d_v, alpha, beta);
     MIPM_CHECK_LAUNCH(h);
     return MIPM_OK;
 }

@@ -73,8 +73,8 @@ class AdaptiveRegularization:
 
 @dataclass
 class IPMOptions:
-    """src/utils.jl:69-105. kkt_system: "K2" (MadNLP.SparseKKTSystem, the default) or "Normal"
-    (MadIPM.NormalKKTSystem). linear-solver options of the B200 solver: ordering, ir_steps."""
+    """src/utils.jl:69-105. kkt_system: "K2" (MadNLP.SparseKKTSystem, the default), "K2.5" (MadNLP.ScaledSparseKKTSystem)
+    or "Normal" (MadIPM.NormalKKTSystem). linear-solver options of the B200 solver: ordering, ir_steps."""
     tol: float = 1e-8
     kkt_system: str = "K2"
     max_iter: int = 3000
@@ -254,8 +254,9 @@ class MPCSolver:
             else:
                 self.aug_nz = z(len(Cj))
                 self.linear_solver = B200Solver(self.h, m, Cp, Cj, self.aug_nz, _lib.MIPM_CHOLESKY, opt.ordering, opt.ir_steps, ib)
-        elif opt.kkt_system == "K2":
-            # MadNLP.SparseKKTSystem: COO values [pr_diag; hess; jac(+slack); du_diag], lower triangular
+        elif opt.kkt_system in ("K2", "K2.5"):
+            # MadNLP.SparseKKTSystem (K2.5: ScaledSparseKKTSystem, same pattern): COO values [pr_diag; hess; jac(+slack);
+            # du_diag], lower triangular
             nnzh, nnzj = qp.nnzh, len(I)
             KI = np.concatenate([np.arange(n), qp.Hrows, n + I, n + np.arange(m)]).astype(np.int32)
             KJ = np.concatenate([np.arange(n), qp.Hcols, J, n + np.arange(m)]).astype(np.int32)
@@ -268,6 +269,12 @@ class MPCSolver:
             self.du_diag = self.aug_raw_V[n + nnzh + nnzj:]
             self.aug_nz = z(len(rowval))
             self.linear_solver = B200Solver(self.h, n + m, colptr, rowval, self.aug_nz, _lib.MIPM_LDL, opt.ordering, opt.ir_steps, ib)
+            if opt.kkt_system == "K2.5":
+                # unscaled values + their index arrays on the device: build_kkt! scales them by S into the COO buffer
+                self.scaling_factor = z(n)
+                self.hess_raw, self.jac_raw = z(nnzh), z(nnzj)
+                self.d_H_I, self.d_H_J = _dev(qp.Hrows + ib, dev, torch.int32), _dev(qp.Hcols + ib, dev, torch.int32)
+                self.d_J_J = _dev(J + ib, dev, torch.int32)
         else:
             raise ValueError(opt.kkt_system)
         # ---- bind the device vectors once
@@ -285,12 +292,12 @@ class MPCSolver:
         self._mv = mv
         self.h.mpc_bind(mv)
         md = MpcModel()
-        md.kkt_kind = 0 if opt.kkt_system == "Normal" else 1
+        md.kkt_kind = 0 if opt.kkt_system == "Normal" else 1        # (K2.5 runs the fine-grained sequence only)
         md.exact_order = int(opt.exact_assembly_order)
         md.nx, md.c0 = nx, 0.0
         md.d_ATx, md.d_cvec, md.d_aug_nz = P(self.AT_x), P(self.cvec), P(self.aug_nz)
         md.d_Hx = P(self.Hx) if qp.nnzh > 0 else None
-        md.d_aug_raw_V = P(self.aug_raw_V) if opt.kkt_system == "K2" else None
+        md.d_aug_raw_V = P(self.aug_raw_V) if opt.kkt_system in ("K2", "K2.5") else None
         md.d_buffer_n, md.d_buffer_m = P(self.buffer_n), P(self.buffer_m)
         self._md = md
         self.h.mpc_set_model(md)
@@ -348,6 +355,8 @@ class MPCSolver:
         self.h.spmv_cache_values(self.AT_x)       # the values stay fixed until the next compress_jacobian!
         if self.opt.kkt_system == "Normal":
             self.h.normal_set_jacobian(self.AT_x)
+        elif self.opt.kkt_system == "K2.5":
+            self.h.copy(len(self.Aj), self.A_V, self.jac_raw)
         else:
             self.h.copy(len(self.Aj), self.A_V, self.jac)
 
@@ -355,14 +364,18 @@ class MPCSolver:
         """hess_coord! values times obj_scale (the raw values were uploaded by _madnlp_initialize)."""
         if self.qp.nnzh > 0 and self.obj_scale != 1.0:
             self.h.axpby(self.Hx.numel(), self.obj_scale, self.Hx, 0.0, self.Hx)
-            if self.opt.kkt_system == "K2":
-                self.h.axpby(self.hess.numel(), self.obj_scale, self.hess, 0.0, self.hess)
+            if self.opt.kkt_system in ("K2", "K2.5"):
+                hv = self.hess if self.opt.kkt_system == "K2" else self.hess_raw
+                self.h.axpby(hv.numel(), self.obj_scale, hv, 0.0, hv)
 
     def build_kkt(self):
         """build_kkt!: normalkkt.jl:180-194 (Normal) / MadNLP.transfer! (K2)."""
         if self.opt.kkt_system == "Normal":
             self.h.normal_assemble(self.pr_diag, self.aug_nz, self.opt.exact_assembly_order)
         else:
+            if self.opt.kkt_system == "K2.5":       # S W S and J S into the COO buffer, then the same transfer
+                self.h.k25_scale_values(self.d_H_I, self.d_H_J, self.hess_raw, self.hess, self.d_J_J, self.jac_raw, self.jac,
+                                        self.scaling_factor, index_base=self.opt.index_base)
             self.h.k2_transfer(self.aug_raw_V, self.aug_nz)
 
     def factorize_wrapper(self):
@@ -381,6 +394,10 @@ class MPCSolver:
             h.normal_solve_stage(1, w, self.buffer_n, self.buffer_m)
             h.spmv(1, -1.0, self.AT_x, self.buffer_m, 1.0, self.buffer_n)     # r1 - A' dy
             h.normal_solve_stage(2, w, self.buffer_n, self.buffer_m)
+        elif self.opt.kkt_system == "K2.5":
+            h.reduce_rhs_scaled(w, self.scaling_factor)
+            self.linear_solver.solve(w)
+            h.finish_aug_solve_scaled(w, self.scaling_factor)
         else:
             h.reduce_rhs(w)
             self.linear_solver.solve(w)       # primal_dual(w) = first n+m entries, in place
@@ -393,10 +410,13 @@ class MPCSolver:
         n, m = self.n, self.m
         h = self.h
         h.spmv(1, alpha, self.AT_x, v[n:n + m], beta, w[:n])
-        if self.hH is not None and self.opt.kkt_system == "K2":
+        if self.hH is not None and self.opt.kkt_system in ("K2", "K2.5"):
             self.hH.hess_spmv(alpha, self.Hx, v[:self.nx], 1.0, w[:self.nx])
         h.spmv(0, alpha, self.AT_x, v[:n], beta, w[n:n + m])
-        h.kktmul(w, v, alpha, beta)
+        if self.opt.kkt_system == "K2.5":
+            h.kktmul_scaled(w, v, alpha, beta)
+        else:
+            h.kktmul(w, v, alpha, beta)
         return w
 
     # ------------------------------------------------------------------ src/linear_solver.jl
@@ -430,7 +450,10 @@ class MPCSolver:
         """src/linear_solver.jl:6-17."""
         t0 = time.perf_counter()
         for _ in range(3):
-            self.h.set_aug_diagonal_reg(self.del_w, self.del_c)
+            if self.opt.kkt_system == "K2.5":
+                self.h.set_aug_diagonal_reg_scaled(self.del_w, self.del_c, self.scaling_factor)
+            else:
+                self.h.set_aug_diagonal_reg(self.del_w, self.del_c)
             self.factorize_wrapper()
             if self.linear_solver.is_factorized():
                 break
@@ -487,6 +510,8 @@ class MPCSolver:
             up_(self.Hx, H["H_full"])
             if opt.kkt_system == "K2":
                 up_(self.hess, H["H_tril"])
+            elif opt.kkt_system == "K2.5":
+                up_(self.hess_raw, H["H_tril"])
         h.init_bounds(n, opt.bound_relax_factor, opt.bound_push, opt.bound_fac, self.x, self.xl, self.xu)
         self.con_scale = np.ones(m)
         self.obj_scale = 1.0
@@ -534,6 +559,8 @@ class MPCSolver:
         h.fill(self.n, 1.0, self.reg), h.fill(self.n, 1.0, self.pr_diag), h.fill(self.m, 0.0, self.du_diag)
         h.fill(self.nlb, 0.0, self.l_lower), h.fill(self.nub, 0.0, self.u_lower)
         h.fill(self.nlb, 1.0, self.l_diag), h.fill(self.nub, 1.0, self.u_diag)
+        if opt.kkt_system == "K2.5":
+            h.fill(self.n, 1.0, self.scaling_factor)
         self.init_regularization()
         self.compress_hessian()
         self.compress_jacobian()
@@ -696,7 +723,7 @@ class MPCSolver:
 
     def _use_fused(self):
         return (self.opt.fused and self.opt.max_ncorr <= 0 and not self.opt.check_residual
-                and self.opt.linear_solver == "b200"
+                and self.opt.linear_solver == "b200" and self.opt.kkt_system != "K2.5"
                 and isinstance(self.opt.step_rule, (AdaptiveStep, ConservativeStep, MehrotraAdaptiveStep)))
 
     def _mpc_iteration_fused(self):

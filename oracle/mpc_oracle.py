@@ -173,6 +173,7 @@ class MPCOracle:
         self._reg_state = list(self.opt.regularization)
         if self.opt.linear_solver == "auto":
             self.opt.linear_solver = "ldl" if self.opt.kkt_system == "Normal" else "splu"
+        self.scaling_factor = np.ones(n)
         self._build_model()
         self._create_kkt_system()
 
@@ -235,8 +236,8 @@ class MPCOracle:
                 self.C_p, self.C_j = sparse_ref.build_normal_system(m, n, Ap, Aj)
             self.C_x = np.zeros(len(self.C_j))
             self.ls = _LinearSolver(m, self.C_p, self.C_j, self.opt.linear_solver, self.opt.ordering)
-        elif self.opt.kkt_system == "K2":
-            # MadNLP.SparseKKTSystem (App. B): COO [pr_diag; hess; jac; slack; du_diag], lower triangular
+        elif self.opt.kkt_system in ("K2", "K2.5"):
+            # MadNLP.SparseKKTSystem / ScaledSparseKKTSystem (App. B): same pattern, K2.5 = S K2 S: COO [pr_diag; hess; jac; slack; du_diag], lower triangular
             qp = self.qp
             I = np.concatenate([np.arange(n), qp.Hrows, n + self.A_I, n + np.arange(m)]).astype(np.int64)
             J = np.concatenate([np.arange(n), qp.Hcols, self.A_J, n + np.arange(m)]).astype(np.int64)
@@ -273,7 +274,12 @@ class MPCOracle:
                                                          self.C_p, self.C_j, D)
         else:
             hess = self.obj_scale * self.qp.Hvals
-            V = np.concatenate([self.pr_diag, hess, self.jac_V, self.du_diag])
+            jac = self.jac_V
+            if self.opt.kkt_system == "K2.5":       # ScaledSparseKKTSystem: S W S, J S
+                sf = self.scaling_factor
+                hess = hess * sf[self.qp.Hrows] * sf[self.qp.Hcols]
+                jac = jac * sf[self.A_J]
+            V = np.concatenate([self.pr_diag, hess, jac, self.du_diag])
             self.aug_nz = sparse_ref.transfer(len(self.aug_rowval), V, self.aug_map)
         self.timers["assembly"] += time.perf_counter() - t0
 
@@ -296,6 +302,19 @@ class MPCOracle:
         """solve!(kkt, w): reduce_rhs! -> reduced solve -> finish_aug_solve!.
         Normal: normalkkt.jl:196-219; K2: MadNLP (App. B)."""
         wx, wy, wzl, wzu = self._split(w)
+        if self.opt.kkt_system == "K2.5":
+            # solve!(::ScaledSparseKKTSystem): l_diag = x - xl, u_diag = xu - x are positive; the primal block is scaled by S
+            sf = self.scaling_factor
+            np.add.at(wx, self.ind_lb, wzl / self.l_diag)
+            np.add.at(wx, self.ind_ub, wzu / self.u_diag)
+            t0 = time.perf_counter()
+            sol = self.ls.solve(np.concatenate([wx * sf, wy]))
+            self.timers["solve"] += time.perf_counter() - t0
+            wx[:] = sol[: self.n] * sf
+            wy[:] = sol[self.n:]
+            wzl[:] = (wzl - self.l_lower * wx[self.ind_lb]) / self.l_diag
+            wzu[:] = (-wzu + self.u_lower * wx[self.ind_ub]) / self.u_diag
+            return w
         # reduce_rhs!
         np.subtract.at(wx, self.ind_lb, wzl / self.l_diag)
         np.subtract.at(wx, self.ind_ub, wzu / self.u_diag)
@@ -324,7 +343,7 @@ class MPCOracle:
         wx, wy, wzl, wzu = self._split(w)
         vx, vy, vzl, vzu = self._split(v)
         Hx = 0.0
-        if self.opt.kkt_system == "K2" and self.qp.nnzh > 0:
+        if self.opt.kkt_system in ("K2", "K2.5") and self.qp.nnzh > 0:
             Hx = np.zeros(self.n)
             Hx[: self.nx] = self.obj_scale * (self.Hfull @ vx[: self.nx])
         wx[:] = alpha * (self._jtprod(vy) + Hx) + beta * wx
@@ -333,8 +352,9 @@ class MPCOracle:
         wy += alpha * self.du_diag * vy
         np.subtract.at(wx, self.ind_lb, alpha * vzl)
         np.add.at(wx, self.ind_ub, alpha * vzu)
-        wzl[:] = beta * wzl + alpha * (vx[self.ind_lb] * self.l_lower - vzl * self.l_diag)
-        wzu[:] = beta * wzu + alpha * (vx[self.ind_ub] * self.u_lower + vzu * self.u_diag)
+        sgn = -1.0 if self.opt.kkt_system == "K2.5" else 1.0       # K2.5 keeps l_diag, u_diag with the opposite sign
+        wzl[:] = beta * wzl + alpha * (vx[self.ind_lb] * self.l_lower - sgn * vzl * self.l_diag)
+        wzu[:] = beta * wzu + alpha * (vx[self.ind_ub] * self.u_lower + sgn * vzu * self.u_diag)
         return w
 
     def _solve_system(self):
@@ -371,9 +391,26 @@ class MPCOracle:
             raise ValueError(r[0])
 
     def _set_aug_diagonal_reg(self):
-        """src/kernels.jl:124-136."""
+        """src/kernels.jl:124-136; ScaledSparseKKTSystem (K2.5): src/kernels.jl:139-149 + MadNLP._set_aug_diagonal!."""
         self.reg[:] = self.del_w
         self.du_diag[:] = self.del_c
+        if self.opt.kkt_system == "K2.5":
+            self.l_diag[:] = self.x[self.ind_lb] - self.xl[self.ind_lb]      # (X - Xl), positive
+            self.u_diag[:] = self.xu[self.ind_ub] - self.x[self.ind_ub]      # (Xu - X), positive
+            self.l_lower[:] = self.zl[self.ind_lb]
+            self.u_lower[:] = self.zu[self.ind_ub]
+            xlzu, xuzl = np.zeros(self.n), np.zeros(self.n)
+            xlzu[self.ind_ub] = self.u_lower
+            xlzu[self.ind_lb] *= self.l_diag
+            xuzl[self.ind_lb] = self.l_lower
+            xuzl[self.ind_ub] *= self.u_diag
+            self.pr_diag[:] = xlzu + xuzl
+            sf = np.ones(self.n)
+            sf[self.ind_lb] *= np.sqrt(self.l_diag)
+            sf[self.ind_ub] *= np.sqrt(self.u_diag)
+            self.scaling_factor = sf
+            self.pr_diag += self.reg * sf ** 2
+            return
         self.l_diag[:] = self.xl[self.ind_lb] - self.x[self.ind_lb]
         self.u_diag[:] = self.x[self.ind_ub] - self.xu[self.ind_ub]
         self.l_lower[:] = self.zl[self.ind_lb]
@@ -445,6 +482,7 @@ class MPCOracle:
         self.u_lower[:] = 0.0
         self.l_diag[:] = 1.0
         self.u_diag[:] = 1.0
+        self.scaling_factor = np.ones(self.n)
 
     def initialize(self):
         """src/solver.jl:127-189."""

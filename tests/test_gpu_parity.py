@@ -411,10 +411,26 @@ def test_julia_calling_convention(built, key, fused):
     _check_trace(got, g["trace"], g["iter"], g["status"], tol=tol)
 
 
+@pytest.mark.parametrize("index_base", [0, 1])
+@pytest.mark.parametrize("name", ["simple_lp", "qp_m60_window", "mixed_lp_m120", "lp_m40_ub", "boxqp_n20"])
+def test_k25_scaled_kkt_system(built, name, index_base):
+    """K2.5 = MadNLP.ScaledSparseKKTSystem (test/runtests.jl:107-120, test/test_gpu.jl:9): the fused diagonal
+    fill with the sign-flipped l_diag / u_diag (src/kernels.jl:139-149), the scaled assembly and the scaled solve must
+    reproduce the oracle's K2.5 iterates at 1e-8 and the K2 results at 1e-6 like the reference's own test."""
+    from madipm_jl_b200.solver import madipm
+    from tests.golden.make_golden import CASES
+    qp = CASES[name]()
+    ref = oracle_madipm(qp, kkt_system="K2.5")
+    got = madipm(qp, kkt_system="K2.5", index_base=index_base)
+    _check_trace(got, ref.trace, ref.iter, ref.status)
+    k2 = GOLD[name + "/K2"]
+    assert got.status == k2["status"] and got.iter == k2["iter"] and abs(got.objective - k2["objective"]) <= 1e-6
+
+
 def test_simple_lp_reference_pin_on_gpu(built):
     """test/test_gpu.jl:4-22 + runtests.jl:144-198: status only in the reference; we also pin objective 1.0."""
     from madipm_jl_b200.solver import madipm
-    for kkt in ("K2", "Normal"):
+    for kkt in ("K2", "K2.5", "Normal"):
         s = madipm(simple_lp(), kkt_system=kkt)
         assert s.status == "SOLVE_SUCCEEDED" and abs(s.objective - 1.0) < 1e-8
         assert np.allclose(s.solution, [0.5, 0.5], atol=1e-6) and np.allclose(s.multipliers, [-1.0], atol=1e-6)

@@ -168,3 +168,18 @@ def test_ldl_with_permutation():
         assert L.factorize(low.data) and L.inertia() == (n, 0, 0)
         b = rng.standard_normal(n)
         assert np.abs(M @ L.solve(b) - b).max() < 1e-12
+
+
+@pytest.mark.parametrize("make", [simple_lp, lambda: random_sparse_qp(60, 200, 4, 9, structure="window", window=10),
+                                  lambda: random_sparse_lp(40, 160, 5, 7, structure="uniform", ub_fraction=0.5)])
+def test_k25_scaled_kkt_system_matches_k2(make):
+    """test/runtests.jl:107-120: MadNLP.ScaledSparseKKTSystem (K2.5) must reproduce the K2 results (status, iterations,
+    objective, solution, constraints, multipliers at 1e-6); simple_lp is the reference's own fixture."""
+    qp = make()
+    ref = madipm(qp, kkt_system="K2")
+    k25 = madipm(qp, kkt_system="K2.5")
+    assert k25.status == ref.status == "SOLVE_SUCCEEDED"
+    assert k25.iter == ref.iter
+    assert abs(k25.objective - ref.objective) <= 1e-6
+    for f in ("solution", "constraints", "multipliers"):
+        assert np.abs(getattr(k25, f) - getattr(ref, f)).max() <= 1e-6
