@@ -329,6 +329,30 @@ int mipm_mpc_iter_begin(mipm_handle h, double del_w, double del_c, double *out, 
 int mipm_mpc_refactor(mipm_handle h, double del_w, double del_c, int *status);
 int mipm_mpc_iter_rest(mipm_handle h, double mu_min, int step_rule, double tau_param, int ir_steps);
 
+/* ------------------------------------------------------------------ batches ---------- */
+/* BASELINE config C5 (a batch of independent LPs / QPs; the reference solves them one after the other). The B units
+ * are STACKED into one block-diagonal problem -- x, bounds, multipliers and KKT vectors of unit u occupy
+ * [off_n[u], off_n[u+1]) of the variable blocks and [off_m[u], off_m[u+1]) of the row blocks, A and H are block
+ * diagonal -- and bound / analysed exactly like a single problem (mipm_mpc_bind, mipm_spmv_setup,
+ * mipm_normal_symbolic, mipm_ls_analyze: the elimination forest has one tree per unit). Element-wise kernels, SpMVs,
+ * assembly, factorization and solves then run ONCE per IPM phase for all units; the entry points below do what is
+ * per unit (reductions, step lengths, centering, barrier value, termination) with one CTA per unit:
+ *   mipm_batch_configure           unit offsets (host arrays of B + 1), after mipm_mpc_bind
+ *   mipm_batch_set_active          active[B] (host): a unit with active = 0 keeps its iterate (it has terminated)
+ *   mipm_batch_amax / _dot         per-unit norms / dot products of stacked vectors (scaling, objective), out[B]
+ *   mipm_batch_init_point_stage    mipm_init_point_stage per unit: a[B], b[B] in, out[B x 5]
+ *   mipm_batch_iter_begin / _rest  mipm_mpc_iter_begin / mipm_mpc_iter_rest for the batch: out[B x 16]; the status
+ *                                  is that of the stacked factorization (mipm_mpc_refactor retries for all units);
+ *                                  no residual check (entries 11-14 are 0). */
+int mipm_batch_configure(mipm_handle h, int64_t n_units, const int64_t *off_n, const int64_t *off_m);
+int mipm_batch_set_active(mipm_handle h, const int32_t *active);
+int mipm_batch_amax(mipm_handle h, int by_rows, const double *d_x, double *out);
+int mipm_batch_dot(mipm_handle h, const double *d_x, const double *d_y, double *out);
+int mipm_batch_init_point_stage(mipm_handle h, int stage, const double *a, const double *b, double kappa,
+                                double *out);
+int mipm_batch_iter_begin(mipm_handle h, double del_w, double del_c, double *out, int *status);
+int mipm_batch_iter_rest(mipm_handle h, double mu_min, int step_rule, double tau_param, int ir_steps);
+
 /* ------------------------------------------------------------------ diagnostics ---- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t mipm_launch_count(mipm_handle h);

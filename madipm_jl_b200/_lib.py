@@ -70,6 +70,8 @@ SYMBOLS = [
     "mipm_residual_norms", "mipm_init_point_stage", "mipm_init_bounds", "mipm_amax", "mipm_axpby", "mipm_fill", "mipm_copy", "mipm_gather", "mipm_scatter", "mipm_dot",
     "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk", "mipm_mehrotra_adaptive_step", "mipm_set_aug_diagonal_reg_scaled", "mipm_k25_scale_values",
     "mipm_reduce_rhs_scaled", "mipm_finish_aug_solve_scaled", "mipm_kktmul_scaled",
+    "mipm_batch_configure", "mipm_batch_set_active", "mipm_batch_amax", "mipm_batch_dot", "mipm_batch_init_point_stage",
+    "mipm_batch_iter_begin", "mipm_batch_iter_rest",
 ]
 
 _lib = None
@@ -274,6 +276,43 @@ class Handle:
 
     def mpc_iter_rest(self, mu_min, step_rule, tau_param, ir_steps):
         self.check(self.lib.mipm_mpc_iter_rest(self.h, C.c_double(mu_min), C.c_int(step_rule), C.c_double(tau_param), C.c_int(ir_steps)))
+
+    # ---- batches of stacked independent units (BASELINE config C5)
+    def batch_configure(self, off_n, off_m):
+        off_n = np.ascontiguousarray(off_n, dtype=np.int64)
+        off_m = np.ascontiguousarray(off_m, dtype=np.int64)
+        self._nb = len(off_n) - 1
+        self.check(self.lib.mipm_batch_configure(self.h, C.c_int64(self._nb), _ptr(off_n), _ptr(off_m)))
+
+    def batch_set_active(self, active):
+        a = np.ascontiguousarray(active, dtype=np.int32)
+        self.check(self.lib.mipm_batch_set_active(self.h, _ptr(a)))
+
+    def batch_amax(self, by_rows, x):
+        out = np.zeros(self._nb)
+        self.check(self.lib.mipm_batch_amax(self.h, C.c_int(int(by_rows)), _ptr(x), _ptr(out)))
+        return out
+
+    def batch_dot(self, x, y):
+        out = np.zeros(self._nb)
+        self.check(self.lib.mipm_batch_dot(self.h, _ptr(x), _ptr(y), _ptr(out)))
+        return out
+
+    def batch_init_point_stage(self, stage, a=None, b=None, kappa=0.0):
+        out = np.zeros((self._nb, 5))
+        a = None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        b = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        self.check(self.lib.mipm_batch_init_point_stage(self.h, C.c_int(stage), _ptr(a), _ptr(b), C.c_double(kappa), _ptr(out)))
+        return out
+
+    def batch_iter_begin(self, del_w, del_c):
+        out = np.zeros((self._nb, 16))
+        st = C.c_int()
+        self.check(self.lib.mipm_batch_iter_begin(self.h, C.c_double(del_w), C.c_double(del_c), _ptr(out), C.byref(st)))
+        return out, st.value == MIPM_OK
+
+    def batch_iter_rest(self, mu_min, step_rule, tau_param, ir_steps):
+        self.check(self.lib.mipm_batch_iter_rest(self.h, C.c_double(mu_min), C.c_int(step_rule), C.c_double(tau_param), C.c_int(ir_steps)))
 
     def mpc_bind(self, vec: MpcVectors):
         self.check(self.lib.mipm_mpc_bind(self.h, C.byref(vec)))

@@ -103,3 +103,240 @@ def solve_batch(make_model, n_units, solve_fn=None, threads=1, grid_limit=0, **k
     dist.all_gather_object(gathered, mine)
     flat = sorted((d for part in gathered for d in part), key=lambda d: d["index"])
     return [UnitResult(**d) for d in flat]
+
+
+# ------------------------------------------------------------------ stacked batch: one set of launches per IPM phase
+def stack_models(models):
+    """B independent QuadraticModels as ONE block-diagonal model (variables, rows, A and H of unit u shifted by the
+    offsets off_n[u], off_m[u]); returns (stacked model, off_n, off_m)."""
+    import numpy as np
+    from .problems import QuadraticModel
+    off_n = np.concatenate([[0], np.cumsum([q.nvar for q in models])]).astype(np.int64)
+    off_m = np.concatenate([[0], np.cumsum([q.ncon for q in models])]).astype(np.int64)
+    cat = lambda f: np.concatenate([f(q) for q in models]) if models else np.zeros(0)
+    st = QuadraticModel(
+        c=cat(lambda q: q.c),
+        Hrows=np.concatenate([q.Hrows.astype(np.int64) + off_n[u] for u, q in enumerate(models)]),
+        Hcols=np.concatenate([q.Hcols.astype(np.int64) + off_n[u] for u, q in enumerate(models)]),
+        Hvals=cat(lambda q: q.Hvals),
+        Arows=np.concatenate([q.Arows.astype(np.int64) + off_m[u] for u, q in enumerate(models)]),
+        Acols=np.concatenate([q.Acols.astype(np.int64) + off_n[u] for u, q in enumerate(models)]),
+        Avals=cat(lambda q: q.Avals),
+        lcon=cat(lambda q: q.lcon), ucon=cat(lambda q: q.ucon), lvar=cat(lambda q: q.lvar), uvar=cat(lambda q: q.uvar),
+        c0=0.0, x0=cat(lambda q: q.x0), y0=cat(lambda q: q.y0), name="stack_of_%d" % len(models))
+    return st, off_n, off_m
+
+
+class BatchedMPCSolver:
+    """BASELINE config C5 as the reference would need it on a GPU: B independent LPs / QPs advance in lock-step through ONE
+    set of kernel launches per IPM phase (the reference's mpc! loop, src/solver.jl:332-360, runs one problem at a time).
+    The units are stacked into a block-diagonal problem for everything that is element-wise or linear algebra (assembly,
+    the task-graph factorization of the elimination FOREST, solves, SpMVs); step lengths, centering parameter, barrier
+    value, scaling and termination stay per unit (mipm_batch_*: one CTA per unit). Every unit's iterates are those of
+    solving it alone (tests compare each unit with its own oracle trace). Default options only (AdaptiveStep /
+    ConservativeStep, no Gondzio corrections), all-equality rows (no slack columns), no residual check."""
+
+    def __init__(self, models, **kwargs):
+        import numpy as np
+        from . import solver as S
+        self.models = list(models)
+        self.B = len(self.models)
+        if self.B < 1:
+            raise ValueError("empty batch")
+        if any(np.any(q.lcon != q.ucon) for q in self.models):
+            raise NotImplementedError("batched path: all-equality rows only (no slack columns)")
+        stacked, self.off_n, self.off_m = stack_models(self.models)
+        kwargs = dict(kwargs)
+        kwargs["fused"] = True
+        self.s = S.MPCSolver(stacked, **kwargs)
+        if not isinstance(self.s.opt.step_rule, (S.AdaptiveStep, S.ConservativeStep)) or self.s.opt.max_ncorr > 0:
+            raise NotImplementedError("batched path: AdaptiveStep / ConservativeStep without Gondzio corrections")
+        if self.s.opt.kkt_system not in ("Normal", "K2"):
+            raise NotImplementedError("batched path: NormalKKTSystem or K2")
+        self.s.h.batch_configure(self.off_n, self.off_m)
+        self._seg = lambda a, off, u: a[off[u]:off[u + 1]]
+
+    # ---- MadNLP.initialize! + set_scaling! with per-unit objective scaling
+    def _initialize(self):
+        import numpy as np
+        import torch
+        from . import solver as S
+        s, h, opt = self.s, self.s.h, self.s.opt
+        B, off_n = self.B, self.off_n
+        H = s._host
+        up_ = lambda t, a: t.copy_(a, non_blocking=True)
+        up_(s.x, H["x0"]), up_(s.xl, H["xl"]), up_(s.xu, H["xu"]), up_(s.rhs, H["rhs"]), up_(s.cvec, H["c"])
+        up_(s.y, H["y0"]), up_(s.A_V, H["A_V"])
+        qp = s.qp
+        if qp.nnzh > 0:
+            up_(s.Hx, H["H_full"])
+            if opt.kkt_system == "K2":
+                up_(s.hess, H["H_tril"])
+        h.init_bounds(s.n, opt.bound_relax_factor, opt.bound_push, opt.bound_fac, s.x, s.xl, s.xu)
+        s.con_scale = np.ones(s.m)
+        self.obj_scale = np.ones(B)
+        if opt.scaling:
+            if s._amax_A > 100.0:
+                raise NotImplementedError("batched path: |A_ij| <= 100 (identity constraint scaling)")
+            if qp.nnzh > 0:
+                h.copy(s.n, s.cvec, s.f)
+                h.hess_spmv(1.0, s.Hx, s.x, 1.0, s.f)
+                gn = h.batch_amax(0, s.f)
+            else:
+                gn = h.batch_amax(0, s.cvec)
+            with np.errstate(divide="ignore"):
+                self.obj_scale = np.where(gn > 0, np.minimum(1.0, 100.0 / gn), 1.0)
+        if np.any(self.obj_scale != 1.0):
+            scale_n = torch.from_numpy(np.repeat(self.obj_scale, np.diff(off_n))).to(s.device)
+            s.cvec.mul_(scale_n)                      # rare path: per-unit objective scaling on the stacked vector
+            if qp.nnzh > 0:
+                raise NotImplementedError("batched path: QP units need ||grad f(x0)|| <= 100 (identity objective scaling)")
+        s.zl.zero_(), s.zu.zero_()
+        self.norm_b = h.batch_amax(1, s.rhs) if s.m else np.zeros(B)
+        h.fill(s.n, 0.0, s.jacl)
+        h.fill(s.n, 1.0, s.reg), h.fill(s.n, 1.0, s.pr_diag), h.fill(s.m, 0.0, s.du_diag)
+        h.fill(s.nlb, 0.0, s.l_lower), h.fill(s.nub, 0.0, s.u_lower)
+        h.fill(s.nlb, 1.0, s.l_diag), h.fill(s.nub, 1.0, s.u_diag)
+        s.init_regularization()
+        s.compress_hessian()
+        s.compress_jacobian()
+        # objective, gradient and constraints at the pushed x0, per unit, BEFORE init_starting_point! moves x: the
+        # reference does not re-evaluate them afterwards (SURVEY quirk A.9: stale values in iteration 0)
+        self.obj_val = self.obj_scale * np.array([q.c0 for q in self.models]) + h.batch_dot(s.cvec, s.x)
+        if qp.nnzh > 0:
+            s.hH.hess_spmv(1.0, s.Hx, s.x, 0.0, s.buffer_n)
+            self.obj_val = self.obj_val + 0.5 * h.batch_dot(s.buffer_n, s.x)
+        s._eval_grad()
+        s._eval_cons()
+        self.norm_c = h.batch_amax(0, s.f)          # ||grad f(x0)||_inf per unit (quirk A.9 x)
+        self._init_starting_point()
+        s.jtprod(s.jacl, s.y)
+
+    def _init_starting_point(self):
+        """src/solver.jl:6-125 with the scalar stages per unit (mipm_batch_init_point_stage)."""
+        import numpy as np
+        s, h = self.s, self.s.h
+        n, m = s.n, s.m
+        N = s.p.numel()
+        h.fill(n, s.del_w, s.reg), h.fill(n, s.del_w, s.pr_diag), h.fill(m, s.del_c, s.du_diag)
+        s.factorize_wrapper()
+        if not s.linear_solver.is_factorized():
+            from .solver import SolveException
+            raise SolveException("initial factorization failed")
+        h.fill(N, 0.0, s.p)
+        h.axpby(m, -1.0, s.c, 0.0, s.p[n:n + m])
+        h.copy(N, s.p, s.d)
+        s.kkt_solve(s.d)
+        h.axpby(n, 1.0, s.d[:n], 1.0, s.x)
+        h.fill(N, 0.0, s.p)
+        h.axpby(n, -1.0, s.f, 0.0, s.p[:n])
+        h.copy(N, s.p, s.d)
+        s.kkt_solve(s.d)
+        h.copy(m, s.d[n:n + m], s.y)
+        s.jtprod(s.jacl, s.y)
+        h.axpby(n, 1.0, s.f, 1.0, s.jacl)
+        mins = h.batch_init_point_stage(0)
+        delta_x = np.maximum(0.0, np.maximum(-1.5 * mins[:, 0], -1.5 * mins[:, 1]))
+        delta_s = np.maximum(0.0, np.maximum(-1.5 * mins[:, 2], -1.5 * mins[:, 3]))
+        st = h.batch_init_point_stage(1, delta_x, delta_s)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            delta_x2 = st[:, 0] / (2 * (st[:, 1] + st[:, 2]))
+            delta_s2 = st[:, 0] / (2 * (st[:, 3] + st[:, 4]))
+        chk = h.batch_init_point_stage(2, delta_x2, delta_s2, s.opt.bound_fac)
+        if s.nlb > 0 and not (np.all(chk[:, 0] > 0.0) and np.all(chk[:, 2] > 0.0)):
+            raise AssertionError("starting point not strictly interior (lower)")
+
+    def solve(self):
+        """solve! for every unit; returns a list of ExecutionStats (one per unit, in order)."""
+        import time
+        import numpy as np
+        import torch
+        from . import solver as S
+        s, h, opt, B = self.s, self.s.h, self.s.opt, self.B
+        t0 = time.perf_counter()
+        s.start_time = time.time()
+        self._initialize()
+        status = [S.REGULAR] * B
+        iters = np.zeros(B, dtype=np.int64)
+        traces = [[] for _ in range(B)]
+        best = np.full(B, np.inf)
+        active = np.ones(B, dtype=np.int32)
+        alpha_p, alpha_d = np.zeros(B), np.zeros(B)
+        mu = np.full(B, opt.mu_init)
+        dobj_last = np.full(B, np.nan)
+        started = False
+        k = 0
+        s.del_w_trace = s.del_w
+        while True:
+            trace_del_w = s.del_w
+            s.update_regularization()
+            out, ok = h.batch_iter_begin(s.del_w, s.del_c)
+            if started:
+                new_obj = self.obj_scale * np.array([q.c0 for q in self.models]) + out[:, 5] + 0.5 * out[:, 6]
+                self.obj_val = np.where(active == 1, new_obj, self.obj_val)
+                alpha_p = np.where(active == 1, out[:, 7], alpha_p)
+                alpha_d = np.where(active == 1, out[:, 8], alpha_d)
+                mu = np.where(active == 1, out[:, 9], mu)
+            for u in range(B):
+                if not active[u]:
+                    continue
+                dobj, nc, ndu, ncompl, dnorm = out[u, :5]
+                inf_pr = nc / max(1.0, self.norm_b[u])
+                inf_du = ndu / max(1.0, self.norm_c[u])
+                inf_compl = ncompl / max(1.0, self.norm_c[u])
+                best[u] = min(best[u], inf_compl)
+                dobj_last[u] = dobj
+                if max(inf_pr, inf_du, inf_compl) <= opt.tol:
+                    status[u] = S.SOLVE_SUCCEEDED
+                elif (inf_compl > opt.divergence_tol * best[u]) and (dobj > max(10.0 * abs(self.obj_val[u]), 1.0)):
+                    status[u] = S.INFEASIBLE_PROBLEM_DETECTED
+                elif self.obj_val[u] < -opt.divergence_tol * max(10.0, abs(dobj), 1.0):
+                    status[u] = S.DIVERGING_ITERATES
+                elif k >= opt.max_iter:
+                    status[u] = S.MAXIMUM_ITERATIONS_EXCEEDED
+                elif not np.isfinite(max(inf_pr, inf_du, inf_compl)):
+                    status[u] = S.INTERNAL_ERROR
+                traces[u].append(dict(k=k, objective=self.obj_val[u] / self.obj_scale[u], dual_objective=dobj / self.obj_scale[u],
+                                      inf_pr=inf_pr, inf_du=inf_du, inf_compl=inf_compl, mu=mu[u], alpha_p=alpha_p[u],
+                                      alpha_d=alpha_d[u], del_w=trace_del_w, dnorm=0.0 if k == 0 else dnorm))
+                if status[u] != S.REGULAR:
+                    active[u] = 0
+                    iters[u] = k
+            if not active.any():
+                break
+            h.batch_set_active(active)
+            for _ in range(2):                       # factorize_regularized_system! retries, for the whole stack
+                if ok:
+                    break
+                s.del_w *= 100.0
+                s.del_c *= 100.0
+                ok = h.mpc_refactor(s.del_w, s.del_c)
+            rule = opt.step_rule
+            ir = max(opt.ir_steps, 1 if s._has_free else 0)       # free variables: refine every solve (like MPCSolver)
+            if isinstance(rule, S.AdaptiveStep):
+                h.batch_iter_rest(opt.mu_min, 0, rule.tau_min, ir)
+            else:
+                h.batch_iter_rest(opt.mu_min, 1, rule.tau, ir)
+            started = True
+            k += 1
+        torch.cuda.synchronize(s.device)
+        total = time.perf_counter() - t0
+        x, y = s.x.cpu().numpy(), s.y.cpu().numpy()
+        zl, zu = s.zl.cpu().numpy(), s.zu.cpu().numpy()
+        h.spmv(0, 1.0, s.AT_x, s.x, 0.0, s.buffer_m)
+        cons = s.buffer_m.cpu().numpy()
+        res = []
+        for u in range(B):
+            sl_n, sl_m = slice(self.off_n[u], self.off_n[u + 1]), slice(self.off_m[u], self.off_m[u + 1])
+            res.append(S.ExecutionStats(
+                status=status[u], iter=int(iters[u]), objective=self.obj_val[u] / self.obj_scale[u],
+                dual_objective=dobj_last[u] / self.obj_scale[u], solution=x[sl_n].copy(), constraints=cons[sl_m].copy(),
+                multipliers=y[sl_m] / self.obj_scale[u], multipliers_L=zl[sl_n] / self.obj_scale[u],
+                multipliers_U=zu[sl_n] / self.obj_scale[u], trace=traces[u], total_time=total, linear_solver_time=0.0,
+                counters=dict(launches=h.launch_count(), iterations_of_the_batch=k, ls_stats=s.linear_solver.stats)))
+        return res
+
+
+def solve_batch_stacked(models, **kwargs):
+    """madipm for a batch of independent models through the stacked path; returns one ExecutionStats per model."""
+    return BatchedMPCSolver(models, **kwargs).solve()

@@ -141,6 +141,13 @@ struct Handle {
     bool has_model = false;
     mipm_mpc_model model{};
 
+    // ---- batch of independent problems stacked into one (BASELINE config C5): per-unit offsets and scalar blocks
+    int nb_units = 0;
+    DBuf<int64_t> d_uoff_n, d_uoff_m;
+    DBuf<int> d_uactive;
+    DBuf<double> d_usc, d_uin, d_uout;
+    std::vector<double> h_ubuf;
+
     // ---- mpc vectors (+ inverse maps variable -> position in the lb / ub block, -1 if none)
     DBuf<int32_t> d_inv_lb, d_inv_ub;
     bool bound = false;

@@ -738,6 +738,259 @@ __global__ void __launch_bounds__(TB) k_init_bounds(int64_t n, double tol, doubl
 
 }  // namespace
 
+
+// ------------------------------------------------------------------ batches of independent problems (BASELINE config C5)
+// B independent LPs / QPs are STACKED into one block-diagonal problem: every element-wise kernel above, the SpMVs, the
+// KKT assembly and the task-graph factorization / solves (a forest: one elimination tree per unit) run unchanged on the
+// stacked vectors, so all units advance through ONE set of launches per IPM phase. What is per unit -- reductions, step
+// lengths, centering parameter, barrier value, termination -- is done by the kernels below: one CTA per unit (block
+// reductions only, deterministic), unit u owning variables [off_n[u], off_n[u+1]) and rows [off_m[u], off_m[u+1]) and a
+// scalar block of its own. A unit that has terminated stops moving (its step is skipped).
+struct UB {
+    const int64_t *off_n, *off_m;
+    const int *active;
+    double *sc;         // B x SC_COUNT
+    double *uin;        // B x 4: per-unit inputs from the host (init stages)
+    double *uout;       // B x 8: per-unit outputs to the host (init stages, norms)
+};
+#define UNIT_STRIDE(i, off) for (int64_t i = (off)[blockIdx.x] + threadIdx.x; i < (off)[blockIdx.x + 1]; i += TB)
+
+template <int NV>
+__device__ void block_reduce_vals(double (&acc)[NV], const int (&op)[NV], double *out)
+{
+    __shared__ double sm[NV][TB / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] = comb(acc[q], __shfl_xor_sync(0xffffffffu, acc[q], o), op[q]);
+        if (lane == 0) sm[q][warp] = acc[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        const int q = threadIdx.x;
+        double v = sm[q][0];
+        for (int w = 1; w < TB / 32; ++w) v = comb(v, sm[q][w], op[q]);
+        out[q] = v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TB) kb_amax(const double *x, const int64_t *off, double *out, int stride)
+{
+    double acc[1] = {0.0};
+    UNIT_STRIDE(i, off) acc[0] = comb(acc[0], fabs(x[i]), OP_MAX);
+    const int op[1] = {OP_MAX};
+    block_reduce_vals<1>(acc, op, out + (size_t)blockIdx.x * stride);
+}
+__global__ void __launch_bounds__(TB) kb_dot(const double *x, const double *y, const int64_t *off, double *out, int stride)
+{
+    double acc[1] = {0.0};
+    UNIT_STRIDE(i, off) acc[0] += x[i] * y[i];
+    const int op[1] = {OP_SUM};
+    block_reduce_vals<1>(acc, op, out + (size_t)blockIdx.x * stride);
+}
+// k_init0 / k_init1 / k_init2 per unit (src/solver.jl:41-118)
+__global__ void __launch_bounds__(TB) kb_init0(V v, UB ub)
+{
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    UNIT_STRIDE(i, ub.off_n) {
+        double r = v.jacl[i], l = v.xl[i], u = v.xu[i], x = v.x[i];
+        bool fl = isfinite(l), fu = isfinite(u);
+        double zl = v.zl[i], zu = v.zu[i];
+        if (fl && fu) { zl = 0.5 * r; zu = -0.5 * r; }
+        else if (fl) zl = r;
+        else if (fu) zu = -r;
+        v.zl[i] = zl;
+        v.zu[i] = zu;
+        if (v.inv_lb[i] >= 0) { acc[0] = fmin(acc[0], x - l); acc[2] = fmin(acc[2], zl); }
+        if (v.inv_ub[i] >= 0) { acc[1] = fmin(acc[1], u - x); acc[3] = fmin(acc[3], zu); }
+    }
+    const int op[4] = {OP_MIN, OP_MIN, OP_MIN, OP_MIN};
+    block_reduce_vals<4>(acc, op, ub.uout + 8 * (size_t)blockIdx.x);
+}
+__global__ void __launch_bounds__(TB) kb_init1(V v, UB ub)
+{
+    const double delta_x = ub.uin[4 * (size_t)blockIdx.x], delta_s = ub.uin[4 * (size_t)blockIdx.x + 1];
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    UNIT_STRIDE(i, ub.off_n) {
+        bool lb = v.inv_lb[i] >= 0, ubd = v.inv_ub[i] >= 0;
+        double x = v.x[i];
+        if (lb) x = x + delta_x;
+        if (ubd) x = x - delta_x;
+        v.x[i] = x;
+        if (lb) {
+            double zl = v.zl[i] + (1.0 + delta_s);
+            v.zl[i] = zl;
+            double l = v.xl[i];
+            acc[0] += x * zl - l * zl;
+            acc[1] += zl;
+            acc[3] += x - l;
+        }
+        if (ubd) {
+            double zu = v.zu[i] + (1.0 + delta_s);
+            v.zu[i] = zu;
+            double u = v.xu[i];
+            acc[0] += u * zu - x * zu;
+            acc[2] += zu;
+            acc[4] += u - x;
+        }
+    }
+    const int op[5] = {OP_SUM, OP_SUM, OP_SUM, OP_SUM, OP_SUM};
+    block_reduce_vals<5>(acc, op, ub.uout + 8 * (size_t)blockIdx.x);
+}
+__global__ void __launch_bounds__(TB) kb_init2(V v, UB ub, double kappa)
+{
+    const double delta_x2 = ub.uin[4 * (size_t)blockIdx.x], delta_s2 = ub.uin[4 * (size_t)blockIdx.x + 1];
+    double acc[4] = {DBL_MAX, DBL_MAX, DBL_MAX, DBL_MAX};
+    UNIT_STRIDE(i, ub.off_n) {
+        bool lb = v.inv_lb[i] >= 0, ubd = v.inv_ub[i] >= 0;
+        double x = v.x[i], l = v.xl[i], u = v.xu[i];
+        if (lb) x = x + delta_x2;
+        if (ubd) x = x - delta_x2;
+        if (x < l) x = l + fmin(kappa * fmax(1.0, l), kappa * (u - l));
+        else if (u < x) x = u - fmin(kappa * fmax(1.0, u), kappa * (u - l));
+        v.x[i] = x;
+        if (lb) { double zl = v.zl[i] + delta_s2; v.zl[i] = zl; acc[0] = fmin(acc[0], zl); acc[2] = fmin(acc[2], x - l); }
+        if (ubd) { double zu = v.zu[i] + delta_s2; v.zu[i] = zu; acc[1] = fmin(acc[1], zu); acc[3] = fmin(acc[3], u - x); }
+    }
+    const int op[4] = {OP_MIN, OP_MIN, OP_MIN, OP_MIN};
+    block_reduce_vals<4>(acc, op, ub.uout + 8 * (size_t)blockIdx.x);
+}
+// k_termination per unit; also counts the unit's lower / upper bounds into sc[SC_SUMS + 4..5] (dual objective terms)
+__global__ void __launch_bounds__(TB) kb_termination(V v, UB ub)
+{
+    double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    UNIT_STRIDE(i, ub.off_n) {
+        double x = v.x[i], zl = v.zl[i], zu = v.zu[i];
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        double rd = fabs(((v.f[i] - zl) + zu) + v.jacl[i]);
+        acc[4] = comb(acc[4], rd, OP_MAX);
+        acc[6] = comb(acc[6], fabs(v.d[i]), OP_MAX);
+        if (jl >= 0) {
+            double xl = v.xl[i];
+            acc[1] += zl * xl;
+            acc[5] = comb(acc[5], fabs((x - xl) * zl), OP_MAX);
+        }
+        if (ju >= 0) {
+            double xu = v.xu[i];
+            acc[2] += zu * xu;
+            acc[5] = comb(acc[5], fabs((xu - x) * zu), OP_MAX);
+        }
+    }
+    UNIT_STRIDE(i, ub.off_m) {
+        acc[0] -= v.y[i] * v.rhs[i];
+        acc[3] = comb(acc[3], fabs(v.c[i]), OP_MAX);
+    }
+    const int op[7] = {OP_SUM, OP_SUM, OP_SUM, OP_MAX, OP_MAX, OP_MAX, OP_MAX};
+    block_reduce_vals<7>(acc, op, ub.sc + (size_t)blockIdx.x * SC_COUNT + SC_TERM);
+}
+// set_correction_rhs! with the unit's own barrier value (the predictive right-hand side has no per-unit scalar)
+__global__ void __launch_bounds__(TB) kb_set_rhs_corr(V v, UB ub)
+{
+    const double mu = ub.sc[(size_t)blockIdx.x * SC_COUNT + SC_MU];
+    double *px = v.p, *py = v.p + v.n, *pzl = v.p + v.n + v.m, *pzu = v.p + v.n + v.m + v.nlb;
+    UNIT_STRIDE(i, ub.off_n) {
+        double x = v.x[i], zl = v.zl[i], zu = v.zu[i];
+        px[i] = ((-v.f[i] + zl) - zu) - v.jacl[i];
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) pzl[jl] = ((v.xl[i] - x) * zl + mu) - v.corr_lb[jl];
+        if (ju >= 0) pzu[ju] = ((v.xu[i] - x) * zu - mu) - v.corr_ub[ju];
+    }
+    UNIT_STRIDE(i, ub.off_m) py[i] = -v.c[i];
+}
+// k_alpha_max per unit. mode 0: tau given; mode 1: AdaptiveStep tau = max(1 - mu_u, tau)
+__global__ void __launch_bounds__(TB) kb_alpha_max(V v, UB ub, int mode, double tau)
+{
+    double *sc = ub.sc + (size_t)blockIdx.x * SC_COUNT;
+    if (mode == 1) tau = fmax(1.0 - sc[SC_MU], tau);
+    const double *dx = v.d, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
+    double acc[4] = {1.0, 1.0, 1.0, 1.0};
+    UNIT_STRIDE(i, ub.off_n) {
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        double dxi = dx[i];
+        if (jl >= 0) {
+            if (dxi < 0.0) acc[0] = fmin(acc[0], (-v.x[i] + v.xl[i]) * tau / dxi);
+            double dz = dzl[jl];
+            if (dz < 0.0) acc[2] = fmin(acc[2], (-v.zl[i]) * tau / dz);
+        }
+        if (ju >= 0) {
+            if (dxi > 0.0) acc[1] = fmin(acc[1], (-v.x[i] + v.xu[i]) * tau / dxi);
+            double dz = dzu[ju], zu = v.zu[i];
+            if ((dz < 0.0) && (zu + dz < 0.0)) acc[3] = fmin(acc[3], (-zu) * tau / dz);
+        }
+    }
+    const int op[4] = {OP_MIN, OP_MIN, OP_MIN, OP_MIN};
+    block_reduce_vals<4>(acc, op, sc + SC_ALPHA);
+    if (threadIdx.x == 0) {
+        sc[SC_ALPHA_P] = fmin(sc[SC_ALPHA + 0], sc[SC_ALPHA + 1]);
+        sc[SC_ALPHA_D] = fmin(sc[SC_ALPHA + 2], sc[SC_ALPHA + 3]);
+        sc[SC_TAU] = tau;
+    }
+}
+// k_predictor_measures per unit
+__global__ void __launch_bounds__(TB) kb_predictor_measures(V v, UB ub, double mu_min)
+{
+    double *sc = ub.sc + (size_t)blockIdx.x * SC_COUNT;
+    const double *dx = v.d, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
+    const double ap = sc[SC_ALPHA_P], ad = sc[SC_ALPHA_D];
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    UNIT_STRIDE(i, ub.off_n) {
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) {
+            acc[0] += ((v.x[i] + ap * dx[i]) - v.xl[i]) * (v.zl[i] + ad * dzl[jl]);
+            acc[2] += (v.x[i] - v.xl[i]) * v.zl[i];
+            v.corr_lb[jl] = dx[i] * dzl[jl];
+            acc[4] += 1.0;
+        }
+        if (ju >= 0) {
+            acc[1] += (v.xu[i] - (v.x[i] + ap * dx[i])) * (v.zu[i] + ad * dzu[ju]);
+            acc[3] += (v.xu[i] - v.x[i]) * v.zu[i];
+            v.corr_ub[ju] = dx[i] * dzu[ju];
+            acc[4] += 1.0;
+        }
+    }
+    const int op[5] = {OP_SUM, OP_SUM, OP_SUM, OP_SUM, OP_SUM};
+    block_reduce_vals<5>(acc, op, sc + SC_SUMS);
+    if (threadIdx.x == 0) {
+        const double cnt = sc[SC_SUMS + 4];         // number of bounds of this unit (exact in floating point)
+        double mu_aff = 0.0, mu_cur = 0.0, sigma = 1.0;
+        if (cnt > 0) {
+            mu_aff = (sc[SC_SUMS + 0] + sc[SC_SUMS + 1]) / cnt;
+            mu_cur = (sc[SC_SUMS + 2] + sc[SC_SUMS + 3]) / cnt;
+            const double rr = mu_aff / mu_cur;
+            sigma = fmin(fmax(rr * rr * rr, 1e-6), 10.0);
+        }
+        sc[SC_MU_AFF] = mu_aff;
+        sc[SC_MU_CURR] = mu_cur;
+        sc[SC_MU] = fmax(mu_min, sigma * mu_cur);
+    }
+}
+// k_apply_step per unit; a unit that has terminated keeps its iterate
+__global__ void __launch_bounds__(TB) kb_apply_step(V v, UB ub, double c2)
+{
+    if (ub.active && !ub.active[blockIdx.x]) return;
+    const double *sc = ub.sc + (size_t)blockIdx.x * SC_COUNT;
+    const double ap = sc[SC_ALPHA_P], ad = sc[SC_ALPHA_D], c1 = DBL_EPSILON * sc[SC_MU];
+    const double *dx = v.d, *dy = v.d + v.n, *dzl = v.d + v.n + v.m, *dzu = v.d + v.n + v.m + v.nlb;
+    UNIT_STRIDE(i, ub.off_n) {
+        double x = v.x[i] + ap * dx[i];
+        v.x[i] = x;
+        int jl = v.inv_lb[i], ju = v.inv_ub[i];
+        if (jl >= 0) {
+            v.zl[i] = v.zl[i] + ad * dzl[jl];
+            double xl = v.xl[i];
+            if (x - xl < c1) v.xl[i] = xl - c2 * fmax(1.0, fabs(x));
+        }
+        if (ju >= 0) {
+            v.zu[i] = v.zu[i] + ad * dzu[ju];
+            double xu = v.xu[i];
+            if (xu - x < c1) v.xu[i] = xu + c2 * fmax(1.0, fabs(x));
+        }
+    }
+    UNIT_STRIDE(i, ub.off_m) v.y[i] = v.y[i] + ad * dy[i];
+}
+
 static unsigned red_grid(Handle *h, int64_t len)
 {
     int64_t g = (len + TB - 1) / TB;
@@ -1344,6 +1597,184 @@ int mipm_mpc_iter_rest(mipm_handle hh, double mu_min, int step_rule, double tau_
     if (md.d_Hx) {
         if ((rc = mipm_hess_spmv(hh, 1.0, md.d_Hx, m.d_x, 0.0, md.d_buffer_n)) != MIPM_OK) return rc;
         k_dot<<<red_grid(h, std::max<int64_t>(md.nx, 1)), TB, 0, h->stream>>>(md.nx, md.d_buffer_n, m.d_x, h->d_partials.p, h->d_counter.p, sc + SC_OBJ + 1);
+        MIPM_CHECK_LAUNCH(h);
+        if ((rc = mipm_axpby(hh, md.nx, 1.0, md.d_buffer_n, 1.0, m.d_f)) != MIPM_OK) return rc;
+    }
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_c, m.d_rhs, (size_t)m.m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = mipm_spmv(hh, 0, 1.0, md.d_ATx, m.d_x, -1.0, m.d_c)) != MIPM_OK) return rc;
+    return mipm_spmv(hh, 1, 1.0, md.d_ATx, m.d_y, 0.0, m.d_jacl);
+}
+
+/* ------------------------------------------------------------------ batches (stacked independent units) ---- */
+static UB make_ub(Handle *h)
+{
+    UB ub;
+    ub.off_n = h->d_uoff_n.p; ub.off_m = h->d_uoff_m.p; ub.active = h->d_uactive.p;
+    ub.sc = h->d_usc.p; ub.uin = h->d_uin.p; ub.uout = h->d_uout.p;
+    return ub;
+}
+
+int mipm_batch_configure(mipm_handle hh, int64_t n_units, const int64_t *off_n, const int64_t *off_m)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (n_units < 1 || n_units > (1 << 20) || !off_n || !off_m) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (!h->bound) return fail(h, MIPM_ERR_STATE, "mipm_mpc_bind (stacked vectors) has not been called");
+    if (off_n[0] != 0 || off_m[0] != 0 || off_n[n_units] != h->v.n || off_m[n_units] != h->v.m)
+        return fail(h, MIPM_ERR_ARG, "unit offsets must start at 0 and end at the stacked sizes");
+    for (int64_t u = 0; u < n_units; ++u)
+        if (off_n[u + 1] < off_n[u] || off_m[u + 1] < off_m[u]) return fail(h, MIPM_ERR_ARG, "unit offsets must be monotone");
+    std::vector<int64_t> a(off_n, off_n + n_units + 1), b(off_m, off_m + n_units + 1);
+    std::vector<int> act((size_t)n_units, 1);
+    MIPM_CUDA(h, h->d_uoff_n.upload(a, h->stream));
+    MIPM_CUDA(h, h->d_uoff_m.upload(b, h->stream));
+    MIPM_CUDA(h, h->d_uactive.upload(act, h->stream));
+    MIPM_CUDA(h, h->d_usc.alloc((size_t)n_units * SC_COUNT));
+    MIPM_CUDA(h, h->d_uin.alloc((size_t)n_units * 4));
+    MIPM_CUDA(h, h->d_uout.alloc((size_t)n_units * 8));
+    MIPM_CUDA(h, cudaMemsetAsync(h->d_usc.p, 0, (size_t)n_units * SC_COUNT * sizeof(double), h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->h_ubuf.assign((size_t)n_units * SC_COUNT, 0.0);
+    h->nb_units = (int)n_units;
+    return MIPM_OK;
+}
+
+#define BATCH_OR_FAIL(h)                                                                                    \
+    VIEW_OR_FAIL(h);                                                                                        \
+    if ((h)->nb_units < 1) return fail((h), MIPM_ERR_STATE, "mipm_batch_configure has not been called");    \
+    const UB ub = make_ub(h);                                                                               \
+    const unsigned B = (unsigned)(h)->nb_units
+
+int mipm_batch_set_active(mipm_handle hh, const int32_t *active)
+{
+    Handle *h = (Handle *)hh;
+    BATCH_OR_FAIL(h);
+    (void)ub;
+    if (!active) return fail(h, MIPM_ERR_ARG, "null argument");
+    MIPM_CUDA(h, cudaMemcpyAsync(h->d_uactive.p, active, B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));      // the host array may be reused right away
+    return MIPM_OK;
+}
+
+/* per-unit max |x_i| (by_rows = 0: d_x is a stacked vector over the variables; 1: over the constraint rows) */
+int mipm_batch_amax(mipm_handle hh, int by_rows, const double *d_x, double *out)
+{
+    Handle *h = (Handle *)hh;
+    BATCH_OR_FAIL(h);
+    if (!d_x || !out) return fail(h, MIPM_ERR_ARG, "null argument");
+    kb_amax<<<B, TB, 0, h->stream>>>(d_x, by_rows ? ub.off_m : ub.off_n, ub.uout, 8);
+    MIPM_CHECK_LAUNCH(h);
+    MIPM_CUDA(h, cudaMemcpyAsync(h->h_ubuf.data(), ub.uout, (size_t)B * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (unsigned u = 0; u < B; ++u) out[u] = h->h_ubuf[(size_t)u * 8];
+    return MIPM_OK;
+}
+
+/* per-unit dot products of two stacked variable vectors (objective terms) */
+int mipm_batch_dot(mipm_handle hh, const double *d_x, const double *d_y, double *out)
+{
+    Handle *h = (Handle *)hh;
+    BATCH_OR_FAIL(h);
+    if (!d_x || !d_y || !out) return fail(h, MIPM_ERR_ARG, "null argument");
+    kb_dot<<<B, TB, 0, h->stream>>>(d_x, d_y, ub.off_n, ub.uout, 8);
+    MIPM_CHECK_LAUNCH(h);
+    MIPM_CUDA(h, cudaMemcpyAsync(h->h_ubuf.data(), ub.uout, (size_t)B * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (unsigned u = 0; u < B; ++u) out[u] = h->h_ubuf[(size_t)u * 8];
+    return MIPM_OK;
+}
+
+/* mipm_init_point_stage for every unit: a[B], b[B] are the per-unit shifts, out is B x 5 */
+int mipm_batch_init_point_stage(mipm_handle hh, int stage, const double *a, const double *b, double kappa, double *out)
+{
+    Handle *h = (Handle *)hh;
+    BATCH_OR_FAIL(h);
+    if (!out || (stage > 0 && (!a || !b))) return fail(h, MIPM_ERR_ARG, "null argument");
+    if (stage > 0) {
+        for (unsigned u = 0; u < B; ++u) { h->h_ubuf[(size_t)u * 4] = a[u]; h->h_ubuf[(size_t)u * 4 + 1] = b[u]; }
+        MIPM_CUDA(h, cudaMemcpyAsync(ub.uin, h->h_ubuf.data(), (size_t)B * 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    if (stage == 0) kb_init0<<<B, TB, 0, h->stream>>>(v, ub);
+    else if (stage == 1) kb_init1<<<B, TB, 0, h->stream>>>(v, ub);
+    else if (stage == 2) kb_init2<<<B, TB, 0, h->stream>>>(v, ub, kappa);
+    else return fail(h, MIPM_ERR_ARG, "stage must be 0, 1 or 2");
+    MIPM_CHECK_LAUNCH(h);
+    MIPM_CUDA(h, cudaMemcpyAsync(h->h_ubuf.data(), ub.uout, (size_t)B * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (unsigned u = 0; u < B; ++u)
+        for (int q = 0; q < 5; ++q) out[(size_t)u * 5 + q] = h->h_ubuf[(size_t)u * 8 + q];
+    return MIPM_OK;
+}
+
+/* mipm_mpc_iter_begin for the whole batch: out is B x 16 (same entries per unit), *status as mipm_ls_factorize for the
+ * stacked matrix (one unit's breakdown makes every unit retry with more regularization). */
+int mipm_batch_iter_begin(mipm_handle hh, double del_w, double del_c, double *out, int *status)
+{
+    Handle *h = (Handle *)hh;
+    BATCH_OR_FAIL(h);
+    int rc = fused_ready(h);
+    if (rc != MIPM_OK) return rc;
+    if (!out || !status) return fail(h, MIPM_ERR_ARG, "null argument");
+    kb_termination<<<B, TB, 0, h->stream>>>(v, ub);
+    MIPM_CHECK_LAUNCH(h);
+    if ((rc = fused_factorize(h, del_w, del_c)) != MIPM_OK) return rc;
+    int info[4];
+    MIPM_CUDA(h, cudaMemcpyAsync(h->h_ubuf.data(), ub.sc, (size_t)B * SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaMemcpyAsync(info, h->d_info.p, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    *status = (info[0] == 0) ? MIPM_OK : MIPM_ERR_NOT_FACTORIZED;
+    for (unsigned u = 0; u < B; ++u) {
+        const double *sc = h->h_ubuf.data() + (size_t)u * SC_COUNT;
+        double *o = out + (size_t)u * 16;
+        o[0] = (sc[SC_TERM + 0] + sc[SC_TERM + 1]) - sc[SC_TERM + 2];
+        o[1] = sc[SC_TERM + 3]; o[2] = sc[SC_TERM + 4]; o[3] = sc[SC_TERM + 5]; o[4] = sc[SC_TERM + 6];
+        o[5] = sc[SC_OBJ]; o[6] = sc[SC_OBJ + 1];
+        o[7] = sc[SC_ALPHA_P]; o[8] = sc[SC_ALPHA_D]; o[9] = sc[SC_MU]; o[10] = sc[SC_MU_CURR];
+        o[11] = o[12] = o[13] = o[14] = 0.0;        // (no residual check in the batched sequence)
+        o[15] = sc[SC_TAU];
+    }
+    return MIPM_OK;
+}
+
+/* mipm_mpc_iter_rest for the whole batch (step_rule 0 = AdaptiveStep, 1 = ConservativeStep). */
+int mipm_batch_iter_rest(mipm_handle hh, double mu_min, int step_rule, double tau_param, int ir_steps)
+{
+    Handle *h = (Handle *)hh;
+    BATCH_OR_FAIL(h);
+    int rc = fused_ready(h);
+    if (rc != MIPM_OK) return rc;
+    if (step_rule != 0 && step_rule != 1) return fail(h, MIPM_ERR_ARG, "step_rule must be 0 (adaptive) or 1 (conservative)");
+    const mipm_mpc_model &md = h->model;
+    const mipm_mpc_vectors &m = h->v;
+    const unsigned g = red_grid(h, nmax);
+    const int64_t N = m.n + m.m + m.nlb + m.nub;
+    // prediction_step!
+    k_set_rhs<<<g, TB, 0, h->stream>>>(v, 0, 0.0, nullptr);
+    MIPM_CHECK_LAUNCH(h);
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_d, m.d_p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = fused_kkt_solve(h, m.d_d, ir_steps)) != MIPM_OK) return rc;
+    kb_alpha_max<<<B, TB, 0, h->stream>>>(v, ub, 0, 1.0);
+    MIPM_CHECK_LAUNCH(h);
+    kb_predictor_measures<<<B, TB, 0, h->stream>>>(v, ub, mu_min);
+    MIPM_CHECK_LAUNCH(h);
+    // mehrotra_correction_direction!
+    kb_set_rhs_corr<<<B, TB, 0, h->stream>>>(v, ub);
+    MIPM_CHECK_LAUNCH(h);
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_d, m.d_p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = fused_kkt_solve(h, m.d_d, ir_steps)) != MIPM_OK) return rc;
+    // update_step_size!, apply_step!
+    kb_alpha_max<<<B, TB, 0, h->stream>>>(v, ub, step_rule == 0 ? 1 : 0, tau_param);
+    MIPM_CHECK_LAUNCH(h);
+    kb_apply_step<<<B, TB, 0, h->stream>>>(v, ub, pow(DBL_EPSILON, 0.75));
+    MIPM_CHECK_LAUNCH(h);
+    // evaluate_model!
+    kb_dot<<<B, TB, 0, h->stream>>>(md.d_cvec, m.d_x, ub.off_n, ub.sc + SC_OBJ, SC_COUNT);
+    MIPM_CHECK_LAUNCH(h);
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_f, md.d_cvec, (size_t)m.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (md.d_Hx) {
+        if ((rc = mipm_hess_spmv(hh, 1.0, md.d_Hx, m.d_x, 0.0, md.d_buffer_n)) != MIPM_OK) return rc;
+        kb_dot<<<B, TB, 0, h->stream>>>(md.d_buffer_n, m.d_x, ub.off_n, ub.sc + SC_OBJ + 1, SC_COUNT);
         MIPM_CHECK_LAUNCH(h);
         if ((rc = mipm_axpby(hh, md.nx, 1.0, md.d_buffer_n, 1.0, m.d_f)) != MIPM_OK) return rc;
     }

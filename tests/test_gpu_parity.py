@@ -580,6 +580,36 @@ def test_c5_units_match_oracle_traces(built):
         assert close(st.objective, g["objective"])
 
 
+@pytest.mark.parametrize("kkt", ["Normal", "K2"])
+def test_c5_stacked_batch_matches_oracle_traces(built, kkt):
+    """BASELINE configs[4] through the batched path (SURVEY 8e line 1): 8 units stacked into one block-diagonal problem,
+    ONE set of launches per IPM phase, per-unit step lengths / barrier / termination (mipm_batch_*). Every unit must
+    reproduce ITS OWN oracle trace (the units converge after different numbers of iterations)."""
+    from madipm_jl_b200.batch import solve_batch_stacked
+    from madipm_jl_b200.problems import config_c5
+    models = [config_c5(i) for i in range(8)]
+    res = solve_batch_stacked(models, kkt_system=kkt)
+    for i, st in enumerate(res):
+        if kkt == "Normal":
+            g = _full("c5_u%d/Normal" % i)
+            _check_trace(st, g["trace"], g["iter"], g["status"])
+            assert close(st.objective, g["objective"])
+        else:
+            ref = oracle_madipm(models[i], kkt_system="K2")
+            _check_trace(st, ref.trace, ref.iter, ref.status)
+
+
+def test_stacked_batch_of_unequal_units(built):
+    """Units of different sizes and bound patterns (upper bounds, a QP) in one stacked batch."""
+    from madipm_jl_b200.batch import solve_batch_stacked
+    models = [random_sparse_lp(40, 160, 5, 7, structure="uniform", ub_fraction=0.5), simple_lp(),
+              random_sparse_qp(60, 200, 4, 9, structure="window", window=10), random_sparse_lp(300, 1500, 5, 7, structure="window", window=20)]
+    res = solve_batch_stacked(models, kkt_system="K2")
+    for qp, st in zip(models, res):
+        ref = oracle_madipm(qp, kkt_system="K2")
+        _check_trace(st, ref.trace, ref.iter, ref.status)
+
+
 def test_distributed_solver_single_rank_matches_oracle(built):
     """Config C4's solver path with one rank (no process group): staged factorization / solve through the
     border root must reproduce the oracle's iterates on a block-angular LP. The 2-GPU run of the same code
