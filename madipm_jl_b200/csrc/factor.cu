@@ -21,6 +21,7 @@
 // moved global -> shared by TMA bulk copies (cp.async.bulk + mbarrier complete_tx, 16 columns per stage, 4 stages),
 // so the K loop overlaps copies and math without staging through registers.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -656,6 +657,14 @@ int ls_device_setup(Handle *h)
 {
     const LsSymbolic &S = h->sym;
     const int ns = S.ns;
+    const bool tlog = std::getenv("MIPM_ANALYZE_LOG") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto tlog_stage = [&](const char *name) {
+        if (!tlog) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "device setup: %s %.3f s\n", name, std::chrono::duration<double>(now - t_prev).count());
+        t_prev = now;
+    };
     MIPM_CUDA(h, cudaSetDevice(h->device));
     // a re-analysis must not release buffers the side stream is still zero-filling
     if (h->side) MIPM_CUDA(h, cudaStreamSynchronize(h->side));
@@ -817,6 +826,7 @@ int ls_device_setup(Handle *h)
             }
         if (tasks.size() > (size_t)(1 << 30) || sched.size() > (size_t)INT32_MAX - 16) return fail(h, MIPM_ERR_ARG, "schedule too large");
     }
+    tlog_stage("task list");
     h->leaf_off = leaf_off;
     h->n_leaf = n_leaf;
     h->root_task_begin = root_task_begin;
@@ -848,9 +858,10 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, h->d_perm.upload(S.perm, st));
     MIPM_CUDA(h, h->d_child_idx.upload(S.child_idx, st));
     MIPM_CUDA(h, h->d_a2l.upload(S.a2l, st));
-    MIPM_CUDA(h, h->d_full_ptr.upload(S.full_ptr, st));
-    MIPM_CUDA(h, h->d_full_col.upload(S.full_col, st));
-    MIPM_CUDA(h, h->d_full_val.upload(S.full_val, st));
+    h->d_full_ptr.release();        // refinement operator: built and uploaded on first use (ls_solve_impl)
+    h->d_full_col.release();
+    h->d_full_val.release();
+    tlog_stage("uploads");
     // + 64 doubles: a tile's bulk copies may read past the end of the last panel (rows that are never used)
     MIPM_CUDA(h, h->d_L.alloc((size_t)std::max<int64_t>(S.nnz_l, 1) + 64));
     h->L_cur = h->d_L.p;
@@ -868,11 +879,13 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, h->d_r.alloc((size_t)std::max<int64_t>(S.n, 1)));
     MIPM_CUDA(h, cudaMemsetAsync(h->d_L.p + std::max<int64_t>(S.nnz_l, 1), 0, 64 * sizeof(double), st));
     if (h->d_L2.p) MIPM_CUDA(h, cudaMemsetAsync(h->d_L2.p + S.nnz_l, 0, 64 * sizeof(double), st));
+    tlog_stage("workspace allocation");
     {
         int rc = ls_solve_setup(h, finfo.data(), small.data());
         if (rc != MIPM_OK) return rc;
     }
     MIPM_CUDA(h, cudaStreamSynchronize(st));
+    tlog_stage("solve setup + sync");
     if (!h->side) {
         MIPM_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
         MIPM_CUDA(h, cudaEventCreateWithFlags(&h->ev_factor_done, cudaEventDisableTiming));

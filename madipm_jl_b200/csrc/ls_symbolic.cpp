@@ -222,6 +222,39 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
 
 static inline int64_t trap(int64_t k, int64_t r) { return k * (k + 1) / 2 + k * r; }
 
+// Full symmetric CSR of the input matrix with the position of every value in the caller's lower-CSC array: the operator
+// of the refinement residual r = b - K x. Rows come out sorted (two column-major sweeps).
+void ls_build_full_csr(LsSymbolic &S)
+{
+    const int64_t n = S.n;
+    const int32_t *colptr = S.in_colptr.data(), *rowval = S.in_rowval.data();
+    S.full_ptr.assign((size_t)n + 1, 0);
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+            int32_t i = rowval[p];
+            S.full_ptr[(size_t)i + 1]++;
+            if (i != j) S.full_ptr[(size_t)j + 1]++;
+        }
+    for (int64_t i = 0; i < n; ++i) S.full_ptr[(size_t)i + 1] += S.full_ptr[(size_t)i];
+    S.full_col.resize((size_t)S.full_ptr[(size_t)n]);
+    S.full_val.resize((size_t)S.full_ptr[(size_t)n]);
+    std::vector<int64_t> pf(S.full_ptr.begin(), S.full_ptr.end() - 1);
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+            int32_t i = rowval[p];
+            S.full_col[(size_t)pf[(size_t)i]] = (int32_t)j;
+            S.full_val[(size_t)pf[(size_t)i]++] = p;
+        }
+    for (int64_t j = 0; j < n; ++j)
+        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+            int32_t i = rowval[p];
+            if (i != j) {
+                S.full_col[(size_t)pf[(size_t)j]] = i;
+                S.full_val[(size_t)pf[(size_t)j]++] = p;
+            }
+        }
+}
+
 #define TLOG(name) do { if (tlog) { auto now_ = std::chrono::steady_clock::now(); std::fprintf(stderr, "analyze stage before %s: %.3f s\n", name, std::chrono::duration<double>(now_ - t_prev).count()); t_prev = now_; } } while (0)
 std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
                        const LsOptions &opt, const int32_t *user_perm, LsSymbolic &S)
@@ -241,47 +274,33 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
             if (i < j || i >= n) return "rowval outside the lower triangle";
         }
     }
-    // ---- full symmetric adjacency (no diagonal) + full CSR with value positions
+    // ---- full symmetric adjacency (no diagonal). The full CSR with value positions (iterative refinement only) is
+    // built on first use from the kept copy of the pattern: ls_build_full_csr.
+    S.in_colptr.assign(colptr, colptr + n + 1);
+    S.in_rowval.assign(rowval, rowval + nnz);
     std::vector<int64_t> xadj((size_t)n + 1, 0);
-    S.full_ptr.assign((size_t)n + 1, 0);
     for (int64_t j = 0; j < n; ++j)
         for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
             int32_t i = rowval[p];
-            S.full_ptr[(size_t)i + 1]++;
             if (i != j) {
-                S.full_ptr[(size_t)j + 1]++;
                 xadj[(size_t)i + 1]++;
                 xadj[(size_t)j + 1]++;
             }
         }
-    for (int64_t i = 0; i < n; ++i) {
-        xadj[(size_t)i + 1] += xadj[(size_t)i];
-        S.full_ptr[(size_t)i + 1] += S.full_ptr[(size_t)i];
-    }
+    for (int64_t i = 0; i < n; ++i) xadj[(size_t)i + 1] += xadj[(size_t)i];
     std::vector<int32_t> adj((size_t)xadj[(size_t)n]);
-    S.full_col.resize((size_t)S.full_ptr[(size_t)n]);
-    S.full_val.resize((size_t)S.full_ptr[(size_t)n]);
     {
-        std::vector<int64_t> pa(xadj.begin(), xadj.end() - 1), pf(S.full_ptr.begin(), S.full_ptr.end() - 1);
-        // column-major sweep emits, for every row, its columns in ascending order:
-        // first the upper part (j > i) would come later, so do two sweeps to keep rows sorted.
-        // sweep 1: entries (i, j) with j < i come from column j at row i -> ascending j.
+        std::vector<int64_t> pa(xadj.begin(), xadj.end() - 1);
+        // two column-major sweeps keep every adjacency list sorted: first the neighbours j < i, then those > i
         for (int64_t j = 0; j < n; ++j)
             for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
                 int32_t i = rowval[p];
-                S.full_col[(size_t)pf[(size_t)i]] = (int32_t)j;
-                S.full_val[(size_t)pf[(size_t)i]++] = p;
                 if (i != j) adj[(size_t)pa[(size_t)i]++] = (int32_t)j;
             }
-        // sweep 2: mirrored entries (j, i) for i > j: row j gets column i, ascending i within column j
         for (int64_t j = 0; j < n; ++j)
             for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
                 int32_t i = rowval[p];
-                if (i != j) {
-                    S.full_col[(size_t)pf[(size_t)j]] = i;
-                    S.full_val[(size_t)pf[(size_t)j]++] = p;
-                    adj[(size_t)pa[(size_t)j]++] = i;
-                }
+                if (i != j) adj[(size_t)pa[(size_t)j]++] = i;
             }
     }
     TLOG("0");

@@ -47,7 +47,8 @@ struct LsSymbolic {
     std::vector<int64_t> level_ptr;            // nlev+1
     std::vector<int32_t> level_sn;             // supernodes grouped by level
     std::vector<int64_t> a2l;                  // nnz_a: destination of each input nonzero in L storage
-    // full symmetric CSR of the input matrix in ORIGINAL numbering (for refinement SpMV)
+    std::vector<int32_t> in_colptr, in_rowval;  // copy of the analysed pattern (0-based)
+    // full symmetric CSR of the input matrix in ORIGINAL numbering (refinement residual): filled by ls_build_full_csr
     std::vector<int64_t> full_ptr;             // n+1
     std::vector<int32_t> full_col;
     std::vector<int64_t> full_val;             // index into the caller's nzval
@@ -61,6 +62,8 @@ struct LsSymbolic {
 // colptr/rowval: lower-triangular CSC, 0-based. Returns "" on success or an error message.
 std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
                        const LsOptions &opt, const int32_t *user_perm, LsSymbolic &out);
+
+void ls_build_full_csr(LsSymbolic &S);
 
 // Nested-dissection ordering (level-structure separators, George & Liu) of the graph of a
 // symmetric matrix given by its full adjacency (no self loops). perm[new] = old.

@@ -550,6 +550,16 @@ int ls_solve_impl(Handle *h, double *d_x, int ir_steps)
     MIPM_CUDA(h, cudaMemcpyAsync(h->d_b.p, d_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     int rc = solve_once(h, h->d_b.p, d_x, 0);
     if (rc != MIPM_OK) return rc;
+    if (ir_steps > 0 && !h->d_full_ptr.p) {      // first refinement: build the symmetric operator of the residual
+        ls_build_full_csr(h->sym);
+        MIPM_CUDA(h, h->d_full_ptr.upload(h->sym.full_ptr, st));
+        MIPM_CUDA(h, h->d_full_col.upload(h->sym.full_col, st));
+        MIPM_CUDA(h, h->d_full_val.upload(h->sym.full_val, st));
+        MIPM_CUDA(h, cudaStreamSynchronize(st));
+        std::vector<int64_t>().swap(h->sym.full_ptr);
+        std::vector<int32_t>().swap(h->sym.full_col);
+        std::vector<int64_t>().swap(h->sym.full_val);
+    }
     for (int it = 0; it < ir_steps; ++it) {
         k_sym_residual<<<grid_for(n * 32, 256), 256, 0, st>>>(n, h->d_full_ptr.p, h->d_full_col.p, h->d_full_val.p, h->d_nzval,
                                                             d_x, h->d_b.p, h->d_r.p);

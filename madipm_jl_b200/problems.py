@@ -186,6 +186,50 @@ def config_c2(seed=2, scale=1.0):
     return random_sparse_lp(m, n, 8, seed, structure="window", window=50)
 
 
+def mesh_sparse_lp(grid, cols_per_cell, k, radius, seed):
+    """LP whose rows are the cells of a grid x grid mesh: every column has k nonzeros in distinct cells within +-radius
+    (both directions) of its home cell. A A' then is a 2-D mesh graph with a thick stencil, whose nested-dissection
+    separators grow like grid * 2 * radius: fronts with thousands of columns, the regime where the factorization is
+    bound by the FP64 tensor pipe instead of latency (the band structure of config_c2 keeps every front below 300
+    columns). Feasible and bounded by construction like random_sparse_lp."""
+    rng = np.random.default_rng(seed)
+    m = grid * grid
+    n = m * cols_per_cell
+    home = np.repeat(np.arange(m, dtype=np.int64), cols_per_cell)
+    hy, hx = home // grid, home % grid
+    w = 2 * radius + 1
+    assert w * w >= k
+    keys = rng.random((n, w * w))
+    off = np.argpartition(keys, k - 1, axis=1)[:, :k]
+    dy, dx = off // w - radius, off % w - radius
+    cy = np.clip(hy[:, None] + dy, 0, grid - 1)
+    cx = np.clip(hx[:, None] + dx, 0, grid - 1)
+    rows = np.sort(cy * grid + cx, axis=1)
+    # clipping at the mesh boundary can repeat a cell inside a column: keep the first occurrence of each
+    keep = np.ones_like(rows, dtype=bool)
+    keep[:, 1:] = rows[:, 1:] != rows[:, :-1]
+    cols = np.repeat(np.arange(n, dtype=np.int64), k).reshape(n, k)
+    rows, cols = rows[keep], cols[keep]
+    vals = rng.standard_normal(len(rows))
+    vals = np.sign(vals) * np.maximum(np.abs(vals), 1e-2)
+    xs = rng.uniform(0.5, 1.5, n)
+    b = np.zeros(m)
+    np.add.at(b, rows, vals * xs[cols])
+    ys = rng.standard_normal(m)
+    zs = rng.uniform(0.0, 1.0, n)
+    c = zs.copy()
+    np.add.at(c, cols, vals * ys[rows])
+    return QuadraticModel(c=c, Hrows=[], Hcols=[], Hvals=[], Arows=rows, Acols=cols, Avals=vals, lcon=b, ucon=b.copy(),
+                          lvar=np.zeros(n), uvar=np.full(n, np.inf), x0=np.zeros(n),
+                          name=f"lp_mesh_g{grid}_c{cols_per_cell}_k{k}_r{radius}_s{seed}",
+                          meta=dict(m=m, n=n, k=k, seed=seed, structure="mesh", grid=grid, radius=radius))
+
+
+def config_c2_mesh(seed=6, scale=1.0):
+    """The harder sibling of config_c2 (same 8 nnz/col, 5 columns per row): 2-D mesh locality, root separator ~2000 columns."""
+    return mesh_sparse_lp(max(8, int(round(256 * np.sqrt(scale)))), 5, 8, 3, seed)
+
+
 def config_c3(seed=3, scale=1.0):
     m, n = int(150_000 * scale), int(500_000 * scale)
     return random_sparse_qp(m, n, 5, seed, structure="window", window=50)

@@ -235,7 +235,19 @@ class MPCSolver:
             self.H_full_host = fv[Hmap - ib]
             self.Hx = z(len(Hj))
         self.cvec = z(n)
-        self._stage_problem()
+        # pinned staging of the numeric problem data on a helper thread: page-locking ~100 MB takes as long as the whole
+        # symbolic analysis of a large problem and is independent of it (joined at the end of the constructor)
+        import threading
+        stage_err = []
+
+        def _stage():
+            try:
+                torch.cuda.set_device(self.device)
+                self._stage_problem()
+            except Exception as exc:       # surfaced after the join
+                stage_err.append(exc)
+        stager = threading.Thread(target=_stage)
+        stager.start()
         # ---- KKT system
         self.buffer_n, self.buffer_m = z(n), z(m)
         self.l_diag, self.u_diag, self.l_lower, self.u_lower = z(nlb), z(nub), z(nlb), z(nub)
@@ -303,6 +315,9 @@ class MPCSolver:
         self.h.mpc_set_model(md)
         # a variable with no finite bound keeps pr_diag = del_w (1e-10): the KKT system is then badly
         # conditioned from the first iteration on, so the fused path refines every solve from the start
+        stager.join()
+        if stage_err:
+            raise stage_err[0]
         self._has_free = (nlb + nub > 0 or n > 0) and bool(np.any(~np.isfinite(lfull) & ~np.isfinite(ufull)))
         self._fused_started = False
         self._fused_ir = max(opt.ir_steps, 1 if self._has_free else 0)
@@ -484,18 +499,24 @@ class MPCSolver:
         """Pinned host copies of the numeric problem data (the host side of `convert(QuadraticModel{T, CuVector}, qp)`,
         README.md:77): every solve() uploads them again, so a timed solve includes its host->device traffic."""
         qp, nx, ns, m = self.qp, self.nx, self.ns, self.m
-        # page-locking costs ~0.1 ms per array: only worth it when the array is large enough for the copy to matter
-        def pin(a):
-            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
-            return t.pin_memory() if t.numel() >= 65536 else t
+        # ONE page-locked slab for all arrays (a pinned allocation per array costs tens of milliseconds each); small
+        # problems stay in pageable memory (page-locking costs more than their copies)
         zs = np.zeros(ns)
-        self._host = dict(
-            x0=pin(np.concatenate([qp.x0, zs])), c=pin(np.concatenate([qp.c, zs])), y0=pin(qp.y0),
-            xl=pin(np.concatenate([qp.lvar, qp.lcon[self.ind_ineq]])), xu=pin(np.concatenate([qp.uvar, qp.ucon[self.ind_ineq]])),
-            rhs=pin(np.where(qp.lcon == qp.ucon, qp.lcon, 0.0)), A_V=pin(self.A_V_host))
+        arrays = dict(
+            x0=np.concatenate([qp.x0, zs]), c=np.concatenate([qp.c, zs]), y0=qp.y0,
+            xl=np.concatenate([qp.lvar, qp.lcon[self.ind_ineq]]), xu=np.concatenate([qp.uvar, qp.ucon[self.ind_ineq]]),
+            rhs=np.where(qp.lcon == qp.ucon, qp.lcon, 0.0), A_V=self.A_V_host)
         if qp.nnzh > 0:
-            self._host["H_full"] = pin(self.H_full_host)
-            self._host["H_tril"] = pin(qp.Hvals)
+            arrays["H_full"] = self.H_full_host
+            arrays["H_tril"] = qp.Hvals
+        total = sum(len(a) for a in arrays.values())
+        slab = torch.empty(max(total, 1), dtype=torch.float64, pin_memory=(total >= 65536))
+        self._host, off = {}, 0
+        for name, a in arrays.items():
+            view = slab[off:off + len(a)]
+            view.numpy()[:] = a
+            self._host[name] = view
+            off += len(a)
         self._amax_A = float(np.abs(self.A_V_host).max()) if len(self.A_V_host) else 0.0
         self.h2d_bytes_per_solve = int(sum(t.numel() * 8 for t in self._host.values()))
 

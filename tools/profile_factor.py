@@ -9,12 +9,12 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from madipm_jl_b200 import _lib  # noqa: E402
-from madipm_jl_b200.problems import config_c2  # noqa: E402
+from madipm_jl_b200.problems import config_c2, config_c2_mesh  # noqa: E402
 
 
 def main():
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-    qp = config_c2(seed=2, scale=scale)
+    qp = config_c2_mesh(scale=scale) if os.environ.get("PROFILE_CONFIG") == "mesh" else config_c2(seed=2, scale=scale)
     m, n = qp.ncon, qp.nvar
     Bp, Bj, Bm = _lib.coo_to_csr(m, n, qp.Arows, qp.Acols)
     h = _lib.Handle(device=0, stream=torch.cuda.current_stream().cuda_stream)
@@ -39,7 +39,8 @@ def main():
     print("factor ms", 1e3 * (time.perf_counter() - t))
     for _ in range(3):
         pr_ = h.ls_factorize_profile(Cx)
-        print({k_: round(v["ms"], 4) for k_, v in pr_.items()})
+        print({k_: round(v["ms"], 4) for k_, v in pr_.items()}, "update TF/s (busy-time rate x grid): %.2f" % (
+            pr_["update"]["work"] / max(pr_["update"]["ms"], 1e-9) / 1e9), "factor TF/s: %.2f" % (h.ls_stats()["flops"] / pr_["kernel"]["ms"] / 1e9))
     out = os.environ.get("PROFILE_OUT")
     if out:
         os.environ["MIPM_TASK_TRACE"] = out + "_trace.csv"
