@@ -6,8 +6,13 @@ workload : config C2 = synthetic sparse LP, m=200,000 constraints, n=1,000,000 v
            rows drawn within +-50 of each column's home row (uniformly random rows make chol(AA')
            ~90% dense = 147 GB at this size: SURVEY fact 8), NormalKKTSystem + supernodal Cholesky.
 step     : one pass of the mpc! loop body (src/solver.jl:333-359): termination test, KKT assembly,
-           numeric factorization, predictor + corrector solves (each with residual check and one
-           round of iterative refinement), ratio tests, step, model re-evaluation.
+           numeric factorization, predictor + corrector solves (each with the residual check of
+           solve_system!; no refinement round is needed on this workload), ratio tests, step,
+           model re-evaluation.
+extras   : after the headline measurement the same run also reports (key "extras"): BASELINE configs[4] (1 024
+           independent LPs through the stacked batch path, sharded over the ranks), configs[3] (the block-angular
+           LP with the distributed solver over all ranks: the one config with an exchange step), the mesh variant
+           of C2 with fronts of thousands of columns (rank 0, N = 1) and a second CPU point (SciPy SuperLU).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S]
 
@@ -33,7 +38,8 @@ sys.path.insert(0, ROOT)
 # (profiles/ncu_factor_persistent_r01_final_raw.csv), keyed by --scale; None when not captured for that size
 TRAFFIC_BYTES = {}
 try:
-    for _k, _v in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "factor_traffic_r01.json"))).items():
+    _tp = [os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", f) for f in ("factor_traffic_r02.json", "factor_traffic_r01.json")]
+    for _k, _v in json.load(open([f for f in _tp if os.path.exists(f)][0])).items():
         try:
             TRAFFIC_BYTES[float(_k)] = float(_v)
         except (TypeError, ValueError):
@@ -154,6 +160,129 @@ def run_reference(args, rank, world, out):
     print(json.dumps(line), file=out, flush=True)
 
 
+def run_extras(args, rank, world, local_rank, peaks, barrier):
+    """The other BASELINE configs in the same run (never allowed to break the headline line)."""
+    import torch
+    import torch.distributed as dist
+    out = {}
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- C5: 1 024 independent LPs (m=500, n=2 000), sharded over the ranks, each shard one stacked batch
+    try:
+        from madipm_jl_b200.batch import BatchedMPCSolver, shard_range
+        from madipm_jl_b200.problems import config_c5
+        n_units = max(world, int(1024 * min(1.0, args.scale)))
+        lo, hi = shard_range(n_units, rank, world)
+        t0 = time.perf_counter()
+        b = BatchedMPCSolver([config_c5(i) for i in range(lo, hi)], kkt_system="Normal", device=local_rank)
+        torch.cuda.synchronize()
+        t_ctor = time.perf_counter() - t0
+        b.solve()                                   # warm-up
+        barrier()
+        t1 = time.perf_counter()
+        res = b.solve()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t1)
+        ok = sum(r.status == "SOLVE_SUCCEEDED" for r in res)
+        okt = torch.tensor([ok], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(okt)
+        out["c5"] = {"workload": "C5: %d independent LPs m=500 n=2000 5 nnz/col, %d per rank, stacked batch path" % (n_units, hi - lo),
+                     "units": n_units, "solve_s": dt, "lps_per_s": n_units / dt, "succeeded": int(okt.item()),
+                     "construct_s_rank0": t_ctor, "batch_iterations_rank0": res[0].counters["iterations_of_the_batch"],
+                     "scaling": "weak-free (independent units, no collective)"}
+        del b, res
+        torch.cuda.empty_cache()
+    except Exception as exc:      # noqa: BLE001
+        out["c5"] = {"error": repr(exc)}
+
+    # ---- C4: block-angular multicommodity-flow LP, distributed solver over all ranks (strong scaling)
+    try:
+        from madipm_jl_b200.problems import config_c4
+        from madipm_jl_b200.solver import MPCSolver
+        qp = config_c4(scale=args.scale)
+        t0 = time.perf_counter()
+        s4 = MPCSolver(qp, kkt_system="Normal", linear_solver="distributed", n_border=qp.meta["n_border"], device=local_rank)
+        torch.cuda.synchronize()
+        t_ctor = time.perf_counter() - t0
+        s4.solve()                                  # warm-up
+        s4.k = 0
+        s4.trace = []
+        barrier()
+        t1 = time.perf_counter()
+        r4 = s4.solve()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t1)
+        st4 = s4.linear_solver.stats
+        out["c4"] = {"workload": "C4: block-angular multicommodity flow m=%d n=%d, %d linking rows, distributed solver on %d rank(s)"
+                                 % (qp.ncon, qp.nvar, qp.meta["n_border"], world),
+                     "status": r4.status, "iterations": r4.iter, "solve_s": dt, "iter_per_s": r4.iter / dt, "objective": r4.objective,
+                     "construct_s_rank0": t_ctor, "scaling": "strong (one LP over all ranks, all-reduce of the root Schur block)",
+                     "local_symbolic_rank0": {k_: st4[k_] for k_ in ("n", "nnz_l", "flops", "n_supernodes", "n_levels", "max_front_cols")}}
+        del s4, r4, qp
+        torch.cuda.empty_cache()
+    except Exception as exc:      # noqa: BLE001
+        out["c4"] = {"error": repr(exc)}
+
+    if world == 1 and rank == 0:
+        # ---- mesh variant of C2: fronts with thousands of columns (tensor-pipe bound updates)
+        try:
+            from madipm_jl_b200.problems import config_c2_mesh
+            from madipm_jl_b200.solver import MPCSolver
+            qp = config_c2_mesh(scale=args.scale)
+            sm = MPCSolver(qp, kkt_system="Normal", device=local_rank)
+            sm.solve()
+            sm.k = 0
+            sm.trace = []
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            rm = sm.solve()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t1
+            pf = sm.h.ls_factorize_profile(sm.aug_nz)
+            stm = sm.linear_solver.stats
+            kms = pf["kernel"]["ms"]
+            out["c2_mesh"] = {"workload": "mesh variant of C2: LP m=%d n=%d 8 nnz/col, rows within +-3 cells on a 2-D mesh" % (qp.ncon, qp.nvar),
+                              "status": rm.status, "iterations": rm.iter, "solve_s": dt, "iter_per_s": rm.iter / dt,
+                              "symbolic": {k_: stm[k_] for k_ in ("n", "nnz_l", "flops", "n_supernodes", "n_levels", "max_front_cols", "max_front_rows")},
+                              "roofline": {"kernel": "k_factor_tasks", "bound": "tensor", "achieved": stm["flops"] / kms / 1e9,
+                                           "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": stm["flops"] / kms / 1e9 / peaks["fp64_tflops"],
+                                           "avg_launch_ms": kms,
+                                           "update_tasks_tflops": pf["update"]["work"] / pf["update"]["ms"] / 1e9,
+                                           "update_tasks_frac": pf["update"]["work"] / pf["update"]["ms"] / 1e9 / peaks["fp64_tflops"]},
+                              "factor_classes": pf}
+            del sm, rm, qp
+            torch.cuda.empty_cache()
+        except Exception as exc:      # noqa: BLE001
+            out["c2_mesh"] = {"error": repr(exc)}
+        # ---- second CPU point: the same restatement with SciPy SuperLU as the linear solver (SURVEY 8d)
+        if not args.no_cpu_baseline:
+            try:
+                from oracle.mpc_oracle import MPCOracle
+                qp, _ = make_workload(args.scale)
+                tb = time.time()
+                o = MPCOracle(qp, kkt_system="Normal", linear_solver="splu", fast_symbolic=True)
+                o.start_time = time.time()
+                o.initialize()
+                nit, tc = 0, time.perf_counter()
+                while nit < 2 and o.mpc_iteration():
+                    nit += 1
+                dtc = time.perf_counter() - tc
+                out["cpu_superlu"] = {"value": nit / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+                                      "sample": "%d full-size C2 iterations of the CPU restatement with scipy.sparse.linalg.splu (SuperLU, COLAMD) as "
+                                                "linear solver; setup %.1fs untimed; no multithreaded sparse direct solver exists in this image"
+                                                % (nit, time.time() - tb - dtc), "timers_s": o.timers}
+            except Exception as exc:      # noqa: BLE001
+                out["cpu_superlu"] = {"error": repr(exc)}
+    return out
+
+
 def _claim_stdout():
     """Keep stdout for the ONE JSON line: native libraries (NCCL prints its version banner with
     printf) get fd 1 redirected to stderr; the returned file object writes to the real stdout."""
@@ -172,6 +301,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="scale m and n of the workload (testing only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C4 / C5 / mesh / SuperLU blocks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -205,7 +335,10 @@ def main():
     # ---------------- e2e: the public solve call with host buffers (H2D of the model, D2H of the result)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    solver.solve()          # untimed warm-up solve: first-use costs (module load, cooperative launch setup)
+    t_first = time.perf_counter()
+    solver.solve()          # warm-up solve: first-use costs (module load, cooperative launch setup); reported as "cold"
+    torch.cuda.synchronize()
+    t_first = time.perf_counter() - t_first
     solver.k = 0
     solver.trace = []
     barrier()
@@ -306,18 +439,22 @@ def main():
     # Dominant kernel of the step: k_factor_persistent (one cooperative launch = one numeric factorization,
     # ~60% of the step). Its FLOPs go through the FP64 tensor pipe (DMMA), so the bound is "tensor"; achieved =
     # algorithmic flops of the factorization (sum_j colcount_j^2) / average launch duration (CUDA events).
-    kernel_ms = sum(prof[c]["ms"] for c in ("extend_add", "diag", "trsm", "update"))
+    kernel_ms = prof["kernel"]["ms"]           # span of the task kernel (first task start .. last task end, %globaltimer)
     achieved = st["flops"] / kernel_ms / 1e9
     upd = prof["update"]
-    roof = {"kernel": "k_factor_persistent", "bound": "tensor", "achieved": achieved, "peak": peaks["fp64_tflops"],
+    roof = {"kernel": "k_factor_tasks", "bound": "tensor", "achieved": achieved, "peak": peaks["fp64_tflops"],
             "unit": "TFLOP/s", "frac": achieved / peaks["fp64_tflops"], "traffic": TRAFFIC_BYTES.get(args.scale),
             "peak_source": "FP64 " + peaks["fp64_src"] + "; MEASURED_PEAKS.json has no FP64 entry",
             "avg_launch_ms": kernel_ms, "algorithmic_flops_per_launch": st["flops"],
             "share_of_step": kernel_ms / ms_per_step,
-            "update_phases": {"tflops": upd["work"] / upd["ms"] / 1e9, "frac": upd["work"] / upd["ms"] / 1e9 / peaks["fp64_tflops"],
-                              "ms": upd["ms"], "algorithmic_flops": upd["work"]},
-            "note": "phases inside the launch are timed with %globaltimer (stages.factor_classes); the diag and "
-                    "extend-add phases are latency / HBM bound, only trsm + update run on the tensor pipe"}
+            "update_tasks": {"tflops": upd["work"] / upd["ms"] / 1e9, "frac": upd["work"] / upd["ms"] / 1e9 / peaks["fp64_tflops"],
+                             "cta_ms": upd["ms"], "algorithmic_flops": upd["work"],
+                             "what": "algorithmic update flops / (busy time of the trailing-update tasks summed over CTAs / grid): "
+                                     "the rate the tensor-pipe tasks sustain while they run"},
+            "note": "avg_launch_ms is the span of the task kernel from its own %globaltimer stamps (CUDA-event time of the whole "
+                    "factorization incl. zero-fill + scatter is stages.factorization.ms); stages.factor_classes gives the CTA-busy "
+                    "time per task class and the dependency wait; the kernel is bound by the critical path of the elimination tree "
+                    "(profiles/r02_notes.md), not by the tensor pipe or HBM"}
 
     # ---------------- CPU baseline: oracle on a bounded sample of the same workload (rank 0, N=1)
     cpu = None
@@ -337,13 +474,20 @@ def main():
                          "nnz(L)=%d); setup %.1fs untimed; host has %d cores" % (nit, o.ls.nnzL, time.time() - tb - dtc, os.cpu_count()),
                "timers_s": o.timers}
 
+    opt_ir, opt_tol = solver.opt.ir_steps, solver.opt.tol
+    extras = None
+    if not args.no_extras:
+        del solver, h
+        torch.cuda.empty_cache()
+        extras = run_extras(args, rank, world, local_rank, peaks, barrier)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wname, "kkt_system": "NormalKKTSystem", "linear_solver": "supernodal Cholesky (own)",
-                       "ordering": "nested dissection", "ir_steps": solver.opt.ir_steps, "tol": solver.opt.tol,
+                       "ordering": "nested dissection", "ir_steps": opt_ir, "tol": opt_tol,
                        "l2": "inputs larger than L2 (L+U = %.0f MB)" % (8e-6 * (st["nnz_l"] + st["update_doubles"])),
                        "parallelism": "replicas x%d" % world, "scale": args.scale},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / max(iters_total, 1),
@@ -361,6 +505,9 @@ def main():
             "symbolic": {k_: st[k_] for k_ in ("n", "nnz_a", "nnz_l", "nnz_l_exact", "flops", "n_supernodes", "n_levels",
                                               "max_front_cols", "max_front_rows", "update_doubles", "n_launches")},
             "setup_s": t_setup, "final_objective": res.objective,
+            "cold": {"construct_s": t_setup, "first_solve_s": t_first, "cold_time_to_1e-8_s": t_setup + t_first,
+                     "what": "MPCSolver(qp) (host symbolic analysis + uploads) + the first solve() of the process"},
+            "extras": extras,
         }
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
