@@ -114,10 +114,10 @@ struct Handle {
     bool l_prezeroed = false;
     DBuf<int64_t> d_gat_off;         // transposed child maps of the forward solve (fronts with many children)
     DBuf<int32_t> d_gat_ptr, d_gat_src;
-    struct I2 { int x, y; };
-    DBuf<I2> d_solve_tasks;          // task list of the solves (kind, id), see solve.cu
-    DBuf<int> d_solve_prog;          // per front: forward children done | backward done; [2 ns] = ticket counter
-    int n_solve_fwd = 0, n_solve_tasks = 0;
+    struct I4 { int x, y, z, w; };
+    DBuf<I4> d_solve_tasks;          // task list of the solves (kind, id, part, 0), see solve.cu
+    DBuf<int> d_solve_prog;          // per front: forward children done | backward done | big-front counters x3; [5 ns] = ticket
+    int n_solve_fwd = 0, n_solve_tasks = 0, solve_root_fwd_begin = 0;
     DBuf<int> d_info;                // [0]=first failed column+1 (0 = ok), [1]=#neg pivots, [2]=#zero pivots
     const double *d_nzval = nullptr;
     int64_t n_launch_factor = 0;

@@ -18,11 +18,13 @@ struct SolveParams {
     const int32_t *child_idx, *rel_idx, *row_idx, *perm;
     const int32_t *leaves;      // small leaf fronts, one warp each
     int n_leaf;
-    const int2 *tasks;          // (kind, id): 0 forward front, 1 forward leaf group, 2 backward front, 3 backward leaf group
+    const int4 *tasks;          // (kind, id, part, 0): 0 forward front, 1 forward leaf group, 2 backward front, 3 backward leaf
+                                // group, 4 forward row tile `part` of a big front, 5 backward column block `part` of a big front
     int task_begin, task_end;
     int root_sn, root_mode;     // staged (distributed) solves: front_forward mode of the border root (0 unless staged)
     int *fprog;                 // per front: children whose forward step is complete
     int *bdone;                 // per front: backward step complete
+    int *yprog, *xprog, *ftiles; // big fronts: forward blocks published, backward blocks published, forward tiles finished
     int *ticket;
     const double *L, *Dinv;
     double *xp, *uvec;
@@ -231,6 +233,210 @@ __device__ void front_backward(const SolveParams &p, int s, double *smem)
     }
 }
 
+// ------------------------------------------------------------------ big fronts: one front, many CTAs
+// A front with thousands of columns (the root separator of a mesh-like problem, the border root of a block-angular
+// one) is a chain of 64-column blocks; handled by ONE CTA it streams its whole panel through one SM (9 ms per solve on
+// the mesh variant of C2). Here the forward sweep is split by 64-row tiles and the backward sweep by 64-column blocks:
+// tile t owns rows [64 t, 64 t + 64) of the front, accumulates  x_t - sum_{b < t} L[t, b] y_b  as the y_b are published
+// (per-front counter yprog, acquire spin) and, if it sits on the diagonal, solves its own block and publishes y_t.
+// The backward task of block b waits for the blocks above it (xprog) and publishes x_b. The critical path per block is
+// one 64 x 64 product + the inverse-block product instead of a whole panel column block.
+constexpr int BIG_PART = 4;     // quarters of a 64-column block handled by the 4 x 64 thread layout
+
+__device__ __forceinline__ int ld_acquire_b(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// acc[r] -= sum_{c < nc} P[(col0 + c) * ld + row0 + r] * yb[c] for the tile's rows r0 <= r < nr; thread (r, q) takes the
+// columns q, q + 4, ...; all loads of a thread are issued before the first use
+__device__ __forceinline__ void tile_update(const double *P, int64_t ld, int row0, int r0, int nr, int col0, int nc, const double *yb,
+                                            double *acc, double *part)
+{
+    const int r = threadIdx.x & 63, q = threadIdx.x >> 6;
+    double sum = 0.0;
+    if (r >= r0 && r < nr) {
+        const double *col = P + (int64_t)col0 * ld + row0 + r;
+        double v[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) { const int c = q + BIG_PART * t; v[t] = (c < nc) ? col[(int64_t)c * ld] : 0.0; }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) sum = fma(v[t], yb[q + BIG_PART * t], sum);
+    }
+    part[q * 64 + r] = sum;
+    __syncthreads();
+    if (threadIdx.x < 64 && r >= r0 && r < nr) acc[r] -= (part[r] + part[64 + r]) + (part[128 + r] + part[192 + r]);
+    __syncthreads();
+}
+
+template <bool LDL>
+__device__ void big_forward_tile(const SolveParams &p, int s, int t, double *smem, int mode)
+{
+    double *acc = smem, *yb = smem + 64, *part = smem + 128;
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, N = f.k + f.r, ld = front_ld(f.k, f.r);
+    const double *P = p.L + f.lp;
+    double *x1 = p.xp + f.c0;
+    double *u = p.uvec + f.rowp;
+    const int tid = threadIdx.x;
+    const int R0 = t * 64, nr = min(64, N - R0);
+    const int nblk = (k + NB - 1) / NB, ntiles = (N + 63) / 64;
+    if (tid < 64) {
+        double v = 0.0;
+        if (tid < nr) {
+            const int row = R0 + tid;
+            if (mode == 2) v = (row < k) ? x1[row] : u[row - k];
+            else {
+                v = (row < k) ? p.b_in[p.perm[f.c0 + row]] : 0.0;
+                const int64_t go = p.gat_off[2 * (int64_t)s];
+                if (go >= 0) {      // children's update vectors, in child order (big fronts always have the transposed map)
+                    const int32_t *gp = p.gat_ptr + go;
+                    const int32_t *gs = p.gat_src + p.gat_off[2 * (int64_t)s + 1];
+                    for (int q = gp[row]; q < gp[row + 1]; ++q) v += p.uvec[gs[q]];
+                }
+            }
+        }
+        acc[tid] = v;
+        yb[tid] = 0.0;
+    }
+    __syncthreads();
+    if (mode == 1) {            // staged solve: the assembled right-hand side is all-reduced before the front is solved
+        if (tid < nr) { const int row = R0 + tid; if (row < k) x1[row] = acc[tid]; else u[row - k] = acc[tid]; }
+        return;
+    }
+    const int nbefore = min(nblk, t);
+    __shared__ int s_avail;
+    for (int b = 0; b < nbefore;) {
+        if (tid == 0) {             // wait for the next block, then take every block published so far in one go
+            int a;
+            while ((a = ld_acquire_b(p.yprog + s)) <= b) __nanosleep(20);
+            s_avail = a;
+        }
+        __syncthreads();
+        const int bend = min(nbefore, s_avail);
+        for (; b < bend; ++b) {
+            const int nc = min(NB, k - b * NB);
+            if (tid < 64) yb[tid] = (tid < nc) ? x1[b * NB + tid] : 0.0;
+            __syncthreads();
+            tile_update(P, ld, R0, 0, nr, b * NB, nc, yb, acc, part);
+        }
+    }
+    if (t < nblk) {             // diagonal tile: y_t = inv(L_tt) acc, published for the tiles below
+        const int jb = t * NB, nbk = min(NB, k - jb);
+        const double *Dv = p.Dinv + (f.dinv + t) * (int64_t)(NB * XS);
+        {
+            const int rr = tid >> 2, q = tid & 3;
+            double a = 0.0, dvv[NB / 4];
+#pragma unroll
+            for (int c = 0; c < NB / 4; ++c) dvv[c] = Dv[(q + 4 * c) * XS + rr];
+#pragma unroll
+            for (int c = 0; c < NB / 4; ++c) a = fma(dvv[c], (q + 4 * c < nbk) ? acc[q + 4 * c] : 0.0, a);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            __syncthreads();
+            if (q == 0) { yb[rr] = (rr < nbk) ? a : 0.0; if (rr < nbk) x1[jb + rr] = a; }
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicAdd(p.yprog + s, 1); }
+        if (nr > nbk) tile_update(P, ld, R0, nbk, nr, jb, nbk, yb, acc, part);     // rows of this tile below the last diagonal block
+    }
+    if (tid < nr && R0 + tid >= k) u[R0 + tid - k] = acc[tid];
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(p.ftiles + s, 1) + 1 == ntiles) {
+            __threadfence();
+            atomicAdd(p.fprog + (f.parent >= 0 ? f.parent : s), 1);
+        }
+    }
+}
+
+template <bool LDL>
+__device__ void big_backward_block(const SolveParams &p, int s, int b, double *smem)
+{
+    double *S = smem, *wb = smem + NB * LDS, *xr = wb + NB;
+    const FrontInfo f = p.fi[s];
+    const int k = f.k, r = f.r, N = f.k + f.r, ld = front_ld(f.k, f.r);
+    const double *P = p.L + f.lp;
+    double *x1 = p.xp + f.c0;
+    const int32_t *rows = p.row_idx + f.rowp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool cached = r <= XR_MAX;
+    if (cached) for (int i = tid; i < r; i += 256) xr[i] = p.xp[rows[i]];
+    const int nblk = (k + NB - 1) / NB;
+    const int jb = b * NB, nb = min(NB, k - jb);
+    const double *Dv = p.Dinv + (f.dinv + b) * (int64_t)(NB * XS);
+    for (int idx = tid; idx < NB * NB; idx += 256) S[(idx >> 6) * LDS + (idx & 63)] = Dv[(idx >> 6) * XS + (idx & 63)];
+    if (tid < NB) wb[tid] = 0.0;
+    const int q0 = warp * 8;
+    double acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+    const double *col = P + (int64_t)(jb + q0) * ld;
+    auto rows_range = [&](int i0, int i1) {         // acc[c] += sum_{i0 <= i < i1} L[i, jb + q0 + c] xfull[i]
+        if (q0 >= nb) return;
+        for (int i = i0 + lane; i < i1; i += 32) {
+            const double xv = (i < k) ? x1[i] : (cached ? xr[i - k] : p.xp[rows[i - k]]);
+            double v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = (q0 + c < nb) ? col[(int64_t)c * ld + i] : 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = fma(v[c], xv, acc[c]);
+        }
+    };
+    // the rows below the supernode first (ancestors' x: known), then the blocks above this one as they are published
+    // (from the far end; every block published so far is taken in one go), the block right above it last
+    __shared__ int s_avail;
+    __syncthreads();
+    rows_range(k, N);
+    for (int done_t = nblk; done_t > b + 1;) {
+        if (tid == 0) {
+            int a;
+            while ((a = ld_acquire_b(p.xprog + s)) < nblk - (done_t - 1)) __nanosleep(20);
+            s_avail = a;
+        }
+        __syncthreads();
+        const int new_t = max(b + 1, nblk - s_avail);
+        rows_range(NB * new_t, min(NB * done_t, k));
+        done_t = new_t;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+    if (q0 < nb && lane < 8 && q0 + lane < nb) {
+        double a = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (lane == c) a = acc[c];
+        double y = x1[jb + q0 + lane];
+        if (LDL) y = y / col[(int64_t)lane * ld + jb + q0 + lane];
+        wb[q0 + lane] = y - a;
+    }
+    __syncthreads();
+    {
+        const int cc = tid >> 2, q = tid & 3;
+        double a = 0.0;
+        for (int rr = cc + q; rr < NB; rr += 4) a = fma(S[cc * LDS + rr], wb[rr], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (q == 0 && cc < nb) {
+            x1[jb + cc] = a;
+            double *o = p.x_out + p.perm[f.c0 + jb + cc];
+            *o = p.accumulate ? *o + a : a;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(p.xprog + s, 1);
+        if (b == 0) atomicExch(p.bdone + s, 1);
+    }
+}
+
 // Small leaf fronts in the solves: one warp per front, L11 (k <= SL_K) applied by direct substitution.
 template <bool LDL>
 __device__ void leaf_forward(const SolveParams &p, int s)
@@ -322,11 +528,26 @@ __global__ void __launch_bounds__(256, 3) k_solve_tasks(SolveParams p)
     for (;;) {
         const int t = s_ticket;
         if (t >= p.task_end) break;
-        const int2 tk = p.tasks[t];
+        const int4 tk = p.tasks[t];
         int next = 0;
         unsigned long long tr0 = 0, tr1 = 0;
         if (p.trace && tid == 0) tr0 = tr1 = globaltimer_ns();
-        if (tk.x == 0 || tk.x == 2) {
+        if (tk.x == 4 || tk.x == 5) {
+            const int s = tk.y;
+            const FrontInfo f = p.fi[s];
+            const bool fwd = (tk.x == 4);
+            const int mode = (fwd && s == p.root_sn) ? p.root_mode : 0;
+            if (tid == 0) {
+                if (fwd) { if (f.nchild > 0 && mode != 2) { while (ld_acquire_s(p.fprog + s) < f.nchild) __nanosleep(40); } }
+                else if (f.parent >= 0) { while (ld_acquire_s(p.bdone + f.parent) == 0) __nanosleep(40); }
+                else { while (ld_acquire_s(p.fprog + s) <= f.nchild) __nanosleep(40); }
+                if (p.trace) tr1 = globaltimer_ns();
+                next = p.task_begin + atomicAdd(p.ticket, 1);
+            }
+            __syncthreads();
+            if (fwd) big_forward_tile<LDL>(p, s, tk.z, smem, mode);
+            else big_backward_block<LDL>(p, s, tk.z, smem);
+        } else if (tk.x == 0 || tk.x == 2) {
             const int s = tk.y;
             const FrontInfo f = p.fi[s];
             const bool fwd = (tk.x == 0);
@@ -421,26 +642,43 @@ int ls_solve_setup(Handle *h, const void *finfo_host, const char *small)
     h->grid_solve = prop.sm_count * std::min(occ_s, 4);
     if (h->grid_limit > 0) h->grid_solve = std::min(h->grid_solve, h->grid_limit);
     // ---- task list: forward by level (small leaves first, eight per task), then backward from the root down
-    std::vector<int2> tasks;
+    std::vector<int4> tasks;
     const int n_leaf = h->n_leaf;
-    for (int i = 0; i < n_leaf; i += 8) tasks.push_back(make_int2(1, i));
+    int big_k = 256;            // fronts at least this wide are solved by many CTAs (row tiles forward, column blocks backward)
+    if (const char *e = std::getenv("MIPM_SOLVE_BIG_K")) big_k = std::max(NB, atoi(e));
+    auto is_big = [&](int s2) { return finfo[(size_t)s2].k >= big_k; };
+    for (int i = 0; i < n_leaf; i += 8) tasks.push_back(make_int4(1, i, 0, 0));
+    h->solve_root_fwd_begin = 0;
     for (int l = 0; l < S.n_levels; ++l)
         for (int64_t t = S.level_ptr[(size_t)l]; t < S.level_ptr[(size_t)l + 1]; ++t) {
             const int s2 = S.level_sn[(size_t)t];
-            if (!small[(size_t)s2]) tasks.push_back(make_int2(0, s2));
+            if (small[(size_t)s2]) continue;
+            if (s2 == S.root_sn) h->solve_root_fwd_begin = (int)tasks.size();
+            if (is_big(s2)) {
+                const int ntiles = (finfo[(size_t)s2].k + finfo[(size_t)s2].r + 63) / 64;
+                for (int q = 0; q < ntiles; ++q) tasks.push_back(make_int4(4, s2, q, 0));
+            } else {
+                tasks.push_back(make_int4(0, s2, 0, 0));
+            }
         }
     h->n_solve_fwd = (int)tasks.size();
     for (int l = S.n_levels - 1; l >= 0; --l)
         for (int64_t t = S.level_ptr[(size_t)l]; t < S.level_ptr[(size_t)l + 1]; ++t) {
             const int s2 = S.level_sn[(size_t)t];
-            if (!small[(size_t)s2]) tasks.push_back(make_int2(2, s2));
+            if (small[(size_t)s2]) continue;
+            if (is_big(s2)) {
+                const int nblk = (finfo[(size_t)s2].k + NB - 1) / NB;
+                for (int q = nblk - 1; q >= 0; --q) tasks.push_back(make_int4(5, s2, q, 0));
+            } else {
+                tasks.push_back(make_int4(2, s2, 0, 0));
+            }
         }
-    for (int i = 0; i < n_leaf; i += 8) tasks.push_back(make_int2(3, i));
+    for (int i = 0; i < n_leaf; i += 8) tasks.push_back(make_int4(3, i, 0, 0));
     h->n_solve_tasks = (int)tasks.size();
     h->grid_solve = std::max(1, std::min(h->grid_solve, h->n_solve_tasks));
     MIPM_CUDA(h, h->d_solve_tasks.alloc(std::max<size_t>(tasks.size(), 1)));
-    if (!tasks.empty()) MIPM_CUDA(h, cudaMemcpyAsync(h->d_solve_tasks.p, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    MIPM_CUDA(h, h->d_solve_prog.alloc((size_t)2 * std::max(ns, 1) + 4));
+    if (!tasks.empty()) MIPM_CUDA(h, cudaMemcpyAsync(h->d_solve_tasks.p, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+    MIPM_CUDA(h, h->d_solve_prog.alloc((size_t)5 * std::max(ns, 1) + 4));
     {
         // transposed child maps for the forward solve (fronts with more than GATHER_MIN_CHILDREN children)
         constexpr int GATHER_MIN_CHILDREN = 4;
@@ -449,7 +687,7 @@ int ls_solve_setup(Handle *h, const void *finfo_host, const char *small)
         const bool slots_fit = S.row_ptr[(size_t)ns] < (int64_t)INT32_MAX;
         for (int s = 0; s < ns && slots_fit; ++s) {
             const FrontInfo &f = finfo[(size_t)s];
-            if (f.nchild <= GATHER_MIN_CHILDREN) continue;
+            if (f.nchild <= GATHER_MIN_CHILDREN && !(is_big(s) && f.nchild > 0)) continue;
             const int N = f.k + f.r;
             cnt.assign((size_t)N + 1, 0);
             for (int ci = 0; ci < f.nchild; ++ci) {
@@ -488,17 +726,18 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     SolveParams p;
     p.fi = (const FrontInfo *)h->d_finfo.p; p.child_idx = h->d_child_idx.p; p.rel_idx = h->d_rel_idx.p; p.row_idx = h->d_row_idx.p;
     p.perm = h->d_perm.p; p.leaves = h->d_sched.p + h->leaf_off; p.n_leaf = h->n_leaf;
-    p.tasks = (const int2 *)h->d_solve_tasks.p;
-    p.task_begin = (stage == 1) ? h->n_solve_fwd - 1 : 0;
+    p.tasks = (const int4 *)h->d_solve_tasks.p;
+    p.task_begin = (stage == 1) ? h->solve_root_fwd_begin : 0;
     p.task_end = (stage == 0) ? h->n_solve_fwd : h->n_solve_tasks;
     p.root_sn = (stage >= 0) ? S.root_sn : -1;
     p.root_mode = (stage == 0) ? 1 : ((stage == 1) ? 2 : 0);
-    p.fprog = h->d_solve_prog.p; p.bdone = h->d_solve_prog.p + ns; p.ticket = h->d_solve_prog.p + 2 * (size_t)ns;
+    p.fprog = h->d_solve_prog.p; p.bdone = h->d_solve_prog.p + ns; p.yprog = h->d_solve_prog.p + 2 * (size_t)ns;
+    p.xprog = h->d_solve_prog.p + 3 * (size_t)ns; p.ftiles = h->d_solve_prog.p + 4 * (size_t)ns; p.ticket = h->d_solve_prog.p + 5 * (size_t)ns;
     p.L = h->L_cur; p.Dinv = h->d_Dinv.p; p.xp = h->d_xp.p; p.uvec = h->d_uvec.p;
     p.b_in = b_in; p.x_out = x_out; p.accumulate = accumulate;
     p.gat_off = h->d_gat_off.p; p.gat_ptr = h->d_gat_ptr.p; p.gat_src = h->d_gat_src.p;
-    if (stage == 1) { MIPM_CUDA(h, cudaMemsetAsync(h->d_solve_prog.p + 2 * (size_t)ns, 0, sizeof(int), h->stream)); }   // ticket only
-    else { MIPM_CUDA(h, cudaMemsetAsync(h->d_solve_prog.p, 0, ((size_t)2 * ns + 4) * sizeof(int), h->stream)); }
+    if (stage == 1) { MIPM_CUDA(h, cudaMemsetAsync(h->d_solve_prog.p + 5 * (size_t)ns, 0, sizeof(int), h->stream)); }   // ticket only
+    else { MIPM_CUDA(h, cudaMemsetAsync(h->d_solve_prog.p, 0, ((size_t)5 * ns + 4) * sizeof(int), h->stream)); }
     if (p.task_end <= p.task_begin) return MIPM_OK;
     const char *trace_path = std::getenv("MIPM_SOLVE_TRACE");      // diagnostic only: synchronises
     DBuf<unsigned long long> d_trace;
@@ -515,9 +754,9 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
     h->launches++;
     if (trace_path) {
         std::vector<unsigned long long> tr((size_t)3 * h->n_solve_tasks);
-        std::vector<int2> tk((size_t)h->n_solve_tasks);
+        std::vector<int4> tk((size_t)h->n_solve_tasks);
         MIPM_CUDA(h, cudaMemcpyAsync(tr.data(), d_trace.p, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-        MIPM_CUDA(h, cudaMemcpyAsync(tk.data(), h->d_solve_tasks.p, tk.size() * sizeof(int2), cudaMemcpyDeviceToHost, h->stream));
+        MIPM_CUDA(h, cudaMemcpyAsync(tk.data(), h->d_solve_tasks.p, tk.size() * sizeof(int4), cudaMemcpyDeviceToHost, h->stream));
         MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
         unsigned long long t0 = ~0ull;
         for (size_t i = 0; i < tk.size(); ++i) if (tr[3 * i]) t0 = std::min(t0, tr[3 * i]);
@@ -525,7 +764,7 @@ static int solve_once(Handle *h, const double *b_in, double *x_out, int accumula
             std::fprintf(tf, "task,kind,id,level,k,r,wait_us,start_us,end_us\n");
             for (size_t i = 0; i < tk.size(); ++i) {
                 if (!tr[3 * i]) continue;
-                const bool front = (tk[i].x == 0 || tk[i].x == 2);
+                const bool front = (tk[i].x == 0 || tk[i].x == 2 || tk[i].x == 4 || tk[i].x == 5);
                 const int s2 = tk[i].y;
                 std::fprintf(tf, "%zu,%d,%d,%d,%d,%d,%.2f,%.2f,%.2f\n", i, tk[i].x, s2, front ? S.sn_level[(size_t)s2] : 0,
                              front ? S.sn_ptr[(size_t)s2 + 1] - S.sn_ptr[(size_t)s2] : 0,

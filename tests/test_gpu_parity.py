@@ -610,6 +610,35 @@ def test_stacked_batch_of_unequal_units(built):
         _check_trace(st, ref.trace, ref.iter, ref.status)
 
 
+@pytest.mark.parametrize("big_k", ["64", "128"])
+def test_big_front_solves_split_over_ctas(handle, monkeypatch, big_k):
+    """Fronts at least MIPM_SOLVE_BIG_K columns wide (default 256: root separators of mesh-like problems, border roots)
+    are solved by many CTAs (row tiles forward, column blocks backward, per-front progress counters). Forced on here for
+    medium fronts: Cholesky and LDL' solves, refinement (accumulating mode) and the staged distributed solve."""
+    monkeypatch.setenv("MIPM_SOLVE_BIG_K", big_k)
+    from madipm_jl_b200.problems import block_angular_lp
+    from madipm_jl_b200.solver import madipm
+    Cp, Cj, Cx, K = _normal_matrix(2000, 10000, 5, "uniform", 3)         # one ~1900-column root front
+    h = handle()
+    h.ls_analyze(2000, Cp, Cj, kind=_lib.MIPM_CHOLESKY)
+    assert h.ls_factorize(dev(Cx))
+    b = np.random.default_rng(0).standard_normal(2000)
+    for ir, tol in ((0, 1e-9), (2, 1e-12)):
+        x = dev(b)
+        h.ls_solve(x, ir)
+        xs = x.cpu().numpy()
+        res = np.abs(K @ xs - b).max() / (np.abs(K).sum(axis=1).max() * np.abs(xs).max() + np.abs(b).max())
+        assert res < tol, (ir, res)
+    for name in ("lp_m300_window", "qp_m60_window", "mixed_lp_m120"):       # K2 / LDL' fronts
+        from tests.golden.make_golden import CASES
+        g = GOLD[name + "/K2"]
+        _check_trace(madipm(CASES[name](), kkt_system="K2"), g["trace"], g["iter"], g["status"])
+    qp = block_angular_lp(4, 12, 12, 150, 2)                                # border root of 150 columns: staged solve
+    ref = oracle_madipm(qp, kkt_system="Normal")
+    got = madipm(qp, kkt_system="Normal", linear_solver="distributed", n_border=qp.meta["n_border"])
+    _check_trace(got, ref.trace, ref.iter, ref.status)
+
+
 def test_distributed_solver_single_rank_matches_oracle(built):
     """Config C4's solver path with one rank (no process group): staged factorization / solve through the
     border root must reproduce the oracle's iterates on a block-angular LP. The 2-GPU run of the same code
