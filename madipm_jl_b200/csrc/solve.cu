@@ -644,7 +644,7 @@ int ls_solve_setup(Handle *h, const void *finfo_host, const char *small)
     // ---- task list: forward by level (small leaves first, eight per task), then backward from the root down
     std::vector<int4> tasks;
     const int n_leaf = h->n_leaf;
-    int big_k = 256;            // fronts at least this wide are solved by many CTAs (row tiles forward, column blocks backward)
+    int big_k = 128;            // fronts at least this wide (measured: 128 beats 64, 256 and 512 on C2 and on its mesh variant) are solved by many CTAs (row tiles forward, column blocks backward)
     if (const char *e = std::getenv("MIPM_SOLVE_BIG_K")) big_k = std::max(NB, atoi(e));
     auto is_big = [&](int s2) { return finfo[(size_t)s2].k >= big_k; };
     for (int i = 0; i < n_leaf; i += 8) tasks.push_back(make_int4(1, i, 0, 0));

@@ -612,7 +612,7 @@ def test_stacked_batch_of_unequal_units(built):
 
 @pytest.mark.parametrize("big_k", ["64", "128"])
 def test_big_front_solves_split_over_ctas(handle, monkeypatch, big_k):
-    """Fronts at least MIPM_SOLVE_BIG_K columns wide (default 256: root separators of mesh-like problems, border roots)
+    """Fronts at least MIPM_SOLVE_BIG_K columns wide (default 128: root separators of mesh-like problems, border roots)
     are solved by many CTAs (row tiles forward, column blocks backward, per-front progress counters). Forced on here for
     medium fronts: Cholesky and LDL' solves, refinement (accumulating mode) and the staged distributed solve."""
     monkeypatch.setenv("MIPM_SOLVE_BIG_K", big_k)
