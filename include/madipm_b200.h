@@ -353,6 +353,18 @@ int mipm_batch_init_point_stage(mipm_handle h, int stage, const double *a, const
 int mipm_batch_iter_begin(mipm_handle h, double del_w, double del_c, double *out, int *status);
 int mipm_batch_iter_rest(mipm_handle h, double mu_min, int step_rule, double tau_param, int ir_steps);
 
+/* ------------------------------------------------------------------ preprocessing -- */
+/* Ruiz equilibration on the device: replaces `Dr, Dc = HSL.mc77(A, 0)` of scale_qp (scripts/common.jl:57-100; TODO at
+ * src/solver.jl:147). A is given in COO form (device arrays, index_base); on return A ./ (Dr_i Dc_j) has rows and
+ * columns of infinity norm ~1. max_iter sweeps (MC77's default is 10), stopped early when tol > 0 and
+ * max |1 - norm| <= tol. mipm_scale_coo applies the scaling to a COO value array (H with (Dc, Dc), A with (Dr, Dc)),
+ * like _scale_coo! (scripts/common.jl:37-44). */
+int mipm_ruiz_equilibrate(mipm_handle h, int64_t m, int64_t n, int64_t nnz, const int32_t *d_rows,
+                          const int32_t *d_cols, const double *d_vals, int index_base, int max_iter, double tol,
+                          double *d_Dr, double *d_Dc, int *iters);
+int mipm_scale_coo(mipm_handle h, int64_t nnz, const int32_t *d_rows, const int32_t *d_cols,
+                   const double *d_vals, int index_base, const double *d_Dr, const double *d_Dc, double *d_out);
+
 /* ------------------------------------------------------------------ diagnostics ---- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t mipm_launch_count(mipm_handle h);

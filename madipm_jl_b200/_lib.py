@@ -71,7 +71,7 @@ SYMBOLS = [
     "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk", "mipm_mehrotra_adaptive_step", "mipm_set_aug_diagonal_reg_scaled", "mipm_k25_scale_values",
     "mipm_reduce_rhs_scaled", "mipm_finish_aug_solve_scaled", "mipm_kktmul_scaled",
     "mipm_batch_configure", "mipm_batch_set_active", "mipm_batch_amax", "mipm_batch_dot", "mipm_batch_init_point_stage",
-    "mipm_batch_iter_begin", "mipm_batch_iter_rest",
+    "mipm_batch_iter_begin", "mipm_batch_iter_rest", "mipm_ruiz_equilibrate", "mipm_scale_coo",
 ]
 
 _lib = None
@@ -276,6 +276,18 @@ class Handle:
 
     def mpc_iter_rest(self, mu_min, step_rule, tau_param, ir_steps):
         self.check(self.lib.mipm_mpc_iter_rest(self.h, C.c_double(mu_min), C.c_int(step_rule), C.c_double(tau_param), C.c_int(ir_steps)))
+
+    # ---- preprocessing
+    def ruiz_equilibrate(self, m, n, rows, cols, vals, Dr, Dc, max_iter=10, tol=0.0, index_base=0):
+        it = C.c_int()
+        self.check(self.lib.mipm_ruiz_equilibrate(self.h, C.c_int64(m), C.c_int64(n), C.c_int64(vals.numel()), _ptr(rows), _ptr(cols),
+                                                  _ptr(vals), C.c_int(index_base), C.c_int(max_iter), C.c_double(tol), _ptr(Dr), _ptr(Dc),
+                                                  C.byref(it)))
+        return it.value
+
+    def scale_coo(self, rows, cols, vals, Dr, Dc, out, index_base=0):
+        self.check(self.lib.mipm_scale_coo(self.h, C.c_int64(vals.numel()), _ptr(rows), _ptr(cols), _ptr(vals), C.c_int(index_base),
+                                           _ptr(Dr), _ptr(Dc), _ptr(out)))
 
     # ---- batches of stacked independent units (BASELINE config C5)
     def batch_configure(self, off_n, off_m):

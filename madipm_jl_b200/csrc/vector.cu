@@ -991,6 +991,47 @@ __global__ void __launch_bounds__(TB) kb_apply_step(V v, UB ub, double c2)
     UNIT_STRIDE(i, ub.off_m) v.y[i] = v.y[i] + ad * dy[i];
 }
 
+// ------------------------------------------------------------------ Ruiz equilibration (scripts/common.jl:57-100)
+// scale_qp computes Dr, Dc with HSL.mc77(A, 0) (infinity-norm Ruiz scaling; HSL is closed source and not in the image: the
+// published algorithm is restated -- Ruiz 2001; Knight, Ruiz, Ucar 2014): repeat  r_i = max_j |a_ij| / (Dr_i Dc_j),
+// c_j = max_i |a_ij| / (Dr_i Dc_j);  Dr_i *= sqrt(r_i);  Dc_j *= sqrt(c_j)  (simultaneously) until max |1 - r|, |1 - c| <= tol
+// or max_iter sweeps. One pass over the COO entries per sweep; the maxima are order independent (atomicMax on the bit
+// pattern of non-negative doubles), so the result is deterministic and bit-identical to the sequential restatement.
+__global__ void __launch_bounds__(TB) k_ruiz_max(int64_t nnz, const int32_t *ai, const int32_t *aj, const double *av, int base,
+                                                 const double *dr, const double *dc, unsigned long long *rmax, unsigned long long *cmax)
+{
+    GRID_STRIDE(q, nnz) {
+        const int i = ai[q] - base, j = aj[q] - base;
+        const double v = (fabs(av[q]) / dr[i]) / dc[j];
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+        atomicMax(rmax + i, bits);
+        atomicMax(cmax + j, bits);
+    }
+}
+__global__ void __launch_bounds__(TB) k_ruiz_apply(int64_t m, int64_t n, double *dr, double *dc, unsigned long long *rmax,
+                                                   unsigned long long *cmax, double *partials, unsigned int *counter, double *out)
+{
+    double acc[1] = {0.0};
+    GRID_STRIDE(i, m) {
+        const double r = __longlong_as_double((long long)rmax[i]);
+        rmax[i] = 0ull;
+        if (r > 0.0) { dr[i] = dr[i] * sqrt(r); acc[0] = fmax(acc[0], fabs(1.0 - r)); }
+    }
+    GRID_STRIDE(j, n) {
+        const double c = __longlong_as_double((long long)cmax[j]);
+        cmax[j] = 0ull;
+        if (c > 0.0) { dc[j] = dc[j] * sqrt(c); acc[0] = fmax(acc[0], fabs(1.0 - c)); }
+    }
+    const int op[1] = {OP_MAX};
+    grid_reduce_vals<1>(acc, op, partials, counter, out);
+}
+// A.vals[k] /= Dr[i] Dc[j] (scripts/common.jl:37-44), in place or into `out`
+__global__ void __launch_bounds__(TB) k_scale_coo(int64_t nnz, const int32_t *ai, const int32_t *aj, const double *av, int base,
+                                                  const double *dr, const double *dc, double *out)
+{
+    GRID_STRIDE(q, nnz) out[q] = av[q] / (dr[ai[q] - base] * dc[aj[q] - base]);
+}
+
 static unsigned red_grid(Handle *h, int64_t len)
 {
     int64_t g = (len + TB - 1) / TB;
@@ -1781,6 +1822,52 @@ int mipm_batch_iter_rest(mipm_handle hh, double mu_min, int step_rule, double ta
     MIPM_CUDA(h, cudaMemcpyAsync(m.d_c, m.d_rhs, (size_t)m.m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     if ((rc = mipm_spmv(hh, 0, 1.0, md.d_ATx, m.d_x, -1.0, m.d_c)) != MIPM_OK) return rc;
     return mipm_spmv(hh, 1, 1.0, md.d_ATx, m.d_y, 0.0, m.d_jacl);
+}
+
+/* ------------------------------------------------------------------ preprocessing ---- */
+int mipm_ruiz_equilibrate(mipm_handle hh, int64_t m, int64_t n, int64_t nnz, const int32_t *d_rows, const int32_t *d_cols,
+                          const double *d_vals, int index_base, int max_iter, double tol, double *d_Dr, double *d_Dc, int *iters)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (m < 0 || n < 0 || nnz < 0 || max_iter < 0 || (nnz > 0 && (!d_rows || !d_cols || !d_vals)) || (m > 0 && !d_Dr) || (n > 0 && !d_Dc))
+        return fail(h, MIPM_ERR_ARG, "bad argument");
+    DBuf<unsigned long long> d_max;
+    MIPM_CUDA(h, d_max.alloc((size_t)std::max<int64_t>(m + n, 1)));
+    MIPM_CUDA(h, cudaMemsetAsync(d_max.p, 0, (size_t)std::max<int64_t>(m + n, 1) * sizeof(unsigned long long), h->stream));
+    if (m > 0) { k_fill<<<red_grid(h, m), TB, 0, h->stream>>>(m, 1.0, d_Dr); MIPM_CHECK_LAUNCH(h); }
+    if (n > 0) { k_fill<<<red_grid(h, n), TB, 0, h->stream>>>(n, 1.0, d_Dc); MIPM_CHECK_LAUNCH(h); }
+    int it = 0;
+    for (; it < max_iter; ++it) {
+        if (nnz > 0) {
+            k_ruiz_max<<<red_grid(h, nnz), TB, 0, h->stream>>>(nnz, d_rows, d_cols, d_vals, index_base, d_Dr, d_Dc, d_max.p, d_max.p + m);
+            MIPM_CHECK_LAUNCH(h);
+        }
+        k_ruiz_apply<<<red_grid(h, std::max<int64_t>(std::max(m, n), 1)), TB, 0, h->stream>>>(m, n, d_Dr, d_Dc, d_max.p, d_max.p + m,
+                                                                                           h->d_partials.p, h->d_counter.p, h->d_scal.p);
+        MIPM_CHECK_LAUNCH(h);
+        if (tol > 0.0) {            // the convergence test costs a synchronisation per sweep: only when asked for
+            double dev;
+            int rc = fetch_scalars(h, 1, &dev);
+            if (rc != MIPM_OK) return rc;
+            if (dev <= tol) { ++it; break; }
+        }
+    }
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));      // d_max is released on return
+    if (iters) *iters = it;
+    return MIPM_OK;
+}
+
+int mipm_scale_coo(mipm_handle hh, int64_t nnz, const int32_t *d_rows, const int32_t *d_cols, const double *d_vals, int index_base,
+                   const double *d_Dr, const double *d_Dc, double *d_out)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (nnz < 0 || (nnz > 0 && (!d_rows || !d_cols || !d_vals || !d_Dr || !d_Dc || !d_out))) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (nnz == 0) return MIPM_OK;
+    k_scale_coo<<<red_grid(h, nnz), TB, 0, h->stream>>>(nnz, d_rows, d_cols, d_vals, index_base, d_Dr, d_Dc, d_out);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
 }
 
 }  // extern "C"

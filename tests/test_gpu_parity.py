@@ -427,6 +427,31 @@ def test_k25_scaled_kkt_system(built, name, index_base):
     assert got.status == k2["status"] and got.iter == k2["iter"] and abs(got.objective - k2["objective"]) <= 1e-6
 
 
+def test_ruiz_equilibration_and_standard_form(handle):
+    """Ruiz equilibration on the device (scale_qp, scripts/common.jl:57-100) bit-identical to the
+    sequential restatement; the scaled and the standard-form models solve to the original optimum on the CUDA path."""
+    from madipm_jl_b200.preprocess import scale_qp, standard_form_qp
+    from madipm_jl_b200.solver import madipm
+    from oracle.preprocess_ref import ruiz_equilibrate
+    from madipm_jl_b200.problems import badly_scaled_lp
+    qp = badly_scaled_lp(120, 400, 5, 2)
+    for max_iter, tol in ((10, 0.0), (50, 1e-8)):
+        sq, dr, dc = scale_qp(qp, max_iter=max_iter, tol=tol, return_scaling=True)
+        rr, rc, _ = ruiz_equilibrate(qp.ncon, qp.nvar, qp.Arows, qp.Acols, qp.Avals, max_iter=max_iter, tol=tol)
+        assert np.array_equal(dr, rr) and np.array_equal(dc, rc)
+        assert np.array_equal(sq.Avals, qp.Avals / (rr[qp.Arows] * rc[qp.Acols]))
+    v = np.abs(sq.Avals)
+    rmax = np.zeros(qp.ncon)
+    np.maximum.at(rmax, qp.Arows, v)
+    assert np.abs(rmax[rmax > 0] - 1.0).max() < 1e-6
+    ref = oracle_madipm(qp, kkt_system="K2")
+    for model in (sq, standard_form_qp(qp), standard_form_qp(sq)):
+        got = madipm(model, kkt_system="K2")
+        assert got.status == "SOLVE_SUCCEEDED" and abs(got.objective - ref.objective) <= 1e-6 * max(1.0, abs(ref.objective))
+        got_n = madipm(standard_form_qp(model) if model is sq else model, kkt_system="Normal")
+        assert got_n.status == "SOLVE_SUCCEEDED" and abs(got_n.objective - ref.objective) <= 1e-5 * max(1.0, abs(ref.objective))
+
+
 def test_simple_lp_reference_pin_on_gpu(built):
     """test/test_gpu.jl:4-22 + runtests.jl:144-198: status only in the reference; we also pin objective 1.0."""
     from madipm_jl_b200.solver import madipm

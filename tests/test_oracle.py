@@ -183,3 +183,35 @@ def test_k25_scaled_kkt_system_matches_k2(make):
     assert abs(k25.objective - ref.objective) <= 1e-6
     for f in ("solution", "constraints", "multipliers"):
         assert np.abs(getattr(k25, f) - getattr(ref, f)).max() <= 1e-6
+
+
+def test_standard_form_qp_matches_the_original_problem():
+    """test/runtests.jl:159-164: the standard-form reformulation (src/utils.jl:373-505) solves to the same objective."""
+    from madipm_jl_b200.preprocess import standard_form_qp
+    from madipm_jl_b200.problems import mixed_bounds_lp
+    for qp in (mixed_bounds_lp(30, 90, 4, 1), random_sparse_qp(60, 200, 4, 9, structure="window", window=10),
+               random_sparse_lp(40, 160, 5, 7, structure="uniform", ub_fraction=0.5)):
+        std = standard_form_qp(qp)
+        n_rng = int(np.sum(np.isfinite(qp.lvar) & np.isfinite(qp.uvar) & (qp.lvar < qp.uvar)))
+        ineq = qp.lcon < qp.ucon
+        n_rng += int(np.sum(np.isfinite(qp.lcon[ineq]) & np.isfinite(qp.ucon[ineq])))
+        assert std.nvar == qp.nvar + int(ineq.sum()) + n_rng and std.ncon == qp.ncon + n_rng
+        assert np.all(std.lcon == std.ucon)                   # only equality rows are left
+        assert not np.any(np.isfinite(std.lvar) & np.isfinite(std.uvar) & (std.lvar < std.uvar) & (np.arange(std.nvar) < qp.nvar))
+        a, b = madipm(qp, kkt_system="K2"), madipm(std, kkt_system="K2")
+        assert a.status == b.status == "SOLVE_SUCCEEDED"
+        assert abs(a.objective - b.objective) <= 1e-7 * max(1.0, abs(a.objective))
+
+
+def test_ruiz_restatement_equilibrates():
+    from oracle.preprocess_ref import ruiz_equilibrate
+    rng = np.random.default_rng(0)
+    m, n = 50, 120
+    rows, cols = rng.integers(0, m, 600), rng.integers(0, n, 600)
+    vals = rng.standard_normal(600) * 10.0 ** rng.uniform(-4, 4, 600)
+    dr, dc, it = ruiz_equilibrate(m, n, rows, cols, vals, max_iter=30, tol=1e-6)
+    v = np.abs(vals) / dr[rows] / dc[cols]
+    r, c = np.zeros(m), np.zeros(n)
+    np.maximum.at(r, rows, v)
+    np.maximum.at(c, cols, v)
+    assert np.abs(r[r > 0] - 1).max() < 1e-5 and np.abs(c[c > 0] - 1).max() < 1e-5 and it < 30
