@@ -167,8 +167,7 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[4][2][2], const double *
     const double *xa = sa + l3 * XS + wm * 32 + g;
     const double *yb = sb + l3 * XS + wn * 16 + g;
     if (fmask == 0u) return;
-#pragma unroll 1       // (ptxas 12.9 crashes on the LDL^T instantiation with this loop unrolled)
-    for (int kk = 0; kk < nk4; kk += 4) {
+    auto step = [&](int kk) {
         double a[4], b[2];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) a[mi] = xa[kk * XS + mi * 8];
@@ -184,6 +183,13 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[4][2][2], const double *
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni)
                 if (fmask & (1u << (mi * 2 + ni))) dmma_8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    };
+    if (SCALE) {
+#pragma unroll 1       // (ptxas 12.9 crashes on the LDL^T instantiation with this loop unrolled)
+        for (int kk = 0; kk < nk4; kk += 4) step(kk);
+    } else {
+#pragma unroll 4
+        for (int kk = 0; kk < nk4; kk += 4) step(kk);
     }
 }
 

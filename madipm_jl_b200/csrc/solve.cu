@@ -271,6 +271,32 @@ __device__ __forceinline__ void tile_update(const double *P, int64_t ld, int row
     __syncthreads();
 }
 
+// L2 prefetch of what one big-front task will read, issued before the task waits for its dependencies
+__device__ __forceinline__ void prefetch_big(const SolveParams &p, const FrontInfo &f, bool fwd, int part)
+{
+    const int k = f.k, N = f.k + f.r, ld = front_ld(f.k, f.r);
+    const char *P = reinterpret_cast<const char *>(p.L + f.lp);
+    const int nblk = (k + NB - 1) / NB;
+    if (fwd) {                  // rows [64 part, +64) of the columns before (and of) the tile's diagonal block
+        const int ncol = min(k, (part + 1) * NB);
+        const int64_t row_off = (int64_t)part * 64 * 8;
+        for (int i = threadIdx.x; i < ncol * 4; i += 256)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P + ((int64_t)(i >> 2) * ld) * 8 + row_off + (i & 3) * 128));
+    } else {                    // columns of block `part`, rows from the block down
+        const int jb = part * NB, nc = min(NB, k - jb);
+        const int64_t col_bytes = (int64_t)(N - jb) * 8;
+        const int lines = (int)((col_bytes + 127) >> 7);
+        for (int i = threadIdx.x; i < nc * lines; i += 256) {
+            const int c = i / lines, l = i - c * lines;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P + ((int64_t)(jb + c) * ld + jb) * 8 + (int64_t)l * 128));
+        }
+    }
+    if (part < nblk) {
+        const char *dv = reinterpret_cast<const char *>(p.Dinv + (f.dinv + part) * (int64_t)(NB * XS));
+        for (int i = threadIdx.x; i < NB * XS * 8 / 128; i += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(dv + (int64_t)i * 128));
+    }
+}
+
 template <bool LDL>
 __device__ void big_forward_tile(const SolveParams &p, int s, int t, double *smem, int mode)
 {
@@ -537,6 +563,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_tasks(SolveParams p)
             const FrontInfo f = p.fi[s];
             const bool fwd = (tk.x == 4);
             const int mode = (fwd && s == p.root_sn) ? p.root_mode : 0;
+            if (fwd ? (f.nchild > 0 || tk.z > 0) : true) prefetch_big(p, f, fwd, tk.z);      // the task is going to wait
             if (tid == 0) {
                 if (fwd) { if (f.nchild > 0 && mode != 2) { while (ld_acquire_s(p.fprog + s) < f.nchild) __nanosleep(40); } }
                 else if (f.parent >= 0) { while (ld_acquire_s(p.bdone + f.parent) == 0) __nanosleep(40); }
