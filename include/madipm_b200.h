@@ -329,6 +329,15 @@ int mipm_mpc_iter_begin(mipm_handle h, double del_w, double del_c, double *out, 
 int mipm_mpc_refactor(mipm_handle h, double del_w, double del_c, int *status);
 int mipm_mpc_iter_rest(mipm_handle h, double mu_min, int step_rule, double tau_param, int ir_steps);
 
+/* The same fused iteration around an EXTERNAL linear solver (the distributed block-angular solver, whose staged
+ * factorization / solves have NCCL exchanges between them): the iteration is cut where the normal system is factorized
+ * and solved. NormalKKTSystem only. Per iteration: _ext_begin (measures + diagonals + assembly) -> caller factorizes
+ * aug_nz -> _ext_fetch (the one synchronisation, out[16] as mipm_mpc_iter_begin) -> _ext_phase(0) -> caller solves
+ * buffer_m in place -> _ext_phase(1) -> caller solves buffer_m -> _ext_phase(2). */
+int mipm_mpc_ext_begin(mipm_handle h, double del_w, double del_c);
+int mipm_mpc_ext_fetch(mipm_handle h, double *out);
+int mipm_mpc_ext_phase(mipm_handle h, int phase, double mu_min, int step_rule, double tau_param);
+
 /* ------------------------------------------------------------------ batches ---------- */
 /* BASELINE config C5 (a batch of independent LPs / QPs; the reference solves them one after the other). The B units
  * are STACKED into one block-diagonal problem -- x, bounds, multipliers and KKT vectors of unit u occupy

@@ -71,7 +71,7 @@ SYMBOLS = [
     "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk", "mipm_mehrotra_adaptive_step", "mipm_set_aug_diagonal_reg_scaled", "mipm_k25_scale_values",
     "mipm_reduce_rhs_scaled", "mipm_finish_aug_solve_scaled", "mipm_kktmul_scaled",
     "mipm_batch_configure", "mipm_batch_set_active", "mipm_batch_amax", "mipm_batch_dot", "mipm_batch_init_point_stage",
-    "mipm_batch_iter_begin", "mipm_batch_iter_rest", "mipm_ruiz_equilibrate", "mipm_scale_coo",
+    "mipm_batch_iter_begin", "mipm_batch_iter_rest", "mipm_ruiz_equilibrate", "mipm_scale_coo", "mipm_mpc_ext_begin", "mipm_mpc_ext_fetch", "mipm_mpc_ext_phase",
 ]
 
 _lib = None
@@ -276,6 +276,18 @@ class Handle:
 
     def mpc_iter_rest(self, mu_min, step_rule, tau_param, ir_steps):
         self.check(self.lib.mipm_mpc_iter_rest(self.h, C.c_double(mu_min), C.c_int(step_rule), C.c_double(tau_param), C.c_int(ir_steps)))
+
+    # ---- fused iteration around an external linear solver
+    def mpc_ext_begin(self, del_w, del_c):
+        self.check(self.lib.mipm_mpc_ext_begin(self.h, C.c_double(del_w), C.c_double(del_c)))
+
+    def mpc_ext_fetch(self):
+        out = (C.c_double * 16)()
+        self.check(self.lib.mipm_mpc_ext_fetch(self.h, out))
+        return list(out)
+
+    def mpc_ext_phase(self, phase, mu_min, step_rule, tau_param):
+        self.check(self.lib.mipm_mpc_ext_phase(self.h, C.c_int(phase), C.c_double(mu_min), C.c_int(step_rule), C.c_double(tau_param)))
 
     # ---- preprocessing
     def ruiz_equilibrate(self, m, n, rows, cols, vals, Dr, Dc, max_iter=10, tol=0.0, index_base=0):

@@ -162,8 +162,12 @@ __device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv,
     int nbad = 0, ntiny = 0;                // meaningful in warp 0 / lane 0 only
     double *Ysc = Sinv + (DB - PW) * DLD;   // panel scratch Y(r, j) at Ysc[j * DLD + r - PW]: the part of Sinv above its
                                             // last diagonal block, which the inverse never uses
+    // Only the 16-column panels that hold real columns are factored: the rest of the block is the identity padding. Fronts
+    // of K2 systems and of block-angular problems are mostly narrower than 32 columns (C4: 19 on average), so this is most
+    // of the diagonal-block work there.
+    const int nbr = min(DB, ((nb + PW - 1) / PW) * PW);
 #pragma unroll 1
-    for (int pc = 0; pc < DB; pc += PW) {
+    for (int pc = 0; pc < nbr; pc += PW) {
         if (warp == 0) {
             // lanes 0-15: row i of the 16 x 16 block. lanes 16-31: column i of inv(L11), carried through the SAME
             // instruction stream: with m = e_i in place of the row, step j does m[k] -= (m[j]/d_j) A(k,j), which is
@@ -221,7 +225,7 @@ __device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv,
                 for (int k = 0; k < PW; ++k) Sinv[(pc + i) * DLD + pc + k] = a[k];      // M(k, i), zero above the diagonal
             }
         }
-        const int nbelow = DB - pc - PW;
+        const int nbelow = nbr - pc - PW;
         if (nbelow == 0) break;             // uniform
         __syncthreads();
         DIAG_STAMP(1);
@@ -229,7 +233,8 @@ __device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv,
         {
             const int r = tid & 63, jq = tid >> 6;
             double l4[4] = {0.0, 0.0, 0.0, 0.0};
-            if (r >= pc + PW) {
+            const bool below = r >= pc + PW && r < nbr;
+            if (below) {
                 double x[PW];
 #pragma unroll
                 for (int k = 0; k < PW; ++k) x[k] = S[(pc + k) * DLD + r];
@@ -249,7 +254,7 @@ __device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv,
             }
             __syncthreads();
             DIAG_STAMP(2);
-            if (r >= pc + PW) {
+            if (below) {
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) S[(pc + 4 * jq + jj) * DLD + r] = l4[jj];
             }
@@ -275,6 +280,7 @@ __device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv,
         const int r = tid & 15, c0 = tid >> 4;
 #pragma unroll
         for (int ib = 1; ib < DB / PW; ++ib) {
+            if (ib * PW >= nbr) break;                                   // uniform: identity padding needs no inverse
             const int row0 = ib * PW;
             double t[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -320,7 +326,7 @@ __device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv,
     // ---- write out: the factor (Cholesky: L = L_unit sqrt(D); LDL^T: unit multipliers, D on the diagonal) and its
     // inverse (Cholesky: D^-1/2 inv(L_unit))
     if (tid < DB) {
-        const double d = dv[tid];
+        const double d = (tid < nbr) ? dv[tid] : 1.0;
         const double sq = LDL ? d : sqrt(d);
         dv[tid] = sq;
         invd[tid] = LDL ? 1.0 : 1.0 / sq;
@@ -332,7 +338,8 @@ __device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv,
             const double v = S[cc * DLD + rr];
             P[(int64_t)cc * N + rr] = (rr == cc) ? dv[cc] : (LDL ? v : v * dv[cc]);
         }
-        Dv[cc * ldv + rr] = (rr >= cc) ? Sinv[cc * DLD + rr] * invd[rr] : 0.0;
+        if (rr >= nbr || cc >= nbr) Dv[cc * ldv + rr] = (rr == cc) ? 1.0 : 0.0;       // identity outside the factored panels
+        else Dv[cc * ldv + rr] = (rr >= cc) ? Sinv[cc * DLD + rr] * invd[rr] : 0.0;
     }
     DIAG_STAMP(6);
     if (DBG && dbg && tid == 0) for (int i = 0; i < 7; ++i) dbg[i] = tq[i];

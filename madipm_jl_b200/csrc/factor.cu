@@ -337,6 +337,16 @@ __device__ void task_extend_add(const FactorParams &p, const FrontInfo &f, int q
             // rows of one child column land on distinct parent rows: four independent read-modify-writes in flight
             // per lane (the plain loop is a chain of dependent global round trips)
             int a = b + lane;
+            for (; a + 224 < rc; a += 256) {            // eight in flight: tall children (border rows of block-angular fronts)
+                int rr[8];
+                double sv[8], dv[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { rr[t] = rel[a + 32 * t]; sv[t] = src[a + 32 * t]; }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) dv[t] = dst[rr[t]];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) dst[rr[t]] = dv[t] + sv[t];
+            }
             for (; a + 96 < rc; a += 128) {
                 const int r0 = rel[a], r1 = rel[a + 32], r2 = rel[a + 64], r3 = rel[a + 96];
                 const double s0 = src[a], s1 = src[a + 32], s2 = src[a + 64], s3 = src[a + 96];
@@ -744,7 +754,7 @@ int ls_device_setup(Handle *h)
                 const FrontInfo &f = finfo[(size_t)S.level_sn[(size_t)t]];
                 if (f.nchild > 0) nt += (f.k + f.r + ea_cols / 2 - 1) / (ea_cols / 2);
             }
-            if (ea_cols <= 8 || nt > ea_task_factor * grid_estimate) break;
+            if (ea_cols <= 4 || nt > ea_task_factor * grid_estimate) break;
             ea_cols /= 2;
         }
         std::vector<std::vector<std::vector<Task>>> groups;       // [front in level][group][task]

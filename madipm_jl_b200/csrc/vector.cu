@@ -1870,4 +1870,138 @@ int mipm_scale_coo(mipm_handle hh, int64_t nnz, const int32_t *d_rows, const int
     return MIPM_OK;
 }
 
+/* ------------------------------------------------------------------ fused iteration around an EXTERNAL linear solver ---- */
+// The same device-resident-scalar iteration, cut at the points where the normal system is factorized / solved, for
+// linear solvers that live outside this handle (the distributed block-angular solver: staged factorization and solves
+// with NCCL exchanges in between). NormalKKTSystem only. Sequence per iteration:
+//   mipm_mpc_ext_begin(del_w, del_c)    termination measures + set_aug_diagonal_reg! + build_kkt!   [caller: factorize aug_nz]
+//   mipm_mpc_ext_fetch(out)             the one synchronisation: out[16] as mipm_mpc_iter_begin
+//   mipm_mpc_ext_phase(0, ..)           predictive rhs, d = p, reduce + r2 = A Sigma^-1 r1 - r2      [caller: solve buffer_m]
+//   mipm_mpc_ext_phase(1, ..)           finish the solve + residual norms, ratio test, centering, correction rhs,
+//                                       d = p, reduce + r2                                          [caller: solve buffer_m]
+//   mipm_mpc_ext_phase(2, ..)           finish the solve + residual norms, step rule, apply_step!, evaluate_model!
+static int ext_ready(Handle *h)
+{
+    if (!h->bound) return fail(h, MIPM_ERR_STATE, "mipm_mpc_bind has not been called");
+    if (!h->has_model || h->model.kkt_kind != 0) return fail(h, MIPM_ERR_STATE, "mipm_mpc_set_model (NormalKKTSystem) has not been called");
+    if (!h->has_spmv || !h->has_jac) return fail(h, MIPM_ERR_STATE, "SpMV / normal-equations assembly not set up");
+    return MIPM_OK;
+}
+
+static int ext_solve_pre(Handle *h)
+{
+    mipm_handle hh = (mipm_handle)h;
+    const mipm_mpc_vectors &m = h->v;
+    const mipm_mpc_model &md = h->model;
+    const int64_t N = m.n + m.m + m.nlb + m.nub;
+    int rc;
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_d, m.d_p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = mipm_normal_solve_stage(hh, 0, m.d_d, md.d_buffer_n, md.d_buffer_m)) != MIPM_OK) return rc;
+    return mipm_spmv(hh, 0, 1.0, md.d_ATx, md.d_buffer_n, -1.0, md.d_buffer_m);
+}
+
+static int ext_solve_post(Handle *h, int slot)
+{
+    mipm_handle hh = (mipm_handle)h;
+    const mipm_mpc_vectors &m = h->v;
+    const mipm_mpc_model &md = h->model;
+    const int64_t N = m.n + m.m + m.nlb + m.nub;
+    int rc;
+    if ((rc = mipm_normal_solve_stage(hh, 1, m.d_d, md.d_buffer_n, md.d_buffer_m)) != MIPM_OK) return rc;
+    if ((rc = mipm_spmv(hh, 1, -1.0, md.d_ATx, md.d_buffer_m, 1.0, md.d_buffer_n)) != MIPM_OK) return rc;
+    if ((rc = mipm_normal_solve_stage(hh, 2, m.d_d, md.d_buffer_n, md.d_buffer_m)) != MIPM_OK) return rc;
+    // residual check of solve_system! (src/linear_solver.jl:29-35)
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_w, m.d_p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = mipm_spmv(hh, 1, -1.0, md.d_ATx, m.d_d + m.n, 1.0, m.d_w)) != MIPM_OK) return rc;
+    if ((rc = mipm_spmv(hh, 0, -1.0, md.d_ATx, m.d_d, 1.0, m.d_w + m.n)) != MIPM_OK) return rc;
+    if ((rc = mipm_kktmul(hh, m.d_w, m.d_d, -1.0, 1.0)) != MIPM_OK) return rc;
+    k_two_norms<<<red_grid(h, std::max<int64_t>(N, 1)), TB, 0, h->stream>>>(N, m.d_w, m.d_p, h->d_partials.p, h->d_counter.p,
+                                                                         h->d_sc.p + SC_RES + 2 * slot);
+    MIPM_CHECK_LAUNCH(h);
+    return MIPM_OK;
+}
+
+int mipm_mpc_ext_begin(mipm_handle hh, double del_w, double del_c)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    int rc = ext_ready(h);
+    if (rc != MIPM_OK) return rc;
+    V v = make_view(h, inv_lb_buf(h).p, inv_ub_buf(h).p);
+    const int64_t nmax = std::max<int64_t>(std::max(v.n, v.m), 1);
+    k_termination<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, h->d_partials.p, h->d_counter.p, h->d_sc.p + SC_TERM);
+    MIPM_CHECK_LAUNCH(h);
+    if ((rc = mipm_set_aug_diagonal_reg(hh, del_w, del_c)) != MIPM_OK) return rc;
+    return mipm_normal_assemble(hh, h->v.d_pr_diag, h->model.d_aug_nz, h->model.exact_order);
+}
+
+int mipm_mpc_ext_fetch(mipm_handle hh, double *out)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    int rc = ext_ready(h);
+    if (rc != MIPM_OK) return rc;
+    if (!out) return fail(h, MIPM_ERR_ARG, "null argument");
+    MIPM_CUDA(h, cudaMemcpyAsync(h->h_scal, h->d_sc.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+    const double *sc = h->h_scal;
+    const mipm_mpc_vectors &m = h->v;
+    double dobj = sc[SC_TERM + 0];
+    if (m.nlb > 0) dobj += sc[SC_TERM + 1];
+    if (m.nub > 0) dobj -= sc[SC_TERM + 2];
+    out[0] = dobj;
+    out[1] = sc[SC_TERM + 3]; out[2] = sc[SC_TERM + 4]; out[3] = sc[SC_TERM + 5]; out[4] = sc[SC_TERM + 6];
+    out[5] = sc[SC_OBJ]; out[6] = sc[SC_OBJ + 1];
+    out[7] = sc[SC_ALPHA_P]; out[8] = sc[SC_ALPHA_D]; out[9] = sc[SC_MU]; out[10] = sc[SC_MU_CURR];
+    out[11] = sc[SC_RES + 0]; out[12] = sc[SC_RES + 1]; out[13] = sc[SC_RES + 2]; out[14] = sc[SC_RES + 3];
+    out[15] = sc[SC_TAU];
+    return MIPM_OK;
+}
+
+int mipm_mpc_ext_phase(mipm_handle hh, int phase, double mu_min, int step_rule, double tau_param)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    int rc = ext_ready(h);
+    if (rc != MIPM_OK) return rc;
+    if (phase < 0 || phase > 2 || step_rule < 0 || step_rule > 2) return fail(h, MIPM_ERR_ARG, "bad phase / step rule");
+    V v = make_view(h, inv_lb_buf(h).p, inv_ub_buf(h).p);
+    const mipm_mpc_model &md = h->model;
+    const mipm_mpc_vectors &m = h->v;
+    const int64_t nmax = std::max<int64_t>(std::max(v.n, v.m), 1);
+    const unsigned g = red_grid(h, nmax);
+    double *sc = h->d_sc.p;
+    if (phase == 0) {
+        k_set_rhs<<<g, TB, 0, h->stream>>>(v, 0, 0.0, nullptr);
+        MIPM_CHECK_LAUNCH(h);
+        return ext_solve_pre(h);
+    }
+    if (phase == 1) {
+        if ((rc = ext_solve_post(h, 0)) != MIPM_OK) return rc;
+        k_alpha_max<<<g, TB, 0, h->stream>>>(v, 1.0, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, nullptr, 0.0, sc);
+        MIPM_CHECK_LAUNCH(h);
+        k_predictor_measures<<<g, TB, 0, h->stream>>>(v, mu_min, h->d_partials.p, h->d_counter.p, sc);
+        MIPM_CHECK_LAUNCH(h);
+        k_set_rhs<<<g, TB, 0, h->stream>>>(v, 1, 0.0, sc + SC_MU);
+        MIPM_CHECK_LAUNCH(h);
+        return ext_solve_pre(h);
+    }
+    if ((rc = ext_solve_post(h, 1)) != MIPM_OK) return rc;
+    if (step_rule == 2) {
+        if ((rc = mehrotra_step_launch(h, v, g, tau_param, sc)) != MIPM_OK) return rc;
+    } else {
+        if (step_rule == 0) k_alpha_max<<<g, TB, 0, h->stream>>>(v, 0.0, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, sc, tau_param, sc);
+        else k_alpha_max<<<g, TB, 0, h->stream>>>(v, tau_param, h->d_partials.p, h->d_counter.p, sc + SC_ALPHA, nullptr, 0.0, sc);
+        MIPM_CHECK_LAUNCH(h);
+    }
+    k_apply_step<<<g, TB, 0, h->stream>>>(v, 0.0, 0.0, 0.0, pow(DBL_EPSILON, 0.75), sc);
+    MIPM_CHECK_LAUNCH(h);
+    k_dot<<<red_grid(h, std::max<int64_t>(md.nx, 1)), TB, 0, h->stream>>>(md.nx, md.d_cvec, m.d_x, h->d_partials.p, h->d_counter.p, sc + SC_OBJ);
+    MIPM_CHECK_LAUNCH(h);
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_f, md.d_cvec, (size_t)m.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    MIPM_CUDA(h, cudaMemcpyAsync(m.d_c, m.d_rhs, (size_t)m.m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = mipm_spmv(hh, 0, 1.0, md.d_ATx, m.d_x, -1.0, m.d_c)) != MIPM_OK) return rc;
+    return mipm_spmv(hh, 1, 1.0, md.d_ATx, m.d_y, 0.0, m.d_jacl);
+}
+
 }  // extern "C"

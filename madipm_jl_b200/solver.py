@@ -744,7 +744,7 @@ class MPCSolver:
 
     def _use_fused(self):
         return (self.opt.fused and self.opt.max_ncorr <= 0 and not self.opt.check_residual
-                and self.opt.linear_solver == "b200" and self.opt.kkt_system != "K2.5"
+                and self.opt.kkt_system != "K2.5"
                 and isinstance(self.opt.step_rule, (AdaptiveStep, ConservativeStep, MehrotraAdaptiveStep)))
 
     def _mpc_iteration_fused(self):
@@ -752,7 +752,14 @@ class MPCSolver:
         opt = self.opt
         trace_del_w = self.del_w
         self.update_regularization()                      # host-side schedule (kernels.jl:370-401)
-        out, ok = self.h.mpc_iter_begin(self.del_w, self.del_c)
+        ext = opt.linear_solver != "b200"                 # external (distributed) linear solver: phased entry points
+        if ext:
+            self.h.mpc_ext_begin(self.del_w, self.del_c)
+            self.linear_solver.factorize()
+            ok = self.linear_solver.is_factorized()
+            out = self.h.mpc_ext_fetch()
+        else:
+            out, ok = self.h.mpc_iter_begin(self.del_w, self.del_c)
         if self._fused_started:                            # scalars of the step taken in the previous call
             self.obj_val = self.obj_scale * self.qp.c0 + out[5] + 0.5 * out[6]
             self.alpha_p, self.alpha_d, self.mu, self.mu_curr = out[7], out[8], out[9], out[10]
@@ -790,15 +797,24 @@ class MPCSolver:
                 break
             self.del_w *= 100.0
             self.del_c *= 100.0
-            ok = self.h.mpc_refactor(self.del_w, self.del_c)
+            if ext:
+                self.h.set_aug_diagonal_reg(self.del_w, self.del_c)
+                self.factorize_wrapper()
+                ok = self.linear_solver.is_factorized()
+            else:
+                ok = self.h.mpc_refactor(self.del_w, self.del_c)
             self.cnt["factorizations"] += 1
         rule = opt.step_rule
-        if isinstance(rule, AdaptiveStep):
-            self.h.mpc_iter_rest(opt.mu_min, 0, rule.tau_min, self._fused_ir)
-        elif isinstance(rule, MehrotraAdaptiveStep):
-            self.h.mpc_iter_rest(opt.mu_min, 2, rule.gamma_f, self._fused_ir)
+        code, par = ((0, rule.tau_min) if isinstance(rule, AdaptiveStep) else
+                     (2, rule.gamma_f) if isinstance(rule, MehrotraAdaptiveStep) else (1, rule.tau))
+        if ext:
+            self.h.mpc_ext_phase(0, opt.mu_min, code, par)
+            self.linear_solver.solve(self.buffer_m)
+            self.h.mpc_ext_phase(1, opt.mu_min, code, par)
+            self.linear_solver.solve(self.buffer_m)
+            self.h.mpc_ext_phase(2, opt.mu_min, code, par)
         else:
-            self.h.mpc_iter_rest(opt.mu_min, 1, rule.tau, self._fused_ir)
+            self.h.mpc_iter_rest(opt.mu_min, code, par, self._fused_ir)
         self.cnt["solves"] += 2
         self._fused_started = True
         self.k += 1

@@ -94,6 +94,7 @@ static int run(int nblk, int nb, bool check, int special = 0)
 int main()
 {
     run<false>(1, 64, true); run<false>(1, 37, true); run<true>(1, 64, true); run<true>(1, 50, true);
+    run<false>(1, 5, true); run<false>(1, 16, true); run<true>(1, 20, true); run<true>(1, 33, true); run<false>(1, 48, true); run<false>(444, 20, false);
     run<false>(1, 64, false, 1); run<true>(1, 64, true, 2);
     run<false>(1, 64, false); run<false>(1, 64, false); run<false>(148, 64, false); run<false>(444, 64, false); run<false>(888, 64, false);
     return 0;
