@@ -21,6 +21,7 @@
 // moved global -> shared by TMA bulk copies (cp.async.bulk + mbarrier complete_tx, 16 columns per stage, 4 stages),
 // so the K loop overlaps copies and math without staging through registers.
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -49,9 +50,10 @@ enum { T_EA = 0, T_DIAG = 1, T_PANEL = 2, T_TRAIL = 3, T_LEAF = 4, T_NCLASS = 5 
 struct __align__(16) Task {
     int32_t type, front;
     int32_t a, b, c, d;         // EA: q0, q1, offset of the child ranges | DIAG: jb, K0 | PANEL: jb, K0, row0 | TRAIL: K0, K1, row0, col0
-    int32_t need;               // completions of `front` (children + own earlier tasks) this task waits for
-    int32_t pad;
+    int32_t need;               // completions on the front's chain counter (children + own chain tasks) this task waits for
+    int32_t need_b;             // look-ahead fronts: completions on the second counter (deferred trailing tiles) it waits for
 };
+constexpr int T_DEFERRED = 0x100;   // type flag: the task counts on the second counter
 static_assert(sizeof(Task) == 32, "Task must match Handle::T32");
 
 struct FactorParams {
@@ -62,7 +64,8 @@ struct FactorParams {
     int task_begin, task_end;       // this launch executes tasks [task_begin, task_end)
     double *L, *U, *Dinv, *Dg;
     int *info;
-    int *prog;                      // per front: completions so far
+    int *prog;                      // per front: completions so far on the chain counter (children included)
+    int *prog_b, *done;             // per front: completions of deferred trailing tiles; of all own tasks
     int *ticket;
     unsigned long long *prof;       // 8 per CTA: busy ns per task class, wait ns, first start, last end
     unsigned long long *front_ns;   // optional: completion time of every front
@@ -572,11 +575,13 @@ __global__ void __launch_bounds__(256, 3) k_factor_tasks(FactorParams p)
         int next = 0;
         unsigned long long t0 = 0, t1 = 0;
         FrontInfo f;
-        if (tk.type != T_LEAF) {
+        const int ttype = tk.type & 0xff;
+        if (ttype != T_LEAF) {
             f = p.fi[tk.front];
             if (tid == 0) {
                 t0 = globaltimer_ns();
                 while (ld_acquire(p.prog + tk.front) < tk.need) __nanosleep(40);
+                if (tk.need_b > 0) { while (ld_acquire(p.prog_b + tk.front) < tk.need_b) __nanosleep(40); }
                 asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copies below read what other CTAs wrote
                 t1 = globaltimer_ns();
                 next = p.task_begin + atomicAdd(p.ticket, 1);      // in flight while the task runs
@@ -586,7 +591,7 @@ __global__ void __launch_bounds__(256, 3) k_factor_tasks(FactorParams p)
             next = p.task_begin + atomicAdd(p.ticket, 1);
         }
         __syncthreads();
-        switch (tk.type) {
+        switch (ttype) {
         case T_LEAF: {
             const int li = tk.a + (tid >> 5);
             if ((tid >> 5) < tk.b) leaf_factor<LDL>(p, p.sched[li]);
@@ -600,9 +605,10 @@ __global__ void __launch_bounds__(256, 3) k_factor_tasks(FactorParams p)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes of this task before later bulk copies
         __syncthreads();
         if (tid == 0) {
-            if (tk.type != T_LEAF) {
+            if (ttype != T_LEAF) {
                 __threadfence();
-                const int old = atomicAdd(p.prog + tk.front, 1);
+                atomicAdd(((tk.type & T_DEFERRED) ? p.prog_b : p.prog) + tk.front, 1);
+                const int old = atomicAdd(p.done + tk.front, 1);
                 if (old + 1 == f.total) {
                     if (p.front_ns) p.front_ns[tk.front] = globaltimer_ns();
                     if (f.parent >= 0) {
@@ -613,7 +619,7 @@ __global__ void __launch_bounds__(256, 3) k_factor_tasks(FactorParams p)
             }
             t_last = globaltimer_ns();
             s_busy[5] += t1 - t0;
-            s_busy[tk.type] += t_last - t1;
+            s_busy[ttype] += t_last - t1;
             if (p.trace) {
                 unsigned long long *tr = p.trace + 4 * (size_t)t;
                 tr[0] = t0; tr[1] = t1; tr[2] = t_last; tr[3] = (unsigned long long)read_smid();
@@ -706,9 +712,14 @@ int ls_device_setup(Handle *h)
     if (device_info(h->device, prop) != MIPM_OK) return fail(h, MIPM_ERR_CUDA, "cudaGetDeviceProperties failed");
     if (!prop.cooperative) return fail(h, MIPM_ERR_CUDA, "device does not support cooperative launch");
     const int grid_estimate = prop.sm_count * 3;       // __launch_bounds__(256, 3)
-    // super-panel width: columns whose updates are accumulated in registers before the trailing matrix is touched
-    int SP = 256;
+    // super-panel width: columns whose updates are accumulated in registers before the trailing matrix is touched.
+    // Measured on C1, C2, its mesh variant and C4 (profiles/r02_notes.md): 64 (one block step per panel) is as fast or
+    // faster than 128 / 256 everywhere -- the operand re-reads of a right-looking update hit L2, while a wider panel puts
+    // its left-looking K loops on the dependency chain of the front. Wider panels stay available for sweeps.
+    int SP = 64;
     int ea_task_factor = 4, stagger = 1;
+    int la_min_k = 512;          // fronts at least this wide factor with look-ahead (second progress counter)
+    if (const char *e = std::getenv("MIPM_LOOKAHEAD_MIN")) la_min_k = std::max(2 * NB, atoi(e));
     if (const char *e = std::getenv("MIPM_EA_FACTOR")) ea_task_factor = std::max(1, atoi(e));
     if (const char *e = std::getenv("MIPM_NO_STAGGER")) stagger = (atoi(e) == 0);
     if (const char *e = std::getenv("MIPM_SUPER_PANEL")) SP = std::max(NB, (atoi(e) / NB) * NB);
@@ -723,7 +734,7 @@ int ls_device_setup(Handle *h)
     int root_task_begin = -1;
     auto mk = [](int type, int front, int a, int b, int c, int d) {
         Task t;
-        t.type = type; t.front = front; t.a = a; t.b = b; t.c = c; t.d = d; t.need = 0; t.pad = 0;
+        t.type = type; t.front = front; t.a = a; t.b = b; t.c = c; t.d = d; t.need = 0; t.need_b = 0;
         return t;
     };
     for (int l = 0; l < S.n_levels; ++l) {
@@ -794,32 +805,100 @@ int ls_device_setup(Handle *h)
                 if (!ea.empty()) G.push_back(std::move(ea));
             }
             const size_t n_ea_groups = G.size();
-            for (int J0 = 0; J0 < k;) {
-                int J1 = (k - J0 <= SP + NB) ? k : J0 + SP;
-                for (int jb = J0; jb < J1; jb += NB) {
-                    G.push_back({mk(T_DIAG, s, jb, J0, 0, 0)});
-                    const int j1 = jb + std::min(NB, k - jb);
-                    std::vector<Task> pt;
-                    for (int row0 = j1; row0 < N; row0 += TILE) pt.push_back(mk(T_PANEL, s, jb, J0, row0, 0));
-                    if (!pt.empty()) G.push_back(std::move(pt));
+            auto trailing_starts = [&](int J1) {
+                std::vector<int> st2;
+                for (int x = J1; x < k; x += TILE) st2.push_back(x);
+                for (int x = k; x < N; x += TILE) st2.push_back(x);
+                return st2;
+            };
+            const bool lookahead = k >= la_min_k && (k + SP - 1) / SP >= 2;
+            if (!lookahead) {
+                for (int J0 = 0; J0 < k;) {
+                    int J1 = (k - J0 <= SP + NB) ? k : J0 + SP;
+                    for (int jb = J0; jb < J1; jb += NB) {
+                        G.push_back({mk(T_DIAG, s, jb, J0, 0, 0)});
+                        const int j1 = jb + std::min(NB, k - jb);
+                        std::vector<Task> pt;
+                        for (int row0 = j1; row0 < N; row0 += TILE) pt.push_back(mk(T_PANEL, s, jb, J0, row0, 0));
+                        if (!pt.empty()) G.push_back(std::move(pt));
+                    }
+                    // trailing tiles: tile starts over the remaining panel columns [J1, k) and over the rows below [k, N)
+                    std::vector<int> starts = trailing_starts(J1);
+                    if ((int64_t)starts.size() * ((int64_t)starts.size() + 1) / 2 > (1 << 26)) return fail(h, MIPM_ERR_ARG, "front too large for the tile schedule");
+                    std::vector<Task> tt;
+                    for (size_t tc = 0; tc < starts.size(); ++tc)
+                        for (size_t tr = tc; tr < starts.size(); ++tr) tt.push_back(mk(T_TRAIL, s, J0, J1, starts[tr], starts[tc]));
+                    if (!tt.empty()) G.push_back(std::move(tt));
+                    J0 = J1;
                 }
-                // trailing tiles: tile starts over the remaining panel columns [J1, k) and over the rows below [k, N)
-                std::vector<int> starts;
-                for (int x = J1; x < k; x += TILE) starts.push_back(x);
-                for (int x = k; x < N; x += TILE) starts.push_back(x);
-                if ((int64_t)starts.size() * ((int64_t)starts.size() + 1) / 2 > (1 << 26)) return fail(h, MIPM_ERR_ARG, "front too large for the tile schedule");
-                std::vector<Task> tt;
-                for (size_t tc = 0; tc < starts.size(); ++tc)
-                    for (size_t tr = tc; tr < starts.size(); ++tr) tt.push_back(mk(T_TRAIL, s, J0, J1, starts[tr], starts[tc]));
-                if (!tt.empty()) G.push_back(std::move(tt));
-                J0 = J1;
+                int done = f.nchild;
+                for (auto &g : G) {
+                    for (auto &t2 : g) t2.need = done;
+                    done += (int)g.size();
+                }
+                f.total = done - f.nchild;
+            } else {
+                // Look-ahead for wide fronts: the trailing tiles of panel p are split into the block columns of panel p + 1
+                // (LA: on the chain counter) and the rest (REST: on the second counter). Panel p + 1 only waits for LA(p),
+                // so its diagonal blocks and panel solves run while REST(p) is still being applied; tiles that update the
+                // same C tile stay ordered through the second counter. List order per panel p:
+                //   DIAG(p, first step) | REST(p-1) | remaining steps of panel p | LA(p)          (... | REST(last))
+                std::vector<std::array<int, 2>> panels;
+                for (int J0 = 0; J0 < k;) {
+                    int J1 = (k - J0 <= SP + NB) ? k : J0 + SP;
+                    panels.push_back({J0, J1});
+                    J0 = J1;
+                }
+                int cntA = f.nchild, cntB = 0;           // completions so far on the two counters
+                int needB_chain = 0;                     // REST completed through panel p-2 (what panel p's chain needs)
+                int restB_prev = 0;                      // REST completed through panel p-1
+                for (auto &g : G) { for (auto &t2 : g) t2.need = cntA; cntA += (int)g.size(); }      // extend-add
+                std::vector<Task> rest_prev;             // REST(p-1), emitted after the first DIAG of panel p
+                for (size_t pi = 0; pi < panels.size(); ++pi) {
+                    const int J0 = panels[pi][0], J1 = panels[pi][1];
+                    bool first = true;
+                    for (int jb = J0; jb < J1; jb += NB) {
+                        Task dg = mk(T_DIAG, s, jb, J0, 0, 0);
+                        dg.need = cntA; dg.need_b = needB_chain;
+                        G.push_back({dg});
+                        cntA += 1;
+                        if (first && !rest_prev.empty()) {
+                            G.push_back(std::move(rest_prev));
+                            rest_prev.clear();
+                        }
+                        first = false;
+                        const int j1 = jb + std::min(NB, k - jb);
+                        std::vector<Task> pt;
+                        for (int row0 = j1; row0 < N; row0 += TILE) {
+                            Task q = mk(T_PANEL, s, jb, J0, row0, 0);
+                            q.need = cntA; q.need_b = needB_chain;
+                            pt.push_back(q);
+                        }
+                        if (!pt.empty()) { cntA += (int)pt.size(); G.push_back(std::move(pt)); }
+                    }
+                    const int chain_done = cntA;         // everything of panel p
+                    std::vector<int> starts = trailing_starts(J1);
+                    if ((int64_t)starts.size() * ((int64_t)starts.size() + 1) / 2 > (1 << 26)) return fail(h, MIPM_ERR_ARG, "front too large for the tile schedule");
+                    const int la_end = (pi + 1 < panels.size()) ? panels[pi + 1][1] : J1;     // columns [J1, la_end) = next panel
+                    std::vector<Task> la, rest;
+                    for (size_t tc = 0; tc < starts.size(); ++tc)
+                        for (size_t tr = tc; tr < starts.size(); ++tr) {
+                            Task q = mk(T_TRAIL, s, J0, J1, starts[tr], starts[tc]);
+                            q.need = chain_done;
+                            q.need_b = restB_prev;       // the same C tile was last touched by REST(p-1)
+                            if (starts[tc] < la_end && starts[tc] < k) la.push_back(q);
+                            else { q.type |= T_DEFERRED; rest.push_back(q); }
+                        }
+                    needB_chain = restB_prev;            // panel p+1 needs REST through p-1 ... (see below)
+                    if (!la.empty()) { cntA += (int)la.size(); G.push_back(std::move(la)); }
+                    cntB += (int)rest.size();
+                    // panel p + 1 reads columns that REST(p - 1) updated, not REST(p): its need_b is the count BEFORE this panel's REST
+                    restB_prev = cntB;
+                    rest_prev = std::move(rest);
+                }
+                if (!rest_prev.empty()) G.push_back(std::move(rest_prev));
+                f.total = (cntA - f.nchild) + cntB;
             }
-            int done = f.nchild;
-            for (auto &g : G) {
-                for (auto &t2 : g) t2.need = done;
-                done += (int)g.size();
-            }
-            f.total = done;
             if (s == S.root_sn) {
                 // staged (distributed) factorization: the root's extend-add belongs to stage 0, the rest to stage 1;
                 // the root is alone on the last level, so its groups are appended in order below
@@ -866,7 +945,7 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, cudaMemcpyAsync(h->d_finfo.p, finfo.data(), finfo.size() * sizeof(FrontInfo), cudaMemcpyHostToDevice, st));
     MIPM_CUDA(h, h->d_tasks.alloc(std::max<size_t>(tasks.size(), 1)));
     if (!tasks.empty()) MIPM_CUDA(h, cudaMemcpyAsync(h->d_tasks.p, tasks.data(), tasks.size() * sizeof(Task), cudaMemcpyHostToDevice, st));
-    MIPM_CUDA(h, h->d_prog.alloc((size_t)ns + 4));
+    MIPM_CUDA(h, h->d_prog.alloc((size_t)3 * std::max(ns, 1) + 4));
     MIPM_CUDA(h, h->d_prof.alloc((size_t)8 * (size_t)h->grid_factor));
     MIPM_CUDA(h, h->d_lvl.upload(lvl, st));
     MIPM_CUDA(h, h->d_row_idx.upload(S.row_idx, st));
@@ -940,20 +1019,21 @@ int ls_factorize_staged(Handle *h, const double *d_nzval, int stage)
             MIPM_CUDA(h, cudaMemsetAsync(h->d_U.p, 0, (size_t)std::max<int64_t>(S.update_doubles, 1) * sizeof(double), st));
         }
         MIPM_CUDA(h, cudaMemsetAsync(h->d_info.p, 0, 4 * sizeof(int), st));
-        MIPM_CUDA(h, cudaMemsetAsync(h->d_prog.p, 0, ((size_t)S.ns + 4) * sizeof(int), st));
+        MIPM_CUDA(h, cudaMemsetAsync(h->d_prog.p, 0, ((size_t)3 * std::max(S.ns, 1) + 4) * sizeof(int), st));
         if (S.nnz_a > 0) {
             k_scatter_a<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.nnz_a, h->d_a2l.p, d_nzval, h->L_cur);
             MIPM_CHECK_LAUNCH(h);
         }
     } else {
-        MIPM_CUDA(h, cudaMemsetAsync(h->d_prog.p + S.ns, 0, sizeof(int), st));      // the ticket counter only
+        MIPM_CUDA(h, cudaMemsetAsync(h->d_prog.p + 3 * (size_t)std::max(S.ns, 1), 0, sizeof(int), st));      // the ticket counter only
     }
     if (t1 > t0) {
         FactorParams p;
         p.fi = (const FrontInfo *)h->d_finfo.p; p.child_idx = h->d_child_idx.p; p.rel_idx = h->d_rel_idx.p;
         p.sched = h->d_sched.p; p.tasks = (const Task *)h->d_tasks.p; p.task_begin = t0; p.task_end = t1;
         p.L = h->L_cur; p.U = h->d_U.p; p.Dinv = h->d_Dinv.p; p.Dg = h->d_Dg.p; p.info = h->d_info.p;
-        p.prog = h->d_prog.p; p.ticket = h->d_prog.p + S.ns;
+        p.prog = h->d_prog.p; p.prog_b = h->d_prog.p + std::max(S.ns, 1); p.done = h->d_prog.p + 2 * (size_t)std::max(S.ns, 1);
+        p.ticket = h->d_prog.p + 3 * (size_t)std::max(S.ns, 1);
         p.prof = h->d_prof.p; p.front_ns = h->d_front_ns.p; p.trace = h->d_trace.p;
         p.piv_tol = 1e-13;   // LDL^T: absolute floor on |pivot|
         void *args[] = {&p};
