@@ -716,13 +716,16 @@ int ls_device_setup(Handle *h)
     // Measured on C1, C2, its mesh variant and C4 (profiles/r02_notes.md): 64 (one block step per panel) is as fast or
     // faster than 128 / 256 everywhere -- the operand re-reads of a right-looking update hit L2, while a wider panel puts
     // its left-looking K loops on the dependency chain of the front. Wider panels stay available for sweeps.
-    int SP = 64;
+    // Exception: a level with at least as many wide fronts as the grid has CTAs (a stacked batch of dense blocks) is
+    // throughput bound, not chain bound -- there the wide panel's saving in C traffic wins (C5: 0.278 -> 0.249 s).
+    int SP_narrow = 64, SP_wide = 256;
     int ea_task_factor = 4, stagger = 1;
     int la_min_k = 512;          // fronts at least this wide factor with look-ahead (second progress counter)
     if (const char *e = std::getenv("MIPM_LOOKAHEAD_MIN")) la_min_k = std::max(2 * NB, atoi(e));
     if (const char *e = std::getenv("MIPM_EA_FACTOR")) ea_task_factor = std::max(1, atoi(e));
     if (const char *e = std::getenv("MIPM_NO_STAGGER")) stagger = (atoi(e) == 0);
-    if (const char *e = std::getenv("MIPM_SUPER_PANEL")) SP = std::max(NB, (atoi(e) / NB) * NB);
+    if (const char *e = std::getenv("MIPM_SUPER_PANEL")) SP_narrow = SP_wide = std::max(NB, (atoi(e) / NB) * NB);
+    if (const char *e = std::getenv("MIPM_SUPER_PANEL_WIDE")) SP_wide = std::max(NB, (atoi(e) / NB) * NB);
     // ---- task list: level by level (children before parents); inside a level breadth-first over the fronts' task
     // groups, so that consecutive tickets rarely wait on each other. `sched` keeps the extend-add child ranges, the
     // small-leaf list and the per-level front lists of the solves.
@@ -756,6 +759,9 @@ int ls_device_setup(Handle *h)
             n_reg++;
         }
         lvl.push_back(n_reg);
+        int64_t n_wide = 0;
+        for (int64_t t = f0; t < f1; ++t) n_wide += finfo[(size_t)S.level_sn[(size_t)t]].k > 2 * NB;
+        const int SP = (n_wide >= grid_estimate) ? SP_wide : SP_narrow;
         // columns per extend-add task: EA_COLS, narrower near the root where a level has fewer tasks than CTAs (an
         // extend-add task is a chain of dependent global round trips, so the level costs one task's latency)
         int ea_cols = EA_COLS;

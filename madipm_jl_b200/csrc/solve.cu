@@ -673,7 +673,20 @@ int ls_solve_setup(Handle *h, const void *finfo_host, const char *small)
     const int n_leaf = h->n_leaf;
     int big_k = 128;            // fronts at least this wide (measured: 128 beats 64, 256 and 512 on C2 and on its mesh variant) are solved by many CTAs (row tiles forward, column blocks backward)
     if (const char *e = std::getenv("MIPM_SOLVE_BIG_K")) big_k = std::max(NB, atoi(e));
-    auto is_big = [&](int s2) { return finfo[(size_t)s2].k >= big_k; };
+    // ... unless the level holds at least as many such fronts as the grid has CTAs (a stacked batch of dense blocks): the
+    // fronts are independent, one CTA per front already fills the machine and the tile hand-offs only add latency
+    std::vector<char> level_split((size_t)std::max(S.n_levels, 1), 1);
+    std::vector<int> level_of((size_t)std::max(ns, 1), 0);
+    for (int l = 0; l < S.n_levels; ++l) {
+        int64_t nbig = 0;
+        for (int64_t t = S.level_ptr[(size_t)l]; t < S.level_ptr[(size_t)l + 1]; ++t) {
+            const int s2 = S.level_sn[(size_t)t];
+            level_of[(size_t)s2] = l;
+            nbig += finfo[(size_t)s2].k >= big_k;
+        }
+        if (nbig >= h->grid_solve) level_split[(size_t)l] = 0;
+    }
+    auto is_big = [&](int s2) { return finfo[(size_t)s2].k >= big_k && level_split[(size_t)level_of[(size_t)s2]]; };
     for (int i = 0; i < n_leaf; i += 8) tasks.push_back(make_int4(1, i, 0, 0));
     h->solve_root_fwd_begin = 0;
     for (int l = 0; l < S.n_levels; ++l)
