@@ -130,19 +130,25 @@ __device__ void front_forward(const SolveParams &p, int s, double *smem, int mod
         }
         __syncthreads();
         for (int i = jb + nb + tid; i < N; i += 256) {
-            // 16 independent loads in flight per thread (the panel lives in HBM: latency-bound otherwise)
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            // FWD_ILP independent loads in flight per thread (the panel lives in HBM: latency-bound otherwise); the last
+            // trip is masked instead of walking the remaining columns one dependent load at a time (yb is zero beyond nb)
+            constexpr int FWD_ILP = 16;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             const double *col = P + (int64_t)jb * ld + i;
-            int j = 0;
-            for (; j + 16 <= nb; j += 16) {
-                double v[16];
+#pragma unroll 1
+            for (int j = 0; j < nb; j += FWD_ILP) {
+                double v[FWD_ILP];
 #pragma unroll
-                for (int t = 0; t < 16; ++t) v[t] = col[(int64_t)(j + t) * ld];
+                for (int t = 0; t < FWD_ILP; ++t) v[t] = (j + t < nb) ? col[(int64_t)(j + t) * ld] : 0.0;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) acc[t & 3] = fma(v[t], yb[j + t], acc[t & 3]);
+                for (int t = 0; t < FWD_ILP; t += 4) {
+                    a0 = fma(v[t], yb[j + t], a0);
+                    a1 = fma(v[t + 1], yb[j + t + 1], a1);
+                    a2 = fma(v[t + 2], yb[j + t + 2], a2);
+                    a3 = fma(v[t + 3], yb[j + t + 3], a3);
+                }
             }
-            for (; j < nb; ++j) acc[j & 3] = fma(col[(int64_t)j * ld], yb[j], acc[j & 3]);
-            const double tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            const double tot = (a0 + a1) + (a2 + a3);
             if (i < k) x1[i] -= tot; else u[i - k] -= tot;
         }
         __syncthreads();
@@ -297,10 +303,25 @@ __device__ __forceinline__ void prefetch_big(const SolveParams &p, const FrontIn
     }
 }
 
-template <bool LDL>
-__device__ void big_forward_tile(const SolveParams &p, int s, int t, double *smem, int mode)
+__device__ __forceinline__ void cp_async16_s(void *dst_smem, const void *src)
 {
-    double *acc = smem, *yb = smem + 64, *part = smem + 128;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_s() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int FWD_DSM = 384;    // forward tile: acc (64) | yb (64) | part (256) | inverse block (64 x XS)
+
+// Everything a forward tile reads that does not depend on other tasks is fetched BEFORE the tile waits: the inverse of
+// its diagonal block (cp.async into shared memory), the L tile of the last block it will consume (the critical hand-off:
+// registers), its right-hand-side entries and the gather map of its children's update vectors. After the wait the chain
+// per 64-column block is: see the counter -> 64 values of y -> FMAs from registers -> inverse block from shared memory
+// -> publish. `wait_children`: spin on fprog[s] here (after the preloads) instead of in the caller.
+template <bool LDL>
+__device__ void big_forward_tile(const SolveParams &p, int s, int t, double *smem, int mode, bool wait_children,
+                                 unsigned long long *t_start)
+{
+    double *acc = smem, *yb = smem + 64, *part = smem + 128, *Dsm = smem + FWD_DSM;
     const FrontInfo f = p.fi[s];
     const int k = f.k, N = f.k + f.r, ld = front_ld(f.k, f.r);
     const double *P = p.L + f.lp;
@@ -309,19 +330,57 @@ __device__ void big_forward_tile(const SolveParams &p, int s, int t, double *sme
     const int tid = threadIdx.x;
     const int R0 = t * 64, nr = min(64, N - R0);
     const int nblk = (k + NB - 1) / NB, ntiles = (N + 63) / 64;
+    const int nbefore = min(nblk, t);
+    const int r = tid & 63, q = tid >> 6;
+    // ---- preloads
+    if (t < nblk && mode != 1) {
+        const double *Dv = p.Dinv + (f.dinv + t) * (int64_t)(NB * XS);
+        for (int i = tid; i < NB * XS / 2; i += 256) cp_async16_s(Dsm + 2 * i, Dv + 2 * i);
+    }
+    double vL[16];
+    if (nbefore > 0 && mode != 1) {
+        const int col0 = (nbefore - 1) * NB, nc = min(NB, k - col0);
+        const double *col = P + (int64_t)col0 * ld + R0 + r;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const int c = q + BIG_PART * i; vL[i] = (r < nr && c < nc) ? col[(int64_t)c * ld] : 0.0; }
+    }
+    constexpr int GPRE = 4;
+    double v0 = 0.0;
+    int g0 = 0, g1 = 0, gidx[GPRE];
+    const int32_t *gs = nullptr;
+    if (tid < nr) {
+        const int row = R0 + tid;
+        if (mode != 2) {
+            v0 = (row < k) ? p.b_in[p.perm[f.c0 + row]] : 0.0;
+            const int64_t go = p.gat_off[2 * (int64_t)s];
+            if (go >= 0) {          // children's update vectors, in child order (split fronts always have the transposed map)
+                const int32_t *gp = p.gat_ptr + go;
+                gs = p.gat_src + p.gat_off[2 * (int64_t)s + 1];
+                g0 = gp[row]; g1 = gp[row + 1];
+#pragma unroll
+                for (int i = 0; i < GPRE; ++i) gidx[i] = (g0 + i < g1) ? gs[g0 + i] : 0;
+            }
+        }
+    }
+    if (wait_children) {
+        if (tid == 0) {
+            while (ld_acquire_b(p.fprog + s) < f.nchild) __nanosleep(40);
+            if (t_start) *t_start = globaltimer_ns();
+        }
+        __syncthreads();
+    }
     if (tid < 64) {
-        double v = 0.0;
+        double v = v0;
         if (tid < nr) {
             const int row = R0 + tid;
             if (mode == 2) v = (row < k) ? x1[row] : u[row - k];
-            else {
-                v = (row < k) ? p.b_in[p.perm[f.c0 + row]] : 0.0;
-                const int64_t go = p.gat_off[2 * (int64_t)s];
-                if (go >= 0) {      // children's update vectors, in child order (big fronts always have the transposed map)
-                    const int32_t *gp = p.gat_ptr + go;
-                    const int32_t *gs = p.gat_src + p.gat_off[2 * (int64_t)s + 1];
-                    for (int q = gp[row]; q < gp[row + 1]; ++q) v += p.uvec[gs[q]];
-                }
+            else if (g1 > g0) {
+                double w[GPRE];
+#pragma unroll
+                for (int i = 0; i < GPRE; ++i) w[i] = (g0 + i < g1) ? p.uvec[gidx[i]] : 0.0;
+#pragma unroll
+                for (int i = 0; i < GPRE; ++i) if (g0 + i < g1) v += w[i];
+                for (int qq = g0 + GPRE; qq < g1; ++qq) v += p.uvec[gs[qq]];
             }
         }
         acc[tid] = v;
@@ -332,7 +391,6 @@ __device__ void big_forward_tile(const SolveParams &p, int s, int t, double *sme
         if (tid < nr) { const int row = R0 + tid; if (row < k) x1[row] = acc[tid]; else u[row - k] = acc[tid]; }
         return;
     }
-    const int nbefore = min(nblk, t);
     __shared__ int s_avail;
     for (int b = 0; b < nbefore;) {
         if (tid == 0) {             // wait for the next block, then take every block published so far in one go
@@ -346,23 +404,32 @@ __device__ void big_forward_tile(const SolveParams &p, int s, int t, double *sme
             const int nc = min(NB, k - b * NB);
             if (tid < 64) yb[tid] = (tid < nc) ? x1[b * NB + tid] : 0.0;
             __syncthreads();
-            tile_update(P, ld, R0, 0, nr, b * NB, nc, yb, acc, part);
+            if (b == nbefore - 1) {         // the block this tile waited for last: operands are already in registers
+                double sum = 0.0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sum = fma(vL[i], yb[q + BIG_PART * i], sum);
+                part[q * 64 + r] = sum;
+                __syncthreads();
+                if (tid < nr) acc[tid] -= (part[tid] + part[64 + tid]) + (part[128 + tid] + part[192 + tid]);
+                __syncthreads();
+            } else {
+                tile_update(P, ld, R0, 0, nr, b * NB, nc, yb, acc, part);
+            }
         }
     }
     if (t < nblk) {             // diagonal tile: y_t = inv(L_tt) acc, published for the tiles below
         const int jb = t * NB, nbk = min(NB, k - jb);
-        const double *Dv = p.Dinv + (f.dinv + t) * (int64_t)(NB * XS);
+        cp_async_wait_all_s();
+        __syncthreads();
         {
-            const int rr = tid >> 2, q = tid & 3;
-            double a = 0.0, dvv[NB / 4];
+            const int rr = tid >> 2, qd = tid & 3;
+            double a = 0.0;
 #pragma unroll
-            for (int c = 0; c < NB / 4; ++c) dvv[c] = Dv[(q + 4 * c) * XS + rr];
-#pragma unroll
-            for (int c = 0; c < NB / 4; ++c) a = fma(dvv[c], (q + 4 * c < nbk) ? acc[q + 4 * c] : 0.0, a);
+            for (int c = 0; c < NB / 4; ++c) a = fma(Dsm[(qd + 4 * c) * XS + rr], (qd + 4 * c < nbk) ? acc[qd + 4 * c] : 0.0, a);
             a += __shfl_xor_sync(0xffffffffu, a, 1);
             a += __shfl_xor_sync(0xffffffffu, a, 2);
             __syncthreads();
-            if (q == 0) { yb[rr] = (rr < nbk) ? a : 0.0; if (rr < nbk) x1[jb + rr] = a; }
+            if (qd == 0) { yb[rr] = (rr < nbk) ? a : 0.0; if (rr < nbk) x1[jb + rr] = a; }
         }
         __syncthreads();
         if (tid == 0) { __threadfence(); atomicAdd(p.yprog + s, 1); }
@@ -379,8 +446,11 @@ __device__ void big_forward_tile(const SolveParams &p, int s, int t, double *sme
     }
 }
 
+// Like the forward tile, a backward block fetches what does not depend on other tasks before it waits (for its parent
+// front, then for the blocks above it): its inverse block, the row indices of the ancestors' x it reads, and the L tile
+// under the block right above it (the last hand-off of its chain), kept in registers.
 template <bool LDL>
-__device__ void big_backward_block(const SolveParams &p, int s, int b, double *smem)
+__device__ void big_backward_block(const SolveParams &p, int s, int b, double *smem, unsigned long long *t_start)
 {
     double *S = smem, *wb = smem + NB * LDS, *xr = wb + NB;
     const FrontInfo f = p.fi[s];
@@ -390,21 +460,57 @@ __device__ void big_backward_block(const SolveParams &p, int s, int b, double *s
     const int32_t *rows = p.row_idx + f.rowp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool cached = r <= XR_MAX;
-    if (cached) for (int i = tid; i < r; i += 256) xr[i] = p.xp[rows[i]];
     const int nblk = (k + NB - 1) / NB;
     const int jb = b * NB, nb = min(NB, k - jb);
     const double *Dv = p.Dinv + (f.dinv + b) * (int64_t)(NB * XS);
+    const int q0 = warp * 8;
+    const double *col = P + (int64_t)(jb + q0) * ld;
+    // ---- preloads
+    constexpr int RPRE = XR_MAX / 256;
+    int ridx[RPRE];
+#pragma unroll
+    for (int i = 0; i < RPRE; ++i) ridx[i] = (cached && tid + 256 * i < r) ? rows[tid + 256 * i] : 0;
     for (int idx = tid; idx < NB * NB; idx += 256) S[(idx >> 6) * LDS + (idx & 63)] = Dv[(idx >> 6) * XS + (idx & 63)];
     if (tid < NB) wb[tid] = 0.0;
-    const int q0 = warp * 8;
+    double vB[16];                  // L[64 (b + 1) + lane (+ 32), jb + q0 + c]
+    const int pre0 = NB * (b + 1), pre1 = min(pre0 + NB, k);        // rows of the block right above (empty for the last block)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const bool on = q0 + c < nb;
+        vB[c] = (on && pre0 + lane < pre1) ? col[(int64_t)c * ld + pre0 + lane] : 0.0;
+        vB[8 + c] = (on && pre0 + lane + 32 < pre1) ? col[(int64_t)c * ld + pre0 + lane + 32] : 0.0;
+    }
+    if (tid == 0) {
+        if (f.parent >= 0) { while (ld_acquire_b(p.bdone + f.parent) == 0) __nanosleep(40); }
+        else { while (ld_acquire_b(p.fprog + s) <= f.nchild) __nanosleep(40); }
+        if (t_start) *t_start = globaltimer_ns();
+    }
+    __syncthreads();
+    if (cached) {
+#pragma unroll
+        for (int i = 0; i < RPRE; ++i) if (tid + 256 * i < r) xr[tid + 256 * i] = p.xp[ridx[i]];
+    }
     double acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.0;
-    const double *col = P + (int64_t)(jb + q0) * ld;
+    auto xfull = [&](int i) { return (i < k) ? x1[i] : (cached ? xr[i - k] : p.xp[rows[i - k]]); };
     auto rows_range = [&](int i0, int i1) {         // acc[c] += sum_{i0 <= i < i1} L[i, jb + q0 + c] xfull[i]
         if (q0 >= nb) return;
-        for (int i = i0 + lane; i < i1; i += 32) {
-            const double xv = (i < k) ? x1[i] : (cached ? xr[i - k] : p.xp[rows[i - k]]);
+        int i = i0 + lane;
+        for (; i + 32 < i1; i += 64) {              // two row chunks per trip: 16 loads in flight per lane
+            const double xv = xfull(i), xw = xfull(i + 32);
+            double v[8], w[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const bool on = q0 + c < nb;
+                v[c] = on ? col[(int64_t)c * ld + i] : 0.0;
+                w[c] = on ? col[(int64_t)c * ld + i + 32] : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = fma(w[c], xw, fma(v[c], xv, acc[c]));
+        }
+        for (; i < i1; i += 32) {
+            const double xv = xfull(i);
             double v[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[c] = (q0 + c < nb) ? col[(int64_t)c * ld + i] : 0.0;
@@ -425,7 +531,13 @@ __device__ void big_backward_block(const SolveParams &p, int s, int b, double *s
         }
         __syncthreads();
         const int new_t = max(b + 1, nblk - s_avail);
-        rows_range(NB * new_t, min(NB * done_t, k));
+        rows_range(NB * max(new_t, b + 2), min(NB * done_t, k));
+        if (new_t == b + 1 && q0 < nb) {            // the block right above: operands are already in registers
+            const double xv = (pre0 + lane < pre1) ? x1[pre0 + lane] : 0.0;
+            const double xw = (pre0 + lane + 32 < pre1) ? x1[pre0 + lane + 32] : 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = fma(vB[8 + c], xw, fma(vB[c], xv, acc[c]));
+        }
         done_t = new_t;
         __syncthreads();
     }
@@ -544,9 +656,9 @@ __device__ __forceinline__ int ld_acquire_s(const int *p)
 }
 
 template <bool LDL>
-__global__ void __launch_bounds__(256, 3) k_solve_tasks(SolveParams p)
+__global__ void __launch_bounds__(256, 2) k_solve_tasks(const __grid_constant__ SolveParams p)
 {
-    __shared__ double smem[NB * LDS + NB + XR_MAX];
+    __shared__ __align__(16) double smem[NB * XS + NB + XR_MAX];     // >= FWD_DSM + NB * XS
     __shared__ int s_ticket;
     const int tid = threadIdx.x;
     if (tid == 0) s_ticket = p.task_begin + atomicAdd(p.ticket, 1);
@@ -565,15 +677,12 @@ __global__ void __launch_bounds__(256, 3) k_solve_tasks(SolveParams p)
             const int mode = (fwd && s == p.root_sn) ? p.root_mode : 0;
             if (fwd ? (f.nchild > 0 || tk.z > 0) : true) prefetch_big(p, f, fwd, tk.z);      // the task is going to wait
             if (tid == 0) {
-                if (fwd) { if (f.nchild > 0 && mode != 2) { while (ld_acquire_s(p.fprog + s) < f.nchild) __nanosleep(40); } }
-                else if (f.parent >= 0) { while (ld_acquire_s(p.bdone + f.parent) == 0) __nanosleep(40); }
-                else { while (ld_acquire_s(p.fprog + s) <= f.nchild) __nanosleep(40); }
-                if (p.trace) tr1 = globaltimer_ns();
                 next = p.task_begin + atomicAdd(p.ticket, 1);
+                if (p.trace) tr1 = globaltimer_ns();
             }
             __syncthreads();
-            if (fwd) big_forward_tile<LDL>(p, s, tk.z, smem, mode);
-            else big_backward_block<LDL>(p, s, tk.z, smem);
+            if (fwd) big_forward_tile<LDL>(p, s, tk.z, smem, mode, f.nchild > 0 && mode != 2, p.trace ? &tr1 : nullptr);
+            else big_backward_block<LDL>(p, s, tk.z, smem, p.trace ? &tr1 : nullptr);
         } else if (tk.x == 0 || tk.x == 2) {
             const int s = tk.y;
             const FrontInfo f = p.fi[s];
@@ -675,18 +784,28 @@ int ls_solve_setup(Handle *h, const void *finfo_host, const char *small)
     if (const char *e = std::getenv("MIPM_SOLVE_BIG_K")) big_k = std::max(NB, atoi(e));
     // ... unless the level holds at least as many such fronts as the grid has CTAs (a stacked batch of dense blocks): the
     // fronts are independent, one CTA per front already fills the machine and the tile hand-offs only add latency
+    // Near the root a level has fewer fronts than the machine has SMs and the solve is a chain of hand-offs: there every
+    // front of two or more row tiles is split (a hand-off between tiles costs less than a block step inside one CTA).
+    int sparse_level = 96;      // a level with at most this many fronts is latency bound
+    if (const char *e = std::getenv("MIPM_SOLVE_SPARSE_LEVEL")) sparse_level = atoi(e);
     std::vector<char> level_split((size_t)std::max(S.n_levels, 1), 1);
     std::vector<int> level_of((size_t)std::max(ns, 1), 0);
     for (int l = 0; l < S.n_levels; ++l) {
-        int64_t nbig = 0;
+        int64_t nbig = 0, nfront = 0;
         for (int64_t t = S.level_ptr[(size_t)l]; t < S.level_ptr[(size_t)l + 1]; ++t) {
             const int s2 = S.level_sn[(size_t)t];
             level_of[(size_t)s2] = l;
             nbig += finfo[(size_t)s2].k >= big_k;
+            nfront += !small[(size_t)s2];
         }
         if (nbig >= h->grid_solve) level_split[(size_t)l] = 0;
+        else if (nfront <= sparse_level) level_split[(size_t)l] = 2;
     }
-    auto is_big = [&](int s2) { return finfo[(size_t)s2].k >= big_k && level_split[(size_t)level_of[(size_t)s2]]; };
+    auto is_big = [&](int s2) {
+        const char m = level_split[(size_t)level_of[(size_t)s2]];
+        const FrontInfo &f2 = finfo[(size_t)s2];
+        return (m >= 1 && f2.k >= big_k) || (m == 2 && f2.k + f2.r > 2 * NB);
+    };
     for (int i = 0; i < n_leaf; i += 8) tasks.push_back(make_int4(1, i, 0, 0));
     h->solve_root_fwd_begin = 0;
     for (int l = 0; l < S.n_levels; ++l)
