@@ -38,7 +38,11 @@ enum {
     MIPM_ERR_NOT_FACTORIZED = 6  /* pivot breakdown: maps to is_factorized(ls) == false            */
 };
 
-enum { MIPM_CHOLESKY = 0, MIPM_LDL = 1 };                 /* cudss_algorithm analogue, test/test_gpu.jl:9-11 */
+/* cudss_algorithm analogue (test/test_gpu.jl:9-11, scripts/benchmarks_gpu.jl:42). MIPM_LDL is for the quasi-definite K2
+ * system (its analysis delays the dual vertices). MIPM_LDL_DEFINITE: the square-root-free LDL^T kernels on a matrix that is
+ * positive definite up to rounding (the normal equations with cudss_algorithm = LDL): ordering as for Cholesky, and a
+ * non-positive pivot late in an ill-conditioned solve is not a breakdown. */
+enum { MIPM_CHOLESKY = 0, MIPM_LDL = 1, MIPM_LDL_DEFINITE = 2 };
 enum { MIPM_ORDER_ND = 0, MIPM_ORDER_NATURAL = 1, MIPM_ORDER_USER = 2 };
 
 /* ------------------------------------------------------------------ lifecycle ------ */

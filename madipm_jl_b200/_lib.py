@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmadipm_b200.so")
 
 MIPM_OK, MIPM_ERR_ARG, MIPM_ERR_CUDA, MIPM_ERR_ALLOC, MIPM_ERR_STATE, MIPM_ERR_DUPLICATE, MIPM_ERR_NOT_FACTORIZED = range(7)
-MIPM_CHOLESKY, MIPM_LDL = 0, 1
+MIPM_CHOLESKY, MIPM_LDL, MIPM_LDL_DEFINITE = 0, 1, 2
 MIPM_ORDER_ND, MIPM_ORDER_NATURAL, MIPM_ORDER_USER = 0, 1, 2
 
 _ERRNAMES = {1: "MIPM_ERR_ARG", 2: "MIPM_ERR_CUDA", 3: "MIPM_ERR_ALLOC", 4: "MIPM_ERR_STATE",

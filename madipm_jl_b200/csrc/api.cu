@@ -562,7 +562,7 @@ int mipm_ls_analyze(mipm_handle hh, int64_t n, const int32_t *colptr, const int3
 {
     Handle *h = (Handle *)hh;
     if (h && !h->host_only) use_handle(h);
-    if (!h || n < 0 || !colptr || (kind != MIPM_CHOLESKY && kind != MIPM_LDL)) return fail(h, MIPM_ERR_ARG, "bad argument");
+    if (!h || n < 0 || !colptr || (kind != MIPM_CHOLESKY && kind != MIPM_LDL && kind != MIPM_LDL_DEFINITE)) return fail(h, MIPM_ERR_ARG, "bad argument");
     int64_t nnz = colptr[n] - index_base;
     if (nnz < 0 || (nnz > 0 && !rowval)) return fail(h, MIPM_ERR_ARG, "bad column pointer");
     std::vector<int32_t> cp((size_t)n + 1), ri((size_t)nnz), up;
@@ -573,7 +573,7 @@ int mipm_ls_analyze(mipm_handle hh, int64_t n, const int32_t *colptr, const int3
         for (int64_t k = 0; k < n; ++k) up[(size_t)k] = user_perm[k] - index_base;
     }
     LsOptions opt;
-    opt.kind = kind;
+    opt.kind = (kind == MIPM_LDL_DEFINITE) ? MIPM_CHOLESKY : kind;      // the analysis of a definite matrix has no K2 rule
     opt.ordering = ordering;
     if (const char *s = std::getenv("MIPM_ND_LEAF")) opt.nd_leaf = std::max(1, atoi(s));
     if (const char *s = std::getenv("MIPM_LDL_DELAY")) opt.ldl_delay_all = (std::strcmp(s, "first") != 0);
@@ -585,6 +585,8 @@ int mipm_ls_analyze(mipm_handle hh, int64_t n, const int32_t *colptr, const int3
     h->factorized = false;
     std::string e = ls_analyze(n, cp.data(), ri.data(), opt, up.empty() ? nullptr : up.data(), h->sym);
     if (!e.empty()) return fail(h, MIPM_ERR_ARG, e);
+    h->ldl_definite = (kind == MIPM_LDL_DEFINITE);
+    if (h->ldl_definite) h->sym.kind = MIPM_LDL;
     h->has_ls = true;
     if (!h->host_only) return ls_device_setup(h);
     return MIPM_OK;

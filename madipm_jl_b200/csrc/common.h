@@ -88,6 +88,7 @@ struct Handle {
     // ---- linear solver
     LsSymbolic sym;
     bool has_ls = false, factorized = false;
+    bool ldl_definite = false;   // MIPM_LDL_DEFINITE: LDL^T kernels on a definite matrix (normal equations)
     int n_tasks = 0, grid_factor = 0, grid_solve = 0;
     int grid_limit = 0;              // cap on the persistent kernels' grid (0 = whole GPU)
     int root_task_begin = -1;        // first task of the border (root) front's own factorization, -1 = no border

@@ -47,6 +47,11 @@ static_assert(2 * TILE * XS <= SMEM_DOUBLES, "TRSM epilogue: X and inv(L11) tile
 static_assert(NB == mipm_diag::DB && LDS == mipm_diag::DLD, "diag_block.cuh is written for 64 x 64 blocks, ld 65");
 enum { T_EA = 0, T_DIAG = 1, T_PANEL = 2, T_TRAIL = 3, T_LEAF = 4, T_NCLASS = 5 };
 
+#ifndef MIPM_FACTOR_OCC
+#define MIPM_FACTOR_OCC 3
+#endif
+constexpr int FACTOR_OCC = MIPM_FACTOR_OCC;     // CTAs of the task kernel per SM (register budget 65536 / 256 / FACTOR_OCC)
+
 struct __align__(16) Task {
     int32_t type, front;
     int32_t a, b, c, d;         // EA: q0, q1, offset of the child ranges | DIAG: jb, K0 | PANEL: jb, K0, row0 | TRAIL: K0, K1, row0, col0
@@ -547,7 +552,7 @@ __device__ void task_trail(const FactorParams &p, Pipe &pp, const FrontInfo &f, 
 }
 
 template <bool LDL>
-__global__ void __launch_bounds__(256, 3) k_factor_tasks(FactorParams p)
+__global__ void __launch_bounds__(256, FACTOR_OCC) k_factor_tasks(FactorParams p)
 {
     extern __shared__ __align__(128) double smem[];
     __shared__ int s_ticket;
@@ -637,7 +642,7 @@ __global__ void __launch_bounds__(256, 3) k_factor_tasks(FactorParams p)
 }
 
 // Micro-benchmark of the same pipelined tile code: C (n x n, lower tiles) -= X X' with K = kdim (X: n x kdim, ld even).
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, FACTOR_OCC)
 k_bench_syrk(int n, int kdim, double *C, int64_t ldc, const double *X, int64_t ldx)
 {
     extern __shared__ __align__(128) double smem[];
@@ -711,7 +716,7 @@ int ls_device_setup(Handle *h)
     DeviceInfo prop;
     if (device_info(h->device, prop) != MIPM_OK) return fail(h, MIPM_ERR_CUDA, "cudaGetDeviceProperties failed");
     if (!prop.cooperative) return fail(h, MIPM_ERR_CUDA, "device does not support cooperative launch");
-    const int grid_estimate = prop.sm_count * 3;       // __launch_bounds__(256, 3)
+    const int grid_estimate = prop.sm_count * FACTOR_OCC;
     // super-panel width: columns whose updates are accumulated in registers before the trailing matrix is touched.
     // Measured on C1, C2, its mesh variant and C4 (profiles/r02_notes.md): 64 (one block step per panel) is as fast or
     // faster than 128 / 256 everywhere -- the operand re-reads of a right-looking update hit L2, while a wider panel puts
@@ -1041,7 +1046,7 @@ int ls_factorize_staged(Handle *h, const double *d_nzval, int stage)
         p.prog = h->d_prog.p; p.prog_b = h->d_prog.p + std::max(S.ns, 1); p.done = h->d_prog.p + 2 * (size_t)std::max(S.ns, 1);
         p.ticket = h->d_prog.p + 3 * (size_t)std::max(S.ns, 1);
         p.prof = h->d_prof.p; p.front_ns = h->d_front_ns.p; p.trace = h->d_trace.p;
-        p.piv_tol = 1e-13;   // LDL^T: absolute floor on |pivot|
+        p.piv_tol = h->ldl_definite ? 1e-300 : 1e-13;   // LDL^T: absolute floor on |pivot| (K2: the dual regularization is 1e-10)
         void *args[] = {&p};
         const void *fn = (S.kind == MIPM_LDL) ? (const void *)k_factor_tasks<true> : (const void *)k_factor_tasks<false>;
         // cooperative launch: guarantees that every CTA is resident, which the dependency spins rely on
@@ -1076,14 +1081,14 @@ extern "C" int mipm_ls_analyze_border(mipm_handle hh, int64_t n, const int32_t *
     using namespace mipm;
     Handle *h = (Handle *)hh;
     if (h && !h->host_only) use_handle(h);
-    if (!h || n < 0 || !colptr || n_border < 1 || n_border > n || (kind != MIPM_CHOLESKY && kind != MIPM_LDL))
+    if (!h || n < 0 || !colptr || n_border < 1 || n_border > n || (kind != MIPM_CHOLESKY && kind != MIPM_LDL && kind != MIPM_LDL_DEFINITE))
         return fail(h, MIPM_ERR_ARG, "bad argument");
     int64_t nnz = colptr[n] - index_base;
     std::vector<int32_t> cp((size_t)n + 1), ri((size_t)std::max<int64_t>(nnz, 0));
     for (int64_t j = 0; j <= n; ++j) cp[(size_t)j] = colptr[j] - index_base;
     for (int64_t q = 0; q < nnz; ++q) ri[(size_t)q] = rowval[q] - index_base;
     LsOptions opt;
-    opt.kind = kind;
+    opt.kind = (kind == MIPM_LDL_DEFINITE) ? MIPM_CHOLESKY : kind;
     opt.ordering = MIPM_ORDER_ND;
     opt.n_border = n_border;
     if (const char *s = std::getenv("MIPM_ND_LEAF")) opt.nd_leaf = std::max(1, atoi(s));
@@ -1091,6 +1096,8 @@ extern "C" int mipm_ls_analyze_border(mipm_handle hh, int64_t n, const int32_t *
     h->factorized = false;
     std::string e = ls_analyze(n, cp.data(), ri.data(), opt, nullptr, h->sym);
     if (!e.empty()) return fail(h, MIPM_ERR_ARG, e);
+    h->ldl_definite = (kind == MIPM_LDL_DEFINITE);
+    if (h->ldl_definite) h->sym.kind = MIPM_LDL;
     h->has_ls = true;
     if (!h->host_only) return ls_device_setup(h);
     return MIPM_OK;

@@ -278,6 +278,44 @@ def badly_scaled_lp(m, n, k, seed):
                           lcon=qp.lcon * f, ucon=qp.ucon * f, lvar=qp.lvar, uvar=qp.uvar, x0=qp.x0, name=f"badscale_lp_m{m}_n{n}_s{seed}")
 
 
+def degenerate_lp(m, n, k, seed, n_dup=0, cond=1.0):
+    """LP that stresses the linear algebra instead of being a friendly random instance:
+      * primal degenerate: only m // 2 entries of x* are positive (fewer than m), the rest sit on their bound;
+      * dual degenerate: a tenth of the zero entries also has z* = 0 (no strict complementarity there);
+      * `cond` > 1 multiplies the columns by factors log-uniform in [1/cond, 1], so A D A' gets ill-conditioned early;
+      * `n_dup` > 0 appends copies of the first rows (consistent right-hand sides): A loses full row rank. The normal
+        equations are then singular (NormalKKTSystem needs full row rank, like the reference); K2 with LDL' and the
+        dual regularization still solves the LP.
+    Feasible and bounded by construction (b = A x*, c = A'y* + z*)."""
+    rng = np.random.default_rng(seed)
+    rows, cols = _sparsity(rng, m, n, k, "uniform", 0)
+    vals = rng.standard_normal(len(rows))
+    vals = np.sign(vals) * np.maximum(np.abs(vals), 1e-2)
+    if cond > 1.0:
+        vals = vals * np.exp(rng.uniform(-np.log(cond), 0.0, n))[cols]
+    xs = np.zeros(n)
+    pos = rng.permutation(n)[: max(1, m // 2)]
+    xs[pos] = rng.uniform(0.5, 1.5, len(pos))
+    zs = np.where(xs > 0, 0.0, rng.uniform(0.1, 1.0, n))
+    zero = np.flatnonzero(xs == 0)
+    zs[zero[rng.random(len(zero)) < 0.1]] = 0.0
+    if n_dup > 0:
+        extra = [(m + d, c_, v_) for d in range(n_dup) for c_, v_ in zip(cols[rows == d], vals[rows == d])]
+        rows = np.concatenate([rows, np.array([e[0] for e in extra], dtype=rows.dtype)])
+        cols = np.concatenate([cols, np.array([e[1] for e in extra], dtype=cols.dtype)])
+        vals = np.concatenate([vals, np.array([e[2] for e in extra])])
+    mm = m + n_dup
+    b = np.zeros(mm)
+    np.add.at(b, rows, vals * xs[cols])
+    ys = rng.standard_normal(mm)
+    c = zs.copy()
+    np.add.at(c, cols, vals * ys[rows])
+    return QuadraticModel(c=c, Hrows=[], Hcols=[], Hvals=[], Arows=rows, Acols=cols, Avals=vals, lcon=b, ucon=b.copy(),
+                          lvar=np.zeros(n), uvar=np.full(n, np.inf), x0=np.zeros(n),
+                          name=f"degenerate_lp_m{m}_n{n}_k{k}_s{seed}_dup{n_dup}_cond{cond:g}",
+                          meta=dict(m=mm, n=n, k=k, seed=seed, n_dup=n_dup, cond=cond, objective=float(c @ xs)))
+
+
 def bound_constrained_qp(n, seed):
     """Convex QP with bounds only (m = 0), like MadNLPTests.DenseDummyQP(x0; m=0) in test/runtests.jl:64."""
     rng = np.random.default_rng(seed)

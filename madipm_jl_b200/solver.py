@@ -95,6 +95,11 @@ class IPMOptions:
     rethrow_error: bool = False
     # B200Solver options (the analogue of cudss_algorithm / ir options of MadNLPGPU.CUDSSSolver)
     ordering: int = _lib.MIPM_ORDER_ND
+    # cudss_algorithm of MadNLPGPU.CUDSSSolver (test/test_gpu.jl:9-16 uses CHOLESKY for the normal equations,
+    # scripts/benchmarks_gpu.jl:42 LDL): "auto" = "CHOLESKY" for NormalKKTSystem, "LDL" for K2 / K2.5. "LDL" with the
+    # normal equations runs the square-root-free kernels: a pivot that rounding made non-positive late in an
+    # ill-conditioned solve is then not a breakdown (no x100 regularization retry), as with the oracle's LDL'.
+    cudss_algorithm: str = "auto"
     ir_steps: int = 0             # refinement rounds inside every linear solve (on the reduced system)
     # adaptive refinement on the full unreduced KKT system, driven by the residual that
     # solve_system! computes anyway (src/linear_solver.jl:29-35): refine while
@@ -163,7 +168,7 @@ class B200Solver:
         return self.h.ls_inertia()
 
     def introduce(self):
-        return "madipm_b200 supernodal %s" % ("LDL^T" if self.kind == _lib.MIPM_LDL else "Cholesky")
+        return "madipm_b200 supernodal %s" % ("Cholesky" if self.kind == _lib.MIPM_CHOLESKY else "LDL^T")
 
 
 class MPCSolver:
@@ -204,7 +209,7 @@ class MPCSolver:
         self.x, self.xl, self.xu, self.zl, self.zu, self.f = z(n), z(n), z(n), z(n), z(n), z(n)
         self.y, self.c, self.rhs, self.jacl = z(m), z(m), z(m), z(n)
         N = n + m + nlb + nub
-        self.d, self.p, self._w1, self._w2 = z(N), z(N), z(N), z(N)
+        self.d, self.p, self._w1, self._w2, self._w3 = z(N), z(N), z(N), z(N), z(N)
         self.correction_lb, self.correction_ub = z(nlb), z(nub)
         ib = int(opt.index_base)
         self.d_ind_lb = _dev(self.ind_lb + ib, dev, torch.int64)
@@ -265,10 +270,15 @@ class MPCSolver:
                 self.linear_solver = DistributedB200Solver(m, Cp - ib, Cj - ib, self._aug_nz_ext, opt.n_border, opt.device, stream)
             else:
                 self.aug_nz = z(len(Cj))
-                self.linear_solver = B200Solver(self.h, m, Cp, Cj, self.aug_nz, _lib.MIPM_CHOLESKY, opt.ordering, opt.ir_steps, ib)
+                if opt.cudss_algorithm not in ("auto", "CHOLESKY", "LDL"):
+                    raise ValueError("cudss_algorithm must be 'auto', 'CHOLESKY' or 'LDL'")
+                kind = _lib.MIPM_LDL_DEFINITE if opt.cudss_algorithm == "LDL" else _lib.MIPM_CHOLESKY
+                self.linear_solver = B200Solver(self.h, m, Cp, Cj, self.aug_nz, kind, opt.ordering, opt.ir_steps, ib)
         elif opt.kkt_system in ("K2", "K2.5"):
             # MadNLP.SparseKKTSystem (K2.5: ScaledSparseKKTSystem, same pattern): COO values [pr_diag; hess; jac(+slack);
             # du_diag], lower triangular
+            if opt.cudss_algorithm not in ("auto", "LDL"):
+                raise ValueError("the K2 / K2.5 systems are indefinite: cudss_algorithm must be 'auto' or 'LDL'")
             nnzh, nnzj = qp.nnzh, len(I)
             KI = np.concatenate([np.arange(n), qp.Hrows, n + I, n + np.arange(m)]).astype(np.int32)
             KJ = np.concatenate([np.arange(n), qp.Hcols, J, n + np.arange(m)]).astype(np.int32)
@@ -446,15 +456,22 @@ class MPCSolver:
         self.residual_ratio = norm_w / max(1.0, norm_p)
         nref = 0
         while self.residual_ratio > self.opt.refine_tol and nref < self.opt.max_refine:
-            # d += K^-1 (p - K d), then the reference's residual check again
-            self.kkt_solve(self._w1)
-            self.h.axpby(N, 1.0, self._w1, 1.0, self.d)
+            # d += K^-1 (p - K d), then the reference's residual check again. A round that does not reduce the residual is
+            # taken back: on ill-conditioned systems the correction carries the same error as the solve it corrects.
+            self.h.copy(N, self._w1, self._w3)
+            self.kkt_solve(self._w3)
+            self.h.axpby(N, 1.0, self._w3, 1.0, self.d)
             self.h.copy(N, self.p, self._w1)
             self.kkt_mul(self._w1, self.d, -1.0, 1.0)
             norm_w, norm_p = self.h.residual_norms(self._w1, self.p)
             prev, self.residual_ratio = self.residual_ratio, norm_w / max(1.0, norm_p)
             nref += 1
             self.cnt["refinements"] = self.cnt.get("refinements", 0) + 1
+            if not (self.residual_ratio < prev):
+                self.h.axpby(N, -1.0, self._w3, 1.0, self.d)
+                self.residual_ratio = prev
+                self.cnt["refinements_rejected"] = self.cnt.get("refinements_rejected", 0) + 1
+                break
             if not (self.residual_ratio < 0.5 * prev):
                 break
         if np.isnan(self.residual_ratio) or (self.opt.check_residual and self.residual_ratio > self.opt.tol_linear_solve):

@@ -691,3 +691,76 @@ def test_concurrent_batch_matches_sequential(built):
         assert a.status == b.status == "SOLVE_SUCCEEDED"
         assert a.iter == b.iter
         assert a.objective == b.objective          # same kernels, same schedule per unit: bit-identical
+
+
+# ------------------------------------------------------------------ degenerate / ill-conditioned / rank-deficient LPs
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("kkt", ["Normal", "K2"])
+def test_degenerate_lp_matches_oracle(built, kkt, fused):
+    """Primal and dual degenerate LP (fewer positive x* than rows, z* = 0 on some of the zeros): still on the oracle's
+    iterates at 1e-8."""
+    from madipm_jl_b200.problems import degenerate_lp
+    from madipm_jl_b200.solver import madipm
+    qp = degenerate_lp(300, 1200, 5, 11)
+    ref = oracle_madipm(qp, kkt_system=kkt)
+    got = madipm(qp, kkt_system=kkt, fused=fused)
+    assert ref.status == "SOLVE_SUCCEEDED"
+    _check_trace(got, ref.trace, ref.iter, ref.status)
+    assert close(got.objective, qp.meta["objective"], 1e-6)
+
+
+@pytest.mark.parametrize("opts", [dict(fused=True), dict(fused=False), dict(fused=True, cudss_algorithm="LDL"),
+                                  dict(fused=False, cudss_algorithm="LDL"), dict(fused=False, max_refine=0)])
+@pytest.mark.parametrize("kkt", ["Normal", "K2"])
+def test_ill_conditioned_lp_converges_like_oracle(built, kkt, opts):
+    """Columns scaled over six decades on top of the degeneracy: A D A' reaches condition numbers beyond 1e16 in the last
+    iterations. Two correct solvers no longer agree to 1e-8 per iterate there (the oracle's Normal and K2 runs differ by
+    3e-6 in the final objective), so the bar is: same status, iteration count within +-2, early iterates and final
+    objective within 1e-5. The fine-grained path used to stall here because a refinement round that made the residual
+    worse was kept; it is now taken back."""
+    from madipm_jl_b200.problems import degenerate_lp
+    from madipm_jl_b200.solver import madipm
+    if kkt == "K2" and "cudss_algorithm" in opts:
+        pytest.skip("K2 is LDL^T already")
+    qp = degenerate_lp(300, 1200, 5, 12, cond=1e6)
+    ref = oracle_madipm(qp, kkt_system=kkt)
+    got = madipm(qp, kkt_system=kkt, **opts)
+    assert ref.status == got.status == "SOLVE_SUCCEEDED"
+    assert abs(got.iter - ref.iter) <= 2
+    # the column scaling alone gives cond(A A') ~ 1e12 at the starting point: iterates agree to ~1e-6, not 1e-8
+    _check_trace(got, ref.trace[:9], got.iter, ref.status, tol=1e-5)
+    assert close(got.objective, ref.objective, 1e-5)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_rank_deficient_lp(built, fused):
+    """Duplicated constraint rows: the normal equations are singular, the Cholesky factorization breaks down, the x100
+    regularization retries (src/linear_solver.jl:6-17) cannot repair a matrix without dual regularization and the solve
+    ends with the same status as the oracle's; the K2 system (dual regularization, LDL') solves the LP."""
+    from madipm_jl_b200.problems import degenerate_lp
+    from madipm_jl_b200.solver import madipm
+    qp = degenerate_lp(300, 1200, 5, 13, n_dup=8)
+    ref_n = oracle_madipm(qp, kkt_system="Normal")
+    got_n = madipm(qp, kkt_system="Normal", fused=fused)
+    assert got_n.status == ref_n.status != "SOLVE_SUCCEEDED"
+    ref = oracle_madipm(qp, kkt_system="K2")
+    got = madipm(qp, kkt_system="K2", fused=fused)
+    _check_trace(got, ref.trace, ref.iter, ref.status, tol=1e-7)
+    assert close(got.objective, qp.meta["objective"], 1e-6)
+
+
+def test_regularization_retry_end_to_end(built):
+    """factorize_regularized_system! driven for real (src/linear_solver.jl:6-17): on this LP (m = 2 000, columns scaled over
+    seven decades) rounding makes a Cholesky pivot non-positive in the last iterations, is_factorized turns false, the
+    solver multiplies the regularization by 100, refactorizes and still converges. With cudss_algorithm = "LDL" the same
+    matrices factor without retries."""
+    from madipm_jl_b200.problems import degenerate_lp
+    from madipm_jl_b200.solver import madipm
+    qp = degenerate_lp(2000, 8000, 5, 16, cond=1e7)
+    chol = madipm(qp, kkt_system="Normal", max_iter=100)
+    assert chol.status == "SOLVE_SUCCEEDED"
+    assert chol.counters["factorizations"] > chol.iter + 1            # at least one retry happened
+    ldl = madipm(qp, kkt_system="Normal", cudss_algorithm="LDL", max_iter=100)
+    assert ldl.status == "SOLVE_SUCCEEDED"
+    assert ldl.counters["factorizations"] == ldl.iter + 1
+    assert close(chol.objective, ldl.objective, 1e-4)

@@ -215,3 +215,21 @@ def test_ruiz_restatement_equilibrates():
     np.maximum.at(r, rows, v)
     np.maximum.at(c, cols, v)
     assert np.abs(r[r > 0] - 1).max() < 1e-5 and np.abs(c[c > 0] - 1).max() < 1e-5 and it < 30
+
+
+def test_degenerate_lp_generator_and_oracle():
+    """The degenerate / rank-deficient generator: the constructed point is optimal (the oracle reaches its objective), and
+    duplicated rows make the normal equations singular for the oracle as well (NormalKKTSystem needs full row rank)."""
+    from madipm_jl_b200.problems import degenerate_lp
+    from oracle.mpc_oracle import madipm
+    qp = degenerate_lp(60, 240, 4, 21)
+    r = madipm(qp, kkt_system="Normal")
+    assert r.status == "SOLVE_SUCCEEDED"
+    assert abs(r.objective - qp.meta["objective"]) <= 1e-6 * max(1.0, abs(r.objective))
+    dup = degenerate_lp(60, 240, 4, 22, n_dup=3)
+    assert dup.ncon == 63
+    with np.errstate(all="ignore"):
+        assert madipm(dup, kkt_system="Normal").status != "SOLVE_SUCCEEDED"
+    rk = madipm(dup, kkt_system="K2")
+    assert rk.status == "SOLVE_SUCCEEDED"
+    assert abs(rk.objective - dup.meta["objective"]) <= 1e-6 * max(1.0, abs(rk.objective))
