@@ -20,8 +20,15 @@
 namespace mipm_diag {
 
 constexpr int DB = 64;          // block size
-constexpr int DLD = 65;         // shared-memory leading dimension
+constexpr int DLD = 68;         // shared-memory leading dimension (68 % 16 == 4: conflict-free DMMA fragment loads)
 constexpr int PW = 16;          // panel width
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
 
 // Branch-free reciprocal for a normal, finite, non-zero argument: MUFU seed (relative error 2^-23) and two Newton steps.
 // (__drcp_rn ends in a slow-path branch that keeps ptxas from overlapping it with independent work.) Arguments outside
@@ -88,43 +95,97 @@ __device__ __noinline__ void careful_panel(double *S, double *Sinv, double *dv, 
     }
 }
 
-// Rank-16 update of the trailing block (8 NCOL rows / columns). Lane = row (two halves of 32), warp w = columns
-// w, w + 8, ...: the row operand is read conflict-free (consecutive rows), the column operand is a broadcast.
-template <int NCOL>
-__device__ __forceinline__ void trailing_update(double *S, const double *Ysc, const double *invd, int pc, int lane, int warp)
+// Rank-16 update of the trailing block on the FP64 tensor pipe: C(r, c) -= sum_j Y(r, j) / d_j * Y(c, j) over the lower
+// 8 x 8 tiles of the nbelow x nbelow block (21 / 10 / 3 tiles for 48 / 32 / 16 rows). `next_diag`: only the three tiles of
+// the next 16 x 16 diagonal block (they are on the critical path: the next panel factorization reads them); otherwise all
+// the other tiles. Tiles are dealt round-robin to the `nw` worker warps (`wi` = index of this warp among them).
+// Fragment convention of mma.m8n8k4: a = A[g][l3], b = B[l3][g], c[e] = C[g][2 l3 + e] with g = lane / 4, l3 = lane % 4.
+__device__ __forceinline__ void trailing_tiles(double *S, const double *Ysc, const double *invd, int pc, int nbelow, int lane,
+                                               int wi, int nw, bool next_diag)
 {
-    constexpr int NBELOW = 8 * NCOL;
-    constexpr bool TWO = NBELOW > 32;
-    const bool h1 = TWO && (lane + 32) < NBELOW;
-    const double *Yr = Ysc + pc + lane;
-    double acc0[NCOL], acc1[NCOL];
+    const int g = lane >> 2, l3 = lane & 3;
+    const int nt = nbelow >> 3, g0 = pc + PW;
+    int turn = 0;                                               // (no integer division: this sits on the critical path)
+    for (int ti = next_diag ? 0 : 2; ti < (next_diag ? min(nt, 2) : nt); ++ti)
+        for (int tj = 0; tj <= ti; ++tj) {
+            const bool mine = (turn == wi);
+            if (++turn == nw) turn = 0;
+            if (!mine) continue;
+            const double *ya = Ysc + pc + 8 * ti + g;           // Y(g0 + 8 ti + g, .)
+            const double *yb = Ysc + pc + 8 * tj + g;           // Y(g0 + 8 tj + g, .)
+            double a[PW / 4], b[PW / 4];
 #pragma unroll
-    for (int t = 0; t < NCOL; ++t) acc0[t] = acc1[t] = 0.0;
-    if (lane < NBELOW) {
-#pragma unroll
-        for (int j = 0; j < PW; ++j) {
-            const double dj = invd[pc + j];
-            const double y0 = Yr[j * DLD] * dj;
-            const double y1 = h1 ? Yr[j * DLD + 32] * dj : 0.0;
-#pragma unroll
-            for (int t = 0; t < NCOL; ++t) {
-                const double yc = Ysc[j * DLD + pc + warp + 8 * t];
-                acc0[t] = fma(y0, yc, acc0[t]);
-                if (TWO) acc1[t] = fma(y1, yc, acc1[t]);
+            for (int q = 0; q < PW / 4; ++q) {
+                const int j = 4 * q + l3;
+                a[q] = ya[j * DLD] * invd[pc + j];
+                b[q] = yb[j * DLD];
             }
-        }
-        const int g0 = pc + PW;
+            double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-        for (int t = 0; t < NCOL; ++t) {
-            const int c = warp + 8 * t;
-            if (lane >= c) S[(g0 + c) * DLD + g0 + lane] -= acc0[t];
-            if (h1) S[(g0 + c) * DLD + g0 + lane + 32] -= acc1[t];
+            for (int q = 0; q < PW / 4; ++q) dmma884(c0, c1, a[q], b[q]);
+            const int row = g0 + 8 * ti + g, col = g0 + 8 * tj + 2 * l3;
+            if (row >= col) S[col * DLD + row] -= c0;
+            if (row >= col + 1) S[(col + 1) * DLD + row] -= c1;
+        }
+}
+
+// Block row ib >= 1 of inv(L_unit) (the diagonal blocks are in place):  M_ij = -M_ii sum_{k=16j}^{16i-1} L_ik M_kj, both
+// products on the FP64 tensor pipe. 8 x 8 output tiles (2 x 2 ib of them) dealt to the nw worker warps; T = L M goes
+// through the destination rows of Sinv between the two products. `sync` is the barrier of the worker set.
+template <typename SyncF>
+__device__ __forceinline__ void inverse_block_row(const double *S, double *Sinv, int ib, int lane, int wi, int nw, SyncF sync)
+{
+    const int g = lane >> 2, l3 = lane & 3;
+    const int row0 = ib * PW, ntile = 4 * ib;
+    double t0[2], t1[2];
+    // T(row0 + r, c) = sum_{k = 16 (c / 16)}^{row0 - 1} L(row0 + r, k) M(k, c): tile = (ti, tc), widest K first
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int tile = wi + nw * u;
+        t0[u] = t1[u] = 0.0;
+        if (tile < ntile) {
+            const int ti = tile & 1, tc = tile >> 1;
+            const double *la = S + row0 + 8 * ti + g;                    // L(row0 + 8 ti + g, k) at la[k * DLD]
+            const double *mb = Sinv + (8 * tc + g) * DLD;               // M(k, 8 tc + g) at mb[k]
+            for (int k = PW * (tc >> 1); k < row0; k += 4) dmma884(t0[u], t1[u], la[(k + l3) * DLD], mb[k + l3]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int tile = wi + nw * u;
+        if (tile < ntile) {
+            const int ti = tile & 1, tc = tile >> 1;
+            Sinv[(8 * tc + 2 * l3) * DLD + row0 + 8 * ti + g] = t0[u];
+            Sinv[(8 * tc + 2 * l3 + 1) * DLD + row0 + 8 * ti + g] = t1[u];
+        }
+    }
+    sync();
+    // M(row0 + r, c) = -sum_{k' <= r} M_ii(r, k') T(row0 + k', c)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int tile = wi + nw * u;
+        t0[u] = t1[u] = 0.0;
+        if (tile < ntile) {
+            const int ti = tile & 1, tc = tile >> 1;
+            const double *ma = Sinv + row0 * DLD + row0 + 8 * ti + g;   // M_ii(8 ti + g, k') at ma[k' * DLD]
+            const double *tb = Sinv + (8 * tc + g) * DLD + row0;        // T(row0 + k', 8 tc + g) at tb[k']
+            for (int k = 0; k < 8 * (ti + 1); k += 4) dmma884(t0[u], t1[u], ma[(k + l3) * DLD], tb[k + l3]);
+        }
+    }
+    sync();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int tile = wi + nw * u;
+        if (tile < ntile) {
+            const int ti = tile & 1, tc = tile >> 1;
+            Sinv[(8 * tc + 2 * l3) * DLD + row0 + 8 * ti + g] = -t0[u];
+            Sinv[(8 * tc + 2 * l3 + 1) * DLD + row0 + 8 * ti + g] = -t1[u];
         }
     }
 }
 
-// smem: [0, 64*65) S | [4160, 4160+256) dv, invd, spare | [4416, 4416+4160) Sinv (its upper right corner doubles as
-// the panel scratch during the factorization).  Needs 8576 doubles.
+// smem: [0, 64*68) S | [4352, 4352+256) dv, invd, spare | [4608, 4608+4352) Sinv (its upper right corner doubles as
+// the panel scratch during the factorization).  Needs 8960 doubles.
 // P: the block inside the front panel (column-major, leading dimension N); nb <= 64 valid rows / columns.
 // preloaded: S already holds the block (lower triangle inside nb, identity elsewhere); P is then only written.
 // Dv: 64 x 64 column-major output with column stride ldv, inverse of the stored factor (identity outside nb).
@@ -166,8 +227,16 @@ __device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv,
     // of K2 systems and of block-angular problems are mostly narrower than 32 columns (C4: 19 on average), so this is most
     // of the diagonal-block work there.
     const int nbr = min(DB, ((nb + PW - 1) / PW) * PW);
+    // Warp 0 owns the serial chain (the 16 x 16 panel factorizations). Everything else that panel q - 1 leaves behind --
+    // the trailing update outside the next diagonal block and block row q - 1 of the inverse -- runs on warps 1-7 WHILE
+    // warp 0 factors panel q, so the chain per panel is: factor -> rows below (all warps) -> next diagonal block.
+    auto workers_sync = [] { asm volatile("bar.sync 1, 224;" ::: "memory"); };
 #pragma unroll 1
     for (int pc = 0; pc < nbr; pc += PW) {
+        if (warp != 0 && pc > 0) {
+            trailing_tiles(S, Ysc, invd, pc - PW, nbr - pc, lane, warp - 1, 7, false);
+            if (pc >= 2 * PW) inverse_block_row(S, Sinv, pc / PW - 1, lane, warp - 1, 7, workers_sync);
+        }
         if (warp == 0) {
             // lanes 0-15: row i of the 16 x 16 block. lanes 16-31: column i of inv(L11), carried through the SAME
             // instruction stream: with m = e_i in place of the row, step j does m[k] -= (m[j]/d_j) A(k,j), which is
@@ -260,9 +329,13 @@ __device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv,
             }
         }
         // trailing block -= Y D^-1 Y'
-        if (nbelow == 48) trailing_update<6>(S, Ysc, invd, pc, lane, warp);
-        else if (nbelow == 32) trailing_update<4>(S, Ysc, invd, pc, lane, warp);
-        else trailing_update<2>(S, Ysc, invd, pc, lane, warp);
+#ifdef DIAG_EXP_TIME
+        long long tt0 = clock64();
+#endif
+        if (warp < 3) trailing_tiles(S, Ysc, invd, pc, nbelow, lane, warp, 3, true);      // the next diagonal block only
+#ifdef DIAG_EXP_TIME
+        if (DBG && dbg) tq[4] += clock64() - tt0;
+#endif
         __syncthreads();
         DIAG_STAMP(3);
     }
@@ -274,53 +347,10 @@ __device__ __forceinline__ void diag_block(double *P, int N, int nb, double *Dv,
     }
     if (LDL && tid < nb && dv[tid] < 0.0) atomicAdd(&info[1], 1);
 
-    // ---- inv(L_unit), block rows i = 1..3 (the diagonal blocks are in place):  M_ij = -M_ii sum_{k=j}^{i-1} L_ik M_kj.
-    // Thread (r, c0) owns row 16 i + r of the columns c0 + 16 jb, jb < i.
-    {
-        const int r = tid & 15, c0 = tid >> 4;
-#pragma unroll
-        for (int ib = 1; ib < DB / PW; ++ib) {
-            if (ib * PW >= nbr) break;                                   // uniform: identity padding needs no inverse
-            const int row0 = ib * PW;
-            double t[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-            for (int jb = 0; jb < 3; ++jb) {
-                if (jb < ib) {
-                    const int c = c0 + PW * jb;
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-                    for (int k = PW * jb; k < row0; k += 4) {           // block-aligned start: M is zero above its diagonal
-                        s0 = fma(S[k * DLD + row0 + r], Sinv[c * DLD + k], s0);
-                        s1 = fma(S[(k + 1) * DLD + row0 + r], Sinv[c * DLD + k + 1], s1);
-                        s2 = fma(S[(k + 2) * DLD + row0 + r], Sinv[c * DLD + k + 2], s2);
-                        s3 = fma(S[(k + 3) * DLD + row0 + r], Sinv[c * DLD + k + 3], s3);
-                    }
-                    t[jb] = (s0 + s1) + (s2 + s3);
-                }
-            }
-#pragma unroll
-            for (int jb = 0; jb < 3; ++jb) if (jb < ib) Sinv[(c0 + PW * jb) * DLD + row0 + r] = t[jb];
-            __syncthreads();
-#pragma unroll
-            for (int jb = 0; jb < 3; ++jb) {
-                if (jb < ib) {
-                    const int c = c0 + PW * jb;
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < PW; k += 4) {                   // M_ii is zero above its diagonal
-                        s0 = fma(Sinv[(row0 + k) * DLD + row0 + r], Sinv[c * DLD + row0 + k], s0);
-                        s1 = fma(Sinv[(row0 + k + 1) * DLD + row0 + r], Sinv[c * DLD + row0 + k + 1], s1);
-                        s2 = fma(Sinv[(row0 + k + 2) * DLD + row0 + r], Sinv[c * DLD + row0 + k + 2], s2);
-                        s3 = fma(Sinv[(row0 + k + 3) * DLD + row0 + r], Sinv[c * DLD + row0 + k + 3], s3);
-                    }
-                    t[jb] = -((s0 + s1) + (s2 + s3));
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int jb = 0; jb < 3; ++jb) if (jb < ib) Sinv[(c0 + PW * jb) * DLD + row0 + r] = t[jb];
-            __syncthreads();
-        }
+    // ---- the last block row of inv(L_unit) (the earlier ones were computed in the shadow of the panel factorizations)
+    if (nbr > PW) {
+        inverse_block_row(S, Sinv, nbr / PW - 1, lane, warp, 8, [] { __syncthreads(); });
+        __syncthreads();
     }
     DIAG_STAMP(5);
     // ---- write out: the factor (Cholesky: L = L_unit sqrt(D); LDL^T: unit multipliers, D on the diagonal) and its

@@ -40,11 +40,11 @@ constexpr int EA_COLS = 32;                     // parent-front columns per exte
 constexpr int KC = 16;                          // columns per pipeline stage
 constexpr int NSTAGE = 4;
 constexpr int STAGE_DOUBLES = 2 * KC * XS;      // A and B operand of one stage
-constexpr int SMEM_DOUBLES = NSTAGE * STAGE_DOUBLES;            // 8704 doubles = 69,632 B (>= diag task, = TRSM epilogue)
+constexpr int DIAG_DOUBLES = 2 * NB * mipm_diag::DLD + 4 * NB;      // diag task: S + scratch + Sinv
+constexpr int SMEM_DOUBLES = (NSTAGE * STAGE_DOUBLES > DIAG_DOUBLES) ? NSTAGE * STAGE_DOUBLES : DIAG_DOUBLES;   // 8960 doubles = 71,680 B
 constexpr int SMEM_BYTES = SMEM_DOUBLES * 8 + NSTAGE * KC * 8 + 64;   // + pivots of each stage (LDL^T) + mbarrier
-static_assert(2 * NB * LDS + 4 * NB <= SMEM_DOUBLES, "diag task: S + scratch + Sinv must fit the stage buffers");
 static_assert(2 * TILE * XS <= SMEM_DOUBLES, "TRSM epilogue: X and inv(L11) tiles must fit the stage buffers");
-static_assert(NB == mipm_diag::DB && LDS == mipm_diag::DLD, "diag_block.cuh is written for 64 x 64 blocks, ld 65");
+static_assert(NB == mipm_diag::DB, "diag_block.cuh is written for 64 x 64 blocks");
 enum { T_EA = 0, T_DIAG = 1, T_PANEL = 2, T_TRAIL = 3, T_LEAF = 4, T_NCLASS = 5 };
 
 #ifndef MIPM_FACTOR_OCC
@@ -462,7 +462,7 @@ __device__ void task_diag(const FactorParams &p, Pipe &pp, const FrontInfo &f, i
         gemm_tile<LDL>(acc, pp, P + jb, P + jb, true, ld, K0, jb, 0, 0, p.Dg + f.c0, frag_mask(nb, nb, true));
         double *S = smem;
         acc_foreach(acc, [&](int rr, int cc, double val) {
-            S[cc * LDS + rr] = (rr < nb && cc < nb && rr >= cc) ? Pd[(int64_t)cc * ld + rr] - val : ((rr == cc) ? 1.0 : 0.0);
+            S[cc * mipm_diag::DLD + rr] = (rr < nb && cc < nb && rr >= cc) ? Pd[(int64_t)cc * ld + rr] - val : ((rr == cc) ? 1.0 : 0.0);
         });
         pre = true;
     }

@@ -6,7 +6,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
-constexpr int NB = 64, LDS = 65;
+constexpr int NB = 64;
 #include "../madipm_jl_b200/csrc/diag_block.cuh"
 
 template <bool LDL>
@@ -45,7 +45,7 @@ static int run(int nblk, int nb, bool check, int special = 0)
     cudaMalloc(&A, h.size() * 8); cudaMalloc(&Dinv, (size_t)nblk * NB * NB * 8); cudaMalloc(&info, 16); cudaMalloc(&cyc, (nblk + 16) * 8);
     cudaMemcpy(A, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
     cudaMemset(info, 0, 16);
-    size_t smem = 2 * 64 * 68 * 8;
+    size_t smem = (2 * 64 * 68 + 256) * 8;
     cudaFuncSetAttribute(k<LDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<LDL><<<nblk, 256, smem>>>(A, N, nb, Dinv, info, cyc, 1);
     cudaError_t e = cudaDeviceSynchronize();

@@ -25,6 +25,11 @@ __global__ void k(double *out, long long *cyc, double seed, int n)
             if (OP == 7) x = (x > 0.5 && x < 1e300) ? x : y;          // compare + select
             if (OP == 8) x = x + y;
             if (OP == 9) { x = fma(x, y, 1e-9); y = fma(y, x, 1e-9); }   // 2 interleaved... still dependent
+            if (OP == 10) { double c1 = y; asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(x), "+d"(c1) : "d"(1e-3), "d"(1e-3)); y = c1; }
+            if (OP == 11) { double c1 = y, d0 = x * 0.5, d1 = y * 0.5;     // two independent accumulator pairs
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(x), "+d"(c1) : "d"(1e-3), "d"(1e-3));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(1e-3), "d"(1e-3));
+                y = c1 + d0 + d1; }
         }
     }
     long long c1 = clock64();
@@ -51,6 +56,8 @@ int main()
     run<5>("sqrt dependent", 1.7, out, cyc);
     run<6>("LDS.64 + cvt dependent", 3.0, out, cyc);
     run<7>("cmp+select dependent", 1.0, out, cyc);
+    run<10>("DMMA m8n8k4 dependent", 1.0, out, cyc);
+    run<11>("2 DMMA independent + 2 DADD", 1.0, out, cyc);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
