@@ -136,7 +136,8 @@ k_gather32(int64_t n, const double *__restrict__ src, const int32_t *__restrict_
 }
 
 // Row runs for k_spmv_stream: consecutive rows, at most SPMV_CAP nonzeros and 256 rows per block.
-static std::vector<int32_t> spmv_blocks(const std::vector<int32_t> &ptr)
+constexpr int ASM_ROWS = 256;
+static std::vector<int32_t> spmv_blocks(const std::vector<int32_t> &ptr, int max_rows = 256)
 {
     const int64_t nrows = (int64_t)ptr.size() - 1;
     std::vector<int32_t> blk;
@@ -144,7 +145,7 @@ static std::vector<int32_t> spmv_blocks(const std::vector<int32_t> &ptr)
     int64_t r = 0;
     while (r < nrows) {
         int64_t e = r + 1;      // at least one row (a long row stands alone)
-        while (e < nrows && e - r < 256 && ptr[(size_t)e + 1] - ptr[(size_t)r] <= SPMV_CAP) ++e;
+        while (e < nrows && e - r < max_rows && ptr[(size_t)e + 1] - ptr[(size_t)r] <= SPMV_CAP) ++e;
         blk.push_back((int32_t)e);
         r = e;
     }
@@ -314,6 +315,26 @@ int mipm_normal_symbolic(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap
     Handle *h = (Handle *)hh;
     if (h && !h->host_only) use_handle(h);
     if (!h || !Ap || (!Aj && m > 0 && Ap[m] != index_base) || !Cp || !Cj || !nnzC) return fail(h, MIPM_ERR_ARG, "null argument");
+    // Handles that own a GPU build the pattern and the term map on the device (normal_device.cu); analysis-only handles
+    // and MIPM_HOST_SYMBOLIC=1 take the host sweep. Both produce the same arrays.
+    if (!h->host_only && !std::getenv("MIPM_HOST_SYMBOLIC")) {
+        std::vector<int32_t> cp, cj, tp;
+        int rc = normal_symbolic_device(h, m, n, Ap, Aj, index_base, cp, cj, tp);
+        if (rc != MIPM_OK) return rc;
+        *Cp = host_copy(cp, index_base);
+        *Cj = host_copy(cj, index_base);
+        *nnzC = h->nsym.nnz_c;
+        if (!*Cp || !*Cj) return fail(h, MIPM_ERR_ALLOC, "host allocation failed");
+        h->has_normal = true;
+        h->has_jac = false;
+        MIPM_CUDA(h, h->d_term_w.alloc((size_t)h->nsym.n_terms));
+        std::vector<int32_t> blk = spmv_blocks(tp, ASM_ROWS);
+        h->asm_nblk = (int64_t)blk.size() - 1;
+        MIPM_CUDA(h, h->d_asm_blk.upload(blk, h->stream));
+        MIPM_CUDA(h, h->d_D.alloc((size_t)n));
+        MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+        return MIPM_OK;
+    }
     std::string e = normal_symbolic_host(m, n, Ap, Aj, index_base, h->nsym);
     if (!e.empty()) return fail(h, e.find("duplicate") != std::string::npos ? MIPM_ERR_DUPLICATE : MIPM_ERR_ARG, e);
     *Cp = host_copy(h->nsym.Cp, index_base);
@@ -330,7 +351,7 @@ int mipm_normal_symbolic(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap
         MIPM_CUDA(h, h->d_term_k.upload(h->nsym.term_k, h->stream));
         MIPM_CUDA(h, h->d_term_w.alloc((size_t)h->nsym.n_terms));
         {
-            std::vector<int32_t> blk = spmv_blocks(h->nsym.term_ptr);       // runs of stored entries, <= 2048 terms each
+            std::vector<int32_t> blk = spmv_blocks(h->nsym.term_ptr, ASM_ROWS);       // runs of stored entries, <= 2048 terms each
             h->asm_nblk = (int64_t)blk.size() - 1;
             MIPM_CUDA(h, h->d_asm_blk.upload(blk, h->stream));
         }
@@ -565,9 +586,7 @@ int mipm_ls_analyze(mipm_handle hh, int64_t n, const int32_t *colptr, const int3
     if (!h || n < 0 || !colptr || (kind != MIPM_CHOLESKY && kind != MIPM_LDL && kind != MIPM_LDL_DEFINITE)) return fail(h, MIPM_ERR_ARG, "bad argument");
     int64_t nnz = colptr[n] - index_base;
     if (nnz < 0 || (nnz > 0 && !rowval)) return fail(h, MIPM_ERR_ARG, "bad column pointer");
-    std::vector<int32_t> cp((size_t)n + 1), ri((size_t)nnz), up;
-    for (int64_t j = 0; j <= n; ++j) cp[(size_t)j] = colptr[j] - index_base;
-    for (int64_t p = 0; p < nnz; ++p) ri[(size_t)p] = rowval[p] - index_base;
+    std::vector<int32_t> up;
     if (ordering == MIPM_ORDER_USER && user_perm) {
         up.resize((size_t)n);
         for (int64_t k = 0; k < n; ++k) up[(size_t)k] = user_perm[k] - index_base;
@@ -575,6 +594,7 @@ int mipm_ls_analyze(mipm_handle hh, int64_t n, const int32_t *colptr, const int3
     LsOptions opt;
     opt.kind = (kind == MIPM_LDL_DEFINITE) ? MIPM_CHOLESKY : kind;      // the analysis of a definite matrix has no K2 rule
     opt.ordering = ordering;
+    opt.host_a2l = h->host_only;
     if (const char *s = std::getenv("MIPM_ND_LEAF")) opt.nd_leaf = std::max(1, atoi(s));
     if (const char *s = std::getenv("MIPM_LDL_DELAY")) opt.ldl_delay_all = (std::strcmp(s, "first") != 0);
     if (const char *s = std::getenv("MIPM_RELAX")) {
@@ -583,7 +603,7 @@ int mipm_ls_analyze(mipm_handle hh, int64_t n, const int32_t *colptr, const int3
     }
     h->has_ls = false;
     h->factorized = false;
-    std::string e = ls_analyze(n, cp.data(), ri.data(), opt, up.empty() ? nullptr : up.data(), h->sym);
+    std::string e = ls_analyze(n, colptr, rowval, index_base, opt, up.empty() ? nullptr : up.data(), h->sym);
     if (!e.empty()) return fail(h, MIPM_ERR_ARG, e);
     h->ldl_definite = (kind == MIPM_LDL_DEFINITE);
     if (h->ldl_definite) h->sym.kind = MIPM_LDL;

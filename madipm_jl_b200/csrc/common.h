@@ -50,7 +50,8 @@ struct DBuf {
         pooled = false;
         return cudaMalloc((void **)&p, count * sizeof(T));
     }
-    cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {
+    template <typename A>
+    cudaError_t upload(const std::vector<T, A> &h, cudaStream_t s) {
         cudaError_t e = alloc(h.size());
         if (e != cudaSuccess || h.empty()) return e;
         return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
@@ -203,6 +204,8 @@ inline void use_handle(const Handle *h)
 
 // implemented in the .cu files
 int ls_device_setup(Handle *h);
+int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap, const int32_t *Aj, int index_base,
+                           std::vector<int32_t> &Cp, std::vector<int32_t> &Cj, std::vector<int32_t> &term_ptr_host);
 int ls_solve_setup(Handle *h, const void *finfo_host, const char *small_leaf);
 int ls_factorize_impl(Handle *h, const double *d_nzval);
 int ls_solve_impl(Handle *h, double *d_x, int ir_steps);

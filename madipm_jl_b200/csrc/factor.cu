@@ -300,6 +300,40 @@ __device__ __forceinline__ void trsm_product(double (&acc)[4][2][2], const doubl
 
 // ------------------------------------------------------------------ tasks of the factorization
 __global__ void __launch_bounds__(256)
+k_build_a2l(int64_t n, int64_t nnz, const int32_t *__restrict__ colptr, const int32_t *__restrict__ rowval,
+            const int32_t *__restrict__ iperm, const int32_t *__restrict__ col2sn, const int32_t *__restrict__ sn_ptr,
+            const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ row_idx, const int64_t *__restrict__ lp,
+            int64_t *__restrict__ a2l, int *__restrict__ bad)
+{
+    // destination of every input nonzero in the panel storage (the host version is ls_build_a2l, ls_symbolic.cpp)
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    int64_t lo = 0, hi = n;                 // column of position p: last j with colptr[j] <= p
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (colptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    const int32_t a = iperm[rowval[p]], b = iperm[lo];
+    const int32_t r = max(a, b), c = min(a, b);
+    const int32_t s = col2sn[c];
+    const int32_t c0 = sn_ptr[s], c1 = sn_ptr[s + 1];
+    const int64_t k = c1 - c0, r0 = row_ptr[s], nr = row_ptr[s + 1] - r0;
+    int64_t tt;
+    if (r < c1) {
+        tt = r - c0;
+    } else {
+        int64_t x = 0, y = nr;              // lower bound of r in the front's row list
+        while (x < y) {
+            const int64_t mid = (x + y) >> 1;
+            if (row_idx[r0 + mid] < r) x = mid + 1; else y = mid;
+        }
+        if (x >= nr || row_idx[r0 + x] != r) { *bad = 1; a2l[p] = 0; return; }
+        tt = k + x;
+    }
+    a2l[p] = lp[s] + (int64_t)(c - c0) * ((k + nr + 1) & ~(int64_t)1) + tt;
+}
+
+__global__ void __launch_bounds__(256)
 k_scatter_a(int64_t nnz, const int64_t *__restrict__ a2l, const double *__restrict__ Ax, double *__restrict__ L)
 {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -963,7 +997,29 @@ int ls_device_setup(Handle *h)
     MIPM_CUDA(h, h->d_rel_idx.upload(S.rel_idx, st));
     MIPM_CUDA(h, h->d_perm.upload(S.perm, st));
     MIPM_CUDA(h, h->d_child_idx.upload(S.child_idx, st));
-    MIPM_CUDA(h, h->d_a2l.upload(S.a2l, st));
+    DBuf<int32_t> t_colptr, t_rowval, t_iperm, t_col2sn, t_snptr;
+    DBuf<int64_t> t_rowptr, t_lp;
+    DBuf<int> t_bad;
+    const bool device_a2l = S.a2l.empty() && S.nnz_a > 0;
+    if (device_a2l) {
+        // scatter map built on the device from the pattern (the host copy would be 8 bytes per nonzero to compute,
+        // page in and upload)
+        MIPM_CUDA(h, t_colptr.upload(S.in_colptr, st));
+        MIPM_CUDA(h, t_rowval.upload(S.in_rowval, st));
+        MIPM_CUDA(h, t_iperm.upload(S.iperm, st));
+        MIPM_CUDA(h, t_col2sn.upload(S.col2sn, st));
+        MIPM_CUDA(h, t_snptr.upload(S.sn_ptr, st));
+        MIPM_CUDA(h, t_rowptr.upload(S.row_ptr, st));
+        MIPM_CUDA(h, t_lp.upload(S.lp, st));
+        MIPM_CUDA(h, t_bad.alloc(1));
+        MIPM_CUDA(h, cudaMemsetAsync(t_bad.p, 0, sizeof(int), st));
+        MIPM_CUDA(h, h->d_a2l.alloc((size_t)S.nnz_a));
+        k_build_a2l<<<grid_for(S.nnz_a, 256), 256, 0, st>>>(S.n, S.nnz_a, t_colptr.p, t_rowval.p, t_iperm.p, t_col2sn.p, t_snptr.p,
+                                                            t_rowptr.p, h->d_row_idx.p, t_lp.p, h->d_a2l.p, t_bad.p);
+        MIPM_CHECK_LAUNCH(h);
+    } else {
+        MIPM_CUDA(h, h->d_a2l.upload(S.a2l, st));
+    }
     h->d_full_ptr.release();        // refinement operator: built and uploaded on first use (ls_solve_impl)
     h->d_full_col.release();
     h->d_full_val.release();
@@ -990,7 +1046,10 @@ int ls_device_setup(Handle *h)
         int rc = ls_solve_setup(h, finfo.data(), small.data());
         if (rc != MIPM_OK) return rc;
     }
+    int a2l_bad = 0;
+    if (device_a2l) MIPM_CUDA(h, cudaMemcpyAsync(&a2l_bad, t_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     MIPM_CUDA(h, cudaStreamSynchronize(st));
+    if (a2l_bad) return fail(h, MIPM_ERR_ARG, "input entry outside the symbolic structure (internal error)");
     tlog_stage("solve setup + sync");
     if (!h->side) {
         MIPM_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
@@ -1083,18 +1142,15 @@ extern "C" int mipm_ls_analyze_border(mipm_handle hh, int64_t n, const int32_t *
     if (h && !h->host_only) use_handle(h);
     if (!h || n < 0 || !colptr || n_border < 1 || n_border > n || (kind != MIPM_CHOLESKY && kind != MIPM_LDL && kind != MIPM_LDL_DEFINITE))
         return fail(h, MIPM_ERR_ARG, "bad argument");
-    int64_t nnz = colptr[n] - index_base;
-    std::vector<int32_t> cp((size_t)n + 1), ri((size_t)std::max<int64_t>(nnz, 0));
-    for (int64_t j = 0; j <= n; ++j) cp[(size_t)j] = colptr[j] - index_base;
-    for (int64_t q = 0; q < nnz; ++q) ri[(size_t)q] = rowval[q] - index_base;
     LsOptions opt;
     opt.kind = (kind == MIPM_LDL_DEFINITE) ? MIPM_CHOLESKY : kind;
     opt.ordering = MIPM_ORDER_ND;
     opt.n_border = n_border;
+    opt.host_a2l = h->host_only;
     if (const char *s = std::getenv("MIPM_ND_LEAF")) opt.nd_leaf = std::max(1, atoi(s));
     h->has_ls = false;
     h->factorized = false;
-    std::string e = ls_analyze(n, cp.data(), ri.data(), opt, nullptr, h->sym);
+    std::string e = ls_analyze(n, colptr, rowval, index_base, opt, nullptr, h->sym);
     if (!e.empty()) return fail(h, MIPM_ERR_ARG, e);
     h->ldl_definite = (kind == MIPM_LDL_DEFINITE);
     if (h->ldl_definite) h->sym.kind = MIPM_LDL;

@@ -22,17 +22,61 @@ namespace mipm {
 
 namespace {
 
-// BFS over the vertices whose region[v] == rid, starting at root. Fills `order` (BFS order)
-// and `lvl_ptr` (start of each level in `order`). `stamp[v] = tag` marks visited vertices.
-void bfs_levels(const std::vector<int64_t> &xadj, const std::vector<int32_t> &adj,
-                const std::vector<int32_t> &region, int32_t rid, int32_t root,
-                std::vector<int32_t> &stamp, int32_t tag, std::vector<int32_t> &order,
+// Adjacency of the permuted graph split at the diagonal: for every new index r, low[r] = {c < r} and / or high[r] = {c > r}
+// (unsorted), built vertex by vertex from the full adjacency by the host threads.
+void split_permuted_adjacency(int64_t n, int nth, const std::vector<int64_t> &xadj, const uvector<int32_t> &adj,
+                              const std::vector<int32_t> &perm, const std::vector<int32_t> &ip,
+                              uvector<int64_t> *lptr, uvector<int32_t> *lidx, uvector<int64_t> *hptr, uvector<int32_t> *hidx)
+{
+    uvector<int32_t> lc((size_t)n);
+    run_host_threads(nth, [&](int t) {
+        for (int64_t r = n * t / nth; r < n * (t + 1) / nth; ++r) {
+            const int32_t v = perm[(size_t)r];
+            int32_t c = 0;
+            for (int64_t p = xadj[(size_t)v]; p < xadj[(size_t)v + 1]; ++p) c += ip[(size_t)adj[(size_t)p]] < r;
+            lc[(size_t)r] = c;
+        }
+    });
+    if (lptr) lptr->resize((size_t)n + 1);
+    if (hptr) hptr->resize((size_t)n + 1);
+    int64_t lo = 0, hi = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        const int32_t v = perm[(size_t)r];
+        if (lptr) (*lptr)[(size_t)r] = lo;
+        if (hptr) (*hptr)[(size_t)r] = hi;
+        lo += lc[(size_t)r];
+        hi += (xadj[(size_t)v + 1] - xadj[(size_t)v]) - lc[(size_t)r];
+    }
+    if (lptr) { (*lptr)[(size_t)n] = lo; lidx->resize((size_t)lo); }
+    if (hptr) { (*hptr)[(size_t)n] = hi; hidx->resize((size_t)hi); }
+    run_host_threads(nth, [&](int t) {
+        for (int64_t r = n * t / nth; r < n * (t + 1) / nth; ++r) {
+            const int32_t v = perm[(size_t)r];
+            int64_t wl = lptr ? (*lptr)[(size_t)r] : 0, wh = hptr ? (*hptr)[(size_t)r] : 0;
+            for (int64_t p = xadj[(size_t)v]; p < xadj[(size_t)v + 1]; ++p) {
+                const int32_t c = ip[(size_t)adj[(size_t)p]];
+                if (c < r) { if (lptr) (*lidx)[(size_t)wl++] = c; }
+                else if (hptr) (*hidx)[(size_t)wh++] = c;
+            }
+        }
+    });
+}
+
+// mark[v] = region id of v (high word) | tag of the last search that reached v (low word): one load per edge.
+inline uint64_t mark_key(int32_t rid, int32_t tag) { return ((uint64_t)(uint32_t)rid << 32) | (uint32_t)tag; }
+
+// BFS over the vertices of region rid, starting at root. Fills `order` (BFS order)
+// and `lvl_ptr` (start of each level in `order`). Visited vertices get the tag.
+void bfs_levels(const int64_t *xadj, const int32_t *adj,
+                std::vector<uint64_t> &mark, int32_t rid, int32_t root,
+                int32_t tag, std::vector<int32_t> &order,
                 std::vector<int64_t> &lvl_ptr)
 {
+    const uint64_t visited = mark_key(rid, tag);
     order.clear();
     lvl_ptr.clear();
     order.push_back(root);
-    stamp[root] = tag;
+    mark[root] = visited;
     lvl_ptr.push_back(0);
     size_t head = 0;
     while (head < order.size()) {
@@ -41,9 +85,10 @@ void bfs_levels(const std::vector<int64_t> &xadj, const std::vector<int32_t> &ad
         for (; head < end; ++head) {
             int32_t v = order[head];
             for (int64_t p = xadj[v]; p < xadj[v + 1]; ++p) {
-                int32_t w = adj[p];
-                if (region[w] == rid && stamp[w] != tag) {
-                    stamp[w] = tag;
+                const int32_t w = adj[p];
+                const uint64_t mw = mark[w];
+                if ((int32_t)(mw >> 32) == rid && mw != visited) {
+                    mark[w] = visited;
                     order.push_back(w);
                 }
             }
@@ -55,13 +100,12 @@ void bfs_levels(const std::vector<int64_t> &xadj, const std::vector<int32_t> &ad
 
 }  // namespace
 
-void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
-                             const std::vector<int32_t> &adj, int leaf_size,
+void order_nested_dissection(int64_t n, const int64_t *xadj, const int32_t *adj, int leaf_size,
                              std::vector<int32_t> &perm)
 {
     perm.assign((size_t)n, -1);
     if (n == 0) return;
-    std::vector<int32_t> region((size_t)n, 0), stamp((size_t)n, -1);
+    std::vector<uint64_t> mark((size_t)n, 0);
     struct Item { std::vector<int32_t> verts; int64_t lo; bool connected; };
     std::vector<Item> stack;
     {
@@ -73,7 +117,7 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
         stack.push_back(std::move(it));
     }
     // Sub-graphs are independent once split, so they are dissected by a small pool of host threads. Tasks touch
-    // disjoint entries of region / stamp / perm; region ids and stamp tags come from atomic counters, and a task's
+    // disjoint entries of mark / perm; region ids and stamp tags come from atomic counters, and a task's
     // result depends only on its vertex set, so the ordering does not depend on the schedule.
     std::atomic<int32_t> next_rid{1}, tag_counter{0};
     std::mutex mu;
@@ -97,33 +141,11 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
         const int64_t nv = (int64_t)it.verts.size();
         if (nv == 0) return;
         const int32_t rid = next_rid.fetch_add(1);
-        for (int32_t v : it.verts) region[v] = rid;
+        for (int32_t v : it.verts) mark[v] = mark_key(rid, 0);
 
-        if (!it.connected) {
-            // split into connected components
-            tag = tag_counter.fetch_add(1) + 1;
-            int64_t lo = it.lo;
-            bool single = true;
-            std::vector<Item> comps;
-            for (int32_t v : it.verts) {
-                if (stamp[v] == tag) continue;
-                bfs_levels(xadj, adj, region, rid, v, stamp, tag, order, lvl);
-                if ((int64_t)order.size() == nv) break;  // one component: fall through
-                single = false;
-                Item c;
-                c.verts = order;
-                c.lo = lo;
-                c.connected = true;
-                lo += (int64_t)order.size();
-                comps.push_back(std::move(c));
-            }
-            if (!single) {
-                push_items(comps);
-                return;
-            }
-        }
-
-        // pseudo-peripheral root: start at a minimum-degree vertex, iterate on the last level
+        // pseudo-peripheral root: start at a minimum-degree vertex, iterate on the last level. The first search doubles
+        // as the connectivity test of a freshly split part: if it does not reach every vertex, the part is cut into its
+        // connected components instead.
         int32_t root = it.verts[0];
         {
             int64_t bestdeg = INT64_MAX;
@@ -135,7 +157,24 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
         int64_t best_h = -1;
         for (int round = 0; round < 6; ++round) {
             tag = tag_counter.fetch_add(1) + 1;
-            bfs_levels(xadj, adj, region, rid, root, stamp, tag, order, lvl);
+            bfs_levels(xadj, adj, mark, rid, root, tag, order, lvl);
+            if (round == 0 && !it.connected && (int64_t)order.size() != nv) {
+                tag = tag_counter.fetch_add(1) + 1;
+                int64_t lo = it.lo;
+                std::vector<Item> comps;
+                for (int32_t v : it.verts) {
+                    if (mark[v] == mark_key(rid, tag)) continue;
+                    bfs_levels(xadj, adj, mark, rid, v, tag, order, lvl);
+                    Item c;
+                    c.verts = order;
+                    c.lo = lo;
+                    c.connected = true;
+                    lo += (int64_t)order.size();
+                    comps.push_back(std::move(c));
+                }
+                push_items(comps);
+                return;
+            }
             int64_t h = (int64_t)lvl.size() - 1;
             if (h <= best_h) break;
             best_h = h;
@@ -169,7 +208,7 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
         // thin the separator: keep only level-j vertices adjacent to level j+1
         tag = tag_counter.fetch_add(1) + 1;  // stamp level j+1 vertices with tag
         for (int64_t t = best_lvl[(size_t)j + 1]; t < best_lvl[(size_t)j + 2]; ++t)
-            stamp[best_order[(size_t)t]] = tag;
+            mark[best_order[(size_t)t]] = mark_key(rid, tag);
         Item A, B;
         std::vector<int32_t> S;
         A.verts.assign(best_order.begin(), best_order.begin() + best_lvl[(size_t)j]);
@@ -178,7 +217,7 @@ void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
             bool touches = false;
             for (int64_t p = xadj[v]; p < xadj[v + 1] && !touches; ++p) {
                 int32_t w = adj[p];
-                touches = (region[w] == rid && stamp[w] == tag);
+                touches = (mark[w] == mark_key(rid, tag));
             }
             if (touches) S.push_back(v); else A.verts.push_back(v);
         }
@@ -255,8 +294,43 @@ void ls_build_full_csr(LsSymbolic &S)
         }
 }
 
+// Scatter map of the input nonzeros into the panels (independent per column: host threads over column chunks). Handles
+// with a GPU build the same map there (k_build_a2l, factor.cu).
+void ls_build_a2l(LsSymbolic &S, std::string &err)
+{
+    const int64_t n = S.n, nnz = S.nnz_a;
+    const int32_t *colptr = S.in_colptr.data(), *rowval = S.in_rowval.data();
+    S.a2l.resize((size_t)nnz);
+    const int nth = (int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, n / 8192));
+    std::vector<int> bad((size_t)nth, 0);
+    auto work = [&](int t) {
+        const int64_t j0 = n * t / nth, j1 = n * (t + 1) / nth;
+        for (int64_t j = j0; j < j1; ++j)
+            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                int32_t a = S.iperm[(size_t)rowval[p]], b = S.iperm[(size_t)j];
+                int32_t r = std::max(a, b), c = std::min(a, b);
+                int32_t s = S.col2sn[(size_t)c];
+                int32_t c0 = S.sn_ptr[(size_t)s], c1 = S.sn_ptr[(size_t)s + 1];
+                int64_t k = c1 - c0;
+                int64_t nr = S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s];
+                int64_t tt;
+                if (r < c1) {
+                    tt = r - c0;
+                } else {
+                    const int32_t *rb = S.row_idx.data() + S.row_ptr[(size_t)s];
+                    const int32_t *f = std::lower_bound(rb, rb + nr, r);
+                    if (f == rb + nr || *f != r) { bad[(size_t)t] = 1; return; }
+                    tt = k + (f - rb);
+                }
+                S.a2l[(size_t)p] = S.lp[(size_t)s] + (int64_t)(c - c0) * ((k + nr + 1) & ~(int64_t)1) + tt;
+            }
+    };
+    run_host_threads(nth, work);
+    for (int v : bad) if (v) err = "input entry outside the symbolic structure (internal error)";
+}
+
 #define TLOG(name) do { if (tlog) { auto now_ = std::chrono::steady_clock::now(); std::fprintf(stderr, "analyze stage before %s: %.3f s\n", name, std::chrono::duration<double>(now_ - t_prev).count()); t_prev = now_; } } while (0)
-std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
+std::string ls_analyze(int64_t n, const int32_t *colptr_in, const int32_t *rowval_in, int index_base,
                        const LsOptions &opt, const int32_t *user_perm, LsSymbolic &S)
 {
     const bool tlog = std::getenv("MIPM_ANALYZE_LOG") != nullptr;
@@ -265,43 +339,85 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
     S.n = n;
     S.kind = opt.kind;
     if (n < 0) return "negative dimension";
-    const int64_t nnz = n > 0 ? colptr[n] : 0;
+    const int64_t nnz = n > 0 ? (int64_t)colptr_in[n] - index_base : 0;
+    if (nnz < 0) return "bad column pointer";
     S.nnz_a = nnz;
-    for (int64_t j = 0; j < n; ++j) {
-        if (colptr[j + 1] < colptr[j]) return "colptr not monotone";
-        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-            int32_t i = rowval[p];
-            if (i < j || i >= n) return "rowval outside the lower triangle";
-        }
+    // 0-based copy of the pattern, kept for the refinement operator and the device-side scatter map; everything below
+    // works on the copy
+    S.in_colptr.resize((size_t)n + 1);
+    S.in_rowval.resize((size_t)nnz);
+    {
+        const int nt0 = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), nnz / 65536));
+        run_host_threads(nt0, [&](int t) {
+            for (int64_t j = (n + 1) * t / nt0; j < (n + 1) * (t + 1) / nt0; ++j) S.in_colptr[(size_t)j] = colptr_in[j] - index_base;
+            for (int64_t p = nnz * t / nt0; p < nnz * (t + 1) / nt0; ++p) S.in_rowval[(size_t)p] = rowval_in[p] - index_base;
+        });
     }
+    const int32_t *colptr = S.in_colptr.data(), *rowval = S.in_rowval.data();
+    // Column chunks with about equal numbers of stored entries for the host threads of the passes below
+    const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(host_threads(), n / 4096), (int64_t)(1 << 25) / std::max<int64_t>(n, 1)));
+    std::vector<int64_t> chunk((size_t)nth + 1, n);
+    chunk[0] = 0;
+    if (n > 0 && colptr[0] != 0) return "column pointer does not start at index_base";
+    for (int64_t j = 0; j < n; ++j)
+        if (colptr[j + 1] < colptr[j]) return "colptr not monotone";
+    for (int t = 1; t < nth; ++t)
+        chunk[(size_t)t] = std::lower_bound(colptr, colptr + n + 1, (int32_t)(nnz * t / nth)) - colptr;
+    for (int t = 1; t <= nth; ++t) chunk[(size_t)t] = std::min<int64_t>(std::max(chunk[(size_t)t], chunk[(size_t)t - 1]), n);
+    chunk[(size_t)nth] = n;
     // ---- full symmetric adjacency (no diagonal). The full CSR with value positions (iterative refinement only) is
     // built on first use from the kept copy of the pattern: ls_build_full_csr.
-    S.in_colptr.assign(colptr, colptr + n + 1);
-    S.in_rowval.assign(rowval, rowval + nnz);
+    // Transposition by column chunks: thread t counts, per row, the entries of its columns (cntT[t][i]); a prefix over
+    // the threads turns the counts into write cursors, so every adjacency list comes out as {j < i ascending} followed by
+    // {j > i in column order}, exactly what two sequential column-major sweeps produce.
     std::vector<int64_t> xadj((size_t)n + 1, 0);
-    for (int64_t j = 0; j < n; ++j)
-        for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-            int32_t i = rowval[p];
-            if (i != j) {
-                xadj[(size_t)i + 1]++;
-                xadj[(size_t)j + 1]++;
-            }
-        }
-    for (int64_t i = 0; i < n; ++i) xadj[(size_t)i + 1] += xadj[(size_t)i];
-    std::vector<int32_t> adj((size_t)xadj[(size_t)n]);
+    uvector<int32_t> adj;
     {
-        std::vector<int64_t> pa(xadj.begin(), xadj.end() - 1);
-        // two column-major sweeps keep every adjacency list sorted: first the neighbours j < i, then those > i
-        for (int64_t j = 0; j < n; ++j)
-            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-                int32_t i = rowval[p];
-                if (i != j) adj[(size_t)pa[(size_t)i]++] = (int32_t)j;
+        std::vector<int32_t> cntT((size_t)nth * (size_t)n, 0), lowcnt((size_t)n, 0);
+        std::vector<int> bad((size_t)nth, 0);
+        run_host_threads(nth, [&](int t) {
+            int32_t *ct = cntT.data() + (size_t)t * (size_t)n;
+            for (int64_t j = chunk[(size_t)t]; j < chunk[(size_t)t + 1]; ++j) {
+                int32_t lc = 0;
+                for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                    const int32_t i = rowval[p];
+                    if (i < j || i >= n) { bad[(size_t)t] = 1; return; }
+                    if (i != j) { ct[i]++; ++lc; }
+                }
+                lowcnt[(size_t)j] = lc;
             }
-        for (int64_t j = 0; j < n; ++j)
-            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-                int32_t i = rowval[p];
-                if (i != j) adj[(size_t)pa[(size_t)j]++] = i;
+        });
+        for (int v : bad) if (v) return "rowval outside the lower triangle";
+        // per row: counts -> exclusive prefix over the threads; degree
+        run_host_threads(nth, [&](int t) {
+            for (int64_t i = n * t / nth; i < n * (t + 1) / nth; ++i) {
+                int32_t run = 0;
+                for (int u = 0; u < nth; ++u) {
+                    int32_t &c = cntT[(size_t)u * (size_t)n + (size_t)i];
+                    const int32_t v = c;
+                    c = run;
+                    run += v;
+                }
+                xadj[(size_t)i + 1] = (int64_t)run + lowcnt[(size_t)i];
             }
+        });
+        for (int64_t i = 0; i < n; ++i) xadj[(size_t)i + 1] += xadj[(size_t)i];
+        adj.resize((size_t)xadj[(size_t)n]);
+        run_host_threads(nth, [&](int t) {
+            int32_t *ct = cntT.data() + (size_t)t * (size_t)n;
+            for (int64_t j = chunk[(size_t)t]; j < chunk[(size_t)t + 1]; ++j)
+                for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
+                    const int32_t i = rowval[p];
+                    if (i != j) adj[(size_t)(xadj[(size_t)i] + ct[i]++)] = (int32_t)j;
+                }
+        });
+        run_host_threads(nth, [&](int t) {
+            for (int64_t j = chunk[(size_t)t]; j < chunk[(size_t)t + 1]; ++j) {
+                int64_t w = xadj[(size_t)j + 1] - lowcnt[(size_t)j];
+                for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p)
+                    if (rowval[p] != j) adj[(size_t)w++] = rowval[p];
+            }
+        });
     }
     TLOG("0");
     // ---- ordering
@@ -328,10 +444,10 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
                 if (adj[(size_t)p] < ni) ai.push_back(adj[(size_t)p]);
             xi[(size_t)v + 1] = (int64_t)ai.size();
         }
-        order_nested_dissection(ni, xi, ai, opt.nd_leaf, perm0);
+        order_nested_dissection(ni, xi.data(), ai.data(), opt.nd_leaf, perm0);
         for (int64_t v = ni; v < n; ++v) perm0.push_back((int32_t)v);
     } else {
-        order_nested_dissection(n, xadj, adj, opt.nd_leaf, perm0);
+        order_nested_dissection(n, xadj.data(), adj.data(), opt.nd_leaf, perm0);
     }
     if (opt.kind == 1 /*LDL*/ && opt.ordering != 2) {
         // Quasi-definite safeguard for K2 = [Q+Sigma A'; A delta_c I]: a vertex whose diagonal
@@ -385,45 +501,84 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
     for (int64_t k = 0; k < n; ++k) ip0[(size_t)perm0[(size_t)k]] = (int32_t)k;
 
     TLOG("1");
-    // ---- strictly-lower adjacency in the permuted numbering: lowadj[r] = {c < r}
-    auto build_lowadj = [&](const std::vector<int32_t> &ip, std::vector<int64_t> &lptr, std::vector<int32_t> &lidx) {
-        lptr.assign((size_t)n + 1, 0);
-        for (int64_t j = 0; j < n; ++j)
-            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-                int32_t i = rowval[p];
-                if (i == j) continue;
-                int32_t a = ip[(size_t)i], b = ip[(size_t)j];
-                lptr[(size_t)std::max(a, b) + 1]++;
-            }
-        for (int64_t i = 0; i < n; ++i) lptr[(size_t)i + 1] += lptr[(size_t)i];
-        lidx.resize((size_t)lptr[(size_t)n]);
-        std::vector<int64_t> pos(lptr.begin(), lptr.end() - 1);
-        for (int64_t j = 0; j < n; ++j)
-            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-                int32_t i = rowval[p];
-                if (i == j) continue;
-                int32_t a = ip[(size_t)i], b = ip[(size_t)j];
-                lidx[(size_t)pos[(size_t)std::max(a, b)]++] = std::min(a, b);
-            }
-    };
-    std::vector<int64_t> lptr;
-    std::vector<int32_t> lidx;
-    build_lowadj(ip0, lptr, lidx);
+    // ---- adjacency in the perm0 numbering split at the diagonal: lowadj[r] = {c < r} (rows of the lower triangle, for
+    // the elimination tree), below0[c] = {r > c} (columns, for the column counts)
+    uvector<int64_t> lptr, b0ptr;
+    uvector<int32_t> lidx, b0idx;
+    split_permuted_adjacency(n, nth, xadj, adj, perm0, ip0, &lptr, &lidx, &b0ptr, &b0idx);
 
     TLOG("2");
-    // ---- elimination tree + off-diagonal column counts (row-subtree traversal)
-    std::vector<int32_t> parent((size_t)n, -1), flag((size_t)n);
+    // ---- elimination tree (Liu, path compression through `anc`) ...
+    std::vector<int32_t> parent((size_t)n, -1);
     std::vector<int64_t> cnt((size_t)n, 0);
-    for (int64_t k = 0; k < n; ++k) {
-        flag[(size_t)k] = (int32_t)k;
-        for (int64_t p = lptr[(size_t)k]; p < lptr[(size_t)k + 1]; ++p) {
-            int32_t i = lidx[(size_t)p];
-            for (; flag[(size_t)i] != k; i = parent[(size_t)i]) {
-                if (parent[(size_t)i] == -1) parent[(size_t)i] = (int32_t)k;
-                cnt[(size_t)i]++;
-                flag[(size_t)i] = (int32_t)k;
+    {
+        std::vector<int32_t> anc((size_t)n, -1);
+        for (int64_t k = 0; k < n; ++k)
+            for (int64_t p = lptr[(size_t)k]; p < lptr[(size_t)k + 1]; ++p) {
+                int32_t i = lidx[(size_t)p];
+                while (i != -1 && i < k) {
+                    const int32_t nx = anc[(size_t)i];
+                    anc[(size_t)i] = (int32_t)k;
+                    if (nx == -1) parent[(size_t)i] = (int32_t)k;
+                    i = nx;
+                }
             }
+        // ... and off-diagonal column counts in O(nnz alpha) (Gilbert, Ng & Peyton: skeleton leaves of the row subtrees
+        // found through first descendants in a postorder, overlaps removed at least common ancestors)
+        std::vector<int32_t> post1((size_t)n), first((size_t)n, -1), maxfirst((size_t)n, -1), prevleaf((size_t)n, -1);
+        {
+            // any postorder: children lists by counting sort, iterative DFS
+            std::vector<int32_t> head((size_t)n + 1, -1), next((size_t)n, -1), stk;
+            for (int64_t v = n - 1; v >= 0; --v) {           // children of a node in ascending order
+                const int32_t pv = parent[(size_t)v];
+                next[(size_t)v] = head[(size_t)(pv + 1)];
+                head[(size_t)(pv + 1)] = (int32_t)v;
+            }
+            int64_t k = 0;
+            for (int32_t r = head[0]; r != -1; r = next[(size_t)r]) {
+                stk.push_back(r);
+                while (!stk.empty()) {
+                    const int32_t v = stk.back();
+                    const int32_t c = head[(size_t)v + 1];
+                    if (c != -1) { head[(size_t)v + 1] = next[(size_t)c]; stk.push_back(c); }
+                    else { post1[(size_t)k++] = v; stk.pop_back(); }
+                }
+            }
+            if (k != n) return "postorder failed";
         }
+        std::vector<int64_t> &delta = cnt;
+        for (int64_t k = 0; k < n; ++k) {
+            int32_t j = post1[(size_t)k];
+            delta[(size_t)j] = (first[(size_t)j] == -1) ? 1 : 0;        // leaves of the tree start with their diagonal
+            for (; j != -1 && first[(size_t)j] == -1; j = parent[(size_t)j]) first[(size_t)j] = (int32_t)k;
+        }
+        for (int64_t i = 0; i < n; ++i) anc[(size_t)i] = (int32_t)i;
+        for (int64_t k = 0; k < n; ++k) {
+            const int32_t j = post1[(size_t)k];
+            if (parent[(size_t)j] != -1) delta[(size_t)parent[(size_t)j]]--;
+            for (int64_t p = b0ptr[(size_t)j]; p < b0ptr[(size_t)j + 1]; ++p) {
+                const int32_t i = b0idx[(size_t)p];                     // entry (i, j), i > j
+                if (first[(size_t)j] <= maxfirst[(size_t)i]) continue;  // j is not a leaf of the row subtree of i
+                maxfirst[(size_t)i] = first[(size_t)j];
+                const int32_t jprev = prevleaf[(size_t)i];
+                prevleaf[(size_t)i] = j;
+                delta[(size_t)j]++;
+                if (jprev != -1) {                                      // subsequent leaf: remove the overlap at the lca
+                    int32_t q = jprev;
+                    while (q != anc[(size_t)q]) q = anc[(size_t)q];
+                    for (int32_t sidx = jprev; sidx != q;) {
+                        const int32_t sp = anc[(size_t)sidx];
+                        anc[(size_t)sidx] = q;
+                        sidx = sp;
+                    }
+                    delta[(size_t)q]--;
+                }
+            }
+            if (parent[(size_t)j] != -1) anc[(size_t)j] = parent[(size_t)j];
+        }
+        for (int64_t j = 0; j < n; ++j)                                 // parents have larger indices than children
+            if (parent[(size_t)j] != -1) cnt[(size_t)parent[(size_t)j]] += cnt[(size_t)j];
+        for (int64_t j = 0; j < n; ++j) cnt[(size_t)j] -= 1;           // off-diagonal count
     }
     if (opt.n_border > 0) {
         // treat the border block as structurally dense: a chain in the elimination tree with the column
@@ -546,27 +701,9 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
 
     TLOG("5");
     // ---- strictly-lower column structure of the permuted matrix: below[c] = {r > c}
-    std::vector<int64_t> bptr((size_t)n + 1, 0);
-    std::vector<int32_t> bidx;
-    {
-        for (int64_t j = 0; j < n; ++j)
-            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-                int32_t i = rowval[p];
-                if (i == j) continue;
-                int32_t a = S.iperm[(size_t)i], b = S.iperm[(size_t)j];
-                bptr[(size_t)std::min(a, b) + 1]++;
-            }
-        for (int64_t i = 0; i < n; ++i) bptr[(size_t)i + 1] += bptr[(size_t)i];
-        bidx.resize((size_t)bptr[(size_t)n]);
-        std::vector<int64_t> pos(bptr.begin(), bptr.end() - 1);
-        for (int64_t j = 0; j < n; ++j)
-            for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-                int32_t i = rowval[p];
-                if (i == j) continue;
-                int32_t a = S.iperm[(size_t)i], b = S.iperm[(size_t)j];
-                bidx[(size_t)pos[(size_t)std::min(a, b)]++] = std::max(a, b);
-            }
-    }
+    uvector<int64_t> bptr;
+    uvector<int32_t> bidx;
+    split_permuted_adjacency(n, nth, xadj, adj, S.perm, S.iperm, nullptr, nullptr, &bptr, &bidx);
     TLOG("6");
     // ---- supernode parents, children, row structures (merge original entries + children)
     S.sn_parent.assign((size_t)ns, -1);
@@ -656,36 +793,13 @@ std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
         for (int32_t s = 0; s < ns; ++s) S.level_sn[(size_t)pos[(size_t)S.sn_level[(size_t)s]]++] = s;
     }
     TLOG("8");
-    // ---- scatter map of the input nonzeros into the panels (independent per column: host threads over column chunks)
-    S.a2l.resize((size_t)nnz);
-    {
-        const int nth = (int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, n / 8192));
-        std::vector<int> bad((size_t)nth, 0);
-        auto work = [&](int t) {
-            const int64_t j0 = n * t / nth, j1 = n * (t + 1) / nth;
-            for (int64_t j = j0; j < j1; ++j)
-                for (int64_t p = colptr[j]; p < colptr[j + 1]; ++p) {
-                    int32_t a = S.iperm[(size_t)rowval[p]], b = S.iperm[(size_t)j];
-                    int32_t r = std::max(a, b), c = std::min(a, b);
-                    int32_t s = S.col2sn[(size_t)c];
-                    int32_t c0 = S.sn_ptr[(size_t)s], c1 = S.sn_ptr[(size_t)s + 1];
-                    int64_t k = c1 - c0;
-                    int64_t nr = S.row_ptr[(size_t)s + 1] - S.row_ptr[(size_t)s];
-                    int64_t tt;
-                    if (r < c1) {
-                        tt = r - c0;
-                    } else {
-                        const int32_t *rb = S.row_idx.data() + S.row_ptr[(size_t)s];
-                        const int32_t *f = std::lower_bound(rb, rb + nr, r);
-                        if (f == rb + nr || *f != r) { bad[(size_t)t] = 1; return; }
-                        tt = k + (f - rb);
-                    }
-                    S.a2l[(size_t)p] = S.lp[(size_t)s] + (int64_t)(c - c0) * ((k + nr + 1) & ~(int64_t)1) + tt;
-                }
-        };
-        run_host_threads(nth, work);
-        for (int v : bad) if (v) return "input entry outside the symbolic structure (internal error)";
+    TLOG("9");
+    if (opt.host_a2l) {
+        std::string err;
+        ls_build_a2l(S, err);
+        if (!err.empty()) return err;
     }
+    TLOG("10");
     return "";
 }
 

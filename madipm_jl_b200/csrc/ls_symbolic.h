@@ -4,10 +4,22 @@
 // exercised on a CPU-only box through an analysis-only handle.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace mipm {
+
+// std::vector without value-initialization: large arrays are first touched by the host threads that fill them (a single
+// thread faulting in 100 MB of fresh pages costs as much as the pass that uses them).
+template <typename T>
+struct DefaultInitAlloc : std::allocator<T> {
+    template <typename U> struct rebind { using other = DefaultInitAlloc<U>; };
+    template <typename U> void construct(U *p) noexcept { ::new ((void *)p) U; }
+    template <typename U, typename... Args> void construct(U *p, Args &&...args) { ::new ((void *)p) U(std::forward<Args>(args)...); }
+};
+template <typename T> using uvector = std::vector<T, DefaultInitAlloc<T>>;
 
 struct LsOptions {
     int kind = 0;            // MIPM_CHOLESKY / MIPM_LDL
@@ -26,6 +38,8 @@ struct LsOptions {
     // Distributed (block-angular) use: the last n_border vertices are kept last, in their given order, and form
     // ONE final dense supernode (the root separator whose Schur block is all-reduced across GPUs).
     int64_t n_border = 0;
+    // scatter map of the input nonzeros on the host (analysis-only handles, tools); handles with a GPU build it there
+    bool host_a2l = true;
 };
 
 struct LsSymbolic {
@@ -46,8 +60,8 @@ struct LsSymbolic {
     std::vector<int32_t> child_idx;            // children in ascending order
     std::vector<int64_t> level_ptr;            // nlev+1
     std::vector<int32_t> level_sn;             // supernodes grouped by level
-    std::vector<int64_t> a2l;                  // nnz_a: destination of each input nonzero in L storage
-    std::vector<int32_t> in_colptr, in_rowval;  // copy of the analysed pattern (0-based)
+    uvector<int64_t> a2l;                      // nnz_a: destination of each input nonzero in L storage (empty: built on the device)
+    uvector<int32_t> in_colptr, in_rowval;     // copy of the analysed pattern (0-based)
     // full symmetric CSR of the input matrix in ORIGINAL numbering (refinement residual): filled by ls_build_full_csr
     std::vector<int64_t> full_ptr;             // n+1
     std::vector<int32_t> full_col;
@@ -59,16 +73,16 @@ struct LsSymbolic {
     int32_t root_sn = -1;                      // the border supernode when n_border > 0
 };
 
-// colptr/rowval: lower-triangular CSC, 0-based. Returns "" on success or an error message.
-std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval,
+// colptr/rowval: lower-triangular CSC in `index_base`; user_perm 0-based. Returns "" on success or an error message.
+std::string ls_analyze(int64_t n, const int32_t *colptr, const int32_t *rowval, int index_base,
                        const LsOptions &opt, const int32_t *user_perm, LsSymbolic &out);
+void ls_build_a2l(LsSymbolic &S, std::string &err);
 
 void ls_build_full_csr(LsSymbolic &S);
 
 // Nested-dissection ordering (level-structure separators, George & Liu) of the graph of a
 // symmetric matrix given by its full adjacency (no self loops). perm[new] = old.
-void order_nested_dissection(int64_t n, const std::vector<int64_t> &xadj,
-                             const std::vector<int32_t> &adj, int leaf_size,
+void order_nested_dissection(int64_t n, const int64_t *xadj, const int32_t *adj, int leaf_size,
                              std::vector<int32_t> &perm);
 
 }  // namespace mipm
