@@ -20,7 +20,7 @@
 #   MadNLP.transfer! (K2)             cuda_wrapper.jl:12-24            -> mipm_k2_transfer
 #   MadNLP.jtprod!                    normalkkt.jl:176-178             -> mipm_spmv
 #   MadNLP.solve!(::NormalKKT, w)     normalkkt.jl:196-219             -> mipm_normal_solve_stage x3 + mipm_spmv x2 + mipm_ls_solve
-#   MadNLP.mul!(w, ::NormalKKT, v)    normalkkt.jl:221-233             -> mipm_spmv x2 + mipm_kktmul
+#   MadNLP.mul!(w, ::NormalKKT, v)    normalkkt.jl:221-233             -> mipm_spmv_pair + mipm_kktmul
 #   MadIPM.solve_system!              linear_solver.jl:19-44           -> the above + mipm_residual_norms
 #   MadIPM.init_starting_point!       solver.jl:6-125                  -> mipm_init_point_stage (+ fills / axpbys)
 #   MadIPM.set_aug_diagonal_reg!      kernels.jl:124-149               -> mipm_set_aug_diagonal_reg[_scaled]
@@ -251,8 +251,11 @@ end
 function LinearAlgebra.mul!(w::MadNLP.AbstractKKTVector{T}, kkt::GPUNormalKKT, v::MadNLP.AbstractKKTVector,
                             alpha = one(T), beta = zero(T)) where {T}
     h = ensure_spmv(kkt)
-    spmv!(h, 1, alpha, kkt.AT.nzVal, MadNLP.dual(v), beta, MadNLP.primal(w))
-    spmv!(h, 0, alpha, kkt.AT.nzVal, MadNLP.primal(v), beta, MadNLP.dual(w))
+    # A v_x -> w_y and A' v_y -> w_x are independent: one launch
+    check(h, ccall((:mipm_spmv_pair, libmadipm), Cint,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}),
+                   h.ptr, devptr(kkt.AT.nzVal), alpha, devptr(MadNLP.primal(v)), beta, devptr(MadNLP.dual(w)),
+                   alpha, devptr(MadNLP.dual(v)), beta, devptr(MadNLP.primal(w))))
     check(h, ccall((:mipm_kktmul, libmadipm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble),
                    h.ptr, devptr(MadNLP.full(w)), devptr(MadNLP.full(v)), alpha, beta))
     return w

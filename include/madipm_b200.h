@@ -172,6 +172,12 @@ int mipm_spmv_setup(mipm_handle h, int64_t m, int64_t n, const int32_t *Ap, cons
                     int index_base);
 int mipm_spmv(mipm_handle h, int trans, double alpha, const double *d_Ax, const double *d_x,
               double beta, double *d_y);
+/* The two products of one phase in ONE launch: y1 = alpha1 A x1 + beta1 y1 (length m) and y2 = alpha2 A' x2 + beta2 y2
+ * (length n). They are independent of each other in evaluate_model! (c = A x - b and jacl = A' y, src/solver.jl:319-326)
+ * and in the residual of solve_system! / mul!(w, kkt, d) (w_y -= A d_x, w_x -= A' d_y: src/linear_solver.jl:29-35,
+ * normalkkt.jl:221-233). Falls back to two mipm_spmv calls when no column-ordered copy of the values is cached. */
+int mipm_spmv_pair(mipm_handle h, const double *d_Ax, double alpha1, const double *d_x1, double beta1, double *d_y1,
+                   double alpha2, const double *d_x2, double beta2, double *d_y2);
 /* Tells the library that the CSR values at d_Ax stay unchanged until the next call of this function (in MadIPM
  * compress_jacobian!, normalkkt.jl:163-172, is their only writer): a column-ordered copy is kept so that
  * mul!(y, AT', x) streams its values instead of gathering them through the position map. mipm_spmv uses the copy

@@ -61,7 +61,7 @@ SYMBOLS = [
     "mipm_ls_analyze", "mipm_ls_factorize", "mipm_ls_factorize_async", "mipm_ls_status", "mipm_ls_solve",
     "mipm_ls_inertia", "mipm_ls_stats", "mipm_ls_symbolic",
     "mipm_ls_analyze_border", "mipm_ls_factorize_stage", "mipm_ls_solve_stage", "mipm_ls_root_info",
-    "mipm_set_grid_limit", "mipm_spmv_setup", "mipm_spmv", "mipm_spmv_cache_values", "mipm_hess_setup", "mipm_hess_spmv",
+    "mipm_set_grid_limit", "mipm_spmv_setup", "mipm_spmv", "mipm_spmv_pair", "mipm_spmv_cache_values", "mipm_hess_setup", "mipm_hess_spmv",
     "mipm_mpc_set_model", "mipm_mpc_iter_begin", "mipm_mpc_refactor", "mipm_mpc_iter_rest",
     "mipm_mpc_bind", "mipm_set_aug_diagonal_reg", "mipm_set_predictive_rhs", "mipm_set_correction_rhs",
     "mipm_get_correction", "mipm_set_extra_correction", "mipm_get_complementarity_measure",
@@ -245,6 +245,11 @@ class Handle:
 
     def spmv(self, trans, alpha, Ax, x, beta, y):
         self.check(self.lib.mipm_spmv(self.h, C.c_int(trans), C.c_double(alpha), _ptr(Ax), _ptr(x), C.c_double(beta), _ptr(y)))
+
+    def spmv_pair(self, Ax, alpha1, x1, beta1, y1, alpha2, x2, beta2, y2):
+        """y1 = alpha1 A x1 + beta1 y1 and y2 = alpha2 A' x2 + beta2 y2 in one launch."""
+        self.check(self.lib.mipm_spmv_pair(self.h, _ptr(Ax), C.c_double(alpha1), _ptr(x1), C.c_double(beta1), _ptr(y1),
+                                           C.c_double(alpha2), _ptr(x2), C.c_double(beta2), _ptr(y2)))
 
     def set_grid_limit(self, max_ctas):
         self.check(self.lib.mipm_set_grid_limit(self.h, C.c_int(int(max_ctas))))

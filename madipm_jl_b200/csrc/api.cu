@@ -94,20 +94,24 @@ k_spmv_csr(int64_t m, const int32_t *__restrict__ rowptr, const int32_t *__restr
 // CSR index) and A' y (columns of the CSC index; POS = values reached through the position map when no
 // column-ordered copy of the values has been cached).
 constexpr int SPMV_CAP = 2048;
+struct SpmvJob {
+    const int32_t *blk, *ptr, *idx, *pos;      // row runs, segment pointers, gather indices, optional value positions
+    const double *val, *x;
+    double alpha, beta;
+    double *y;
+    int lanes;                                  // threads that share a row in step 2 (power of two <= 32)
+    int nblk;
+};
+
 template <bool POS>
-__global__ void __launch_bounds__(256)
-k_spmv_stream(const int32_t *__restrict__ blk, const int32_t *__restrict__ ptr, const int32_t *__restrict__ idx,
-              const int32_t *__restrict__ pos, const double *__restrict__ val, const double *__restrict__ x,
-              double alpha, double beta, double *__restrict__ y)
+__device__ __forceinline__ void spmv_stream_block(const SpmvJob &j, int b, double *prod, double *red)
 {
-    __shared__ double prod[SPMV_CAP];
-    __shared__ double red[8];
-    const int r0 = blk[blockIdx.x], r1 = blk[blockIdx.x + 1];
-    const int p0 = ptr[r0], p1 = ptr[r1];
+    const int r0 = j.blk[b], r1 = j.blk[b + 1];
+    const int p0 = j.ptr[r0], p1 = j.ptr[r1];
     const int tid = threadIdx.x;
     if (p1 - p0 > SPMV_CAP) {               // one long row
         double acc = 0.0;
-        for (int p = p0 + tid; p < p1; p += 256) acc = fma(POS ? __ldg(val + pos[p]) : val[p], __ldg(x + idx[p]), acc);
+        for (int p = p0 + tid; p < p1; p += 256) acc = fma(POS ? __ldg(j.val + j.pos[p]) : j.val[p], __ldg(j.x + j.idx[p]), acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if ((tid & 31) == 0) red[tid >> 5] = acc;
@@ -115,18 +119,59 @@ k_spmv_stream(const int32_t *__restrict__ blk, const int32_t *__restrict__ ptr, 
         if (tid == 0) {
             double t = 0.0;
             for (int w = 0; w < 8; ++w) t += red[w];
-            y[r0] = (beta == 0.0) ? alpha * t : alpha * t + beta * y[r0];
+            j.y[r0] = (j.beta == 0.0) ? j.alpha * t : j.alpha * t + j.beta * j.y[r0];
         }
         return;
     }
-    for (int p = p0 + tid; p < p1; p += 256) prod[p - p0] = (POS ? __ldg(val + pos[p]) : val[p]) * __ldg(x + idx[p]);
-    __syncthreads();
-    for (int row = r0 + tid; row < r1; row += 256) {
-        const int a = ptr[row] - p0, b = ptr[row + 1] - p0;
-        double acc = 0.0;
-        for (int q = a; q < b; ++q) acc += prod[q];
-        y[row] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * y[row];
+    // step 1: products, eight independent loads in flight per thread
+    {
+        const int np = p1 - p0;
+        int q = tid;
+        for (; q + 768 < np; q += 1024) {
+            double v[4];
+            int c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = POS ? __ldg(j.val + j.pos[p0 + q + 256 * u]) : j.val[p0 + q + 256 * u];
+                c[u] = j.idx[p0 + q + 256 * u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) prod[q + 256 * u] = v[u] * __ldg(j.x + c[u]);
+        }
+        for (; q < np; q += 256) prod[q] = (POS ? __ldg(j.val + j.pos[p0 + q]) : j.val[p0 + q]) * __ldg(j.x + j.idx[p0 + q]);
     }
+    __syncthreads();
+    // step 2: `lanes` threads per row add strided partial sums and combine them by shuffles (fixed order: deterministic)
+    const int g = j.lanes, per = 256 / g;
+    const int sub = tid / g, l = tid & (g - 1);
+    for (int base = r0; base < r1; base += per) {
+        const int row = base + sub;
+        double acc = 0.0;
+        if (row < r1) {
+            const int a = j.ptr[row] - p0, e = j.ptr[row + 1] - p0;
+            for (int q = a + l; q < e; q += g) acc += prod[q];
+        }
+        for (int o = g >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (row < r1 && l == 0) j.y[row] = (j.beta == 0.0) ? j.alpha * acc : j.alpha * acc + j.beta * j.y[row];
+    }
+}
+
+template <bool POS>
+__global__ void __launch_bounds__(256) k_spmv_stream(SpmvJob j)
+{
+    __shared__ double prod[SPMV_CAP];
+    __shared__ double red[8];
+    spmv_stream_block<POS>(j, blockIdx.x, prod, red);
+}
+
+// Two independent products in one launch (A x and A' y of the same iteration phase): blocks [0, a.nblk) run job a,
+// the rest job b.
+__global__ void __launch_bounds__(256) k_spmv_stream_pair(SpmvJob a, SpmvJob b)
+{
+    __shared__ double prod[SPMV_CAP];
+    __shared__ double red[8];
+    if ((int)blockIdx.x < a.nblk) spmv_stream_block<false>(a, blockIdx.x, prod, red);
+    else spmv_stream_block<false>(b, blockIdx.x - a.nblk, prod, red);
 }
 
 __global__ void __launch_bounds__(256)
@@ -136,8 +181,9 @@ k_gather32(int64_t n, const double *__restrict__ src, const int32_t *__restrict_
 }
 
 // Row runs for k_spmv_stream: consecutive rows, at most SPMV_CAP nonzeros and 256 rows per block.
-constexpr int ASM_ROWS = 256;
-static std::vector<int32_t> spmv_blocks(const std::vector<int32_t> &ptr, int max_rows = 256)
+constexpr int ASM_ROWS = 1024;
+template <typename Vec>
+static std::vector<int32_t> spmv_blocks(const Vec &ptr, int max_rows = 256)
 {
     const int64_t nrows = (int64_t)ptr.size() - 1;
     std::vector<int32_t> blk;
@@ -158,6 +204,15 @@ inline int spmv_group(int64_t nnz, int64_t rows)
     double avg = rows > 0 ? (double)nnz / (double)rows : 1.0;
     int g = 2;
     while (g < 32 && g < avg) g *= 2;
+    return g;
+}
+
+// threads per row in step 2 of the streaming SpMV: rows of a few entries are summed by one thread
+inline int stream_lanes(int64_t nnz, int64_t rows)
+{
+    const double avg = rows > 0 ? (double)nnz / (double)rows : 1.0;
+    int g = 1;
+    while (g < 32 && 8.0 * g <= avg) g *= 2;
     return g;
 }
 
@@ -297,15 +352,16 @@ int mipm_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *
 {
     if (n_rows < 0 || n_cols < 0 || nnz < 0 || (nnz > 0 && (!Ai || !Aj)) || !Bp || (nnz > 0 && (!Bj || !Bmap)))
         return MIPM_ERR_ARG;
-    std::vector<int32_t> i0((size_t)nnz), j0((size_t)nnz);
-    for (int64_t k = 0; k < nnz; ++k) {
-        i0[(size_t)k] = Ai[k] - index_base;
-        j0[(size_t)k] = Aj[k] - index_base;
-        if (i0[(size_t)k] < 0 || i0[(size_t)k] >= n_rows || j0[(size_t)k] < 0 || j0[(size_t)k] >= n_cols) return MIPM_ERR_ARG;
-    }
-    coo_to_csr_host(n_rows, nnz, i0.data(), j0.data(), Bp, Bj, Bmap);
+    if (nnz >= (int64_t)INT32_MAX) return MIPM_ERR_ARG;
+    for (int64_t k = 0; k < nnz; ++k)
+        if (Aj[k] < index_base || Aj[k] - index_base >= n_cols) return MIPM_ERR_ARG;
+    // stable counting sort by row (the reference's loop order, src/utils.jl:158-207), rows dealt to the host threads
+    if (!stable_bucket_parallel(n_rows, nnz, Ai, index_base, Bp, [&](int64_t d, int64_t k) {
+            Bj[d] = Aj[k];
+            Bmap[d] = k + index_base;
+        }))
+        return MIPM_ERR_ARG;
     for (int64_t i = 0; i <= n_rows; ++i) Bp[i] += index_base;
-    for (int64_t k = 0; k < nnz; ++k) { Bj[k] += index_base; Bmap[k] += index_base; }
     return MIPM_OK;
 }
 
@@ -393,8 +449,8 @@ int mipm_normal_assemble(mipm_handle hh, const double *d_pr_diag, double *d_Cx, 
             k_normal_assemble_exact<<<grid_for(S.nnz_c, 256), 256, 0, h->stream>>>(
                 S.nnz_c, h->d_term_ptr.p, h->d_term_pi.p, h->d_term_pj.p, h->d_term_k.p, h->d_ATx, h->d_D.p, d_Cx);
         else {
-            k_spmv_stream<false><<<(unsigned)h->asm_nblk, 256, 0, h->stream>>>(h->d_asm_blk.p, h->d_term_ptr.p, h->d_term_k.p, nullptr,
-                                                                               h->d_term_w.p, h->d_D.p, 1.0, 0.0, d_Cx);
+            SpmvJob j{h->d_asm_blk.p, h->d_term_ptr.p, h->d_term_k.p, nullptr, h->d_term_w.p, h->d_D.p, 1.0, 0.0, d_Cx, 1, (int)h->asm_nblk};
+            k_spmv_stream<false><<<(unsigned)h->asm_nblk, 256, 0, h->stream>>>(j);
         }
         MIPM_CHECK_LAUNCH(h);
     }
@@ -444,22 +500,24 @@ int mipm_spmv_setup(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap, con
     MIPM_NEED_DEVICE(h);
     if (m < 0 || n < 0 || !Ap) return fail(h, MIPM_ERR_ARG, "bad argument");
     int64_t nnz = Ap[m] - index_base;
-    std::vector<int32_t> rp((size_t)m + 1), cj((size_t)nnz), cp((size_t)n + 1, 0), ri((size_t)nnz), pos((size_t)nnz);
+    if (nnz < 0 || (nnz > 0 && !Aj)) return fail(h, MIPM_ERR_ARG, "bad row pointer");
+    uvector<int32_t> rp((size_t)m + 1), cj((size_t)nnz), cp((size_t)n + 1), ri((size_t)nnz), pos((size_t)nnz);
     for (int64_t i = 0; i <= m; ++i) rp[(size_t)i] = Ap[i] - index_base;
-    for (int64_t p = 0; p < nnz; ++p) {
-        cj[(size_t)p] = Aj[p] - index_base;
-        if (cj[(size_t)p] < 0 || cj[(size_t)p] >= n) return fail(h, MIPM_ERR_ARG, "column index out of range");
-        cp[(size_t)cj[(size_t)p] + 1]++;
-    }
-    for (int64_t k = 0; k < n; ++k) cp[(size_t)k + 1] += cp[(size_t)k];
+    if (m > 0 && rp[0] != 0) return fail(h, MIPM_ERR_ARG, "row pointer does not start at index_base");
+    for (int64_t i = 0; i < m; ++i)
+        if (rp[(size_t)i + 1] < rp[(size_t)i]) return fail(h, MIPM_ERR_ARG, "row pointer not monotone");
+    // CSC index with CSR positions: stable bucket sort of the positions by column (rows ascend inside a column)
+    if (!stable_bucket_parallel(n, nnz, Aj, index_base, cp.data(), [&](int64_t d, int64_t p) { pos[(size_t)d] = (int32_t)p; }))
+        return fail(h, MIPM_ERR_ARG, "column index out of range");
     {
-        std::vector<int32_t> w(cp.begin(), cp.end() - 1);
-        for (int64_t i = 0; i < m; ++i)
-            for (int32_t p = rp[(size_t)i]; p < rp[(size_t)i + 1]; ++p) {
-                int32_t d = w[(size_t)cj[(size_t)p]]++;
-                ri[(size_t)d] = (int32_t)i;
-                pos[(size_t)d] = p;
+        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), nnz / 262144));
+        run_host_threads(T, [&](int t) {
+            for (int64_t p = nnz * t / T; p < nnz * (t + 1) / T; ++p) cj[(size_t)p] = Aj[p] - index_base;
+            for (int64_t d = nnz * t / T; d < nnz * (t + 1) / T; ++d) {
+                const int32_t p = pos[(size_t)d];                      // row of CSR position p
+                ri[(size_t)d] = (int32_t)(std::upper_bound(rp.begin(), rp.end(), p) - rp.begin()) - 1;
             }
+        });
     }
     MIPM_CUDA(h, cudaSetDevice(h->device));
     MIPM_CUDA(h, h->d_sp_rowptr.upload(rp, h->stream));
@@ -484,6 +542,16 @@ int mipm_spmv_setup(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap, con
     return MIPM_OK;
 }
 
+static SpmvJob spmv_job(Handle *h, int trans, double alpha, const double *d_Ax, const double *d_x, double beta, double *d_y)
+{
+    if (trans == 0)
+        return SpmvJob{h->d_sp_blk_rows.p, h->d_sp_rowptr.p, h->d_sp_col.p, nullptr, d_Ax, d_x, alpha, beta, d_y,
+                       stream_lanes(h->sp_nnz, h->sp_m), (int)h->sp_nblk_rows};
+    const bool cached = h->sp_valT_src == d_Ax && d_Ax;
+    return SpmvJob{h->d_sp_blk_cols.p, h->d_sp_colptr.p, h->d_sp_row.p, cached ? nullptr : h->d_sp_pos.p, cached ? h->d_sp_valT.p : d_Ax, d_x,
+                   alpha, beta, d_y, stream_lanes(h->sp_nnz, h->sp_n), (int)h->sp_nblk_cols};
+}
+
 int mipm_spmv(mipm_handle hh, int trans, double alpha, const double *d_Ax, const double *d_x, double beta, double *d_y)
 {
     Handle *h = (Handle *)hh;
@@ -495,21 +563,38 @@ int mipm_spmv(mipm_handle hh, int trans, double alpha, const double *d_Ax, const
     }
     if (trans == 0) {
         if (h->sp_m > 0) {
-            k_spmv_stream<false><<<(unsigned)h->sp_nblk_rows, 256, 0, h->stream>>>(h->d_sp_blk_rows.p, h->d_sp_rowptr.p, h->d_sp_col.p,
-                                                                                  nullptr, d_Ax, d_x, alpha, beta, d_y);
+            k_spmv_stream<false><<<(unsigned)h->sp_nblk_rows, 256, 0, h->stream>>>(spmv_job(h, 0, alpha, d_Ax, d_x, beta, d_y));
             MIPM_CHECK_LAUNCH(h);
         }
     } else {
         if (h->sp_n > 0) {
             if (h->sp_valT_src == d_Ax && d_Ax)      // column-ordered copy cached by mipm_spmv_cache_values
-                k_spmv_stream<false><<<(unsigned)h->sp_nblk_cols, 256, 0, h->stream>>>(h->d_sp_blk_cols.p, h->d_sp_colptr.p, h->d_sp_row.p,
-                                                                                      nullptr, h->d_sp_valT.p, d_x, alpha, beta, d_y);
+                k_spmv_stream<false><<<(unsigned)h->sp_nblk_cols, 256, 0, h->stream>>>(spmv_job(h, 1, alpha, d_Ax, d_x, beta, d_y));
             else
-                k_spmv_stream<true><<<(unsigned)h->sp_nblk_cols, 256, 0, h->stream>>>(h->d_sp_blk_cols.p, h->d_sp_colptr.p, h->d_sp_row.p,
-                                                                                     h->d_sp_pos.p, d_Ax, d_x, alpha, beta, d_y);
+                k_spmv_stream<true><<<(unsigned)h->sp_nblk_cols, 256, 0, h->stream>>>(spmv_job(h, 1, alpha, d_Ax, d_x, beta, d_y));
             MIPM_CHECK_LAUNCH(h);
         }
     }
+    return MIPM_OK;
+}
+
+// y1 = alpha1 A x1 + beta1 y1 and y2 = alpha2 A' x2 + beta2 y2 in ONE launch (the two products of evaluate_model!,
+// src/solver.jl:319-326, and of the residual K d, src/linear_solver.jl:29-35, are independent of each other).
+int mipm_spmv_pair(mipm_handle hh, const double *d_Ax, double alpha1, const double *d_x1, double beta1, double *d_y1,
+                   double alpha2, const double *d_x2, double beta2, double *d_y2)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    if (!h->has_spmv) return fail(h, MIPM_ERR_STATE, "mipm_spmv_setup has not been called");
+    if ((!d_Ax && h->sp_nnz > 0) || (h->sp_n > 0 && (!d_x1 || !d_y2)) || (h->sp_m > 0 && (!d_y1 || !d_x2))) return fail(h, MIPM_ERR_ARG, "null argument");
+    if (h->sp_m == 0 || h->sp_n == 0 || !(h->sp_valT_src == d_Ax && d_Ax)) {      // no column-ordered copy: two launches
+        int rc = mipm_spmv(hh, 0, alpha1, d_Ax, d_x1, beta1, d_y1);
+        if (rc != MIPM_OK) return rc;
+        return mipm_spmv(hh, 1, alpha2, d_Ax, d_x2, beta2, d_y2);
+    }
+    k_spmv_stream_pair<<<(unsigned)(h->sp_nblk_rows + h->sp_nblk_cols), 256, 0, h->stream>>>(spmv_job(h, 0, alpha1, d_Ax, d_x1, beta1, d_y1),
+                                                                                            spmv_job(h, 1, alpha2, d_Ax, d_x2, beta2, d_y2));
+    MIPM_CHECK_LAUNCH(h);
     return MIPM_OK;
 }
 

@@ -313,7 +313,7 @@ int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap_in
     if (m < 0 || n < 0) return fail(h, MIPM_ERR_ARG, "negative dimension");
     S.m = m;
     S.n = n;
-    std::vector<int32_t> Ap((size_t)m + 1);
+    uvector<int32_t> Ap((size_t)m + 1);
     for (int64_t i = 0; i <= m; ++i) Ap[(size_t)i] = Ap_in[i] - index_base;
     if (m > 0 && Ap[0] != 0) return fail(h, MIPM_ERR_ARG, "row pointer does not start at index_base");
     for (int64_t i = 0; i < m; ++i)
@@ -331,25 +331,25 @@ int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap_in
         MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
         return MIPM_OK;
     }
-    // ---- host: 0-based columns, CSC index with CSR positions (rows ascend inside a column), duplicate check
-    std::vector<int32_t> Aj((size_t)nnz), cptr((size_t)n + 1, 0), crow((size_t)nnz), cpos((size_t)nnz);
-    for (int64_t p = 0; p < nnz; ++p) {
-        const int32_t k = Aj_in[p] - index_base;
-        if (k < 0 || k >= n) return fail(h, MIPM_ERR_ARG, "column index out of range");
-        Aj[(size_t)p] = k;
-        cptr[(size_t)k + 1]++;
-    }
-    for (int64_t k = 0; k < n; ++k) cptr[(size_t)k + 1] += cptr[(size_t)k];
+    // ---- host: 0-based columns, CSC index with CSR positions (stable bucket sort by column on the host threads: rows
+    // ascend inside a column), duplicate check
+    uvector<int32_t> Aj((size_t)nnz), cptr((size_t)n + 1), crow((size_t)nnz), cpos((size_t)nnz);
+    if (!stable_bucket_parallel(n, nnz, Aj_in, index_base, cptr.data(), [&](int64_t d, int64_t p) { cpos[(size_t)d] = (int32_t)p; }))
+        return fail(h, MIPM_ERR_ARG, "column index out of range");
     {
-        std::vector<int32_t> pos(cptr.begin(), cptr.end() - 1);
-        for (int64_t i = 0; i < m; ++i)
-            for (int32_t p = Ap[(size_t)i]; p < Ap[(size_t)i + 1]; ++p) {
-                const int32_t d = pos[(size_t)Aj[(size_t)p]]++;
-                if (d > cptr[(size_t)Aj[(size_t)p]] && crow[(size_t)d - 1] == (int32_t)i)
-                    return fail(h, MIPM_ERR_DUPLICATE, "duplicate column inside a row of A");
-                crow[(size_t)d] = (int32_t)i;
-                cpos[(size_t)d] = p;
-            }
+        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), nnz / 262144));
+        run_host_threads(T, [&](int t) {
+            for (int64_t p = nnz * t / T; p < nnz * (t + 1) / T; ++p) Aj[(size_t)p] = Aj_in[p] - index_base;
+            for (int64_t d = nnz * t / T; d < nnz * (t + 1) / T; ++d)
+                crow[(size_t)d] = (int32_t)(std::upper_bound(Ap.begin(), Ap.end(), cpos[(size_t)d]) - Ap.begin()) - 1;
+        });
+        std::vector<int> dup((size_t)T, 0);
+        run_host_threads(T, [&](int t) {
+            for (int64_t k = n * t / T; k < n * (t + 1) / T; ++k)
+                for (int32_t d = cptr[(size_t)k] + 1; d < cptr[(size_t)k + 1]; ++d)
+                    if (crow[(size_t)d] == crow[(size_t)d - 1]) { dup[(size_t)t] = 1; return; }
+        });
+        for (int v : dup) if (v) return fail(h, MIPM_ERR_DUPLICATE, "duplicate column inside a row of A");
     }
     cudaStream_t st = h->stream;
     Scratch sc;

@@ -1521,10 +1521,9 @@ static int fused_solve_system(Handle *h, int ir_steps, int slot)
     if ((rc = fused_kkt_solve(h, m.d_d, ir_steps)) != MIPM_OK) return rc;
     MIPM_CUDA(h, cudaMemcpyAsync(m.d_w, m.d_p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     // mul!(w, kkt, d, -1, 1)
-    if ((rc = mipm_spmv(hh, 1, -1.0, md.d_ATx, m.d_d + m.n, 1.0, m.d_w)) != MIPM_OK) return rc;
+    if ((rc = mipm_spmv_pair(hh, md.d_ATx, -1.0, m.d_d, 1.0, m.d_w + m.n, -1.0, m.d_d + m.n, 1.0, m.d_w)) != MIPM_OK) return rc;
     if (md.d_Hx && md.kkt_kind == 1)
         if ((rc = mipm_hess_spmv(hh, -1.0, md.d_Hx, m.d_d, 1.0, m.d_w)) != MIPM_OK) return rc;
-    if ((rc = mipm_spmv(hh, 0, -1.0, md.d_ATx, m.d_d, 1.0, m.d_w + m.n)) != MIPM_OK) return rc;
     if ((rc = mipm_kktmul(hh, m.d_w, m.d_d, -1.0, 1.0)) != MIPM_OK) return rc;
     k_two_norms<<<red_grid(h, std::max<int64_t>(N, 1)), TB, 0, h->stream>>>(N, m.d_w, m.d_p, h->d_partials.p, h->d_counter.p,
                                                                          h->d_sc.p + SC_RES + 2 * slot);
@@ -1642,8 +1641,7 @@ int mipm_mpc_iter_rest(mipm_handle hh, double mu_min, int step_rule, double tau_
         if ((rc = mipm_axpby(hh, md.nx, 1.0, md.d_buffer_n, 1.0, m.d_f)) != MIPM_OK) return rc;
     }
     MIPM_CUDA(h, cudaMemcpyAsync(m.d_c, m.d_rhs, (size_t)m.m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if ((rc = mipm_spmv(hh, 0, 1.0, md.d_ATx, m.d_x, -1.0, m.d_c)) != MIPM_OK) return rc;
-    return mipm_spmv(hh, 1, 1.0, md.d_ATx, m.d_y, 0.0, m.d_jacl);
+    return mipm_spmv_pair(hh, md.d_ATx, 1.0, m.d_x, -1.0, m.d_c, 1.0, m.d_y, 0.0, m.d_jacl);
 }
 
 /* ------------------------------------------------------------------ batches (stacked independent units) ---- */
@@ -1820,8 +1818,7 @@ int mipm_batch_iter_rest(mipm_handle hh, double mu_min, int step_rule, double ta
         if ((rc = mipm_axpby(hh, md.nx, 1.0, md.d_buffer_n, 1.0, m.d_f)) != MIPM_OK) return rc;
     }
     MIPM_CUDA(h, cudaMemcpyAsync(m.d_c, m.d_rhs, (size_t)m.m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if ((rc = mipm_spmv(hh, 0, 1.0, md.d_ATx, m.d_x, -1.0, m.d_c)) != MIPM_OK) return rc;
-    return mipm_spmv(hh, 1, 1.0, md.d_ATx, m.d_y, 0.0, m.d_jacl);
+    return mipm_spmv_pair(hh, md.d_ATx, 1.0, m.d_x, -1.0, m.d_c, 1.0, m.d_y, 0.0, m.d_jacl);
 }
 
 /* ------------------------------------------------------------------ preprocessing ---- */
@@ -1912,8 +1909,7 @@ static int ext_solve_post(Handle *h, int slot)
     if ((rc = mipm_normal_solve_stage(hh, 2, m.d_d, md.d_buffer_n, md.d_buffer_m)) != MIPM_OK) return rc;
     // residual check of solve_system! (src/linear_solver.jl:29-35)
     MIPM_CUDA(h, cudaMemcpyAsync(m.d_w, m.d_p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if ((rc = mipm_spmv(hh, 1, -1.0, md.d_ATx, m.d_d + m.n, 1.0, m.d_w)) != MIPM_OK) return rc;
-    if ((rc = mipm_spmv(hh, 0, -1.0, md.d_ATx, m.d_d, 1.0, m.d_w + m.n)) != MIPM_OK) return rc;
+    if ((rc = mipm_spmv_pair(hh, md.d_ATx, -1.0, m.d_d, 1.0, m.d_w + m.n, -1.0, m.d_d + m.n, 1.0, m.d_w)) != MIPM_OK) return rc;
     if ((rc = mipm_kktmul(hh, m.d_w, m.d_d, -1.0, 1.0)) != MIPM_OK) return rc;
     k_two_norms<<<red_grid(h, std::max<int64_t>(N, 1)), TB, 0, h->stream>>>(N, m.d_w, m.d_p, h->d_partials.p, h->d_counter.p,
                                                                          h->d_sc.p + SC_RES + 2 * slot);
@@ -2000,8 +1996,7 @@ int mipm_mpc_ext_phase(mipm_handle hh, int phase, double mu_min, int step_rule, 
     MIPM_CHECK_LAUNCH(h);
     MIPM_CUDA(h, cudaMemcpyAsync(m.d_f, md.d_cvec, (size_t)m.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     MIPM_CUDA(h, cudaMemcpyAsync(m.d_c, m.d_rhs, (size_t)m.m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if ((rc = mipm_spmv(hh, 0, 1.0, md.d_ATx, m.d_x, -1.0, m.d_c)) != MIPM_OK) return rc;
-    return mipm_spmv(hh, 1, 1.0, md.d_ATx, m.d_y, 0.0, m.d_jacl);
+    return mipm_spmv_pair(hh, md.d_ATx, 1.0, m.d_x, -1.0, m.d_c, 1.0, m.d_y, 0.0, m.d_jacl);
 }
 
 }  // extern "C"

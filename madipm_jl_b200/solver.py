@@ -434,10 +434,9 @@ class MPCSolver:
         """mul!(w, kkt, v, alpha, beta): normalkkt.jl:221-233 (+ Hessian block for K2)."""
         n, m = self.n, self.m
         h = self.h
-        h.spmv(1, alpha, self.AT_x, v[n:n + m], beta, w[:n])
+        h.spmv_pair(self.AT_x, alpha, v[:n], beta, w[n:n + m], alpha, v[n:n + m], beta, w[:n])     # A v_x and A' v_y in one launch
         if self.hH is not None and self.opt.kkt_system in ("K2", "K2.5"):
             self.hH.hess_spmv(alpha, self.Hx, v[:self.nx], 1.0, w[:self.nx])
-        h.spmv(0, alpha, self.AT_x, v[:n], beta, w[n:n + m])
         if self.opt.kkt_system == "K2.5":
             h.kktmul_scaled(w, v, alpha, beta)
         else:

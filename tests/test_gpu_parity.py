@@ -142,6 +142,12 @@ def test_spmv(handle):
     w = dev(w0)
     h.spmv(1, -1.0, dB, dev(v), 1.0, w)
     assert np.abs(w.cpu().numpy() - (-2.0 * (A.T @ v) + w0)).max() < 1e-12
+    # both products of a phase in one launch (cached values), and its two-launch fallback (uncached values)
+    for vals, f in ((dA, 1.0), (dB, 2.0)):
+        y, w = dev(y0), dev(w0)
+        h.spmv_pair(vals, 1.5, dev(x), -0.5, y, -1.0, dev(v), 1.0, w)
+        assert np.abs(y.cpu().numpy() - (1.5 * f * (A @ x) - 0.5 * y0)).max() < 1e-12
+        assert np.abs(w.cpu().numpy() - (-f * (A.T @ v) + w0)).max() < 1e-12
 
 
 def test_spmv_ragged(handle):
