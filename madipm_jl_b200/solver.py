@@ -174,6 +174,8 @@ class B200Solver:
 class MPCSolver:
     def __init__(self, qp, **kwargs):
         t0 = time.time()
+        self.setup_log = []          # (stage, seconds since the start of the constructor): where construction time goes
+        _mark = lambda name: self.setup_log.append((name, time.time() - t0))
         self.opt = IPMOptions(**kwargs)
         opt = self.opt
         if not torch.cuda.is_available():
@@ -189,16 +191,53 @@ class MPCSolver:
             raise NotImplementedError("maximization models (MadNLP obj_sign = -1) are outside the hot-path scope: negate c, H, c0")
         self.ind_ineq = np.flatnonzero(lcon != ucon)
         nx, ns = qp.nvar, len(self.ind_ineq)
+        self.nx, self.ns = nx, ns
+        self.n, self.m = nx + ns, qp.ncon
+        n, m = self.n, self.m
+        if opt.kkt_system == "Normal" and qp.nnzh > 0:
+            raise ValueError("The KKT system NormalKKTSystem supports only linear programs.")  # normalkkt.jl:45-48
+        ib = int(opt.index_base)
+        self.A_V_host = np.concatenate([qp.Avals, -np.ones(ns)])
+        # ---- Hessian operator (MadIPMOperator symmetric=true, cuda_wrapper.jl:62-68): host part
+        if qp.nnzh > 0:
+            hr, hc, hv = qp.Hrows.astype(np.int64), qp.Hcols.astype(np.int64), qp.Hvals
+            off = hr != hc
+            fr = np.concatenate([hr, hc[off]]).astype(np.int32)
+            fc = np.concatenate([hc, hr[off]]).astype(np.int32)
+            fv = np.concatenate([hv, hv[off]])
+            Hp, Hj, Hmap = _lib.coo_to_csr(nx, nx, fr + ib, fc + ib, index_base=ib)
+            self.H_full_host = fv[Hmap - ib]
+        # Pinned staging of the numeric problem data on a helper thread while this thread does the host-only index work
+        # below: page-locking ~100 MB takes tens of milliseconds, and the driver serialises it with device allocations,
+        # so it is joined before the first one.
+        import threading
+        stage_err = []
+
+        def _stage():
+            try:
+                torch.cuda.set_device(self.device)
+                self._stage_problem()
+            except Exception as exc:       # surfaced after the join
+                stage_err.append(exc)
+        stager = threading.Thread(target=_stage)
+        stager.start()
         lfull = np.concatenate([lvar, lcon[self.ind_ineq]])
         ufull = np.concatenate([uvar, ucon[self.ind_ineq]])
         self.ind_lb = np.flatnonzero(np.isfinite(lfull)).astype(np.int64)
         self.ind_ub = np.flatnonzero(np.isfinite(ufull)).astype(np.int64)
-        self.nx, self.ns = nx, ns
-        self.n, self.m = nx + ns, qp.ncon
         self.nlb, self.nub = len(self.ind_lb), len(self.ind_ub)
-        n, m, nlb, nub = self.n, self.m, self.nlb, self.nub
-        if opt.kkt_system == "Normal" and qp.nnzh > 0:
-            raise ValueError("The KKT system NormalKKTSystem supports only linear programs.")  # normalkkt.jl:45-48
+        nlb, nub = self.nlb, self.nub
+        # ---- Jacobian with slack columns (normalkkt.jl:70-79) in CSR through coo_to_csr
+        I = np.concatenate([qp.Arows, self.ind_ineq]).astype(np.int32)
+        J = np.concatenate([qp.Acols, nx + np.arange(ns)]).astype(np.int32)
+        self.A_I, self.A_J = I, J
+        _mark("index sets")
+        Ap, Aj, Amap = _lib.coo_to_csr(m, n, I + ib, J + ib, index_base=ib)      # in index_base like the inputs
+        _mark("coo_to_csr")
+        stager.join()
+        if stage_err:
+            raise stage_err[0]
+        _mark("staging thread joined")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.h = _lib.Handle(device=opt.device, stream=stream)
         if opt.grid_limit:
@@ -211,55 +250,31 @@ class MPCSolver:
         N = n + m + nlb + nub
         self.d, self.p, self._w1, self._w2, self._w3 = z(N), z(N), z(N), z(N), z(N)
         self.correction_lb, self.correction_ub = z(nlb), z(nub)
-        ib = int(opt.index_base)
         self.d_ind_lb = _dev(self.ind_lb + ib, dev, torch.int64)
         self.d_ind_ub = _dev(self.ind_ub + ib, dev, torch.int64)
-        # ---- Jacobian with slack columns (normalkkt.jl:70-79) in CSR through coo_to_csr
-        I = np.concatenate([qp.Arows, self.ind_ineq]).astype(np.int32)
-        J = np.concatenate([qp.Acols, nx + np.arange(ns)]).astype(np.int32)
-        self.A_I, self.A_J = I, J
-        self.A_V_host = np.concatenate([qp.Avals, -np.ones(ns)])
-        Ap, Aj, Amap = _lib.coo_to_csr(m, n, I + ib, J + ib, index_base=ib)      # in index_base like the inputs
+        _mark("vectors")
         self.h.spmv_setup(m, n, Ap, Aj, index_base=ib)
+        _mark("spmv_setup")
         self._Ap_abi, self._Aj_abi = Ap, Aj
         self.Ap, self.Aj, self.A_csr_map = Ap - ib, Aj - ib, Amap - ib            # 0-based copies for the host logic
         self.AT_x = z(len(Aj))                      # AT.nzVal: CSR-ordered values of A
         self.A_V = z(len(Aj))                       # A.V: COO-ordered values (jac + slack), like kkt.A.V
         self.d_A_csr_map = _dev(Amap, dev, torch.int64)                            # as returned (index_base)
-        # ---- Hessian operator (MadIPMOperator symmetric=true, cuda_wrapper.jl:62-68)
         self.hH = None
         if qp.nnzh > 0:
-            hr, hc, hv = qp.Hrows.astype(np.int64), qp.Hcols.astype(np.int64), qp.Hvals
-            off = hr != hc
-            fr = np.concatenate([hr, hc[off]]).astype(np.int32)
-            fc = np.concatenate([hc, hr[off]]).astype(np.int32)
-            fv = np.concatenate([hv, hv[off]])
-            Hp, Hj, Hmap = _lib.coo_to_csr(nx, nx, fr + ib, fc + ib, index_base=ib)
             self.hH = self.h
             self.h.hess_setup(nx, Hp, Hj, index_base=ib)
-            self.H_full_host = fv[Hmap - ib]
             self.Hx = z(len(Hj))
         self.cvec = z(n)
-        # pinned staging of the numeric problem data on a helper thread: page-locking ~100 MB takes as long as the whole
-        # symbolic analysis of a large problem and is independent of it (joined at the end of the constructor)
-        import threading
-        stage_err = []
-
-        def _stage():
-            try:
-                torch.cuda.set_device(self.device)
-                self._stage_problem()
-            except Exception as exc:       # surfaced after the join
-                stage_err.append(exc)
-        stager = threading.Thread(target=_stage)
-        stager.start()
         # ---- KKT system
         self.buffer_n, self.buffer_m = z(n), z(m)
         self.l_diag, self.u_diag, self.l_lower, self.u_lower = z(nlb), z(nub), z(nlb), z(nub)
         self.reg = z(n)
         if opt.kkt_system == "Normal":
             self.pr_diag, self.du_diag = z(n), z(m)
+            _mark("buffers")
             Cp, Cj = self.h.normal_symbolic(m, n, self._Ap_abi, self._Aj_abi, index_base=ib)
+            _mark("normal_symbolic")
             self.aug_colptr, self.aug_rowval = Cp, Cj
             if opt.linear_solver == "distributed":
                 from .distributed import DistributedB200Solver
@@ -299,6 +314,7 @@ class MPCSolver:
                 self.d_J_J = _dev(J + ib, dev, torch.int32)
         else:
             raise ValueError(opt.kkt_system)
+        _mark("linear solver (analysis + device setup)")
         # ---- bind the device vectors once
         mv = MpcVectors()
         mv.n, mv.m, mv.nlb, mv.nub, mv.index_base = n, m, nlb, nub, ib
@@ -325,9 +341,7 @@ class MPCSolver:
         self.h.mpc_set_model(md)
         # a variable with no finite bound keeps pr_diag = del_w (1e-10): the KKT system is then badly
         # conditioned from the first iteration on, so the fused path refines every solve from the start
-        stager.join()
-        if stage_err:
-            raise stage_err[0]
+        _mark("bind")
         self._has_free = (nlb + nub > 0 or n > 0) and bool(np.any(~np.isfinite(lfull) & ~np.isfinite(ufull)))
         self._fused_started = False
         self._fused_ir = max(opt.ir_steps, 1 if self._has_free else 0)
