@@ -761,6 +761,7 @@ int ls_device_setup(Handle *h)
     int ea_task_factor = 4, stagger = 1;
     int la_min_k = 512;          // fronts at least this wide factor with look-ahead (second progress counter)
     if (const char *e = std::getenv("MIPM_LOOKAHEAD_MIN")) la_min_k = std::max(2 * NB, atoi(e));
+    const bool fuse_diag = std::getenv("MIPM_NO_FUSE_DIAG") == nullptr;
     if (const char *e = std::getenv("MIPM_EA_FACTOR")) ea_task_factor = std::max(1, atoi(e));
     if (const char *e = std::getenv("MIPM_NO_STAGGER")) stagger = (atoi(e) == 0);
     if (const char *e = std::getenv("MIPM_SUPER_PANEL")) SP_narrow = SP_wide = std::max(NB, (atoi(e) / NB) * NB);
@@ -858,10 +859,15 @@ int ls_device_setup(Handle *h)
             };
             const bool lookahead = k >= la_min_k && (k + SP - 1) / SP >= 2;
             if (!lookahead) {
+                // The first diagonal block of panel p + 1 applies panel p's update to its own tile itself (left-looking over
+                // [J0, J1): task_diag with K0 = J0) instead of waiting for a trailing-update task to do it: it is emitted at
+                // the head of panel p's trailing group, so it starts as soon as the panel tiles of p are done and runs
+                // beside the other trailing tiles (one hand-off and one tile round trip less per 64 columns of the chain).
+                bool diag_emitted = false;
                 for (int J0 = 0; J0 < k;) {
                     int J1 = (k - J0 <= SP + NB) ? k : J0 + SP;
                     for (int jb = J0; jb < J1; jb += NB) {
-                        G.push_back({mk(T_DIAG, s, jb, J0, 0, 0)});
+                        if (!(jb == J0 && diag_emitted)) G.push_back({mk(T_DIAG, s, jb, J0, 0, 0)});
                         const int j1 = jb + std::min(NB, k - jb);
                         std::vector<Task> pt;
                         for (int row0 = j1; row0 < N; row0 += TILE) pt.push_back(mk(T_PANEL, s, jb, J0, row0, 0));
@@ -871,8 +877,14 @@ int ls_device_setup(Handle *h)
                     std::vector<int> starts = trailing_starts(J1);
                     if ((int64_t)starts.size() * ((int64_t)starts.size() + 1) / 2 > (1 << 26)) return fail(h, MIPM_ERR_ARG, "front too large for the tile schedule");
                     std::vector<Task> tt;
+                    const bool fuse = fuse_diag && J1 < k;
+                    if (fuse) tt.push_back(mk(T_DIAG, s, J1, J0, 0, 0));
                     for (size_t tc = 0; tc < starts.size(); ++tc)
-                        for (size_t tr = tc; tr < starts.size(); ++tr) tt.push_back(mk(T_TRAIL, s, J0, J1, starts[tr], starts[tc]));
+                        for (size_t tr = tc; tr < starts.size(); ++tr) {
+                            if (fuse && tc == 0 && tr == 0) continue;          // the tile of the next diagonal block
+                            tt.push_back(mk(T_TRAIL, s, J0, J1, starts[tr], starts[tc]));
+                        }
+                    diag_emitted = fuse;
                     if (!tt.empty()) G.push_back(std::move(tt));
                     J0 = J1;
                 }
