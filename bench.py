@@ -325,6 +325,7 @@ def main():
     t0 = time.time()
     solver = MPCSolver(qp, kkt_system="Normal", device=local_rank)
     t_setup = time.time() - t0
+    setup_log = [[n_, round(t_, 4)] for n_, t_ in solver.setup_log]
     st = solver.linear_solver.stats
     h = solver.h
 
@@ -507,7 +508,7 @@ def main():
                                               "max_front_cols", "max_front_rows", "update_doubles", "n_launches")},
             "setup_s": t_setup, "final_objective": res.objective,
             "cold": {"construct_s": t_setup, "first_solve_s": t_first, "cold_time_to_1e-8_s": t_setup + t_first,
-                     "setup_log": [[n_, round(t_, 4)] for n_, t_ in solver.setup_log],
+                     "setup_log": setup_log,
                      "what": "MPCSolver(qp) (symbolic analysis on host and device, uploads; CUDA context already created) + the first solve() of the process"},
             "extras": extras,
         }
