@@ -66,7 +66,11 @@ int mipm_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *
  * the CSR of A (= colptr/rowval of AT, normalkkt.jl:92). Bit-exact with the reference's
  * O(m^2) scan but O(sum of row merges). Also builds, inside the handle, the product-term
  * map that mipm_normal_assemble consumes. *Cp (m+1) and *Cj (nnzC) are library-owned host
- * arrays in index_base. Rows of A must not repeat a column (MIPM_ERR_DUPLICATE). */
+ * arrays in index_base (release with mipm_free). Rows of A must not repeat a column
+ * (MIPM_ERR_DUPLICATE). A handle with a GPU builds both on the device (one CTA per row of the
+ * pattern sorts the row's product terms in shared memory); Ap == Aj == NULL then means "the
+ * matrix registered with mipm_spmv_setup on this handle" (same m, n), whose CSR / CSC index
+ * is already on the device. Analysis-only handles (device < 0) run the host sweep. */
 int mipm_normal_symbolic(mipm_handle h, int64_t m, int64_t n, const int32_t *Ap,
                          const int32_t *Aj, int index_base, int32_t **Cp, int32_t **Cj,
                          int64_t *nnzC);

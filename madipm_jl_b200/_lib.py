@@ -110,11 +110,30 @@ def _ptr(a):
     raise TypeError(type(a))
 
 
+class _Owner:
+    """Frees a library-owned host array when the last numpy view of it is gone."""
+
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            self.lib.mipm_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
 def _take(ptr, count, ctype, dtype):
-    """Copy a library-owned host array into numpy and free it."""
-    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(max(count, 1),))[:count].astype(dtype, copy=True)
-    load().mipm_free(ptr)
-    return arr
+    """numpy view of a library-owned host array (no copy: the patterns the symbolic entry points return are tens of
+    megabytes). The ctypes buffer every view ends up referencing carries the owner object that calls mipm_free."""
+    lib = load()
+    if count <= 0 or np.dtype(ctype) != np.dtype(dtype):
+        arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(max(count, 1),))[:max(count, 0)].astype(dtype, copy=True)
+        lib.mipm_free(ptr)
+        return arr
+    buf = (ctype * count).from_address(ptr.value)
+    buf._owner = _Owner(lib, ptr.value)
+    return np.frombuffer(buf, dtype=dtype)
 
 
 class Handle:
@@ -144,9 +163,11 @@ class Handle:
             raise MipmError(rc, self.lib.mipm_last_error(self.h).decode())
 
     # ---- host symbolic
-    def normal_symbolic(self, m, n, Ap, Aj, index_base=0):
-        Ap = np.ascontiguousarray(Ap, dtype=np.int32)
-        Aj = np.ascontiguousarray(Aj, dtype=np.int32)
+    def normal_symbolic(self, m, n, Ap=None, Aj=None, index_base=0):
+        """Ap = Aj = None: the matrix registered with spmv_setup on this handle (device handles only)."""
+        if Ap is not None:
+            Ap = np.ascontiguousarray(Ap, dtype=np.int32)
+            Aj = np.ascontiguousarray(Aj, dtype=np.int32)
         cp, cj, nnz = C.c_void_p(), C.c_void_p(), C.c_int64()
         self.check(self.lib.mipm_normal_symbolic(self.h, C.c_int64(m), C.c_int64(n), _ptr(Ap), _ptr(Aj),
                                                  C.c_int(index_base), C.byref(cp), C.byref(cj), C.byref(nnz)))

@@ -1,6 +1,8 @@
 // C-ABI entry points: lifecycle, host symbolic builders, KKT assembly kernels, SpMV.
 // Each entry cites in include/madipm_b200.h the reference interface it replaces.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -370,25 +372,25 @@ int mipm_normal_symbolic(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap
 {
     Handle *h = (Handle *)hh;
     if (h && !h->host_only) use_handle(h);
-    if (!h || !Ap || (!Aj && m > 0 && Ap[m] != index_base) || !Cp || !Cj || !nnzC) return fail(h, MIPM_ERR_ARG, "null argument");
+    if (!h || !Cp || !Cj || !nnzC) return fail(h, MIPM_ERR_ARG, "null argument");
+    const bool device_build = !h->host_only && !std::getenv("MIPM_HOST_SYMBOLIC");
+    // Ap == NULL: the matrix registered with mipm_spmv_setup on this handle (device build only)
+    if (!Ap && !(device_build && h->has_spmv)) return fail(h, MIPM_ERR_ARG, "null row pointer (and no matrix registered with mipm_spmv_setup on a device handle)");
+    if (Ap && !Aj && m > 0 && Ap[m] != index_base) return fail(h, MIPM_ERR_ARG, "null argument");
     // Handles that own a GPU build the pattern and the term map on the device (normal_device.cu); analysis-only handles
     // and MIPM_HOST_SYMBOLIC=1 take the host sweep. Both produce the same arrays.
-    if (!h->host_only && !std::getenv("MIPM_HOST_SYMBOLIC")) {
-        std::vector<int32_t> cp, cj, tp;
-        int rc = normal_symbolic_device(h, m, n, Ap, Aj, index_base, cp, cj, tp);
-        if (rc != MIPM_OK) return rc;
-        *Cp = host_copy(cp, index_base);
-        *Cj = host_copy(cj, index_base);
+    if (device_build) {
+        int rc = normal_symbolic_device(h, m, n, Ap, Aj, index_base, Cp, Cj);
+        if (rc != MIPM_OK) {
+            std::free(*Cp); std::free(*Cj);
+            *Cp = *Cj = nullptr;
+            return rc;
+        }
         *nnzC = h->nsym.nnz_c;
-        if (!*Cp || !*Cj) return fail(h, MIPM_ERR_ALLOC, "host allocation failed");
         h->has_normal = true;
         h->has_jac = false;
         MIPM_CUDA(h, h->d_term_w.alloc((size_t)h->nsym.n_terms));
-        std::vector<int32_t> blk = spmv_blocks(tp, ASM_ROWS);
-        h->asm_nblk = (int64_t)blk.size() - 1;
-        MIPM_CUDA(h, h->d_asm_blk.upload(blk, h->stream));
         MIPM_CUDA(h, h->d_D.alloc((size_t)n));
-        MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
         return MIPM_OK;
     }
     std::string e = normal_symbolic_host(m, n, Ap, Aj, index_base, h->nsym);

@@ -205,7 +205,7 @@ inline void use_handle(const Handle *h)
 // implemented in the .cu files
 int ls_device_setup(Handle *h);
 int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap, const int32_t *Aj, int index_base,
-                           std::vector<int32_t> &Cp, std::vector<int32_t> &Cj, std::vector<int32_t> &term_ptr_host);
+                           int32_t **Cp_out, int32_t **Cj_out);
 int ls_solve_setup(Handle *h, const void *finfo_host, const char *small_leaf);
 int ls_factorize_impl(Handle *h, const double *d_nzval);
 int ls_solve_impl(Handle *h, double *d_x, int ir_steps);

@@ -12,6 +12,8 @@
 //      arrays, compact the first term of every distinct j                                      -> exclusive scan
 //   4. one warp per row: move the compacted heads to their final place (Cj, term_ptr).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -301,42 +303,112 @@ int exclusive_scan(Handle *h, Scratch &sc, int64_t n, const int32_t *d_in, int32
     return MIPM_OK;
 }
 
+// duplicate columns inside a row show up as equal rows next to each other inside a column of the CSC index
+__global__ void __launch_bounds__(256)
+k_ns_dup(int64_t nnz, const int32_t *__restrict__ Aj, const int32_t *__restrict__ crow, const int32_t *__restrict__ cpos, int *__restrict__ flag)
+{
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d + 1 >= nnz) return;
+    if (crow[d] == crow[d + 1] && Aj[cpos[d]] == Aj[cpos[d + 1]]) *flag = 1;
+}
+
+// Row runs of the streaming assembly (k_spmv_stream over the term map), computed in parallel: stored entry c starts a
+// new block when its first term lies in another ASM_BUCKET-sized bucket of the term array than the first term of c - 1,
+// or when c or c - 1 has more than ASM_LONG terms. A block of several entries then holds fewer than ASM_BUCKET + ASM_LONG
+// = 2 048 terms (the shared-memory tile of the kernel) and fewer than ASM_BUCKET entries; a long entry stands alone.
+constexpr int ASM_BUCKET = 1536, ASM_LONG = 512;
+__global__ void __launch_bounds__(256) k_asm_block_flags(int64_t nnzc, const int32_t *__restrict__ term_ptr, int32_t *__restrict__ flag)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nnzc) return;
+    int f = 1;
+    if (c > 0) {
+        const int32_t t0 = term_ptr[c - 1], t1 = term_ptr[c], t2 = term_ptr[c + 1];
+        f = (t1 / ASM_BUCKET != t0 / ASM_BUCKET) || (t2 - t1 > ASM_LONG) || (t1 - t0 > ASM_LONG);
+    }
+    flag[c] = f;
+}
+__global__ void __launch_bounds__(256)
+k_asm_block_starts(int64_t nnzc, const int32_t *__restrict__ flag, const int32_t *__restrict__ pos, int32_t *__restrict__ blk, int32_t nblk)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nnzc && flag[c]) blk[pos[c]] = (int32_t)c;
+    if (c == 0) blk[nblk] = (int32_t)nnzc;
+}
+
 }  // namespace
 
-// Returns MIPM_OK and fills the handle's device term map + the host pattern, or an error. `*too_big` is set when the
-// term count does not fit 32-bit segment pointers (same limit as the host builder).
+// Builds the pattern of tril(A A') and the product-term map on the device. Ap_in == nullptr: the matrix registered with
+// mipm_spmv_setup on this handle is used (its CSR / CSC index already lives on the device). Leaves the term map and the
+// assembly blocks in the handle and returns the pattern in malloc'd host arrays (index_base added).
 int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap_in, const int32_t *Aj_in, int index_base,
-                           std::vector<int32_t> &Cp, std::vector<int32_t> &Cj, std::vector<int32_t> &term_ptr_host)
+                           int32_t **Cp_out, int32_t **Cj_out)
 {
+    *Cp_out = nullptr;
+    *Cj_out = nullptr;
     NormalSymbolic &S = h->nsym;
     S = NormalSymbolic();
+    const bool tlog = std::getenv("MIPM_ANALYZE_LOG") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto stage = [&](const char *name) {
+        if (!tlog) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "normal_symbolic (device): %s %.3f s\n", name, std::chrono::duration<double>(now - t_prev).count());
+        t_prev = now;
+    };
     if (m < 0 || n < 0) return fail(h, MIPM_ERR_ARG, "negative dimension");
     S.m = m;
     S.n = n;
-    uvector<int32_t> Ap((size_t)m + 1);
-    for (int64_t i = 0; i <= m; ++i) Ap[(size_t)i] = Ap_in[i] - index_base;
-    if (m > 0 && Ap[0] != 0) return fail(h, MIPM_ERR_ARG, "row pointer does not start at index_base");
-    for (int64_t i = 0; i < m; ++i)
-        if (Ap[(size_t)i + 1] < Ap[(size_t)i]) return fail(h, MIPM_ERR_ARG, "row pointer not monotone");
-    const int64_t nnz = m > 0 ? Ap[(size_t)m] : 0;
-    S.nnz_a = nnz;
-    Cp.assign((size_t)m + 1, 0);
-    Cj.clear();
-    term_ptr_host.assign(1, 0);
-    if (nnz == 0 || m == 0) {
-        MIPM_CUDA(h, h->d_term_ptr.upload(term_ptr_host, h->stream));
+    cudaStream_t st = h->stream;
+    Scratch sc;
+    const int32_t *d_Ap, *d_Aj, *d_cptr, *d_crow, *d_cpos;
+    int64_t nnz = 0;
+    auto finish_empty = [&]() -> int {
+        std::vector<int32_t> one(1, 0);
+        MIPM_CUDA(h, h->d_term_ptr.upload(one, st));
+        MIPM_CUDA(h, h->d_asm_blk.upload(one, st));
+        h->asm_nblk = 0;
         MIPM_CUDA(h, h->d_term_pi.alloc(0));
         MIPM_CUDA(h, h->d_term_pj.alloc(0));
         MIPM_CUDA(h, h->d_term_k.alloc(0));
-        MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
+        MIPM_CUDA(h, cudaStreamSynchronize(st));
+        *Cp_out = (int32_t *)std::malloc(((size_t)m + 1) * sizeof(int32_t));
+        *Cj_out = (int32_t *)std::malloc(sizeof(int32_t));
+        if (!*Cp_out || !*Cj_out) return fail(h, MIPM_ERR_ALLOC, "host allocation failed");
+        for (int64_t i = 0; i <= m; ++i) (*Cp_out)[i] = index_base;
         return MIPM_OK;
-    }
-    // ---- host: 0-based columns, CSC index with CSR positions (stable bucket sort by column on the host threads: rows
-    // ascend inside a column), duplicate check
-    uvector<int32_t> Aj((size_t)nnz), cptr((size_t)n + 1), crow((size_t)nnz), cpos((size_t)nnz);
-    if (!stable_bucket_parallel(n, nnz, Aj_in, index_base, cptr.data(), [&](int64_t d, int64_t p) { cpos[(size_t)d] = (int32_t)p; }))
-        return fail(h, MIPM_ERR_ARG, "column index out of range");
-    {
+    };
+    if (!Ap_in) {
+        if (!h->has_spmv || h->sp_m != m || h->sp_n != n)
+            return fail(h, MIPM_ERR_STATE, "no row pointer given and no matrix of this shape registered with mipm_spmv_setup");
+        nnz = h->sp_nnz;
+        S.nnz_a = nnz;
+        if (nnz == 0 || m == 0) return finish_empty();
+        d_Ap = h->d_sp_rowptr.p; d_Aj = h->d_sp_col.p; d_cptr = h->d_sp_colptr.p; d_crow = h->d_sp_row.p; d_cpos = h->d_sp_pos.p;
+        int *d_dup;
+        MIPM_CUDA(h, sc.get(&d_dup, 1));
+        MIPM_CUDA(h, cudaMemsetAsync(d_dup, 0, sizeof(int), st));
+        k_ns_dup<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, d_Aj, d_crow, d_cpos, d_dup);
+        MIPM_CHECK_LAUNCH(h);
+        int dup = 0;
+        MIPM_CUDA(h, cudaMemcpyAsync(&dup, d_dup, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MIPM_CUDA(h, cudaStreamSynchronize(st));
+        if (dup) return fail(h, MIPM_ERR_DUPLICATE, "duplicate column inside a row of A");
+        stage("registered SpMV index reused, duplicate check");
+    } else {
+        uvector<int32_t> Ap((size_t)m + 1);
+        for (int64_t i = 0; i <= m; ++i) Ap[(size_t)i] = Ap_in[i] - index_base;
+        if (m > 0 && Ap[0] != 0) return fail(h, MIPM_ERR_ARG, "row pointer does not start at index_base");
+        for (int64_t i = 0; i < m; ++i)
+            if (Ap[(size_t)i + 1] < Ap[(size_t)i]) return fail(h, MIPM_ERR_ARG, "row pointer not monotone");
+        nnz = m > 0 ? Ap[(size_t)m] : 0;
+        S.nnz_a = nnz;
+        if (nnz == 0 || m == 0) return finish_empty();
+        // host: 0-based columns, CSC index with CSR positions (stable bucket sort by column on the host threads: rows
+        // ascend inside a column), duplicate check
+        uvector<int32_t> Aj((size_t)nnz), cptr((size_t)n + 1), crow((size_t)nnz), cpos((size_t)nnz);
+        if (!stable_bucket_parallel(n, nnz, Aj_in, index_base, cptr.data(), [&](int64_t d, int64_t p) { cpos[(size_t)d] = (int32_t)p; }))
+            return fail(h, MIPM_ERR_ARG, "column index out of range");
         const int T = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), nnz / 262144));
         run_host_threads(T, [&](int t) {
             for (int64_t p = nnz * t / T; p < nnz * (t + 1) / T; ++p) Aj[(size_t)p] = Aj_in[p] - index_base;
@@ -350,16 +422,24 @@ int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap_in
                     if (crow[(size_t)d] == crow[(size_t)d - 1]) { dup[(size_t)t] = 1; return; }
         });
         for (int v : dup) if (v) return fail(h, MIPM_ERR_DUPLICATE, "duplicate column inside a row of A");
+        stage("host CSC index");
+        int32_t *u_Ap, *u_Aj, *u_cptr, *u_crow, *u_cpos;
+        MIPM_CUDA(h, sc.get(&u_Ap, (size_t)m + 1));
+        MIPM_CUDA(h, sc.get(&u_Aj, (size_t)nnz));
+        MIPM_CUDA(h, sc.get(&u_cptr, (size_t)n + 1));
+        MIPM_CUDA(h, sc.get(&u_crow, (size_t)nnz));
+        MIPM_CUDA(h, sc.get(&u_cpos, (size_t)nnz));
+        MIPM_CUDA(h, cudaMemcpyAsync(u_Ap, Ap.data(), ((size_t)m + 1) * 4, cudaMemcpyHostToDevice, st));
+        MIPM_CUDA(h, cudaMemcpyAsync(u_Aj, Aj.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        MIPM_CUDA(h, cudaMemcpyAsync(u_cptr, cptr.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
+        MIPM_CUDA(h, cudaMemcpyAsync(u_crow, crow.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        MIPM_CUDA(h, cudaMemcpyAsync(u_cpos, cpos.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        MIPM_CUDA(h, cudaStreamSynchronize(st));        // the host vectors go out of scope
+        d_Ap = u_Ap; d_Aj = u_Aj; d_cptr = u_cptr; d_crow = u_crow; d_cpos = u_cpos;
+        stage("uploads");
     }
-    cudaStream_t st = h->stream;
-    Scratch sc;
-    int32_t *d_Ap, *d_Aj, *d_cptr, *d_crow, *d_cpos, *d_row_of, *d_dstart, *d_cnt, *d_ent_off, *d_row_terms, *d_row_nnzc, *d_Cp;
+    int32_t *d_row_of, *d_dstart, *d_cnt, *d_ent_off, *d_row_terms, *d_row_nnzc, *d_Cp;
     int *d_max;
-    MIPM_CUDA(h, sc.get(&d_Ap, (size_t)m + 1));
-    MIPM_CUDA(h, sc.get(&d_Aj, (size_t)nnz));
-    MIPM_CUDA(h, sc.get(&d_cptr, (size_t)n + 1));
-    MIPM_CUDA(h, sc.get(&d_crow, (size_t)nnz));
-    MIPM_CUDA(h, sc.get(&d_cpos, (size_t)nnz));
     MIPM_CUDA(h, sc.get(&d_row_of, (size_t)nnz));
     MIPM_CUDA(h, sc.get(&d_dstart, (size_t)nnz));
     MIPM_CUDA(h, sc.get(&d_cnt, (size_t)nnz));
@@ -368,11 +448,6 @@ int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap_in
     MIPM_CUDA(h, sc.get(&d_row_nnzc, (size_t)m));
     MIPM_CUDA(h, sc.get(&d_Cp, (size_t)m + 1));
     MIPM_CUDA(h, sc.get(&d_max, 1));
-    MIPM_CUDA(h, cudaMemcpyAsync(d_Ap, Ap.data(), ((size_t)m + 1) * 4, cudaMemcpyHostToDevice, st));
-    MIPM_CUDA(h, cudaMemcpyAsync(d_Aj, Aj.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
-    MIPM_CUDA(h, cudaMemcpyAsync(d_cptr, cptr.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
-    MIPM_CUDA(h, cudaMemcpyAsync(d_crow, crow.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
-    MIPM_CUDA(h, cudaMemcpyAsync(d_cpos, cpos.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
     MIPM_CUDA(h, cudaMemsetAsync(d_max, 0, sizeof(int), st));
     const unsigned gp = (unsigned)((nnz + 255) / 256), gm = (unsigned)((m + 255) / 256);
     k_row_of<<<gp, 256, 0, st>>>(m, nnz, d_Ap, d_row_of);
@@ -390,6 +465,7 @@ int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap_in
     MIPM_CUDA(h, cudaMemcpyAsync(&max_terms, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
     MIPM_CUDA(h, cudaStreamSynchronize(st));
     if (T >= (long long)INT32_MAX) return fail(h, MIPM_ERR_ARG, "too many product terms for 32-bit segment pointers");
+    stage("counts + scan (sync)");
     S.n_terms = T;
     MIPM_CUDA(h, h->d_term_pi.alloc((size_t)T));
     MIPM_CUDA(h, h->d_term_pj.alloc((size_t)T));
@@ -430,17 +506,52 @@ int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap_in
     MIPM_CUDA(h, cudaMemcpyAsync(&nnzc, d_total_c, sizeof(nnzc), cudaMemcpyDeviceToHost, st));
     MIPM_CUDA(h, cudaStreamSynchronize(st));
     S.nnz_c = nnzc;
+    stage("term arrays allocated, sort + compaction (sync)");
     int32_t *d_Cj;
     MIPM_CUDA(h, sc.get(&d_Cj, (size_t)nnzc));
     MIPM_CUDA(h, h->d_term_ptr.alloc((size_t)nnzc + 1));
     k_ns_place<<<(unsigned)((m * 32 + 255) / 256), 256, 0, st>>>(m, d_Ap, d_ent_off, d_Cp, d_head_j, d_head_t, d_Cj, h->d_term_ptr.p, (int32_t)T);
     MIPM_CHECK_LAUNCH(h);
-    Cj.resize((size_t)nnzc);
-    term_ptr_host.resize((size_t)nnzc + 1);
-    MIPM_CUDA(h, cudaMemcpyAsync(Cp.data(), d_Cp, ((size_t)m + 1) * 4, cudaMemcpyDeviceToHost, st));
-    MIPM_CUDA(h, cudaMemcpyAsync(Cj.data(), d_Cj, (size_t)nnzc * 4, cudaMemcpyDeviceToHost, st));
-    MIPM_CUDA(h, cudaMemcpyAsync(term_ptr_host.data(), h->d_term_ptr.p, ((size_t)nnzc + 1) * 4, cudaMemcpyDeviceToHost, st));
+    // ---- the pattern goes straight into the arrays the caller receives
+    *Cp_out = (int32_t *)std::malloc(((size_t)m + 1) * sizeof(int32_t));
+    *Cj_out = (int32_t *)std::malloc(std::max<size_t>((size_t)nnzc, 1) * sizeof(int32_t));
+    if (!*Cp_out || !*Cj_out) return fail(h, MIPM_ERR_ALLOC, "host allocation failed");
+    MIPM_CUDA(h, cudaMemcpyAsync(*Cp_out, d_Cp, ((size_t)m + 1) * 4, cudaMemcpyDeviceToHost, st));
+    MIPM_CUDA(h, cudaMemcpyAsync(*Cj_out, d_Cj, (size_t)nnzc * 4, cudaMemcpyDeviceToHost, st));
+    // ---- row runs of the streaming assembly
+    int64_t nblk = 0;
+    if (nnzc > 0) {
+        int32_t *d_flag, *d_pos;
+        MIPM_CUDA(h, sc.get(&d_flag, (size_t)nnzc));
+        MIPM_CUDA(h, sc.get(&d_pos, (size_t)nnzc + 1));
+        const unsigned gc = (unsigned)((nnzc + 255) / 256);
+        k_asm_block_flags<<<gc, 256, 0, st>>>(nnzc, h->d_term_ptr.p, d_flag);
+        MIPM_CHECK_LAUNCH(h);
+        long long *d_nblk;
+        rc = exclusive_scan(h, sc, nnzc, d_flag, d_pos, &d_nblk);
+        if (rc != MIPM_OK) return rc;
+        long long nb = 0;
+        MIPM_CUDA(h, cudaMemcpyAsync(&nb, d_nblk, sizeof(nb), cudaMemcpyDeviceToHost, st));
+        MIPM_CUDA(h, cudaStreamSynchronize(st));
+        nblk = nb;
+        MIPM_CUDA(h, h->d_asm_blk.alloc((size_t)nblk + 1));
+        k_asm_block_starts<<<gc, 256, 0, st>>>(nnzc, d_flag, d_pos, h->d_asm_blk.p, (int32_t)nblk);
+        MIPM_CHECK_LAUNCH(h);
+    } else {
+        std::vector<int32_t> one(1, 0);
+        MIPM_CUDA(h, h->d_asm_blk.upload(one, st));
+    }
+    h->asm_nblk = nblk;
     MIPM_CUDA(h, cudaStreamSynchronize(st));
+    if (index_base != 0) {
+        const int Tt = (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), nnzc / 262144));
+        int32_t *cp = *Cp_out, *cj = *Cj_out;
+        run_host_threads(Tt, [&](int t) {
+            for (int64_t i = (m + 1) * t / Tt; i < (m + 1) * (t + 1) / Tt; ++i) cp[i] += index_base;
+            for (int64_t c = nnzc * t / Tt; c < nnzc * (t + 1) / Tt; ++c) cj[c] += index_base;
+        });
+    }
+    stage("placement, assembly blocks, pattern to the host");
     return MIPM_OK;
 }
 

@@ -273,7 +273,7 @@ class MPCSolver:
         if opt.kkt_system == "Normal":
             self.pr_diag, self.du_diag = z(n), z(m)
             _mark("buffers")
-            Cp, Cj = self.h.normal_symbolic(m, n, self._Ap_abi, self._Aj_abi, index_base=ib)
+            Cp, Cj = self.h.normal_symbolic(m, n, index_base=ib)      # A as registered by spmv_setup above
             _mark("normal_symbolic")
             self.aug_colptr, self.aug_rowval = Cp, Cj
             if opt.linear_solver == "distributed":

@@ -81,11 +81,15 @@ def test_normal_symbolic_device_equals_host_builder(handle, monkeypatch):
     Bp, Bj, Bm = _lib.coo_to_csr(m, n, rows, cols)
     pr = np.random.default_rng(1).uniform(1e-3, 1e3, n)
     out = {}
-    for which in ("device", "host"):
+    for which in ("device", "registered", "host"):
         if which == "host":
             monkeypatch.setenv("MIPM_HOST_SYMBOLIC", "1")
         h = handle()
-        Cp, Cj = h.normal_symbolic(m, n, Bp + 1, Bj + 1, index_base=1)
+        if which == "registered":       # Ap = Aj = NULL: the matrix registered with mipm_spmv_setup, index already on the device
+            h.spmv_setup(m, n, Bp + 1, Bj + 1, index_base=1)
+            Cp, Cj = h.normal_symbolic(m, n, index_base=1)
+        else:
+            Cp, Cj = h.normal_symbolic(m, n, Bp + 1, Bj + 1, index_base=1)
         d_Cx = torch.zeros(len(Cj), dtype=torch.float64, device="cuda")
         h.normal_set_jacobian(dev(vals[Bm]))
         h.normal_assemble(dev(pr), d_Cx, exact_order=True)
@@ -93,8 +97,9 @@ def test_normal_symbolic_device_equals_host_builder(handle, monkeypatch):
         h.normal_assemble(dev(pr), d_Cx, exact_order=False)
         out[which] = (Cp, Cj, exact, d_Cx.cpu().numpy().copy())
     monkeypatch.delenv("MIPM_HOST_SYMBOLIC")
-    for a, b in zip(out["device"], out["host"]):
-        assert np.array_equal(a, b)
+    for which in ("device", "registered"):
+        for a, b in zip(out[which], out["host"]):
+            assert np.array_equal(a, b)
     h = handle()
     Cp, Cj = h.normal_symbolic(3, 2, np.array([0, 2, 2, 3], dtype=np.int32), np.array([0, 1, 1], dtype=np.int32))
     assert list(Cp) == [0, 2, 2, 3] and list(Cj) == [0, 2, 2]
@@ -103,6 +108,12 @@ def test_normal_symbolic_device_equals_host_builder(handle, monkeypatch):
     with pytest.raises(_lib.MipmError) as e:
         h.normal_symbolic(1, 2, np.array([0, 2], dtype=np.int32), np.array([1, 1], dtype=np.int32))
     assert e.value.code == _lib.MIPM_ERR_DUPLICATE
+    h.spmv_setup(1, 2, np.array([0, 2], dtype=np.int32), np.array([1, 1], dtype=np.int32))
+    with pytest.raises(_lib.MipmError) as e:                    # the same check on the registered matrix (device side)
+        h.normal_symbolic(1, 2)
+    assert e.value.code == _lib.MIPM_ERR_DUPLICATE
+    with pytest.raises(_lib.MipmError):                         # no matrix of that shape registered
+        h.normal_symbolic(3, 2)
 
 
 def test_k2_transfer_bit_exact(handle):
