@@ -100,6 +100,29 @@ def test_normal_symbolic_device_equals_host_builder(handle, monkeypatch):
     for which in ("device", "registered"):
         for a, b in zip(out[which], out["host"]):
             assert np.array_equal(a, b)
+    # rows whose term counts sit exactly on and just above the capacities of the two shared-memory sort classes
+    # (2 048 and 16 384 terms): n columns that all hold rows 0 .. c-1 give row 0 exactly n * c product terms
+    for c, ncol in ((32, 64), (32, 65), (64, 256), (64, 257)):
+        rr = np.tile(np.arange(c, dtype=np.int32), ncol)
+        cc = np.repeat(np.arange(ncol, dtype=np.int32), c)
+        Dp, Dj, _ = _lib.coo_to_csr(c, ncol, rr, cc)
+        dvals = dev(np.random.default_rng(c + ncol).standard_normal(len(Dj)))
+        dpr = dev(np.random.default_rng(1).uniform(0.5, 2.0, ncol))
+        res = []
+        for host in (False, True):
+            if host:
+                monkeypatch.setenv("MIPM_HOST_SYMBOLIC", "1")
+            hb = handle()
+            Ep, Ej = hb.normal_symbolic(c, ncol, Dp, Dj)
+            if host:
+                monkeypatch.delenv("MIPM_HOST_SYMBOLIC")
+            d_Ex = torch.zeros(len(Ej), dtype=torch.float64, device="cuda")
+            hb.normal_set_jacobian(dvals)
+            hb.normal_assemble(dpr, d_Ex, exact_order=True)
+            res.append((Ep, Ej, d_Ex.cpu().numpy().copy()))
+        for a, b in zip(*res):
+            assert np.array_equal(a, b)
+        assert len(res[0][1]) == c * (c + 1) // 2                   # dense lower triangle
     h = handle()
     Cp, Cj = h.normal_symbolic(3, 2, np.array([0, 2, 2, 3], dtype=np.int32), np.array([0, 1, 1], dtype=np.int32))
     assert list(Cp) == [0, 2, 2, 3] and list(Cj) == [0, 2, 2]
