@@ -911,14 +911,17 @@ int ls_device_setup(Handle *h)
                 int restB_prev = 0;                      // REST completed through panel p-1
                 for (auto &g : G) { for (auto &t2 : g) t2.need = cntA; cntA += (int)g.size(); }      // extend-add
                 std::vector<Task> rest_prev;             // REST(p-1), emitted after the first DIAG of panel p
+                bool diag_emitted = false;               // the first DIAG of this panel already sits at the head of LA(p-1)
                 for (size_t pi = 0; pi < panels.size(); ++pi) {
                     const int J0 = panels[pi][0], J1 = panels[pi][1];
                     bool first = true;
                     for (int jb = J0; jb < J1; jb += NB) {
-                        Task dg = mk(T_DIAG, s, jb, J0, 0, 0);
-                        dg.need = cntA; dg.need_b = needB_chain;
-                        G.push_back({dg});
-                        cntA += 1;
+                        if (!(jb == J0 && diag_emitted)) {
+                            Task dg = mk(T_DIAG, s, jb, J0, 0, 0);
+                            dg.need = cntA; dg.need_b = needB_chain;
+                            G.push_back({dg});
+                            cntA += 1;
+                        }
                         if (first && !rest_prev.empty()) {
                             G.push_back(std::move(rest_prev));
                             rest_prev.clear();
@@ -938,8 +941,18 @@ int ls_device_setup(Handle *h)
                     if ((int64_t)starts.size() * ((int64_t)starts.size() + 1) / 2 > (1 << 26)) return fail(h, MIPM_ERR_ARG, "front too large for the tile schedule");
                     const int la_end = (pi + 1 < panels.size()) ? panels[pi + 1][1] : J1;     // columns [J1, la_end) = next panel
                     std::vector<Task> la, rest;
+                    // fused diagonal update (see the branch above): the next panel's first diagonal block takes the place of
+                    // the look-ahead tile (J1, J1) with the same two dependency counts
+                    const bool fuse = fuse_diag && J1 < k;
+                    if (fuse) {
+                        Task dg = mk(T_DIAG, s, J1, J0, 0, 0);
+                        dg.need = chain_done; dg.need_b = restB_prev;
+                        la.push_back(dg);
+                    }
+                    diag_emitted = fuse;
                     for (size_t tc = 0; tc < starts.size(); ++tc)
                         for (size_t tr = tc; tr < starts.size(); ++tr) {
+                            if (fuse && tc == 0 && tr == 0) continue;
                             Task q = mk(T_TRAIL, s, J0, J1, starts[tr], starts[tc]);
                             q.need = chain_done;
                             q.need_b = restB_prev;       // the same C tile was last touched by REST(p-1)
