@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmadipm_b200.so")
+LIB_PATH = os.environ.get("MIPM_LIB") or os.path.join(_HERE, "libmadipm_b200.so")      # MIPM_LIB: A/B builds (tools/)
 
 MIPM_OK, MIPM_ERR_ARG, MIPM_ERR_CUDA, MIPM_ERR_ALLOC, MIPM_ERR_STATE, MIPM_ERR_DUPLICATE, MIPM_ERR_NOT_FACTORIZED = range(7)
 MIPM_CHOLESKY, MIPM_LDL, MIPM_LDL_DEFINITE = 0, 1, 2

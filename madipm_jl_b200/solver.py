@@ -549,6 +549,11 @@ class MPCSolver:
             off += len(a)
         self._amax_A = float(np.abs(self.A_V_host).max()) if len(self.A_V_host) else 0.0
         self.h2d_bytes_per_solve = int(sum(t.numel() * 8 for t in self._host.values()))
+        # page-locked landing zone of the results (x, constraints, y, zl, zu), two of them used in turn: the arrays of an
+        # ExecutionStats stay valid until the solve after next on the same solver
+        rtotal = 3 * (nx + ns) + 2 * m
+        self._res_slabs = [torch.empty(max(rtotal, 1), dtype=torch.float64, pin_memory=(rtotal >= 65536)) for _ in range(2)]
+        self._res_turn = 0
 
     def _madnlp_initialize(self):
         """MadNLP.initialize!(cb, ...) + set_scaling! (App. B) on the device; inputs come from pinned host memory."""
@@ -874,7 +879,8 @@ class MPCSolver:
             pass
 
     def solve(self):
-        """solve!(solver): src/solver.jl:362-418."""
+        """solve!(solver): src/solver.jl:362-418. The arrays of the returned ExecutionStats live in page-locked buffers
+        owned by the solver (two sets, used in turn): they stay valid until the solve after next on this solver."""
         self.start_time = time.time()
         t0 = time.perf_counter()
         try:
@@ -894,20 +900,37 @@ class MPCSolver:
                 raise
         torch.cuda.synchronize(self.device)
         total = time.perf_counter() - t0
-        x = self.x.cpu().numpy()
         # stats.constraints = A0 x (unscaled, without the slack columns): device SpMV, then undo both
         self.h.spmv(0, 1.0, self.AT_x, self.x, 0.0, self.buffer_m)
-        cons = self.buffer_m.cpu().numpy()
+        # results: device -> page-locked slab in one go (no pageable staging, no fresh host pages), post-processed in place
+        n, m = self.n, self.m
+        self._res_turn ^= 1
+        slab = self._res_slabs[self._res_turn]
+        parts, off = [], 0
+        for src, ln in ((self.x, n), (self.buffer_m, m), (self.y, m), (self.zl, n), (self.zu, n)):
+            dst = slab[off:off + ln]
+            if ln:
+                dst.copy_(src, non_blocking=True)
+            parts.append(dst.numpy())
+            off += ln
+        torch.cuda.synchronize(self.device)
+        x, cons, mult, zl, zu = parts
         if self.ns:
             cons[self.ind_ineq] += x[self.nx:]         # the (scaled) slack columns are -1
-        cons = cons / self.con_scale
+        if not getattr(self, "_unit_con_scale", True):
+            cons /= self.con_scale
+            mult *= self.con_scale
+        if self.obj_scale != 1.0:
+            mult /= self.obj_scale
+            zl /= self.obj_scale
+            zu /= self.obj_scale
         return ExecutionStats(
             status=self.status, iter=self.k, objective=self.obj_val / self.obj_scale,
             dual_objective=getattr(self, "dobj", float("nan")) / self.obj_scale,
-            solution=x[: self.nx].copy(), constraints=cons,
-            multipliers=self.y.cpu().numpy() * self.con_scale / self.obj_scale,
-            multipliers_L=self.zl.cpu().numpy()[: self.nx] / self.obj_scale,
-            multipliers_U=self.zu.cpu().numpy()[: self.nx] / self.obj_scale,
+            solution=x[: self.nx], constraints=cons,
+            multipliers=mult,
+            multipliers_L=zl[: self.nx],
+            multipliers_U=zu[: self.nx],
             trace=self.trace, total_time=total, linear_solver_time=self.cnt["linear_solver_time"],
             counters=dict(self.cnt, launches=self.h.launch_count(), ls_stats=self.linear_solver.stats),
         )
