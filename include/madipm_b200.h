@@ -340,6 +340,11 @@ typedef struct {
 } mipm_mpc_model;
 int mipm_mpc_set_model(mipm_handle h, const mipm_mpc_model *model);
 int mipm_mpc_iter_begin(mipm_handle h, double del_w, double del_c, double *out, int *status);
+/* The termination measures of the current iterate alone (update_termination_criteria!, src/solver.jl:194-205) into the
+ * same 16 scalars as mipm_mpc_iter_begin, WITHOUT assembling and factorizing the next KKT system. The host calls it
+ * instead of mipm_mpc_iter_begin when the previous measures are within 10 x tol: the iteration that detects convergence
+ * then does not pay for a factorization it never uses (one extra synchronisation in the last one or two iterations). */
+int mipm_mpc_peek(mipm_handle h, double *out);
 int mipm_mpc_refactor(mipm_handle h, double del_w, double del_c, int *status);
 int mipm_mpc_iter_rest(mipm_handle h, double mu_min, int step_rule, double tau_param, int ir_steps);
 

@@ -62,7 +62,7 @@ SYMBOLS = [
     "mipm_ls_inertia", "mipm_ls_stats", "mipm_ls_symbolic",
     "mipm_ls_analyze_border", "mipm_ls_factorize_stage", "mipm_ls_solve_stage", "mipm_ls_root_info",
     "mipm_set_grid_limit", "mipm_spmv_setup", "mipm_spmv", "mipm_spmv_pair", "mipm_spmv_cache_values", "mipm_hess_setup", "mipm_hess_spmv",
-    "mipm_mpc_set_model", "mipm_mpc_iter_begin", "mipm_mpc_refactor", "mipm_mpc_iter_rest",
+    "mipm_mpc_set_model", "mipm_mpc_iter_begin", "mipm_mpc_peek", "mipm_mpc_refactor", "mipm_mpc_iter_rest",
     "mipm_mpc_bind", "mipm_set_aug_diagonal_reg", "mipm_set_predictive_rhs", "mipm_set_correction_rhs",
     "mipm_get_correction", "mipm_set_extra_correction", "mipm_get_complementarity_measure",
     "mipm_get_affine_complementarity_measure", "mipm_get_alpha_max", "mipm_termination_measures",
@@ -294,6 +294,11 @@ class Handle:
         st = C.c_int()
         self.check(self.lib.mipm_mpc_iter_begin(self.h, C.c_double(del_w), C.c_double(del_c), out, C.byref(st)))
         return list(out), st.value == MIPM_OK
+
+    def mpc_peek(self):
+        out = (C.c_double * 16)()
+        self.check(self.lib.mipm_mpc_peek(self.h, out))
+        return list(out)
 
     def mpc_refactor(self, del_w, del_c):
         st = C.c_int()

@@ -1581,6 +1581,21 @@ int mipm_mpc_iter_begin(mipm_handle hh, double del_w, double del_c, double *out,
     return fused_fetch(h, out, status);
 }
 
+int mipm_mpc_peek(mipm_handle hh, double *out)
+{
+    Handle *h = (Handle *)hh;
+    MIPM_NEED_DEVICE(h);
+    int rc = fused_ready(h);
+    if (rc != MIPM_OK) return rc;
+    if (!out) return fail(h, MIPM_ERR_ARG, "null argument");
+    MIPM_CUDA(h, cudaSetDevice(h->device));
+    V v = make_view(h, inv_lb_buf(h).p, inv_ub_buf(h).p);
+    const int64_t nmax = std::max<int64_t>(std::max(v.n, v.m), 1);
+    k_termination<<<red_grid(h, nmax), TB, 0, h->stream>>>(v, h->d_partials.p, h->d_counter.p, h->d_sc.p + SC_TERM);
+    MIPM_CHECK_LAUNCH(h);
+    return fused_fetch(h, out, nullptr);
+}
+
 int mipm_mpc_refactor(mipm_handle hh, double del_w, double del_c, int *status)
 {
     Handle *h = (Handle *)hh;
