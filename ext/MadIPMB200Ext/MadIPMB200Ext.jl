@@ -26,7 +26,7 @@
 #   MadIPM.set_aug_diagonal_reg!      kernels.jl:124-149               -> mipm_set_aug_diagonal_reg[_scaled]
 #   src/kernels.jl vector functions                                    -> mipm_set_* / mipm_get_* (fused)
 #   MadIPM.update_step!(::MehrotraAdaptiveStep) kernels.jl:309-358     -> mipm_mehrotra_adaptive_step (no scalar indexing)
-#   MadIPM.mpc!                       solver.jl:332-360                -> mipm_mpc_iter_begin / _refactor / _iter_rest (one sync per iteration)
+#   MadIPM.mpc!                       solver.jl:332-360                -> mipm_mpc_iter_begin / _peek / _refactor / _iter_rest (one sync per iteration)
 module MadIPMB200Ext
 
 using LinearAlgebra
@@ -509,8 +509,15 @@ function MadIPM.mpc!(s::GPUSolver{T}) where {T}
     while true
         MadNLP.print_iter(s)
         MadIPM.update_regularization!(s, s.opt.regularization)
-        check(h, ccall((:mipm_mpc_iter_begin, libmadipm), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ptr{Cdouble}, Ref{Cint}),
-                       h.ptr, s.del_w, s.del_c, out, st))
+        # close to convergence the measures are read before the next system is factorized (mipm_mpc_peek), so the call
+        # that detects convergence does not pay for a factorization nobody uses
+        peek = started && max(s.inf_pr, s.inf_du, s.inf_compl) <= 10 * s.opt.tol
+        if peek
+            check(h, ccall((:mipm_mpc_peek, libmadipm), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), h.ptr, out))
+        else
+            check(h, ccall((:mipm_mpc_iter_begin, libmadipm), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ptr{Cdouble}, Ref{Cint}),
+                           h.ptr, s.del_w, s.del_c, out, st))
+        end
         if started                                    # scalars of the step taken by the previous mipm_mpc_iter_rest
             s.obj_val = s.cb.obj_scale[] * s.nlp.data.c0 + out[6] + 0.5 * out[7]
             s.alpha_p, s.alpha_d, s.mu, s.mu_curr = out[8], out[9], out[10], out[11]
@@ -522,6 +529,10 @@ function MadIPM.mpc!(s::GPUSolver{T}) where {T}
         s.inf_compl = out[4] / max(1.0, s.norm_c)
         termination_status!(s, out[1])
         MadIPM.is_done(s) && return
+        if peek
+            check(h, ccall((:mipm_mpc_iter_begin, libmadipm), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ptr{Cdouble}, Ref{Cint}),
+                           h.ptr, s.del_w, s.del_c, out, st))
+        end
         ok = st[] == MIPM_OK
         ntrial = 1
         while !ok && ntrial < 3                       # factorize_regularized_system! (linear_solver.jl:6-17)
