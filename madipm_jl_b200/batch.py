@@ -247,7 +247,11 @@ class BatchedMPCSolver:
             raise AssertionError("starting point not strictly interior (lower)")
 
     def solve(self):
-        """solve! for every unit; returns a list of ExecutionStats (one per unit, in order)."""
+        """solve! for every unit; returns a list of ExecutionStats (one per unit, in order). The per-unit bookkeeping
+        between the one synchronisation of an iteration and the launches of its second half is array arithmetic over
+        the units (the GPU idles while it runs); traces are kept as per-iteration arrays and turned into the per-unit
+        list of records on access; the result arrays are views of page-locked buffers owned by the solver (valid
+        until the solve after next)."""
         import time
         import numpy as np
         import torch
@@ -256,14 +260,18 @@ class BatchedMPCSolver:
         t0 = time.perf_counter()
         s.start_time = time.time()
         self._initialize()
-        status = [S.REGULAR] * B
+        CODES = [S.REGULAR, S.SOLVE_SUCCEEDED, S.INFEASIBLE_PROBLEM_DETECTED, S.DIVERGING_ITERATES,
+                 S.MAXIMUM_ITERATIONS_EXCEEDED, S.INTERNAL_ERROR]
+        code = np.zeros(B, dtype=np.int64)               # index into CODES
         iters = np.zeros(B, dtype=np.int64)
-        traces = [[] for _ in range(B)]
         best = np.full(B, np.inf)
         active = np.ones(B, dtype=np.int32)
         alpha_p, alpha_d = np.zeros(B), np.zeros(B)
         mu = np.full(B, opt.mu_init)
         dobj_last = np.full(B, np.nan)
+        c0 = self.obj_scale * np.array([q.c0 for q in self.models])
+        nb1, nc1 = np.maximum(1.0, self.norm_b), np.maximum(1.0, self.norm_c)
+        records = []                                     # per iteration: (k, del_w, active mask, columns)
         started = False
         k = 0
         s.del_w_trace = s.del_w
@@ -271,37 +279,36 @@ class BatchedMPCSolver:
             trace_del_w = s.del_w
             s.update_regularization()
             out, ok = h.batch_iter_begin(s.del_w, s.del_c)
+            act = active == 1
             if started:
-                new_obj = self.obj_scale * np.array([q.c0 for q in self.models]) + out[:, 5] + 0.5 * out[:, 6]
-                self.obj_val = np.where(active == 1, new_obj, self.obj_val)
-                alpha_p = np.where(active == 1, out[:, 7], alpha_p)
-                alpha_d = np.where(active == 1, out[:, 8], alpha_d)
-                mu = np.where(active == 1, out[:, 9], mu)
-            for u in range(B):
-                if not active[u]:
-                    continue
-                dobj, nc, ndu, ncompl, dnorm = out[u, :5]
-                inf_pr = nc / max(1.0, self.norm_b[u])
-                inf_du = ndu / max(1.0, self.norm_c[u])
-                inf_compl = ncompl / max(1.0, self.norm_c[u])
-                best[u] = min(best[u], inf_compl)
-                dobj_last[u] = dobj
-                if max(inf_pr, inf_du, inf_compl) <= opt.tol:
-                    status[u] = S.SOLVE_SUCCEEDED
-                elif (inf_compl > opt.divergence_tol * best[u]) and (dobj > max(10.0 * abs(self.obj_val[u]), 1.0)):
-                    status[u] = S.INFEASIBLE_PROBLEM_DETECTED
-                elif self.obj_val[u] < -opt.divergence_tol * max(10.0, abs(dobj), 1.0):
-                    status[u] = S.DIVERGING_ITERATES
-                elif k >= opt.max_iter:
-                    status[u] = S.MAXIMUM_ITERATIONS_EXCEEDED
-                elif not np.isfinite(max(inf_pr, inf_du, inf_compl)):
-                    status[u] = S.INTERNAL_ERROR
-                traces[u].append(dict(k=k, objective=self.obj_val[u] / self.obj_scale[u], dual_objective=dobj / self.obj_scale[u],
-                                      inf_pr=inf_pr, inf_du=inf_du, inf_compl=inf_compl, mu=mu[u], alpha_p=alpha_p[u],
-                                      alpha_d=alpha_d[u], del_w=trace_del_w, dnorm=0.0 if k == 0 else dnorm))
-                if status[u] != S.REGULAR:
-                    active[u] = 0
-                    iters[u] = k
+                self.obj_val = np.where(act, c0 + out[:, 5] + 0.5 * out[:, 6], self.obj_val)
+                alpha_p = np.where(act, out[:, 7], alpha_p)
+                alpha_d = np.where(act, out[:, 8], alpha_d)
+                mu = np.where(act, out[:, 9], mu)
+            dobj, dnorm = out[:, 0], out[:, 4]
+            inf_pr, inf_du, inf_compl = out[:, 1] / nb1, out[:, 2] / nc1, out[:, 3] / nc1
+            with np.errstate(invalid="ignore"):
+                best = np.where(act & (inf_compl < best), inf_compl, best)          # min(best, inf_compl)
+                dobj_last = np.where(act, dobj, dobj_last)
+                worst = np.where(inf_du > inf_pr, inf_du, inf_pr)                    # max(inf_pr, inf_du, inf_compl) with the
+                worst = np.where(inf_compl > worst, inf_compl, worst)                # comparison order of the scalar code
+                a_obj = np.abs(self.obj_val)
+                thr_inf = np.where(1.0 > 10.0 * a_obj, 1.0, 10.0 * a_obj)             # max(10 |obj|, 1)
+                a_dobj = np.abs(dobj)
+                thr_div = np.where(a_dobj > 10.0, a_dobj, 10.0)
+                new_code = np.select(
+                    [worst <= opt.tol,
+                     (inf_compl > opt.divergence_tol * best) & (dobj > thr_inf),
+                     self.obj_val < -opt.divergence_tol * thr_div,
+                     np.full(B, k >= opt.max_iter),
+                     ~np.isfinite(worst)],
+                    [1, 2, 3, 4, 5], default=0)
+            records.append((k, trace_del_w, act.copy(), self.obj_val / self.obj_scale, dobj / self.obj_scale, inf_pr, inf_du,
+                            inf_compl, mu.copy(), alpha_p.copy(), alpha_d.copy(), np.zeros(B) if k == 0 else dnorm.copy()))
+            done_now = act & (new_code != 0)
+            code = np.where(done_now, new_code, code)
+            iters = np.where(done_now, k, iters)
+            active = np.where(done_now, 0, active).astype(np.int32)
             if not active.any():
                 break
             h.batch_set_active(active)
@@ -321,20 +328,68 @@ class BatchedMPCSolver:
             k += 1
         torch.cuda.synchronize(s.device)
         total = time.perf_counter() - t0
-        x, y = s.x.cpu().numpy(), s.y.cpu().numpy()
-        zl, zu = s.zl.cpu().numpy(), s.zu.cpu().numpy()
         h.spmv(0, 1.0, s.AT_x, s.x, 0.0, s.buffer_m)
-        cons = s.buffer_m.cpu().numpy()
+        n, m = s.n, s.m
+        s._res_turn ^= 1
+        slab = s._res_slabs[s._res_turn]
+        parts, off = [], 0
+        for src, ln in ((s.x, n), (s.buffer_m, m), (s.y, m), (s.zl, n), (s.zu, n)):
+            dst = slab[off:off + ln]
+            if ln:
+                dst.copy_(src, non_blocking=True)
+            parts.append(dst.numpy())
+            off += ln
+        torch.cuda.synchronize(s.device)
+        x, cons, y, zl, zu = parts
+        if np.any(self.obj_scale != 1.0):
+            y /= np.repeat(self.obj_scale, np.diff(self.off_m))
+            sn = np.repeat(self.obj_scale, np.diff(self.off_n))
+            zl /= sn
+            zu /= sn
+        counters = dict(launches=h.launch_count(), iterations_of_the_batch=k, ls_stats=s.linear_solver.stats)
+        obj = self.obj_val / self.obj_scale
+        dob = dobj_last / self.obj_scale
         res = []
         for u in range(B):
-            sl_n, sl_m = slice(self.off_n[u], self.off_n[u + 1]), slice(self.off_m[u], self.off_m[u + 1])
+            n0, n1, m0, m1 = self.off_n[u], self.off_n[u + 1], self.off_m[u], self.off_m[u + 1]
             res.append(S.ExecutionStats(
-                status=status[u], iter=int(iters[u]), objective=self.obj_val[u] / self.obj_scale[u],
-                dual_objective=dobj_last[u] / self.obj_scale[u], solution=x[sl_n].copy(), constraints=cons[sl_m].copy(),
-                multipliers=y[sl_m] / self.obj_scale[u], multipliers_L=zl[sl_n] / self.obj_scale[u],
-                multipliers_U=zu[sl_n] / self.obj_scale[u], trace=traces[u], total_time=total, linear_solver_time=0.0,
-                counters=dict(launches=h.launch_count(), iterations_of_the_batch=k, ls_stats=s.linear_solver.stats)))
+                status=CODES[code[u]], iter=int(iters[u]), objective=obj[u], dual_objective=dob[u],
+                solution=x[n0:n1], constraints=cons[m0:m1], multipliers=y[m0:m1], multipliers_L=zl[n0:n1],
+                multipliers_U=zu[n0:n1], trace=_UnitTrace(records, u), total_time=total, linear_solver_time=0.0,
+                counters=counters))
         return res
+
+
+class _UnitTrace:
+    """Trace of one unit of a batch (a sequence of the same records MPCSolver keeps), materialised on first access from
+    the per-iteration arrays of the whole batch."""
+    _KEYS = ("objective", "dual_objective", "inf_pr", "inf_du", "inf_compl", "mu", "alpha_p", "alpha_d", "dnorm")
+
+    def __init__(self, records, u):
+        self._records, self._u, self._list = records, u, None
+
+    def _get(self):
+        if self._list is None:
+            u, out = self._u, []
+            for rec in self._records:
+                k, del_w, act = rec[0], rec[1], rec[2]
+                if not act[u]:
+                    break
+                d = dict(k=k, del_w=del_w)
+                for name, col in zip(self._KEYS, rec[3:]):
+                    d[name] = float(col[u])
+                out.append(d)
+            self._list = out
+        return self._list
+
+    def __len__(self):
+        return len(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __iter__(self):
+        return iter(self._get())
 
 
 def solve_batch_stacked(models, **kwargs):
