@@ -379,6 +379,8 @@ int mipm_batch_dot(mipm_handle h, const double *d_x, const double *d_y, double *
 int mipm_batch_init_point_stage(mipm_handle h, int stage, const double *a, const double *b, double kappa,
                                 double *out);
 int mipm_batch_iter_begin(mipm_handle h, double del_w, double del_c, double *out, int *status);
+/* mipm_mpc_peek for the whole batch: the termination measures of every unit without the next factorization. */
+int mipm_batch_peek(mipm_handle h, double *out);
 int mipm_batch_iter_rest(mipm_handle h, double mu_min, int step_rule, double tau_param, int ir_steps);
 
 /* ------------------------------------------------------------------ preprocessing -- */

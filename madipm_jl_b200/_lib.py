@@ -71,7 +71,7 @@ SYMBOLS = [
     "mipm_launch_count", "mipm_ls_factorize_profile", "mipm_bench_syrk", "mipm_mehrotra_adaptive_step", "mipm_set_aug_diagonal_reg_scaled", "mipm_k25_scale_values",
     "mipm_reduce_rhs_scaled", "mipm_finish_aug_solve_scaled", "mipm_kktmul_scaled",
     "mipm_batch_configure", "mipm_batch_set_active", "mipm_batch_amax", "mipm_batch_dot", "mipm_batch_init_point_stage",
-    "mipm_batch_iter_begin", "mipm_batch_iter_rest", "mipm_ruiz_equilibrate", "mipm_scale_coo", "mipm_mpc_ext_begin", "mipm_mpc_ext_fetch", "mipm_mpc_ext_phase",
+    "mipm_batch_iter_begin", "mipm_batch_peek", "mipm_batch_iter_rest", "mipm_ruiz_equilibrate", "mipm_scale_coo", "mipm_mpc_ext_begin", "mipm_mpc_ext_fetch", "mipm_mpc_ext_phase",
 ]
 
 _lib = None
@@ -365,6 +365,11 @@ class Handle:
         st = C.c_int()
         self.check(self.lib.mipm_batch_iter_begin(self.h, C.c_double(del_w), C.c_double(del_c), _ptr(out), C.byref(st)))
         return out, st.value == MIPM_OK
+
+    def batch_peek(self):
+        out = np.zeros((self._nb, 16))
+        self.check(self.lib.mipm_batch_peek(self.h, _ptr(out)))
+        return out
 
     def batch_iter_rest(self, mu_min, step_rule, tau_param, ir_steps):
         self.check(self.lib.mipm_batch_iter_rest(self.h, C.c_double(mu_min), C.c_int(step_rule), C.c_double(tau_param), C.c_int(ir_steps)))

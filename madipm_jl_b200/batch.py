@@ -274,12 +274,20 @@ class BatchedMPCSolver:
         records = []                                     # per iteration: (k, del_w, active mask, columns)
         started = False
         k = 0
+        worst = np.full(B, np.inf)
         s.del_w_trace = s.del_w
         while True:
             trace_del_w = s.del_w
             s.update_regularization()
-            out, ok = h.batch_iter_begin(s.del_w, s.del_c)
             act = active == 1
+            # every unit still running is within 10 x tol: read the measures before the next factorization goes out, so
+            # the pass in which the last units converge does not pay for a factorization of the whole stack
+            peek = started and bool(np.all(worst[act] <= 10.0 * opt.tol))
+            ok = True
+            if peek:
+                out = h.batch_peek()
+            else:
+                out, ok = h.batch_iter_begin(s.del_w, s.del_c)
             if started:
                 self.obj_val = np.where(act, c0 + out[:, 5] + 0.5 * out[:, 6], self.obj_val)
                 alpha_p = np.where(act, out[:, 7], alpha_p)
@@ -311,6 +319,8 @@ class BatchedMPCSolver:
             active = np.where(done_now, 0, active).astype(np.int32)
             if not active.any():
                 break
+            if peek:
+                _, ok = h.batch_iter_begin(s.del_w, s.del_c)
             h.batch_set_active(active)
             for _ in range(2):                       # factorize_regularized_system! retries, for the whole stack
                 if ok:

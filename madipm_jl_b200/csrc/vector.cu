@@ -1763,21 +1763,22 @@ int mipm_batch_init_point_stage(mipm_handle hh, int stage, const double *a, cons
 
 /* mipm_mpc_iter_begin for the whole batch: out is B x 16 (same entries per unit), *status as mipm_ls_factorize for the
  * stacked matrix (one unit's breakdown makes every unit retry with more regularization). */
-int mipm_batch_iter_begin(mipm_handle hh, double del_w, double del_c, double *out, int *status)
+// factorize != 0: mipm_batch_iter_begin; 0: mipm_batch_peek (termination measures only)
+static int batch_begin(mipm_handle hh, double del_w, double del_c, double *out, int *status, int factorize)
 {
     Handle *h = (Handle *)hh;
     BATCH_OR_FAIL(h);
     int rc = fused_ready(h);
     if (rc != MIPM_OK) return rc;
-    if (!out || !status) return fail(h, MIPM_ERR_ARG, "null argument");
+    if (!out || (factorize && !status)) return fail(h, MIPM_ERR_ARG, "null argument");
     kb_termination<<<B, TB, 0, h->stream>>>(v, ub);
     MIPM_CHECK_LAUNCH(h);
-    if ((rc = fused_factorize(h, del_w, del_c)) != MIPM_OK) return rc;
+    if (factorize && (rc = fused_factorize(h, del_w, del_c)) != MIPM_OK) return rc;
     int info[4];
     MIPM_CUDA(h, cudaMemcpyAsync(h->h_ubuf.data(), ub.sc, (size_t)B * SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     MIPM_CUDA(h, cudaMemcpyAsync(info, h->d_info.p, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
     MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
-    *status = (info[0] == 0) ? MIPM_OK : MIPM_ERR_NOT_FACTORIZED;
+    if (status) *status = (info[0] == 0) ? MIPM_OK : MIPM_ERR_NOT_FACTORIZED;
     for (unsigned u = 0; u < B; ++u) {
         const double *sc = h->h_ubuf.data() + (size_t)u * SC_COUNT;
         double *o = out + (size_t)u * 16;
@@ -1790,6 +1791,13 @@ int mipm_batch_iter_begin(mipm_handle hh, double del_w, double del_c, double *ou
     }
     return MIPM_OK;
 }
+
+int mipm_batch_iter_begin(mipm_handle hh, double del_w, double del_c, double *out, int *status)
+{
+    return batch_begin(hh, del_w, del_c, out, status, 1);
+}
+
+int mipm_batch_peek(mipm_handle hh, double *out) { return batch_begin(hh, 0.0, 0.0, out, nullptr, 0); }
 
 /* mipm_mpc_iter_rest for the whole batch (step_rule 0 = AdaptiveStep, 1 = ConservativeStep). */
 int mipm_batch_iter_rest(mipm_handle hh, double mu_min, int step_rule, double tau_param, int ir_steps)
