@@ -1534,9 +1534,9 @@ static int fused_solve_system(Handle *h, int ir_steps, int slot)
 static int fused_fetch(Handle *h, double *out, int *status)
 {
     double sc[SC_COUNT];
-    int info[4];
+    int info[4] = {0, 0, 0, 0};
     MIPM_CUDA(h, cudaMemcpyAsync(h->h_scal, h->d_sc.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    MIPM_CUDA(h, cudaMemcpyAsync(info, h->d_info.p, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
+    if (status && h->d_info.p) MIPM_CUDA(h, cudaMemcpyAsync(info, h->d_info.p, sizeof(info), cudaMemcpyDeviceToHost, h->stream));
     MIPM_CUDA(h, cudaStreamSynchronize(h->stream));
     for (int i = 0; i < SC_COUNT; ++i) sc[i] = h->h_scal[i];
     if (status) *status = (info[0] == 0) ? MIPM_OK : MIPM_ERR_NOT_FACTORIZED;
@@ -1585,8 +1585,9 @@ int mipm_mpc_peek(mipm_handle hh, double *out)
 {
     Handle *h = (Handle *)hh;
     MIPM_NEED_DEVICE(h);
-    int rc = fused_ready(h);
-    if (rc != MIPM_OK) return rc;
+    // (also used around an external linear solver, where this handle has no factorization of its own)
+    if (!h->bound) return fail(h, MIPM_ERR_STATE, "mipm_mpc_bind has not been called");
+    if (!h->has_model) return fail(h, MIPM_ERR_STATE, "mipm_mpc_set_model has not been called");
     if (!out) return fail(h, MIPM_ERR_ARG, "null argument");
     MIPM_CUDA(h, cudaSetDevice(h->device));
     V v = make_view(h, inv_lb_buf(h).p, inv_ub_buf(h).p);

@@ -791,16 +791,16 @@ class MPCSolver:
         # Close to convergence (previous measures within 10 x tol) the termination measures are read before the next KKT
         # system is assembled and factorized, so the iteration that detects convergence does not pay for a factorization
         # it never uses; otherwise both go out together and the iteration has one synchronisation.
-        peek = (not ext and self._fused_started and self.status == REGULAR and
+        peek = (self._fused_started and self.status == REGULAR and
                 max(self.inf_pr, self.inf_du, self.inf_compl) <= 10.0 * opt.tol)
         ok = True
-        if ext:
+        if peek:
+            out = self.h.mpc_peek()
+        elif ext:
             self.h.mpc_ext_begin(self.del_w, self.del_c)
             self.linear_solver.factorize()
             ok = self.linear_solver.is_factorized()
             out = self.h.mpc_ext_fetch()
-        elif peek:
-            out = self.h.mpc_peek()
         else:
             out, ok = self.h.mpc_iter_begin(self.del_w, self.del_c)
         if self._fused_started:                            # scalars of the step taken in the previous call
@@ -834,7 +834,11 @@ class MPCSolver:
         self.del_w = new_del_w
         if self.status != REGULAR:
             return False
-        if peek:
+        if peek and ext:
+            self.h.mpc_ext_begin(self.del_w, self.del_c)
+            self.linear_solver.factorize()
+            ok = self.linear_solver.is_factorized()
+        elif peek:
             _, ok = self.h.mpc_iter_begin(self.del_w, self.del_c)
         self.cnt["factorizations"] += 1
         for _ in range(2):                                 # factorize_regularized_system! retries (linear_solver.jl:6-17)
