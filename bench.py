@@ -351,7 +351,7 @@ def main():
     iters_total = res.iter
     n, m = solver.n, solver.m
     h2d = solver.h2d_bytes_per_solve          # pinned problem data uploaded by every solve (solver._stage_problem)
-    d2h = 8 * (3 * n + m)
+    d2h = 8 * (3 * n + 2 * m)               # x, zl, zu, y and the constraint values A x: what solve() copies into its result buffers
     if world > 1:
         tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
