@@ -218,3 +218,26 @@ def test_host_analysis_is_independent_of_the_thread_count(built, monkeypatch):
     for key in a[2]:
         assert np.array_equal(a[2][key], b[2][key]), key
     assert a[3] == b[3]
+
+
+def test_ls_analyze_edge_cases(built):
+    """Host analysis on degenerate inputs: empty and 1 x 1 matrices, diagonal-only patterns, missing diagonals with 1-based
+    indices, and the input checks (non-monotone column pointer, entry above the diagonal, pointer not starting at the base)."""
+    h = _lib.Handle(device=-1)
+    h.ls_analyze(0, np.array([0], dtype=np.int32), np.zeros(0, dtype=np.int32))
+    assert h.ls_stats()["n_supernodes"] == 0
+    h.ls_analyze(1, np.array([0, 1], dtype=np.int32), np.array([0], dtype=np.int32))
+    assert h.ls_stats()["n"] == 1
+    n = 5000
+    h.ls_analyze(n, np.arange(n + 1, dtype=np.int32), np.arange(n, dtype=np.int32))
+    assert h.ls_stats()["nnz_l_exact"] == n
+    h.ls_analyze(3, np.array([1, 2, 3, 3], dtype=np.int32), np.array([2, 3], dtype=np.int32), index_base=1)
+    assert h.ls_stats()["nnz_l_exact"] == 5                  # chain 1 - 2 - 3: no fill, diagonals counted
+    for cp, ri in (([0, 2, 1], [0, 1]), ([0, 1, 2], [1, 0]), ([1, 2, 3], [0, 1])):
+        with pytest.raises(_lib.MipmError):
+            h.ls_analyze(2, np.array(cp, dtype=np.int32), np.array(ri, dtype=np.int32))
+    Bp, Bj, Bm = _lib.coo_to_csr(3, 2, np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
+    assert list(Bp) == [0, 0, 0, 0] and len(Bj) == 0
+    for I, J in (([3], [0]), ([1], [2])):
+        with pytest.raises(_lib.MipmError):
+            _lib.coo_to_csr(3, 2, np.array(I, dtype=np.int32), np.array(J, dtype=np.int32))
