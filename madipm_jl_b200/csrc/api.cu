@@ -1,8 +1,6 @@
 // C-ABI entry points: lifecycle, host symbolic builders, KKT assembly kernels, SpMV.
 // Each entry cites in include/madipm_b200.h the reference interface it replaces.
 #include <algorithm>
-#include <chrono>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 

@@ -5,12 +5,14 @@
 // src/utils.jl:288-301), so both builders are interchangeable bit for bit (tests/test_gpu_parity.py compares them).
 // The reference builds this structure with scalar host loops (src/utils.jl:209-274) and, on the GPU, with a
 // per-entry merge kernel (ext/MadIPMCUDAExt/cuda_wrapper.jl:158-234); here it is
-//   1. CSC index of A with CSR positions (host counting sort, rows ascend inside a column);
+//   1. CSC index of A with CSR positions: the one mipm_spmv_setup registered on the handle (Ap = Aj = NULL), or a
+//      stable bucket sort on the host threads (rows ascend inside a column);
 //   2. one thread per stored entry (i, k): number of entries (j, k), j >= i, of column k       -> exclusive scan
 //   3. one CTA per row i: emit the terms (j, p_j | p_i) of the row, bitonic sort by (j, p_j) in shared memory
 //      (rows with more terms than fit are sorted in a global workspace by the same code), write the sorted term
 //      arrays, compact the first term of every distinct j                                      -> exclusive scan
-//   4. one warp per row: move the compacted heads to their final place (Cj, term_ptr).
+//   4. one warp per row: move the compacted heads to their final place (Cj, term_ptr);
+//   5. row runs of the streaming assembly from a flag + scan pass over term_ptr.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
