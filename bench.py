@@ -47,6 +47,16 @@ try:
 except Exception:
     pass
 
+SOLVE_TRAFFIC = {}
+try:
+    for _k, _v in json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "solve_traffic_r02.json"))).items():
+        try:
+            SOLVE_TRAFFIC[float(_k)] = float(_v)
+        except (TypeError, ValueError):
+            pass
+except Exception:
+    pass
+
 METRIC = "ipm_iterations_per_second"
 UNIT = "iter/s"
 
@@ -433,7 +443,12 @@ def main():
         "factorization": {"ms": fac_ms, "tflops": st["flops"] / fac_ms / 1e9, "flops": st["flops"],
                           "launches": st["n_launches"]},
         "triangular_solve_pair": {"ms": sol_ms, "bound": "hbm", "achieved_gbs": sol_bytes / sol_ms / 1e6,
-                                  "frac": sol_bytes / sol_ms / 1e6 / peaks["hbm_gbs"], "algorithmic_bytes": sol_bytes},
+                                  "frac": sol_bytes / sol_ms / 1e6 / peaks["hbm_gbs"], "algorithmic_bytes": sol_bytes,
+                                  # DRAM bytes of one launch from the ncu capture (the sweeps also stream the inverted
+                                  # diagonal blocks, which the algorithmic figure does not count)
+                                  "traffic": SOLVE_TRAFFIC.get(args.scale),
+                                  "dram_gbs": (SOLVE_TRAFFIC[args.scale] / sol_ms / 1e6) if args.scale in SOLVE_TRAFFIC else None,
+                                  "dram_frac": (SOLVE_TRAFFIC[args.scale] / sol_ms / 1e6 / peaks["hbm_gbs"]) if args.scale in SOLVE_TRAFFIC else None},
         "spmv": {"ms": spmv_ms, "bound": "hbm", "achieved_gbs": spmv_bytes / spmv_ms / 1e6,
                  "frac": spmv_bytes / spmv_ms / 1e6 / peaks["hbm_gbs"]},
         "factor_classes": prof,
