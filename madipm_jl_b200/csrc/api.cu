@@ -387,8 +387,7 @@ int mipm_normal_symbolic(mipm_handle hh, int64_t m, int64_t n, const int32_t *Ap
         *nnzC = h->nsym.nnz_c;
         h->has_normal = true;
         h->has_jac = false;
-        MIPM_CUDA(h, h->d_term_w.alloc((size_t)h->nsym.n_terms));
-        MIPM_CUDA(h, h->d_D.alloc((size_t)n));
+        MIPM_CUDA(h, h->d_D.alloc((size_t)n));          // (d_term_w was allocated by the builder, which used it as scratch)
         return MIPM_OK;
     }
     std::string e = normal_symbolic_host(m, n, Ap, Aj, index_base, h->nsym);

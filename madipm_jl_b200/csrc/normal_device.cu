@@ -279,12 +279,17 @@ k_ns_place(int64_t m, const int32_t *__restrict__ Ap, const int32_t *__restrict_
     if (i == m - 1 && lane == 0) term_ptr[c1] = n_terms;
 }
 
-struct Scratch {       // plain cudaMalloc'd scratch released at scope exit
+struct Scratch {       // scratch released at scope exit: from the stream-ordered pool when the handle uses it (the memory
+                       // then serves the large allocations that follow: factor, update matrices), else cudaMalloc / cudaFree
     std::vector<void *> ptrs;
-    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+    cudaStream_t st = nullptr;
+    bool pooled = false;
+    explicit Scratch(cudaStream_t s, bool p) : st(s), pooled(p) {}
+    ~Scratch() { for (void *p : ptrs) { if (pooled) cudaFreeAsync(p, st); else cudaFree(p); } }
     template <typename T> cudaError_t get(T **p, size_t count) {
         *p = nullptr;
-        cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+        const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        cudaError_t e = pooled ? cudaMallocAsync((void **)p, bytes, st) : cudaMalloc((void **)p, bytes);
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
@@ -362,7 +367,7 @@ int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap_in
     S.m = m;
     S.n = n;
     cudaStream_t st = h->stream;
-    Scratch sc;
+    Scratch sc(st, tl_pooled);
     const int32_t *d_Ap, *d_Aj, *d_cptr, *d_crow, *d_cpos;
     int64_t nnz = 0;
     auto finish_empty = [&]() -> int {
@@ -472,9 +477,10 @@ int normal_symbolic_device(Handle *h, int64_t m, int64_t n, const int32_t *Ap_in
     MIPM_CUDA(h, h->d_term_pi.alloc((size_t)T));
     MIPM_CUDA(h, h->d_term_pj.alloc((size_t)T));
     MIPM_CUDA(h, h->d_term_k.alloc((size_t)T));
-    int32_t *d_head_j, *d_head_t;
-    MIPM_CUDA(h, sc.get(&d_head_j, (size_t)T));
-    MIPM_CUDA(h, sc.get(&d_head_t, (size_t)T));
+    // the compacted heads (2 x 4 bytes per term) live in the buffer of the term weights (8 bytes per term), which
+    // mipm_normal_set_jacobian fills later
+    MIPM_CUDA(h, h->d_term_w.alloc((size_t)std::max<long long>(T, 1)));
+    int32_t *d_head_j = reinterpret_cast<int32_t *>(h->d_term_w.p), *d_head_t = d_head_j + T;
     // ---- sort classes by the number of terms of a row: 128 threads / 24 KB, 512 threads / 192 KB, global workspace
     constexpr int CAP_S = 2048, CAP_L = 16384;
     NsArgs a;
